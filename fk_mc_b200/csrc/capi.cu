@@ -1,0 +1,327 @@
+// C-ABI entry points of libfkmc_b200 (declared in include/fkmc.h): context management, the batched
+// weight evaluators that stand in for configuration_t::calc_ed / calc_chebyshev, the stage-level
+// test entry points and instrumentation.  No CPU fallback: every compute call needs an sm_100 GPU.
+#include <algorithm>
+#include <cstring>
+#include <limits>
+
+#include "common.cuh"
+
+static thread_local std::string g_create_error;
+
+int fkmc_set_error(fkmc_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+
+fkmc_prof_scope::fkmc_prof_scope(fkmc_ctx* c, const char* n) : ctx(c), name(n) {
+    if (!ctx->profiling) return;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, ctx->stream);
+}
+fkmc_prof_scope::~fkmc_prof_scope() {
+    if (!a) return;
+    cudaEventRecord(b, ctx->stream);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    auto& e = ctx->prof[name];
+    e.total_ms += ms;
+    e.launches += 1;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+}
+
+namespace {
+
+template <class T>
+int dalloc(fkmc_ctx* ctx, T** p, size_t n) {
+    if (*p) return FKMC_OK;
+    FKMC_CUDA(ctx, cudaMalloc((void**)p, sizeof(T) * (n ? n : 1)));
+    return FKMC_OK;
+}
+
+}  // namespace
+
+// dense-path workspaces, allocated on first use (a KPM-only context never pays for them)
+int fkmc_ensure_dense_ws(fkmc_ctx* ctx) {
+    const size_t B = ctx->max_batch, N = ctx->N;
+    int rc = 0;
+    rc |= dalloc(ctx, &ctx->d_A, B * N * N);
+    rc |= dalloc(ctx, &ctx->d_W, B * N * FKMC_SYTRD_NB);
+    rc |= dalloc(ctx, &ctx->d_d, B * N);
+    rc |= dalloc(ctx, &ctx->d_e, B * N);
+    rc |= dalloc(ctx, &ctx->d_tau, B * N);
+    rc |= dalloc(ctx, &ctx->d_evals, B * N);
+    rc |= dalloc(ctx, &ctx->d_aux, 2 * B * N);
+    return rc ? FKMC_ERR_CUDA : FKMC_OK;
+}
+
+namespace {
+
+int check_flag(fkmc_ctx* ctx) {
+    int flag = 0;
+    FKMC_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flag) {
+        FKMC_CUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+        return fkmc_set_error(ctx, FKMC_ERR_NOCONV, flag & 1 ? "bisection iteration cap hit" : "Lanczos step cap hit before e_min/e_max stagnated");
+    }
+    return FKMC_OK;
+}
+
+int upload_f(fkmc_ctx* ctx, const int32_t* f, int B) {
+    if (!f) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "f is NULL");
+    if (B < 1 || B > ctx->max_batch) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "B must be in [1, max_batch]");
+    FKMC_CUDA(ctx, cudaSetDevice(ctx->device));
+    FKMC_CUDA(ctx, cudaMemcpyAsync(ctx->d_f, f, sizeof(int32_t) * (size_t)B * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+    return FKMC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fkmc_create(fkmc_ctx** out, int device, int lattice_kind, int L, double t, double tp, int max_batch) {
+    if (!out) return FKMC_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fkmc_set_error(nullptr, FKMC_ERR_NO_DEVICE, "no CUDA device: libfkmc_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fkmc_set_error(nullptr, FKMC_ERR_INVALID, "bad device index");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fkmc_set_error(nullptr, FKMC_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10) return fkmc_set_error(nullptr, FKMC_ERR_NO_DEVICE, "libfkmc_b200 is built for sm_100a only");
+    if (max_batch < 1) return fkmc_set_error(nullptr, FKMC_ERR_INVALID, "max_batch must be >= 1");
+    fkmc_ctx* ctx = new fkmc_ctx();
+    ctx->device = device;
+    ctx->kind = lattice_kind;
+    ctx->L = L;
+    ctx->t = t;
+    ctx->tp = tp;
+    ctx->max_batch = max_batch;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    int rc = fkmc_build_lattice(ctx);
+    if (rc) {
+        g_create_error = ctx->err;
+        delete ctx;
+        return rc;
+    }
+    auto fail = [&](const char* what) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError());
+        fkmc_destroy(ctx);
+        return FKMC_ERR_CUDA;
+    };
+    if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice");
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate");
+    ctx->own_stream = true;
+    const size_t N = ctx->N, Z = ctx->Z, B = max_batch;
+    if (cudaMalloc(&ctx->d_nbr_idx, sizeof(int) * std::max<size_t>(1, Z * N)) != cudaSuccess) return fail("cudaMalloc");
+    if (cudaMalloc(&ctx->d_nbr_val, sizeof(double) * std::max<size_t>(1, Z * N)) != cudaSuccess) return fail("cudaMalloc");
+    if (cudaMalloc(&ctx->d_f, sizeof(int32_t) * B * N) != cudaSuccess) return fail("cudaMalloc");
+    if (cudaMalloc(&ctx->d_out, sizeof(double) * B * 8) != cudaSuccess) return fail("cudaMalloc");
+    if (cudaMalloc(&ctx->d_flag, sizeof(int)) != cudaSuccess) return fail("cudaMalloc");
+    if (cudaMalloc(&ctx->d_moments, sizeof(double) * B * 2 * FKMC_MAX_HALF) != cudaSuccess) return fail("cudaMalloc");
+    if (cudaMalloc(&ctx->d_ab, sizeof(double) * B * 4) != cudaSuccess) return fail("cudaMalloc");
+    cudaMemcpy(ctx->d_nbr_idx, ctx->h_nbr_idx.data(), sizeof(int) * Z * N, cudaMemcpyHostToDevice);
+    cudaMemcpy(ctx->d_nbr_val, ctx->h_nbr_val.data(), sizeof(double) * Z * N, cudaMemcpyHostToDevice);
+    cudaMemset(ctx->d_flag, 0, sizeof(int));
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    if (cudaGetLastError() != cudaSuccess) return fail("context setup");
+    *out = ctx;
+    return FKMC_OK;
+}
+
+int fkmc_destroy(fkmc_ctx* ctx) {
+    if (!ctx) return FKMC_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    fkmc_chain_free(ctx);
+    cudaFree(ctx->d_nbr_idx); cudaFree(ctx->d_nbr_val); cudaFree(ctx->d_A); cudaFree(ctx->d_W); cudaFree(ctx->d_d);
+    cudaFree(ctx->d_e); cudaFree(ctx->d_tau); cudaFree(ctx->d_evals); cudaFree(ctx->d_out); cudaFree(ctx->d_f);
+    cudaFree(ctx->d_flag); cudaFree(ctx->d_moments); cudaFree(ctx->d_ab); cudaFree(ctx->d_aux);
+    cudaFree(ctx->d_chebt); cudaFree(ctx->d_lobatto); cudaFree(ctx->d_dtheta);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return FKMC_OK;
+}
+
+const char* fkmc_last_error(const fkmc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int fkmc_volume(const fkmc_ctx* ctx) { return ctx ? ctx->N : -1; }
+
+int fkmc_set_stream(fkmc_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return FKMC_ERR_INVALID;
+    if (ctx->own_stream && ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return FKMC_OK;
+}
+
+int fkmc_sync(fkmc_ctx* ctx) {
+    if (!ctx) return FKMC_ERR_INVALID;
+    FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FKMC_OK;
+}
+
+int fkmc_hopping_dense(const fkmc_ctx* ctx, double* H) {
+    if (!ctx || !H) return FKMC_ERR_INVALID;
+    const int N = ctx->N;
+    std::memset(H, 0, sizeof(double) * (size_t)N * N);
+    for (int z = 0; z < ctx->Z; ++z)
+        for (int i = 0; i < N; ++i) {
+            const int j = ctx->h_nbr_idx[(size_t)z * N + i];
+            if (j < N) H[(size_t)i * N + j] += ctx->h_nbr_val[(size_t)z * N + i];
+        }
+    return FKMC_OK;
+}
+
+int fkmc_logz_ed_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, double mu_c, double beta, double* evals, double* logZ,
+                         double* cached_exp, double* cached_fermi) {
+    if (!ctx) return FKMC_ERR_INVALID;
+    int rc = upload_f(ctx, f, B);
+    if (rc) return rc;
+    if ((rc = fkmc_ensure_dense_ws(ctx))) return rc;
+    const size_t N = ctx->N;
+    if ((rc = fkmc_launch_build_h(ctx, ctx->d_f, B, U, mu_c, ctx->d_A))) return rc;
+    if ((rc = fkmc_launch_sytrd(ctx, ctx->d_A, ctx->N, B, ctx->d_d, ctx->d_e, ctx->d_tau, ctx->d_W))) return rc;
+    double* dexp = cached_exp ? ctx->d_aux : nullptr;
+    double* dfer = cached_fermi ? ctx->d_aux + (size_t)ctx->max_batch * N : nullptr;
+    if ((rc = fkmc_launch_tridiag_eig(ctx, ctx->d_d, ctx->d_e, ctx->N, B, beta, ctx->d_evals, N, nullptr, 0, ctx->d_out, dexp, dfer)))
+        return rc;
+    if (evals) FKMC_CUDA(ctx, cudaMemcpyAsync(evals, ctx->d_evals, sizeof(double) * B * N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cached_exp) FKMC_CUDA(ctx, cudaMemcpyAsync(cached_exp, dexp, sizeof(double) * B * N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cached_fermi) FKMC_CUDA(ctx, cudaMemcpyAsync(cached_fermi, dfer, sizeof(double) * B * N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (logZ)
+        FKMC_CUDA(ctx, cudaMemcpy2DAsync(logZ, sizeof(double), ctx->d_out, 8 * sizeof(double), sizeof(double), B, cudaMemcpyDeviceToHost,
+                                         ctx->stream));
+    return check_flag(ctx);
+}
+
+int fkmc_eigh_batched(fkmc_ctx* ctx, const int32_t*, int, double, double, double, double*, double*, double*) {
+    return fkmc_set_error(ctx, FKMC_ERR_INVALID, "fkmc_eigh_batched: eigenvector path (calc_ed(true)) is not built yet");
+}
+
+int fkmc_logz_kpm_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, double mu_c, double beta, int M, int G, double* moments,
+                          double* ab, double* logZ) {
+    if (!ctx) return FKMC_ERR_INVALID;
+    if (M < 2 || M % 2 || M > 2 * FKMC_MAX_HALF) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "M must be even and in [2, 32]");
+    int rc = upload_f(ctx, f, B);
+    if (rc) return rc;
+    if ((rc = fkmc_launch_kpm(ctx, ctx->d_f, B, U, mu_c, beta, M, G, ctx->d_moments, ctx->d_ab, ctx->d_out))) return rc;
+    if (moments) FKMC_CUDA(ctx, cudaMemcpyAsync(moments, ctx->d_moments, sizeof(double) * (size_t)B * M, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ab) FKMC_CUDA(ctx, cudaMemcpyAsync(ab, ctx->d_ab, sizeof(double) * (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (logZ) FKMC_CUDA(ctx, cudaMemcpyAsync(logZ, ctx->d_out, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    return check_flag(ctx);
+}
+
+int fkmc_energy_from_spectrum(fkmc_ctx* ctx, const double* evals, int B, double beta, double* out3) {
+    if (!ctx || !evals || !out3) return FKMC_ERR_INVALID;
+    if (B < 1 || B > ctx->max_batch) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "B must be in [1, max_batch]");
+    int rc = fkmc_ensure_dense_ws(ctx);
+    if (rc) return rc;
+    const size_t N = ctx->N;
+    FKMC_CUDA(ctx, cudaMemcpyAsync(ctx->d_evals, evals, sizeof(double) * B * N, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = fkmc_launch_energy(ctx, ctx->d_evals, N, nullptr, 0, ctx->N, B, beta, ctx->d_out))) return rc;
+    std::vector<double> tmp((size_t)B * 8);
+    FKMC_CUDA(ctx, cudaMemcpyAsync(tmp.data(), ctx->d_out, sizeof(double) * B * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < B; ++b) {
+        out3[3 * b + 0] = tmp[8 * b + 1];
+        out3[3 * b + 1] = tmp[8 * b + 2];
+        out3[3 * b + 2] = tmp[8 * b + 0];
+    }
+    return FKMC_OK;
+}
+
+int fkmc_sytrd_batched(fkmc_ctx* ctx, const double* A, int N, int B, double* d, double* e) {
+    if (!ctx || !A || !d || !e || N < 2 || B < 1) return FKMC_ERR_INVALID;
+    FKMC_CUDA(ctx, cudaSetDevice(ctx->device));
+    double *dA = nullptr, *dW = nullptr, *dd = nullptr, *de = nullptr, *dt = nullptr;
+    const size_t n = N, b = B;
+    FKMC_CUDA(ctx, cudaMalloc(&dA, sizeof(double) * b * n * n));
+    FKMC_CUDA(ctx, cudaMalloc(&dW, sizeof(double) * b * n * FKMC_SYTRD_NB));
+    FKMC_CUDA(ctx, cudaMalloc(&dd, sizeof(double) * b * n));
+    FKMC_CUDA(ctx, cudaMalloc(&de, sizeof(double) * b * n));
+    FKMC_CUDA(ctx, cudaMalloc(&dt, sizeof(double) * b * n));
+    FKMC_CUDA(ctx, cudaMemcpyAsync(dA, A, sizeof(double) * b * n * n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = fkmc_launch_sytrd(ctx, dA, N, B, dd, de, dt, dW);
+    if (!rc) {
+        FKMC_CUDA(ctx, cudaMemcpyAsync(d, dd, sizeof(double) * b * n, cudaMemcpyDeviceToHost, ctx->stream));
+        FKMC_CUDA(ctx, cudaMemcpy2DAsync(e, sizeof(double) * (n - 1), de, sizeof(double) * n, sizeof(double) * (n - 1), b,
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+        FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    cudaFree(dA); cudaFree(dW); cudaFree(dd); cudaFree(de); cudaFree(dt);
+    return rc;
+}
+
+int fkmc_tridiag_eigvals_batched(fkmc_ctx* ctx, const double* d, const double* e, int N, int B, double* evals) {
+    if (!ctx || !d || !e || !evals || N < 2 || B < 1) return FKMC_ERR_INVALID;
+    FKMC_CUDA(ctx, cudaSetDevice(ctx->device));
+    double *dd = nullptr, *de = nullptr, *dv = nullptr, *dout = nullptr;
+    const size_t n = N, b = B;
+    FKMC_CUDA(ctx, cudaMalloc(&dd, sizeof(double) * b * n));
+    FKMC_CUDA(ctx, cudaMalloc(&de, sizeof(double) * b * n));
+    FKMC_CUDA(ctx, cudaMalloc(&dv, sizeof(double) * b * n));
+    FKMC_CUDA(ctx, cudaMalloc(&dout, sizeof(double) * b * 8));
+    FKMC_CUDA(ctx, cudaMemsetAsync(de, 0, sizeof(double) * b * n, ctx->stream));
+    FKMC_CUDA(ctx, cudaMemcpyAsync(dd, d, sizeof(double) * b * n, cudaMemcpyHostToDevice, ctx->stream));
+    FKMC_CUDA(ctx, cudaMemcpy2DAsync(de, sizeof(double) * n, e, sizeof(double) * (n - 1), sizeof(double) * (n - 1), b,
+                                     cudaMemcpyHostToDevice, ctx->stream));
+    int rc = fkmc_launch_tridiag_eig(ctx, dd, de, N, B, 1.0, dv, N, nullptr, 0, dout, nullptr, nullptr);
+    if (!rc) {
+        FKMC_CUDA(ctx, cudaMemcpyAsync(evals, dv, sizeof(double) * b * n, cudaMemcpyDeviceToHost, ctx->stream));
+        rc = check_flag(ctx);
+    }
+    cudaFree(dd); cudaFree(de); cudaFree(dv); cudaFree(dout);
+    return rc;
+}
+
+int64_t fkmc_launch_count(const fkmc_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int fkmc_timer_begin(fkmc_ctx* ctx) {
+    if (!ctx) return FKMC_ERR_INVALID;
+    FKMC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    return FKMC_OK;
+}
+
+int fkmc_timer_end(fkmc_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return FKMC_ERR_INVALID;
+    FKMC_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    FKMC_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    FKMC_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return FKMC_OK;
+}
+
+int fkmc_profile_enable(fkmc_ctx* ctx, int on) {
+    if (!ctx) return FKMC_ERR_INVALID;
+    ctx->profiling = on != 0;
+    return FKMC_OK;
+}
+
+int fkmc_profile_get(fkmc_ctx* ctx, const char* family, double* total_ms, int64_t* launches) {
+    if (!ctx || !family) return FKMC_ERR_INVALID;
+    auto it = ctx->prof.find(family);
+    if (total_ms) *total_ms = it == ctx->prof.end() ? 0.0 : it->second.total_ms;
+    if (launches) *launches = it == ctx->prof.end() ? 0 : it->second.launches;
+    return FKMC_OK;
+}
+
+int fkmc_profile_reset(fkmc_ctx* ctx) {
+    if (!ctx) return FKMC_ERR_INVALID;
+    ctx->prof.clear();
+    return FKMC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+// Internal declarations shared by the sm_100a kernels of libfkmc_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/fkmc.h"
+
+#define FKMC_MAX_Z 8        // max neighbours per site (triangular: 6)
+#define FKMC_SYTRD_NB 32    // panel width of the blocked tridiagonalisation
+#define FKMC_MAX_HALF 16    // KPM: M/2 <= 16
+
+struct fkmc_profile_entry {
+    double total_ms = 0;
+    int64_t launches = 0;
+};
+
+struct fkmc_chain_state {
+    bool active = false;
+    fkmc_chain_params p{};
+    int n_chains = 0, M = 0, G = 0;
+    int n_moves = 0;
+    int move_kind[3] = {0, 0, 0};
+    double move_cp[3] = {0, 0, 0};  // cumulative probabilities (std::discrete_distribution)
+    long sweeps_done = 0, measured = 0;
+    // device buffers
+    uint32_t* mt = nullptr;     // [n_chains][625] state + index
+    int32_t* f_cur = nullptr;   // [n_chains][V]
+    int32_t* f_prop = nullptr;  // [n_chains][V]
+    double* logz_cur = nullptr;
+    double* logz_prop = nullptr;
+    double* spec[2] = {nullptr, nullptr};  // [n_chains][N] double-buffered spectrum (exact moves)
+    int32_t* cur_slot = nullptr;           // [n_chains] which of spec[] is current
+    int32_t* prop_move = nullptr;          // [n_chains] move kind of the pending proposal (-1: early-out, weight 0)
+    int32_t* prop_a = nullptr;
+    int32_t* prop_b = nullptr;
+    int64_t* naccept = nullptr;
+    double *s_energy = nullptr, *s_d2energy = nullptr, *s_cenergy = nullptr;  // [max_sweeps][n_chains]
+    int32_t* s_nf = nullptr;
+    // trace [max_steps][n_chains]
+    int32_t *t_move = nullptr, *t_a = nullptr, *t_b = nullptr, *t_acc = nullptr;
+    double *t_w = nullptr, *t_u = nullptr, *t_lz = nullptr;
+};
+
+struct fkmc_ctx {
+    int device = 0;
+    int kind = 0, ndim = 0, L = 0, N = 0, Z = 0;
+    double t = 1, tp = 1;
+    int max_batch = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int64_t launches = 0;
+    int num_sms = 0;
+    size_t smem_optin = 0;
+
+    // lattice tables (host + device).  nbr_idx[z*N + i] = z-th neighbour of site i (N = "none": the
+    // zero slot), nbr_val[z*N + i] = hopping_m(i, nbr) (0 for padding).
+    std::vector<int> h_nbr_idx;
+    std::vector<double> h_nbr_val;
+    int* d_nbr_idx = nullptr;
+    double* d_nbr_val = nullptr;
+
+    // workspaces sized for max_batch
+    double* d_A = nullptr;      // [max_batch][N][N] dense Hamiltonians (column-major, lower triangle live)
+    double* d_W = nullptr;      // [max_batch][N][NB] panel workspace
+    double* d_d = nullptr;      // [max_batch][N]
+    double* d_e = nullptr;      // [max_batch][N]
+    double* d_tau = nullptr;    // [max_batch][N]
+    double* d_evals = nullptr;  // [max_batch][N]
+    double* d_out = nullptr;    // [max_batch][8] per-matrix scalars (logZ, E_c, d2E, ...)
+    int32_t* d_f = nullptr;     // [max_batch][N] staging for host f
+    int* d_flag = nullptr;      // non-convergence flag
+    double* d_moments = nullptr;  // [max_batch][2*FKMC_MAX_HALF]
+    double* d_ab = nullptr;       // [max_batch][4]
+    double* d_aux = nullptr;      // [max_batch][2][N] cached_exp / cached_fermi staging
+
+    // Chebyshev tables for the (M, G) last used
+    int cheb_M = 0, cheb_G = 0;
+    double* d_chebt = nullptr;    // [M][G]
+    double* d_lobatto = nullptr;  // [G]
+    double* d_dtheta = nullptr;   // [G-1]
+
+    fkmc_chain_state chain;
+
+    // instrumentation
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool profiling = false;
+    std::map<std::string, fkmc_profile_entry> prof;
+};
+
+// ---- error helpers ----
+int fkmc_set_error(fkmc_ctx* ctx, int code, const std::string& msg);
+#define FKMC_CUDA(ctx, call)                                                                              \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return fkmc_set_error(ctx, FKMC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+// RAII-less profiling scope: records events around a kernel family when profiling is on
+struct fkmc_prof_scope {
+    fkmc_ctx* ctx;
+    const char* name;
+    cudaEvent_t a = nullptr, b = nullptr;
+    fkmc_prof_scope(fkmc_ctx* c, const char* n);
+    ~fkmc_prof_scope();
+};
+
+// ---- workspaces ----
+int fkmc_ensure_dense_ws(fkmc_ctx* ctx);
+
+// ---- lattice (host) ----
+int fkmc_build_lattice(fkmc_ctx* ctx);
+
+// ---- kernel launchers (each returns an fkmc_status) ----
+// dense H (lower triangle) from f: A[b] = hopping + diag(U f - mu_c)
+int fkmc_launch_build_h(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double* d_A);
+// blocked Householder tridiagonalisation, one CTA per matrix; A is overwritten
+int fkmc_launch_sytrd(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_d, double* d_e, double* d_tau, double* d_W);
+// Sturm bisection + fused logZ / energy: out[b*8 + {0: logZ, 1: E_c, 2: d2E}]
+int fkmc_launch_tridiag_eig(fkmc_ctx* ctx, const double* d_d, const double* d_e, int N, int B, double beta, double* d_evals,
+                            long evals_stride, const int32_t* d_slot, long slot_stride, double* d_out, double* d_exp,
+                            double* d_fermi);
+int fkmc_launch_energy(fkmc_ctx* ctx, const double* d_evals, long evals_stride, const int32_t* d_slot, long slot_stride, int N,
+                       int B, double beta, double* d_out);
+// KPM: Lanczos extremal eigenvalues + Chebyshev moments + logZ
+int fkmc_prepare_cheb(fkmc_ctx* ctx, int M, int G);
+int fkmc_launch_kpm(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, int M, int G,
+                    double* d_moments, double* d_ab, double* d_logz);
+// chains
+int fkmc_chain_free(fkmc_ctx* ctx);
+
+#ifdef __CUDACC__
+// ---- device helpers ----
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// block-wide sum; red must hold >= 33 doubles; all threads get the result.  Two barriers.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double s = lane < nw ? red[lane] : 0.0;
+        s = warp_sum(s);
+        if (lane == 0) red[32] = s;
+    }
+    __syncthreads();
+    return red[32];
+}
+// FP64 tensor-core MMA (SASS: DMMA.8x8x4): D(8x8) += A(8x4) * B(4x8).
+// lane = 4*g + t:  a = A[g][t], b = B[t][g], (c0, c1) = C[g][2t], C[g][2t+1].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+#endif

@@ -1,0 +1,187 @@
+// Eigenvalues of symmetric tridiagonals by Sturm bisection (one CTA per matrix, one thread per
+// eigenvalue) with the free-energy reduction fused in.
+//
+// Replaces the implicit-QR stage of Eigen::SelfAdjointEigenSolver (call site
+// src/configuration.cpp:213) and the cache fill of configuration_t::calc_ed
+// (src/configuration.cpp:226-244): cached_exp = e^{beta eps}, cached_fermi = 1/(1+e^{beta eps}),
+// logZ = sum_i [log(e^{beta eps_0} + e^{-beta (eps_i - eps_0)}) - beta eps_0].
+// Also measure_energy::accumulate (src/measures/energy.cpp:6-26) from a cached spectrum.
+//
+// Sturm count in product form p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (no division; one
+// dependent FMA per row) with periodic power-of-two rescaling; (d_i, e_{i-1}^2) pairs are
+// broadcast from shared memory.
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace {
+
+// number of eigenvalues < x.  de[i] = (d_i, e_{i-1}^2), e_{-1} = 0.
+__device__ __forceinline__ int sturm_count(const double2* __restrict__ de, int n, double x) {
+    double pm1 = 1.0, p = de[0].x - x;
+    if (p == 0.0) p = -DBL_EPSILON;
+    bool neg = p < 0.0;
+    int cnt = neg ? 1 : 0;
+    for (int i0 = 1; i0 < n; i0 += 8) {
+        const int i1 = min(i0 + 8, n);
+        for (int i = i0; i < i1; ++i) {
+            const double2 q = de[i];
+            double pn = fma(q.x - x, p, -(q.y * pm1));
+            if (pn == 0.0) pn = -DBL_EPSILON * p;
+            const bool nneg = pn < 0.0;
+            cnt += (nneg != neg) ? 1 : 0;
+            neg = nneg;
+            pm1 = p;
+            p = pn;
+        }
+        // rescale by a power of two when the pair drifts out of [2^-256, 2^256]
+        const double m = fmax(fabs(p), fabs(pm1));
+        if (m > 1.157920892373162e77) { p *= 8.636168555094445e-78; pm1 *= 8.636168555094445e-78; }
+        else if (m < 8.636168555094445e-78) { p *= 1.157920892373162e77; pm1 *= 1.157920892373162e77; }
+    }
+    return cnt;
+}
+
+// shared-memory block: de[Np] (double2), red[40]
+__global__ void __launch_bounds__(1024)
+tridiag_eig_kernel(const double* __restrict__ d_all, const double* __restrict__ e_all, int N, double beta,
+                   double* __restrict__ evals_all, long evals_stride, const int32_t* __restrict__ slot, long slot_stride,
+                   double* __restrict__ out_all, double* __restrict__ exp_all, double* __restrict__ fermi_all,
+                   int* __restrict__ flag) {
+    extern __shared__ double2 sm2[];
+    double2* de = sm2;
+    double* red = reinterpret_cast<double*>(sm2 + N);
+    const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const double* d = d_all + (size_t)b * N;
+    const double* e = e_all + (size_t)b * N;
+    // scale by max |entry| (as Eigen's solver does) so the product-form recurrence stays in range
+    double mx = 0.0;
+    for (int i = tid; i < N; i += T) mx = fmax(mx, fmax(fabs(d[i]), i < N - 1 ? fabs(e[i]) : 0.0));
+    mx = warp_max(mx);
+    const int lane_ = tid & 31, warp_ = tid >> 5, nw_ = (T + 31) >> 5;
+    if (lane_ == 0) red[warp_] = mx;
+    __syncthreads();
+    mx = 0.0;
+    for (int w = 0; w < nw_; ++w) mx = fmax(mx, red[w]);
+    __syncthreads();
+    const double sc = mx > 0.0 ? mx : 1.0, isc = 1.0 / sc;
+    // Gershgorin bounds of the scaled matrix
+    double lo = DBL_MAX, hi = -DBL_MAX;
+    for (int i = tid; i < N; i += T) {
+        const double el = (i > 0 ? e[i - 1] : 0.0) * isc, er = (i < N - 1 ? e[i] : 0.0) * isc, di = d[i] * isc;
+        de[i] = make_double2(di, el * el);
+        const double rad = fabs(el) + fabs(er);
+        lo = fmin(lo, di - rad);
+        hi = fmax(hi, di + rad);
+    }
+    lo = -warp_max(-lo);
+    hi = warp_max(hi);
+    {
+        if (lane_ == 0) { red[warp_] = lo; red[40 + warp_] = hi; }
+        __syncthreads();
+        double l2 = DBL_MAX, h2 = -DBL_MAX;
+        for (int w = 0; w < nw_; ++w) { l2 = fmin(l2, red[w]); h2 = fmax(h2, red[40 + w]); }
+        lo = l2; hi = h2;
+        __syncthreads();
+    }
+    const double span = fmax(hi - lo, DBL_MIN);
+    lo -= 4.0 * DBL_EPSILON * span + 2.0 * DBL_MIN;
+    hi += 4.0 * DBL_EPSILON * span + 2.0 * DBL_MIN;
+    const double scale = fmax(fabs(lo), fabs(hi));
+
+    double* ev = evals_all + (size_t)b * evals_stride + (slot ? (size_t)slot[b] * slot_stride : 0);
+    double lam = 0.0;
+    for (int k = tid; k < N; k += T) {  // T >= N in practice: one eigenvalue per thread
+        double a = lo, c = hi;
+        int it = 0;
+        for (; it < 128; ++it) {
+            const double mid = 0.5 * (a + c);
+            if (mid <= a || mid >= c) break;
+            if (c - a <= 2.0 * DBL_EPSILON * scale) break;
+            if (sturm_count(de, N, mid) > k) c = mid; else a = mid;
+        }
+        if (it >= 128) atomicOr(flag, 1);
+        lam = 0.5 * (a + c) * sc;
+        ev[k] = lam;
+    }
+    // ---- fused free energy / Fermi caches / energy measure (T >= N assumed for the reduction) ----
+    __shared__ double e0s;
+    if (tid == 0) e0s = lam;  // thread 0 holds the smallest eigenvalue
+    __syncthreads();
+    const double e0 = e0s;
+    double lz = 0.0, ec = 0.0, d2 = 0.0;
+    for (int k = tid; k < N; k += T) {
+        const double x = (T >= N) ? lam : ev[k];
+        const double logw0 = beta * e0;
+        const double w = exp(-beta * (x - e0));
+        const double ex = exp(beta * x);
+        lz = log(exp(logw0) + w) - logw0;
+        ec = x / (1.0 + ex);
+        d2 = x * x / (1.0 + 0.5 * (ex + 1.0 / ex));
+        if (exp_all) exp_all[(size_t)b * N + k] = ex;
+        if (fermi_all) fermi_all[(size_t)b * N + k] = 1.0 / (1.0 + ex);
+    }
+    lz = block_sum(lz, red);
+    ec = block_sum(ec, red);
+    d2 = block_sum(d2, red);
+    if (tid == 0) {
+        out_all[(size_t)b * 8 + 0] = lz;
+        out_all[(size_t)b * 8 + 1] = ec;
+        out_all[(size_t)b * 8 + 2] = 0.5 * d2;
+    }
+}
+
+// energy measure from an existing spectrum
+__global__ void __launch_bounds__(1024)
+energy_kernel(const double* __restrict__ evals_all, long evals_stride, const int32_t* __restrict__ slot, long slot_stride, int N,
+              double beta, double* __restrict__ out_all) {
+    __shared__ double red[40];
+    const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const double* ev = evals_all + (size_t)b * evals_stride + (slot ? (size_t)slot[b] * slot_stride : 0);
+    const double e0 = ev[0];
+    double lz = 0.0, ec = 0.0, d2 = 0.0;
+    for (int k = tid; k < N; k += T) {
+        const double x = ev[k];
+        const double logw0 = beta * e0;
+        const double w = exp(-beta * (x - e0));
+        const double ex = exp(beta * x);
+        lz += log(exp(logw0) + w) - logw0;
+        ec += x / (1.0 + ex);
+        d2 += x * x / (1.0 + 0.5 * (ex + 1.0 / ex));
+    }
+    lz = block_sum(lz, red);
+    ec = block_sum(ec, red);
+    d2 = block_sum(d2, red);
+    if (tid == 0) {
+        out_all[(size_t)b * 8 + 0] = lz;
+        out_all[(size_t)b * 8 + 1] = ec;
+        out_all[(size_t)b * 8 + 2] = 0.5 * d2;
+    }
+}
+
+}  // namespace
+
+int fkmc_launch_tridiag_eig(fkmc_ctx* ctx, const double* d_d, const double* d_e, int N, int B, double beta, double* d_evals,
+                            long evals_stride, const int32_t* d_slot, long slot_stride, double* d_out, double* d_exp,
+                            double* d_fermi) {
+    fkmc_prof_scope ps(ctx, "tridiag_eig");
+    if (N > 1024) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "tridiag_eig: N > 1024 not supported yet");
+    const int T = ((N + 31) / 32) * 32;
+    const size_t smem = sizeof(double2) * N + sizeof(double) * 96;
+    tridiag_eig_kernel<<<B, T, smem, ctx->stream>>>(d_d, d_e, N, beta, d_evals, evals_stride, d_slot, slot_stride, d_out, d_exp,
+                                                    d_fermi, ctx->d_flag);
+    ctx->launches++;
+    FKMC_CUDA(ctx, cudaGetLastError());
+    return FKMC_OK;
+}
+
+int fkmc_launch_energy(fkmc_ctx* ctx, const double* d_evals, long evals_stride, const int32_t* d_slot, long slot_stride, int N,
+                       int B, double beta, double* d_out) {
+    fkmc_prof_scope ps(ctx, "energy");
+    int T = ((N + 31) / 32) * 32;
+    if (T > 1024) T = 1024;
+    energy_kernel<<<B, T, 0, ctx->stream>>>(d_evals, evals_stride, d_slot, slot_stride, N, beta, d_out);
+    ctx->launches++;
+    FKMC_CUDA(ctx, cudaGetLastError());
+    return FKMC_OK;
+}

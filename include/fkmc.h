@@ -1,0 +1,134 @@
+/* fkmc.h -- C ABI of the B200-native fk_mc weight-evaluation hot path (libfkmc_b200.so).
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, returns an int status
+ * (FKMC_OK == 0) and never throws.  Host pointers unless the name ends in `_dev`.
+ * A context owns one GPU's device buffers, its stream and its Chebyshev tables; it is not
+ * re-entrant, but different contexts may be driven from different host threads.
+ *
+ * Each function cites the reference interface (aeantipov/fk_mc, file:line) it replaces; the
+ * binding a maintainer would add on the reference side is shown in INTEGRATION.md.
+ */
+#ifndef FKMC_H_
+#define FKMC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fkmc_ctx fkmc_ctx;
+
+enum fkmc_status {
+    FKMC_OK = 0,
+    FKMC_ERR_INVALID = 1,      /* bad argument (maps to std::logic_error in the C++ wrapper) */
+    FKMC_ERR_CUDA = 2,         /* CUDA runtime error; see fkmc_last_error */
+    FKMC_ERR_NO_DEVICE = 3,    /* no usable sm_100 device: there is NO CPU fallback */
+    FKMC_ERR_NOCONV = 4,       /* bisection / Lanczos iteration cap hit */
+    FKMC_ERR_STATE = 5         /* call sequence error (e.g. run before init) */
+};
+
+/* Lattices: include/fk_mc/lattice/hypercubic.hpp:16-95, src/lattice/hypercubic.cpp:116-203.
+ * Site index is row-major with the LAST coordinate fastest (hypercubic.cpp:31-51). */
+enum fkmc_lattice_kind {
+    FKMC_CUBIC1D = 1,             /* fill_nearest_neighbors<1> */
+    FKMC_CUBIC2D = 2,             /* fill_nearest_neighbors<2> */
+    FKMC_CUBIC3D = 3,             /* fill_nearest_neighbors<3> */
+    FKMC_TRIANGULAR = 4,          /* fill_triangular(t, tp) */
+    FKMC_HONEYCOMB = 5,           /* intended brick wall (symmetric) */
+    FKMC_HONEYCOMB_REF_LOWER = 7  /* literal fill_honeycomb as Eigen's lower-triangle solver sees it */
+};
+
+enum fkmc_move_kind { FKMC_MOVE_FLIP = 0, FKMC_MOVE_ADDREMOVE = 1, FKMC_MOVE_RESHUFFLE = 2 };
+
+/* ---- context ------------------------------------------------------------------------- */
+/* Replaces hypercubic_lattice<D>(L) + fill_* (hypercubic.cpp:7-14,116-203).  max_batch = the
+ * largest B any later call will pass (device workspaces are sized once). */
+int fkmc_create(fkmc_ctx** ctx, int device, int lattice_kind, int L, double t, double tp, int max_batch);
+int fkmc_destroy(fkmc_ctx* ctx);
+const char* fkmc_last_error(const fkmc_ctx* ctx); /* ctx may be NULL: last creation error */
+int fkmc_volume(const fkmc_ctx* ctx);             /* abstract_lattice::volume(), lattice.hpp:20 */
+int fkmc_set_stream(fkmc_ctx* ctx, void* cuda_stream); /* run on a caller-owned cudaStream_t */
+int fkmc_sync(fkmc_ctx* ctx);
+/* dense hopping matrix, row-major H[i*N+j] = hopping_m(i,j) (abstract_lattice::hopping_m, lattice.hpp:22) */
+int fkmc_hopping_dense(const fkmc_ctx* ctx, double* H);
+
+/* ---- weight evaluators (the seam: configuration_t::calc_ed / calc_chebyshev) ------------ */
+/* configuration_t::calc_hamiltonian + calc_ed(false), src/configuration.cpp:79-91,208-246.
+ * f: [B][V] int32 occupations (configuration_t::f_config_).  evals: [B][N] ascending (cached_spectrum)
+ * or NULL.  logZ: [B] (ed_cache::logZ).  cached_exp / cached_fermi: [B][N] or NULL. */
+int fkmc_logz_ed_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, double mu_c, double beta,
+                         double* evals, double* logZ, double* cached_exp, double* cached_fermi);
+
+/* calc_ed(true), src/configuration.cpp:213,216-219: evecs [B][N][N] column-major, column k <-> evals[k]. */
+int fkmc_eigh_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, double mu_c, double beta,
+                      double* evals, double* evecs, double* logZ);
+
+/* chebyshev_eval(max_moment, grid) + calc_chebyshev, include/fk_mc/chebyshev.hpp:21-54,
+ * src/configuration.cpp:94-205.  moments: [B][M] (chebyshev_cache::moments), ab: [B][4] =
+ * {e_min, e_max, a, b}, logZ: [B].  M must be even. */
+int fkmc_logz_kpm_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, double mu_c, double beta, int M, int G,
+                          double* moments, double* ab, double* logZ);
+
+/* measure_energy::accumulate, src/measures/energy.cpp:6-26, from a spectrum: out [B][3] = {E_c, d2E, logZ};
+ * E = E_c - mu_f*N_f + E_ff is finished by the caller. */
+int fkmc_energy_from_spectrum(fkmc_ctx* ctx, const double* evals, int B, double beta, double* out3);
+
+/* ---- stage-level entry points (used by the parity tests) --------------------------------- */
+/* Householder tridiagonalisation of B dense symmetric matrices (lower triangle read),
+ * A: [B][N][N] column-major.  d: [B][N], e: [B][N-1].  Eigen's tridiagonalization_inplace stage of
+ * SelfAdjointEigenSolver (call site src/configuration.cpp:213). */
+int fkmc_sytrd_batched(fkmc_ctx* ctx, const double* A, int N, int B, double* d, double* e);
+/* eigenvalues (ascending) of B symmetric tridiagonals by Sturm bisection */
+int fkmc_tridiag_eigvals_batched(fkmc_ctx* ctx, const double* d, const double* e, int N, int B, double* evals);
+/* device std::mt19937 + libstdc++ distributions: mode 0 raw words, 1 uniform_int(0,V-1), 2 uniform_real(0,1) */
+int fkmc_rng_stream(fkmc_ctx* ctx, int64_t seed, int mode, int V, int count, double* out);
+
+/* ---- device-resident Markov chains (mc_metropolis + moves + measures) -------------------- */
+/* Mirrors fk_mc<L>::define_parameters (include/fk_mc/fk_mc.hxx:177-207) and
+ * mc_metropolis::define_parameters (src/mc_metropolis.cpp:11-19). */
+typedef struct fkmc_chain_params {
+    double beta, U, mu_c, mu_f;
+    double mc_flip, mc_add_remove, mc_reshuffle; /* move weights; a move is registered iff weight > eps */
+    int32_t cheb_moves;                          /* 0: exact moves (src/moves.cpp), 1: src/moves_chebyshev.cpp */
+    double cheb_prefactor;                       /* M = even(int(ln N * prefactor)), G = max(2M,10) */
+    int64_t seed;                                /* chain c uses std::mt19937(seed + chain0 + c), mc_metropolis.cpp:25 */
+    int32_t chain0;                              /* global id of this context's first chain (rank offset) */
+    int32_t nf_start;                            /* randomize_f(rng, nf_start); the exec passes V/2 */
+    int32_t sweep_len;                           /* proposals per sweep */
+    int32_t ntherm_sweeps;                       /* sweeps before measuring starts */
+    int32_t measure_energy;                      /* energy/spectrum measures (exact calc_ed per measured sweep) */
+    int32_t record_trace;                        /* keep per-step (site, weight, u, accepted) for parity tests */
+    int32_t max_sweeps;                          /* capacity of the series / trace buffers */
+} fkmc_chain_params;
+
+int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_params* p);
+/* mc_metropolis::update + measure, n_sweeps times (src/mc_metropolis.cpp:34-61) */
+int fkmc_chain_run_sweeps(fkmc_ctx* ctx, int n_sweeps);
+/* series: [n_measured][n_chains] each (observables_t::energies, d2energies, c_energies, fk_mc.hpp:13-34); any may be NULL */
+int fkmc_chain_get_series(fkmc_ctx* ctx, int* n_measured, double* energies, double* d2energies, double* c_energies,
+                          int32_t* nf);
+/* state: f [n_chains][V], logZ [n_chains], naccept [n_chains] */
+int fkmc_chain_get_state(fkmc_ctx* ctx, int32_t* f, double* logZ, int64_t* naccept, double* spectrum);
+/* trace: [n_steps][n_chains] each; n_steps = sweeps run * sweep_len */
+int fkmc_chain_get_trace(fkmc_ctx* ctx, int* n_steps, int32_t* move, int32_t* site_a, int32_t* site_b, int32_t* accepted,
+                         double* weight, double* u, double* logz_new);
+/* device pointers to the series (for the end-of-run NCCL gather): energies, d2energies, c_energies as
+ * [max_sweeps][n_chains] doubles */
+int fkmc_chain_series_dev(fkmc_ctx* ctx, void** energies, void** d2energies, void** c_energies, int* ld);
+
+/* ---- instrumentation -------------------------------------------------------------------- */
+/* number of kernels this context has launched since creation */
+int64_t fkmc_launch_count(const fkmc_ctx* ctx);
+/* CUDA-event timing on the context's stream: begin/end a region, read milliseconds */
+int fkmc_timer_begin(fkmc_ctx* ctx);
+int fkmc_timer_end(fkmc_ctx* ctx, float* ms);
+/* accumulated device time of one kernel family since the last reset (events around each launch when enabled) */
+int fkmc_profile_enable(fkmc_ctx* ctx, int on);
+int fkmc_profile_get(fkmc_ctx* ctx, const char* family, double* total_ms, int64_t* launches);
+int fkmc_profile_reset(fkmc_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FKMC_H_ */
