@@ -12,6 +12,7 @@
 //      each warp owns a set of columns j and keeps two iterates in shared memory, updating in place;
 //   3. c_m = moment_f(N log(1+e^{-beta(a x+b)}), m) on the G-point Lobatto grid (trapezoid rule) and
 //      logZ = c_0 + 2 sum_{m>=1} c_m mu_m (configuration.cpp:198-202).
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 
@@ -35,6 +36,7 @@ struct kpm_args {
     double* logz;           // [B]
     int* flag;
     int nwarps_cols;        // warps that run the column recursion
+    int vec_doubles;        // size of the shared vector region (>= 2 Nv per column warp and >= the Lanczos need)
 };
 
 // number of eigenvalues of the k x k Lanczos tridiagonal (al[0..k-1], off-diagonals be[1..k-1]) below x
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(384, 1) kpm_kernel(kpm_args P) {
     double* Fg = msc + 64;                 // [G]   F(x_i) on the Lobatto grid
     double* acc = Fg + ((G + 1) & ~1);     // [nwarps][3][HALF+1] per-warp partial traces
     double* vec = acc + nwarps * 3 * (HALF + 1);  // [nwarps_cols][2][Nv]
-    unsigned short* nidx = reinterpret_cast<unsigned short*>(vec + (size_t)P.nwarps_cols * 2 * Nv + (Nv & 1));  // [Z][N]
+    unsigned short* nidx = reinterpret_cast<unsigned short*>(vec + P.vec_doubles);  // [Z][N]
 
     const int32_t* f = P.f + (size_t)b * N;
     for (int i = tid; i < N; i += T) xd[i] = P.U * (double)f[i] - P.mu_c;
@@ -331,17 +333,19 @@ static int launch_kpm_t(fkmc_ctx* ctx, kpm_args& P, int B) {
     // shared memory: fixed part + 2 vectors per column-warp; need >= 2 column warps (Lanczos uses 4 buffers)
     const size_t budget = ctx->smem_optin - 1024;
     int nw = 12;
-    size_t smem = 0;
+    size_t smem = 0, vec_doubles = 0;
+    const size_t lanczos_need = 3 * (size_t)Nv + 2 * KPM_KMAX + 2;
     for (; nw >= 2; --nw) {
         const size_t fixed = sizeof(double) * ((size_t)N + 48 + 64 + ((P.G + 1) & ~1) + (size_t)nw * 3 * (HALF + 1));
-        const size_t vecs = sizeof(double) * ((size_t)nw * 2 * Nv + (Nv & 1));
+        vec_doubles = std::max((size_t)nw * 2 * Nv, lanczos_need);
+        vec_doubles += vec_doubles & 1;
         const size_t idx = sizeof(unsigned short) * (size_t)P.Z * N + 16;
-        smem = fixed + vecs + idx;
-        const size_t lanczos_need = sizeof(double) * (3 * (size_t)Nv + 2 * KPM_KMAX + 2);
-        if (smem <= budget && vecs >= lanczos_need) break;
+        smem = fixed + sizeof(double) * vec_doubles + idx;
+        if (smem <= budget) break;
     }
     if (nw < 2) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: lattice too large for the shared-memory kernel");
     P.nwarps_cols = nw;
+    P.vec_doubles = (int)vec_doubles;
     FKMC_CUDA(ctx, cudaFuncSetAttribute(kpm_kernel<HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kpm_kernel<HALF><<<B, nw * 32, smem, ctx->stream>>>(P);
     ctx->launches++;

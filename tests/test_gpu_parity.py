@@ -1,0 +1,374 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle and the
+committed golden fixtures.  Tolerances (north_star): eigenvalues and free energies within 1e-10
+relative in FP64 -- |d eps| <= 1e-10 max|eps|, |d logZ| <= 1e-10 max(1,|logZ|);
+RNG streams, sites and accept/reject sequences bit-exact."""
+import math
+
+import numpy as np
+import pytest
+import scipy.linalg as sl
+
+import fk_mc_b200 as fk
+import oracle_lib as o
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def ctx8():
+    c = fk.Context("cubic2d", 8, max_batch=64)
+    yield c
+    c.close()
+
+
+# ---------------- RNG ----------------
+@pytest.mark.parametrize("mode,V", [(0, 0), (1, 64), (1, 256), (1, 576), (1, 1000), (2, 0)])
+def test_device_rng_matches_libstdcxx(ctx8, mode, V):
+    assert np.array_equal(ctx8.rng_stream(32167, mode, V, 4000), o.rng_stream(32167, mode, V, 4000))
+
+
+def test_device_rng_fixture_and_negative_seed(ctx8, golden):
+    g = golden["rng"]
+    assert [int(x) for x in ctx8.rng_stream(g["seed"], 0, 0, 40)] == g["raw"]
+    assert [int(x) for x in ctx8.rng_stream(g["seed"], 1, 576, 40)] == g["uniform_int_576"]
+    assert [float(x) for x in ctx8.rng_stream(g["seed"], 2, 0, 40)] == g["uniform_real"]
+    assert int(ctx8.rng_stream(5489, 0, 0, 10000)[-1]) == 4123659995
+    assert np.array_equal(ctx8.rng_stream(-7, 0, 0, 16), o.rng_stream(-7, 0, 0, 16))
+
+
+# ---------------- lattices ----------------
+@pytest.mark.parametrize("kind,L", [("cubic1d", 8), ("cubic2d", 8), ("cubic3d", 4), ("triangular", 6), ("honeycomb", 8),
+                                    ("honeycomb_ref_lower", 8), ("cubic2d", 3)])
+def test_hopping_matrices(kind, L):
+    c = fk.Context(kind, L)
+    assert np.array_equal(c.hopping_dense(), o.hopping_dense(o.KINDS[kind], L))
+    c.close()
+
+
+def test_bad_lattices_rejected():
+    with pytest.raises(fk.FkmcError):
+        fk.Context("cubic2d", 2)
+    with pytest.raises(fk.FkmcError):
+        fk.Context("honeycomb", 7)  # "Need even size", hypercubic.cpp:182
+
+
+# ---------------- stage level: tridiagonal eigenvalues, tridiagonalisation ----------------
+@pytest.mark.parametrize("n", [2, 5, 64, 100, 256, 577, 1024])
+def test_tridiag_bisection(ctx8, n):
+    rng = np.random.default_rng(n)
+    d = rng.normal(size=(4, n)) * 2
+    e = rng.normal(size=(4, n - 1))
+    e[1, ::5] = 0.0      # decoupled blocks
+    e[2] *= 1e-9         # nearly diagonal
+    d[3] = 1.0           # constant diagonal ...
+    e[3] = 0.0           # ... identity: fully degenerate
+    ev = ctx8.tridiag_eigvals(d, e)
+    for b in range(4):
+        ref = sl.eigvalsh_tridiagonal(d[b], e[b]) if n > 2 else np.linalg.eigvalsh(np.diag(d[b]) + np.diag(e[b], 1) + np.diag(e[b], -1))
+        assert np.abs(ev[b] - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+        assert (np.diff(ev[b]) >= 0).all()
+
+
+def test_tridiag_matches_oracle_ql(ctx8):
+    A = o.hopping_dense(o.CUBIC2D, 8) + np.diag(np.arange(64) % 2 * 1.0)
+    d, s = o.tridiag(A)
+    assert np.abs(ctx8.tridiag_eigvals(d, s)[0] - o.tridiag_eig(d, s)).max() <= 1e-13
+
+
+def test_tridiag_large_scale_entries(ctx8):
+    rng = np.random.default_rng(5)
+    d, e = rng.normal(size=(1, 300)) * 1e12, rng.normal(size=(1, 299)) * 1e12
+    ref = sl.eigvalsh_tridiagonal(d[0], e[0])
+    assert np.abs(ctx8.tridiag_eigvals(d, e)[0] - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("n", [2, 3, 31, 32, 33, 64, 100, 257])
+def test_sytrd_preserves_spectrum(ctx8, n):
+    rng = np.random.default_rng(n)
+    A = rng.normal(size=(3, n, n))
+    A = A + np.transpose(A, (0, 2, 1))
+    A[2] = np.diag(rng.normal(size=n))  # already diagonal: every reflector is trivial (tau = 0)
+    lower = np.tril(A)  # the kernel must read the lower triangle only
+    d, e = ctx8.sytrd(lower + 5.0 * np.triu(np.ones((n, n)), 1))
+    for b in range(3):
+        ref = sl.eigvalsh(A[b])
+        got = sl.eigvalsh_tridiagonal(d[b], e[b]) if n > 2 else np.linalg.eigvalsh(np.array([[d[b, 0], e[b, 0]], [e[b, 0], d[b, 1]]]))
+        assert np.abs(ref - got).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+        # similarity invariants: trace and Frobenius norm
+        assert abs(d[b].sum() - np.trace(A[b])) <= 1e-11 * max(1.0, np.abs(ref).max()) * n
+        assert abs((d[b] ** 2).sum() + 2 * (e[b] ** 2).sum() - (A[b] ** 2).sum()) <= 1e-10 * (A[b] ** 2).sum() + 1e-12
+
+
+# ---------------- calc_ed ----------------
+ED_CASES = [("cubic2d", 8, 1.0, 1.0), ("cubic2d", 16, 2.0, 10.0), ("cubic3d", 8, 4.0, 5.0), ("triangular", 24, 2.0, 10.0),
+            ("honeycomb", 24, 2.0, 10.0), ("honeycomb_ref_lower", 24, 2.0, 10.0), ("cubic2d", 32, 2.0, 20.0), ("cubic1d", 12, 1.5, 3.0),
+            ("cubic2d", 5, 0.37, 1000.0)]
+
+
+@pytest.mark.parametrize("kind,L,U,beta", ED_CASES)
+def test_calc_ed_matches_oracle(kind, L, U, beta):
+    c = fk.Context(kind, L, max_batch=5)
+    n = c.N
+    fs = np.stack([o.randomize_f(32167 + i, n, n // 2)[0] for i in range(3)] + [np.zeros(n, np.int32), np.ones(n, np.int32)])
+    r = c.logz_ed(fs, U, U / 2, beta, want_caches=True)
+    for b in range(5):
+        ref = o.calc_ed(o.KINDS[kind], L, fs[b], U, U / 2, beta)
+        assert np.abs(ref["spectrum"] - r["spectrum"][b]).max() <= TOL * np.abs(ref["spectrum"]).max()
+        if np.isfinite(ref["logZ"]):
+            assert abs(ref["logZ"] - r["logZ"][b]) <= TOL * max(1.0, abs(ref["logZ"]))
+        else:  # beta = 1000: the reference's shifted formula underflows to -inf (configuration.cpp:235-242); so must we
+            assert r["logZ"][b] == ref["logZ"]
+        assert (np.diff(r["spectrum"][b]) >= 0).all()
+        fin = np.isfinite(ref["cached_exp"])
+        assert np.allclose(r["cached_exp"][b][fin], ref["cached_exp"][fin], rtol=1e-9 * max(1.0, beta))
+        assert np.allclose(r["cached_fermi"][b], ref["cached_fermi"], rtol=1e-9 * max(1.0, beta), atol=1e-300)
+    c.close()
+
+
+def test_calc_ed_golden_fixtures(golden):
+    for cse in golden["spectra"]["cases"]:
+        c = fk.Context(cse["kind"], cse["L"])
+        r = c.logz_ed(np.array(cse["f"], np.int32), cse["U"], cse["mu_c"], cse["beta"])
+        ref = np.array(cse["spectrum"])
+        assert np.abs(r["spectrum"][0] - ref).max() <= TOL * np.abs(ref).max()
+        assert abs(r["logZ"][0] - cse["logZ"]) <= TOL * max(1.0, abs(cse["logZ"]))
+        c.close()
+
+
+def test_calc_ed_analytic_cases():
+    # checkerboard 4x4 (test/config_test.cpp:10-42, hopping +1) and its logZ(beta = 1)
+    c = fk.Context("cubic2d", 4, t=-1.0)
+    f = np.array([(x + y) % 2 for y in range(4) for x in range(4)], dtype=np.int32)
+    r = c.logz_ed(f, 1.0, 0.5, 1.0)
+    assert r["logZ"][0] == pytest.approx(17.615291438320348, rel=1e-13)
+    assert np.abs(np.abs(r["spectrum"][0][[0, 15]]) - 4.031128874149275).max() < 1e-13
+    c.close()
+    # free cubic3d: eps = -2 sum cos k - mu (highly degenerate spectrum)
+    c = fk.Context("cubic3d", 4)
+    r = c.logz_ed(np.zeros(64, np.int32), 1.0, 0.3, 2.0)
+    ks = np.stack(np.meshgrid(*[np.arange(4)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    exact = np.sort(-2 * np.cos(2 * np.pi * ks / 4).sum(axis=1) - 0.3)
+    assert np.abs(r["spectrum"][0] - exact).max() < 1e-12
+    c.close()
+
+
+def test_calc_ed_full_size_properties():
+    # BASELINE config 2 at full batch: cubic2d L=16, beta=10, U=2, 4096 configurations in one call
+    B, L, U, beta = 4096, 16, 2.0, 10.0
+    c = fk.Context("cubic2d", L, max_batch=B)
+    rng = np.random.default_rng(0)
+    fs = (rng.random((B, 256)) < 0.5).astype(np.int32)
+    r = c.logz_ed(fs, U, U / 2, beta)
+    ev = r["spectrum"]
+    assert (np.diff(ev, axis=1) >= 0).all()
+    # trace and Frobenius invariants of H = T + diag(U f - mu): sum eps = U nf - mu N, sum eps^2 = 4 N t^2 + sum diag^2
+    nf = fs.sum(axis=1)
+    assert np.abs(ev.sum(axis=1) - (U * nf - U / 2 * 256)).max() < 1e-9
+    assert np.abs((ev ** 2).sum(axis=1) - (4 * 256 + ((U * fs - U / 2) ** 2).sum(axis=1))).max() < 1e-8
+    direct = np.log1p(np.exp(-beta * ev)).sum(axis=1)
+    assert np.abs(r["logZ"] - direct).max() <= TOL * np.abs(direct).max()
+    # particle-hole symmetry at half filling: spectrum(f) = -spectrum(1-f) reversed on a bipartite lattice
+    r2 = c.logz_ed(1 - fs[:8], U, U / 2, beta)
+    assert np.abs(r2["spectrum"] + ev[:8, ::-1]).max() < 1e-11
+    # spot check against the oracle
+    for b in (0, 1777, 4095):
+        ref = o.calc_ed(o.CUBIC2D, L, fs[b], U, U / 2, beta)
+        assert np.abs(ref["spectrum"] - ev[b]).max() <= TOL * np.abs(ref["spectrum"]).max()
+    c.close()
+
+
+def test_energy_from_spectrum(ctx8):
+    f, _ = o.randomize_f(1, 64, 32)
+    ed = o.calc_ed(o.CUBIC2D, 8, f, 1.0, 0.5, 3.0)
+    out = ctx8.energy_from_spectrum(ed["spectrum"], 3.0)[0]
+    ex = ed["cached_exp"]
+    assert out[0] == pytest.approx(np.sum(ed["spectrum"] / (1 + ex)), rel=1e-12)
+    assert out[1] == pytest.approx(0.5 * np.sum(ed["spectrum"] ** 2 / (1 + 0.5 * (ex + 1 / ex))), rel=1e-12)
+    assert out[2] == pytest.approx(ed["logZ"], rel=1e-12)
+
+
+def test_argument_errors(ctx8):
+    with pytest.raises(fk.FkmcError) as e:
+        ctx8.logz_ed(np.zeros((65, 64), np.int32), 1.0, 0.5, 1.0)  # B > max_batch
+    assert e.value.code == 1
+    with pytest.raises(fk.FkmcError):
+        ctx8.logz_ed(np.zeros((1, 63), np.int32), 1.0, 0.5, 1.0)
+    with pytest.raises(fk.FkmcError):
+        ctx8.logz_kpm(np.zeros((1, 64), np.int32), 1.0, 0.5, 1.0, 11, 22)  # odd M: assert(cheb_size%2==0), configuration.cpp:114
+    with pytest.raises(fk.FkmcError):
+        ctx8.chain_run_sweeps(1)  # before chain_init
+    with pytest.raises(fk.FkmcError):
+        ctx8.chain_init(4, 1.0, 1.0, mc_add_remove=0.0)  # "No registered moves", mc_metropolis.cpp:35-38
+
+
+# ---------------- calc_chebyshev ----------------
+KPM_CASES = [("cubic2d", 8, 1.0, 1.0), ("cubic2d", 16, 2.0, 10.0), ("cubic3d", 8, 4.0, 5.0), ("triangular", 24, 2.0, 10.0),
+             ("honeycomb", 24, 2.0, 10.0), ("cubic2d", 32, 2.0, 20.0), ("cubic1d", 12, 1.5, 3.0), ("honeycomb_ref_lower", 8, 2.0, 4.0)]
+
+
+@pytest.mark.parametrize("kind,L,U,beta", KPM_CASES)
+def test_calc_chebyshev_matches_oracle(kind, L, U, beta):
+    c = fk.Context(kind, L, max_batch=4)
+    n = c.N
+    M, G = fk.cheb_sizes(n, 2.2)
+    fs = np.stack([o.randomize_f(32167 + i, n, n // 2)[0] for i in range(3)] + [np.zeros(n, np.int32)])
+    r = c.logz_kpm(fs, U, U / 2, beta, M, G)
+    for b in range(4):
+        ref = o.calc_chebyshev(o.KINDS[kind], L, fs[b], U, U / 2, beta, M, G, emode=0)
+        scale = max(abs(ref["e_min"]), abs(ref["e_max"]))
+        assert abs(r["e_min"][b] - ref["e_min"]) <= TOL * scale and abs(r["e_max"][b] - ref["e_max"]) <= TOL * scale
+        assert np.abs(r["moments"][b] - ref["moments"]).max() <= TOL
+        assert abs(r["logZ"][b] - ref["logZ"]) <= TOL * max(1.0, abs(ref["logZ"]))
+        assert r["a"][b] == pytest.approx((r["e_max"][b] - r["e_min"][b]) / 2) and r["moments"][b][0] == 1.0
+    c.close()
+
+
+def test_calc_chebyshev_golden_and_other_sizes(golden):
+    for cse in golden["spectra"]["cases"]:
+        if "kpm" not in cse:
+            continue
+        c = fk.Context(cse["kind"], cse["L"])
+        f = np.array(cse["f"], np.int32)
+        r = c.logz_kpm(f, cse["U"], cse["mu_c"], cse["beta"], cse["M"], cse["G"])
+        assert np.abs(r["moments"][0] - np.array(cse["kpm"]["moments"])).max() <= TOL
+        assert abs(r["logZ"][0] - cse["kpm"]["logZ"]) <= TOL * abs(cse["kpm"]["logZ"])
+        for M, G in [(2, 10), (4, 10), (6, 12), (20, 40), (32, 64)]:  # every template instance family + grid sizes
+            if cse["L"] > 12:
+                break
+            ref = o.calc_chebyshev(o.KINDS[cse["kind"]], cse["L"], f, cse["U"], cse["mu_c"], cse["beta"], M, G)
+            rr = c.logz_kpm(f, cse["U"], cse["mu_c"], cse["beta"], M, G)
+            assert np.abs(rr["moments"][0] - ref["moments"]).max() <= TOL
+            assert abs(rr["logZ"][0] - ref["logZ"]) <= TOL * max(1.0, abs(ref["logZ"]))
+        c.close()
+
+
+def test_kpm_reference_benchmark_tolerances():
+    # test/fast_update_test.cpp:77 (24x24, U=8, T=0.16, seed 32167, M=G=12): KPM vs ED within 5e-2,
+    # and benchmark/fast_update.cpp:67-72 weight agreement within 6e-2 for an add_remove attempt (L=16, U=1, T=0.1)
+    L, U, beta = 24, 8.0, 1 / 0.16
+    c = fk.Context("cubic2d", L, t=-1.0)
+    f, _ = o.randomize_f(32167, L * L, L * L // 2)
+    ed = c.logz_ed(f, U, U / 2, beta)["logZ"][0]
+    kp = c.logz_kpm(f, U, U / 2, beta, 12, 12)["logZ"][0]
+    assert abs((kp - ed) / kp) <= 5e-2
+    c.close()
+    L, U, beta = 16, 1.0, 10.0
+    c = fk.Context("cubic2d", L, t=-1.0, max_batch=2)
+    f, _ = o.randomize_f(32167, 256, 128)
+    g = f.copy()
+    site = int(o.rng_stream(32167, 1, 256, 1)[0])
+    g[site] ^= 1
+    fac = math.exp(beta * U / 2) if g[site] else math.exp(-beta * U / 2)  # moves.cpp:65
+    M = int(math.log(256) * 2.35)
+    M += M % 2
+    e = c.logz_ed(np.stack([f, g]), U, U / 2, beta)["logZ"]
+    k = c.logz_kpm(np.stack([f, g]), U, U / 2, beta, M, 2 * M)["logZ"]
+    assert abs(math.exp(e[1] - e[0]) * fac - math.exp(k[1] - k[0]) * fac) < 6e-2
+    c.close()
+
+
+# ---------------- Markov chains: identical accept/reject sequences ----------------
+CHAIN_CASES = [("cubic2d", 8, 1.0, 1.0, False, 0.0, 0.0), ("cubic2d", 8, 4.0, 4.0, False, 0.5, 0.1), ("cubic2d", 8, 4.0, 4.0, True, 0.5, 0.1),
+               ("cubic2d", 16, 2.0, 10.0, False, 0.0, 0.0), ("cubic3d", 4, 4.0, 5.0, False, 1.0, 0.0), ("triangular", 6, 2.0, 10.0, True, 0.0, 0.0),
+               ("honeycomb", 6, 2.0, 10.0, False, 0.3, 0.0), ("cubic2d", 16, 2.0, 10.0, True, 0.0, 0.0)]
+
+
+def _compare_chain(c, ch, kind, L, U, beta, cheb, flip, resh, nsw, sl_, tr, se, st, seed):
+    p = o.make_params(kind=o.KINDS[kind], L=L, beta=beta, U=U, mc_flip=flip, mc_reshuffle=resh, cheb_moves=cheb, seed=seed,
+                      nsweeps=nsw, sweep_len=sl_, ntherm_sweeps=1)
+    r = o.mc_run(p, rank=ch)
+    t = r["trace"]
+    assert np.array_equal(t["u"], tr["u"][:, ch])                       # same RNG stream, same consumption order
+    assert np.array_equal(t["move"][t["site_a"] >= 0], tr["move"][:, ch][t["site_a"] >= 0])
+    assert np.array_equal(t["site_a"], tr["site_a"][:, ch]) and np.array_equal(t["site_b"], tr["site_b"][:, ch])
+    w, wg = t["weight"], tr["weight"][:, ch]
+    assert np.abs(w - wg).max() <= 1e-9 * max(1.0, np.abs(w).max())      # ratio = exp(dlogZ): dlogZ within 1e-10 |logZ|
+    # accept/reject identical except where |w| sits within tolerance of u (north_star); none expected at these sizes
+    near = np.abs(np.abs(w) - t["u"]) <= 1e-9 * np.maximum(1.0, np.abs(w))
+    assert np.array_equal(t["accepted"][~near], tr["accepted"][:, ch][~near])
+    assert near.sum() == 0
+    assert np.array_equal(r["f_final"], st["f"][ch]) and r["naccept"] == st["naccept"][ch]
+    assert np.abs(r["energies"] - se["energies"][:, ch]).max() <= 1e-9 * max(1.0, np.abs(r["energies"]).max())
+    assert np.abs(r["d2energies"] - se["d2energies"][:, ch]).max() <= 1e-9 * max(1.0, np.abs(r["d2energies"]).max())
+    assert np.abs(r["c_energies"] - se["c_energies"][:, ch]).max() <= 1e-9 * max(1.0, np.abs(r["c_energies"]).max())
+
+
+@pytest.mark.parametrize("kind,L,U,beta,cheb,flip,resh", CHAIN_CASES)
+def test_chain_matches_oracle(kind, L, U, beta, cheb, flip, resh):
+    nch, nsw, sl_ = 4, 3, 16
+    c = fk.Context(kind, L, max_batch=nch)
+    c.chain_init(nch, beta, U, mc_flip=flip, mc_reshuffle=resh, cheb_moves=cheb, seed=32167, sweep_len=sl_, ntherm_sweeps=1,
+                 measure_energy=True, record_trace=True, max_sweeps=nsw + 1)
+    c.chain_run_sweeps(2)
+    c.chain_run_sweeps(nsw - 1)  # resumable in pieces
+    tr, se, st = c.chain_get_trace(), c.chain_get_series(), c.chain_get_state()
+    assert tr["n_steps"] == (nsw + 1) * sl_ and se["n_measured"] == nsw
+    for ch in range(nch):
+        _compare_chain(c, ch, kind, L, U, beta, cheb, flip, resh, nsw, sl_, tr, se, st, 32167)
+    c.close()
+
+
+def test_chain_golden_trace(golden):
+    for t in golden["mc_trace"]["traces"]:
+        c = fk.Context("cubic2d", 8, max_batch=2)
+        c.chain_init(2, t["beta"], t["U"], mc_flip=t["mc_flip"], mc_reshuffle=t["mc_reshuffle"], cheb_moves=t["cheb"], seed=32167,
+                     sweep_len=16, ntherm_sweeps=1, record_trace=True, max_sweeps=4)
+        c.chain_run_sweeps(4)
+        tr, se, st = c.chain_get_trace(), c.chain_get_series(), c.chain_get_state()
+        ch = t["rank"]
+        assert tr["accepted"][:, ch].tolist() == t["accepted"] and tr["site_a"][:, ch].tolist() == t["site_a"]
+        assert np.array_equal(tr["u"][:, ch], np.array(t["u"]))
+        assert np.allclose(tr["weight"][:, ch], t["weight"], rtol=1e-9, atol=1e-12)
+        assert np.allclose(se["energies"][:, ch], t["energies"], rtol=1e-10)
+        assert st["f"][ch].tolist() == t["f_final"]
+        c.close()
+
+
+def test_chain_offset_is_rank_seed():
+    # chain c of a context with chain0 = k is the reference's MPI rank k + c (mc_metropolis.cpp:25)
+    a = fk.Context("cubic2d", 8, max_batch=4)
+    b = fk.Context("cubic2d", 8, max_batch=2)
+    a.chain_init(4, 4.0, 4.0, seed=100, max_sweeps=2)
+    b.chain_init(2, 4.0, 4.0, seed=100, chain0=2, max_sweeps=2)
+    a.chain_run_sweeps(2)
+    b.chain_run_sweeps(2)
+    sa, sb = a.chain_get_state(), b.chain_get_state()
+    assert np.array_equal(sa["f"][2:], sb["f"]) and np.array_equal(sa["logZ"][2:], sb["logZ"])
+    assert np.array_equal(a.chain_get_series()["energies"][:, 2:], b.chain_get_series()["energies"])
+    a.close()
+    b.close()
+
+
+def test_chain_flip_early_out_on_empty_config():
+    # move_flip returns 0 without drawing when the configuration is empty (moves.cpp:8): only u is drawn each step
+    c = fk.Context("cubic2d", 8, max_batch=1)
+    c.chain_init(1, 1.0, 1.0, mc_flip=1.0, mc_add_remove=0.0, nf_start=0, seed=5, sweep_len=8, record_trace=True, max_sweeps=1)
+    c.chain_run_sweeps(1)
+    tr = c.chain_get_trace()
+    # nf_start = 0 makes randomize_f draw nf itself first (configuration.cpp:49); compare with the oracle end to end
+    p = o.make_params(kind=o.CUBIC2D, L=8, beta=1.0, U=1.0, mc_flip=1.0, mc_add_remove=0.0, nf_start=0, seed=5, nsweeps=0, sweep_len=8,
+                      ntherm_sweeps=1)
+    r = o.mc_run(p)
+    assert np.array_equal(r["trace"]["u"], tr["u"][:, 0]) and np.array_equal(r["trace"]["accepted"], tr["accepted"][:, 0])
+    c.close()
+
+
+def test_chain_full_batch_statistics():
+    # 1024 independent chains (BASELINE config 1 shape): mean energy agrees with the oracle's chains within 5 sigma
+    nch, nsw = 1024, 6
+    c = fk.Context("cubic2d", 8, max_batch=nch)
+    c.chain_init(nch, 1.0, 1.0, seed=32167, sweep_len=16, ntherm_sweeps=2, max_sweeps=nsw + 2)
+    c.chain_run_sweeps(nsw + 2)
+    se = c.chain_get_series()
+    assert se["n_measured"] == nsw and np.isfinite(se["energies"]).all()
+    ref = []
+    for ch in range(16):
+        p = o.make_params(kind=o.CUBIC2D, L=8, beta=1.0, U=1.0, seed=32167, nsweeps=nsw, sweep_len=16, ntherm_sweeps=2)
+        r = o.mc_run(p, rank=ch, trace=False)
+        assert np.abs(r["energies"] - se["energies"][:, ch]).max() <= 1e-9 * np.abs(r["energies"]).max()
+        ref.append(r["energies"].mean())
+    m, s = se["energies"].mean(), se["energies"].mean(axis=0).std() / math.sqrt(nch)
+    assert abs(m - np.mean(ref)) <= 5 * (s + np.std(ref) / 4)
+    assert c.launch_count() > 0
+    c.close()
