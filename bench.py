@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Headline benchmark: Metropolis proposals/s of the fk_mc weight-evaluation hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--workload c5] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one sweep (sweep_len = 16 proposals per chain + the per-sweep measurement,
+src/mc_metropolis.cpp:34-61) over every chain resident on the GPU.  Default workload = BASELINE's
+headline configuration: cubic2d L=32 (N=1024), beta=20, U=2, Chebyshev/KPM moves (M=16, G=32) plus
+one exact eigensolve per sweep for the energy measurement, 1024 independent chains per GPU.
+`value` is device-timed with the chains resident in HBM; `e2e` drives the same sweep from HOST
+buffers through the C-ABI evaluators (H2D of every proposal batch, D2H of every result).
+Prints exactly one JSON line on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (lattice, L, beta, U, cheb_moves, chains per GPU, description)
+    "c5": ("cubic2d", 32, 20.0, 2.0, True, 1024, "cubic2d L=32 N=1024 beta=20 U=2, KPM moves M=16 G=32 + exact eigensolve per sweep"),
+    "c2": ("cubic2d", 16, 10.0, 2.0, False, 4096, "cubic2d L=16 N=256 beta=10 U=2, dense eigensolve moves"),
+    "c1": ("cubic2d", 8, 1.0, 1.0, False, 4096, "cubic2d L=8 N=64 beta=1 U=1, dense eigensolve moves"),
+    "c3": ("cubic3d", 8, 5.0, 4.0, False, 1024, "cubic3d L=8 N=512 beta=5 U=4, dense eigensolve moves"),
+    "c4t": ("triangular", 24, 10.0, 2.0, False, 1024, "triangular L=24 N=576 beta=10 U=2, dense eigensolve moves"),
+    "c4h": ("honeycomb", 24, 10.0, 2.0, False, 1024, "honeycomb L=24 N=576 beta=10 U=2, dense eigensolve moves"),
+}
+SWEEP_LEN = 16      # src/mc_metropolis.cpp:14
+SEED = 32167        # test/fast_update_test.cpp:48, benchmark/fast_update.cpp:152
+DMMA_PEAK_TFLOPS = 37.0  # measured on this pool's B200 by tools/probe_dmma.cu (profiles/r01_probe_dmma.txt)
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                                       str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 7]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def kpm_algorithmic_bytes(N, M):
+    """streaming formulation, 24 N^2 (M/2 - 1) + 16 N^2 bytes per proposal."""
+    return 24.0 * N * N * (M / 2 - 1) + 16.0 * N * N
+
+
+def run_reference(args, wl, rank, world):
+    """CPU arm: the oracle restatement of the reference algorithm on all host cores (kind = "port":
+    the reference cannot be built in this image).  P independent chains, chain r seeded SEED + r, as mpirun -np P would."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as o
+    kind, L, beta, U, cheb, chains, desc = wl
+    cores = os.cpu_count() or 1
+    p = o.make_params(kind=o.KINDS[kind], L=L, beta=beta, U=U, cheb_moves=cheb, emode=1, seed=SEED, nsweeps=1, sweep_len=SWEEP_LEN,
+                      ntherm_sweeps=0, measure_energy=True)
+    times = []
+    for it in range(args.warmup + args.steps):
+        sec, _ = o.bench_chains(p, cores, rank0=it * cores)
+        if it >= args.warmup:
+            times.append(sec)
+    ms = 1e3 * float(np.mean(times))
+    value = cores * SWEEP_LEN / (ms * 1e-3)
+    line = {"impl": "reference", "metric": "metropolis_proposals_per_sec", "value": value, "unit": "proposals/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "chains": cores, "sweep_len": SWEEP_LEN, "seed": SEED},
+            "cpu_baseline": {"value": value, "unit": "proposals/s", "cores": cores, "kind": "port",
+                             "sample": "%d chains x 1 sweep (16 proposals + 1 measurement) per step, one chain per host thread" % cores},
+            "e2e": {"value": value, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = WORKLOADS[args.workload]
+    kind, L, beta, U, cheb, chains, desc = wl
+    if args.chains:
+        chains = args.chains
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import fk_mc_b200 as fk
+    from fk_mc_b200 import parallel
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: libfkmc_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    stream = torch.cuda.Stream()
+    ctx = fk.Context(kind, L, max_batch=chains, device=local_rank)
+    ctx.set_stream(stream.cuda_stream)
+    N = ctx.N
+    M, G = fk.cheb_sizes(N, 2.2)
+    total_sweeps = args.warmup + args.steps
+    chain0, _ = parallel.partition_chains(world * chains, world, rank)
+    ctx.chain_init(chains, beta, U, cheb_moves=cheb, seed=SEED, chain0=chain0, sweep_len=SWEEP_LEN, ntherm_sweeps=0,
+                   measure_energy=True, max_sweeps=total_sweeps)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            ctx.chain_run_sweeps(1)
+            flush.zero_()
+        stream.synchronize()
+        ctx.profile_enable(True)
+        ctx.profile_reset()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        launches0 = ctx.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            ctx.chain_run_sweeps(1)
+            flush.zero_()  # L2 flush between timed steps (256 MiB write)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
+        clocks = sampler.stop() if sampler else None
+        launches = ctx.launch_count() - launches0 + args.steps  # + the flush kernels
+        ctx.profile_enable(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    lt = torch.tensor([launches], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    ms_total = float(t.item())
+    proposals = world * chains * SWEEP_LEN * args.steps
+    value = proposals / (ms_total * 1e-3)
+
+    # per-kernel-family device time inside the timed region (events recorded on the launching stream)
+    fam = {}
+    for name in ("kpm", "sytrd", "tridiag_eig", "build_h", "chain_step"):
+        tot, n = ctx.profile_get(name)
+        if n:
+            fam[name] = {"ms_per_launch": tot / n, "launches": n, "share": tot / ms_total}
+    peaks, peak_src = measured_peaks()
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json"))).get("kpm" if cheb else "sytrd")
+    except Exception:
+        pass
+    if cheb:
+        bytes_launch = kpm_algorithmic_bytes(N, M) * chains
+        achieved = bytes_launch / (fam["kpm"]["ms_per_launch"] * 1e-3) * 1e-9
+        roofline = {"kernel": "kpm_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                    "note": "algorithmic bytes of the streaming formulation (SURVEY 8d); the kernel keeps the recursion in shared memory, "
+                            "so DRAM traffic is far below it and frac may exceed 1"}
+    else:
+        fl = 4.0 / 3.0 * N ** 3 * chains
+        achieved = fl / (fam["sytrd"]["ms_per_launch"] * 1e-3) * 1e-12
+        roofline = {"kernel": "sytrd_lower_kernel", "bound": "tensor", "achieved": achieved, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                    "frac": achieved / DMMA_PEAK_TFLOPS, "traffic": traffic, "peak_source": "measured FP64 DMMA (tools/probe_dmma.cu)"}
+    roofline_dense = None
+    if cheb and "sytrd" in fam:
+        fl = 4.0 / 3.0 * N ** 3 * chains
+        a2 = fl / (fam["sytrd"]["ms_per_launch"] * 1e-3) * 1e-12
+        roofline_dense = {"kernel": "sytrd_lower_kernel", "bound": "tensor", "achieved": a2, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                          "frac": a2 / DMMA_PEAK_TFLOPS, "peak_source": "measured FP64 DMMA (tools/probe_dmma.cu)"}
+
+    # ---- e2e: the same sweep driven from HOST buffers through the C-ABI evaluators ----
+    e2e = None
+    if not args.no_e2e:
+        rng = np.random.default_rng(SEED + rank)
+        f_pin = torch.zeros((chains, N), dtype=torch.int32).pin_memory()
+        f_host = f_pin.numpy()
+        f_host[:] = (rng.random((chains, N)) < 0.5)
+        ebmu = math.exp(beta * U / 2)
+        h2d = d2h = 0
+
+        def weight_eval(fh):
+            nonlocal h2d, d2h
+            h2d += fh.nbytes
+            if cheb:
+                r = ctx.logz_kpm(fh, U, U / 2, beta, M, G)
+                d2h += r["moments"].nbytes + 4 * 8 * chains + r["logZ"].nbytes
+            else:
+                r = ctx.logz_ed(fh, U, U / 2, beta)
+                d2h += r["spectrum"].nbytes + r["logZ"].nbytes
+            return r
+
+        def e2e_step(lz_cur):
+            nonlocal h2d, d2h
+            for _ in range(SWEEP_LEN):
+                sites = rng.integers(0, N, size=chains)
+                rows = np.arange(chains)
+                f_host[rows, sites] ^= 1                      # propose in place
+                lz_new = weight_eval(f_host)["logZ"]
+                occ = f_host[rows, sites] == 1
+                w = np.exp(lz_new - lz_cur) * np.where(occ, ebmu, 1 / ebmu)
+                acc = np.abs(w) > rng.random(chains)
+                f_host[rows[~acc], sites[~acc]] ^= 1          # reject: undo
+                lz_cur = np.where(acc, lz_new, lz_cur)
+            if cheb:                                          # measurement sweep: exact spectrum -> energy
+                h2d += f_host.nbytes
+                r = ctx.logz_ed(f_host, U, U / 2, beta)
+                d2h += r["spectrum"].nbytes + r["logZ"].nbytes
+            return lz_cur
+
+        lz = weight_eval(f_host)["logZ"]
+        lz = e2e_step(lz)  # warm-up
+        h2d = d2h = 0
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            lz = e2e_step(lz)
+        torch.cuda.synchronize()
+        e_ms = (time.perf_counter() - t0) * 1e3
+        te = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": proposals / (float(te.item()) * 1e-3), "unit": "proposals/s", "h2d_bytes_per_step": h2d // args.steps,
+               "d2h_bytes_per_step": d2h // args.steps,
+               "path": "fkmc_logz_kpm_batched / fkmc_logz_ed_batched with pinned host f, host-side proposal + accept"}
+
+    # ---- final collective: gather the per-chain series (the only inter-GPU traffic of a run) ----
+    gather_ms = None
+    if world > 1:
+        se = ctx.chain_get_series()
+        loc = torch.from_numpy(se["energies"]).cuda()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        allv = parallel.gather_series(loc, world * chains)
+        torch.cuda.synchronize()
+        gather_ms = (time.perf_counter() - t0) * 1e3
+        assert allv.shape[1] == world * chains
+
+    # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) ----
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as o
+        cores = os.cpu_count() or 1
+        p = o.make_params(kind=o.KINDS[kind], L=L, beta=beta, U=U, cheb_moves=cheb, emode=1, seed=SEED, nsweeps=1, sweep_len=SWEEP_LEN,
+                          ntherm_sweeps=0, measure_energy=True)
+        sec, _ = o.bench_chains(p, cores)
+        cpu_baseline = {"value": cores * SWEEP_LEN / sec, "unit": "proposals/s", "cores": cores, "kind": "port",
+                        "sample": "%d chains x 1 sweep (16 proposals + 1 measurement), one chain per host thread, %.1f s" % (cores, sec)}
+
+    if rank == 0:
+        line = {"metric": "metropolis_proposals_per_sec", "value": value, "unit": "proposals/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": desc, "chains_per_gpu": chains, "sweep_len": SWEEP_LEN, "seed": SEED, "mu_c": U / 2, "mu_f": U / 2,
+                           "moves": "add_remove", "M": M if cheb else None, "G": G if cheb else None,
+                           "l2_flush": "256 MiB device memset between timed steps", "parallelism": "chains sharded, %d per GPU" % chains},
+                "sweeps_per_sec": value / SWEEP_LEN, "roofline": roofline, "roofline_dense": roofline_dense, "kernels": fam,
+                "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks,
+                "final_gather_ms": gather_ms}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -14,6 +14,8 @@ int fkmc_set_error(fkmc_ctx* ctx, int code, const std::string& msg) {
     return code;
 }
 
+// Profiling scopes only RECORD events (no host synchronisation inside the timed region); the
+// elapsed times are resolved when the totals are read.
 fkmc_prof_scope::fkmc_prof_scope(fkmc_ctx* c, const char* n) : ctx(c), name(n) {
     if (!ctx->profiling) return;
     cudaEventCreate(&a);
@@ -23,14 +25,21 @@ fkmc_prof_scope::fkmc_prof_scope(fkmc_ctx* c, const char* n) : ctx(c), name(n) {
 fkmc_prof_scope::~fkmc_prof_scope() {
     if (!a) return;
     cudaEventRecord(b, ctx->stream);
-    cudaEventSynchronize(b);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, a, b);
-    auto& e = ctx->prof[name];
-    e.total_ms += ms;
-    e.launches += 1;
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
+    ctx->pending.push_back({name, a, b});
+}
+
+static void fkmc_profile_resolve(fkmc_ctx* ctx) {
+    for (auto& p : ctx->pending) {
+        cudaEventSynchronize(p.b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, p.a, p.b);
+        auto& e = ctx->prof[p.name];
+        e.total_ms += ms;
+        e.launches += 1;
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    ctx->pending.clear();
 }
 
 namespace {
@@ -141,6 +150,7 @@ int fkmc_destroy(fkmc_ctx* ctx) {
     if (!ctx) return FKMC_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    fkmc_profile_resolve(ctx);
     fkmc_chain_free(ctx);
     cudaFree(ctx->d_nbr_idx); cudaFree(ctx->d_nbr_val); cudaFree(ctx->d_A); cudaFree(ctx->d_W); cudaFree(ctx->d_d);
     cudaFree(ctx->d_e); cudaFree(ctx->d_tau); cudaFree(ctx->d_evals); cudaFree(ctx->d_out); cudaFree(ctx->d_f);
@@ -312,6 +322,7 @@ int fkmc_profile_enable(fkmc_ctx* ctx, int on) {
 
 int fkmc_profile_get(fkmc_ctx* ctx, const char* family, double* total_ms, int64_t* launches) {
     if (!ctx || !family) return FKMC_ERR_INVALID;
+    fkmc_profile_resolve(ctx);
     auto it = ctx->prof.find(family);
     if (total_ms) *total_ms = it == ctx->prof.end() ? 0.0 : it->second.total_ms;
     if (launches) *launches = it == ctx->prof.end() ? 0 : it->second.launches;
@@ -320,6 +331,7 @@ int fkmc_profile_get(fkmc_ctx* ctx, const char* family, double* total_ms, int64_
 
 int fkmc_profile_reset(fkmc_ctx* ctx) {
     if (!ctx) return FKMC_ERR_INVALID;
+    fkmc_profile_resolve(ctx);
     ctx->prof.clear();
     return FKMC_OK;
 }

@@ -18,6 +18,11 @@ struct fkmc_profile_entry {
     int64_t launches = 0;
 };
 
+struct fkmc_pending_event {
+    const char* name;
+    cudaEvent_t a, b;
+};
+
 struct fkmc_chain_state {
     bool active = false;
     fkmc_chain_params p{};
@@ -90,6 +95,7 @@ struct fkmc_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool profiling = false;
     std::map<std::string, fkmc_profile_entry> prof;
+    std::vector<fkmc_pending_event> pending;
 };
 
 // ---- error helpers ----
