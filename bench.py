@@ -214,7 +214,8 @@ def main():
     peaks, peak_src = measured_peaks()
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json"))).get("kpm" if cheb else "sytrd")
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["kpm" if cheb else "sytrd"]
+        traffic = tr["bytes_per_launch"] * chains / tr["units_per_launch"]
     except Exception:
         pass
     if cheb:
