@@ -197,6 +197,30 @@ class Context:
         self._ck(self.lib.fkmc_sytrd_batched(self.h, _ptr(Af, C.c_double), n, B, _ptr(d, C.c_double), _ptr(e, C.c_double)))
         return d, e
 
+    def sy2sb(self, A):
+        """Stage 1 of the two-stage reduction: [B, N, N] symmetric (lower read) -> band storage [B, 9, N]."""
+        A = np.asarray(A, dtype=np.float64)
+        if A.ndim == 2:
+            A = A[None]
+        B, n, _ = A.shape
+        Af = np.ascontiguousarray(np.transpose(A, (0, 2, 1)))
+        AB = np.zeros((B, 9, n))
+        self._ck(self.lib.fkmc_sy2sb_batched(self.h, _ptr(Af, C.c_double), n, B, _ptr(AB, C.c_double)))
+        return AB
+
+    def sb2st(self, AB):
+        """Stage 2: band storage [B, 9, N] -> tridiagonal d [B, N], e [B, N-1]."""
+        AB = np.ascontiguousarray(AB, dtype=np.float64)
+        if AB.ndim == 2:
+            AB = AB[None]
+        B, _, n = AB.shape
+        d, e = np.zeros((B, n)), np.zeros((B, n - 1))
+        self._ck(self.lib.fkmc_sb2st_batched(self.h, _ptr(AB, C.c_double), n, B, _ptr(d, C.c_double), _ptr(e, C.c_double)))
+        return d, e
+
+    def set_option(self, name, value):
+        self._ck(self.lib.fkmc_set_option(self.h, name.encode(), int(value)))
+
     def tridiag_eigvals(self, d, e):
         d = np.ascontiguousarray(d, dtype=np.float64)
         e = np.ascontiguousarray(e, dtype=np.float64)

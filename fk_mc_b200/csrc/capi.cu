@@ -59,12 +59,21 @@ int fkmc_ensure_dense_ws(fkmc_ctx* ctx) {
     int rc = 0;
     rc |= dalloc(ctx, &ctx->d_A, B * N * N);
     rc |= dalloc(ctx, &ctx->d_W, B * N * FKMC_SYTRD_NB);
+    rc |= dalloc(ctx, &ctx->d_AB, B * N * 9);
     rc |= dalloc(ctx, &ctx->d_d, B * N);
     rc |= dalloc(ctx, &ctx->d_e, B * N);
     rc |= dalloc(ctx, &ctx->d_tau, B * N);
     rc |= dalloc(ctx, &ctx->d_evals, B * N);
     rc |= dalloc(ctx, &ctx->d_aux, 2 * B * N);
     return rc ? FKMC_ERR_CUDA : FKMC_OK;
+}
+
+int fkmc_tridiagonalize(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_d, double* d_e) {
+    const bool two = ctx->tridiag_mode == 2 && N >= 16 && fkmc_sy2sb_smem(N) <= ctx->smem_optin && fkmc_sb2st_smem(N) <= ctx->smem_optin;
+    if (!two) return fkmc_launch_sytrd(ctx, d_A, N, B, d_d, d_e, ctx->d_tau, ctx->d_W);
+    int rc = fkmc_launch_sy2sb(ctx, d_A, N, B, ctx->d_AB);
+    if (rc) return rc;
+    return fkmc_launch_sb2st(ctx, ctx->d_AB, N, B, d_d, d_e);
 }
 
 namespace {
@@ -152,6 +161,7 @@ int fkmc_destroy(fkmc_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     fkmc_profile_resolve(ctx);
     fkmc_chain_free(ctx);
+    cudaFree(ctx->d_AB);
     cudaFree(ctx->d_nbr_idx); cudaFree(ctx->d_nbr_val); cudaFree(ctx->d_A); cudaFree(ctx->d_W); cudaFree(ctx->d_d);
     cudaFree(ctx->d_e); cudaFree(ctx->d_tau); cudaFree(ctx->d_evals); cudaFree(ctx->d_out); cudaFree(ctx->d_f);
     cudaFree(ctx->d_flag); cudaFree(ctx->d_moments); cudaFree(ctx->d_ab); cudaFree(ctx->d_aux);
@@ -204,7 +214,7 @@ int fkmc_logz_ed_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, doubl
     if ((rc = fkmc_ensure_dense_ws(ctx))) return rc;
     const size_t N = ctx->N;
     if ((rc = fkmc_launch_build_h(ctx, ctx->d_f, B, U, mu_c, ctx->d_A))) return rc;
-    if ((rc = fkmc_launch_sytrd(ctx, ctx->d_A, ctx->N, B, ctx->d_d, ctx->d_e, ctx->d_tau, ctx->d_W))) return rc;
+    if ((rc = fkmc_tridiagonalize(ctx, ctx->d_A, ctx->N, B, ctx->d_d, ctx->d_e))) return rc;
     double* dexp = cached_exp ? ctx->d_aux : nullptr;
     double* dfer = cached_fermi ? ctx->d_aux + (size_t)ctx->max_batch * N : nullptr;
     if ((rc = fkmc_launch_tridiag_eig(ctx, ctx->d_d, ctx->d_e, ctx->N, B, beta, ctx->d_evals, N, nullptr, 0, ctx->d_out, dexp, dfer)))
@@ -274,6 +284,58 @@ int fkmc_sytrd_batched(fkmc_ctx* ctx, const double* A, int N, int B, double* d, 
     }
     cudaFree(dA); cudaFree(dW); cudaFree(dd); cudaFree(de); cudaFree(dt);
     return rc;
+}
+
+int fkmc_sy2sb_batched(fkmc_ctx* ctx, const double* A, int N, int B, double* AB) {
+    if (!ctx || !A || !AB || N < 2 || B < 1) return FKMC_ERR_INVALID;
+    FKMC_CUDA(ctx, cudaSetDevice(ctx->device));
+    double *dA = nullptr, *dAB = nullptr;
+    const size_t n = N, b = B;
+    FKMC_CUDA(ctx, cudaMalloc(&dA, sizeof(double) * b * n * n));
+    FKMC_CUDA(ctx, cudaMalloc(&dAB, sizeof(double) * b * n * 9));
+    FKMC_CUDA(ctx, cudaMemsetAsync(dAB, 0, sizeof(double) * b * n * 9, ctx->stream));
+    FKMC_CUDA(ctx, cudaMemcpyAsync(dA, A, sizeof(double) * b * n * n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = fkmc_launch_sy2sb(ctx, dA, N, B, dAB);
+    if (!rc) {
+        FKMC_CUDA(ctx, cudaMemcpyAsync(AB, dAB, sizeof(double) * b * n * 9, cudaMemcpyDeviceToHost, ctx->stream));
+        FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    cudaFree(dA); cudaFree(dAB);
+    return rc;
+}
+
+int fkmc_sb2st_batched(fkmc_ctx* ctx, const double* AB, int N, int B, double* d, double* e) {
+    if (!ctx || !AB || !d || !e || N < 3 || B < 1) return FKMC_ERR_INVALID;
+    FKMC_CUDA(ctx, cudaSetDevice(ctx->device));
+    double *dAB = nullptr, *dd = nullptr, *de = nullptr;
+    const size_t n = N, b = B;
+    FKMC_CUDA(ctx, cudaMalloc(&dAB, sizeof(double) * b * n * 9));
+    FKMC_CUDA(ctx, cudaMalloc(&dd, sizeof(double) * b * n));
+    FKMC_CUDA(ctx, cudaMalloc(&de, sizeof(double) * b * n));
+    FKMC_CUDA(ctx, cudaMemcpyAsync(dAB, AB, sizeof(double) * b * n * 9, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = fkmc_launch_sb2st(ctx, dAB, N, B, dd, de);
+    if (!rc) {
+        FKMC_CUDA(ctx, cudaMemcpyAsync(d, dd, sizeof(double) * b * n, cudaMemcpyDeviceToHost, ctx->stream));
+        FKMC_CUDA(ctx, cudaMemcpy2DAsync(e, sizeof(double) * (n - 1), de, sizeof(double) * n, sizeof(double) * (n - 1), b,
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+        FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    cudaFree(dAB); cudaFree(dd); cudaFree(de);
+    return rc;
+}
+
+int fkmc_set_option(fkmc_ctx* ctx, const char* name, int value) {
+    if (!ctx || !name) return FKMC_ERR_INVALID;
+    if (std::string(name) == "tridiag") {
+        if (value != 1 && value != 2) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "tridiag must be 1 or 2");
+        ctx->tridiag_mode = value;
+        return FKMC_OK;
+    }
+    if (std::string(name) == "kpm_generic") {
+        ctx->kpm_force_generic = value != 0;
+        return FKMC_OK;
+    }
+    return fkmc_set_error(ctx, FKMC_ERR_INVALID, std::string("unknown option ") + name);
 }
 
 int fkmc_tridiag_eigvals_batched(fkmc_ctx* ctx, const double* d, const double* e, int N, int B, double* evals) {

@@ -249,7 +249,7 @@ int evaluate_proposals(fkmc_ctx* ctx, const chain_extra& X, const double** lz, i
     } else {
         int rc = fkmc_launch_build_h(ctx, S.f_prop, C, S.p.U, S.p.mu_c, ctx->d_A);
         if (rc) return rc;
-        rc = fkmc_launch_sytrd(ctx, ctx->d_A, N, C, ctx->d_d, ctx->d_e, ctx->d_tau, ctx->d_W);
+        rc = fkmc_tridiagonalize(ctx, ctx->d_A, N, C, ctx->d_d, ctx->d_e);
         if (rc) return rc;
         // spectrum of the proposal goes to the chain's non-current slot: spec[0] + slot * (C*N)
         rc = fkmc_launch_tridiag_eig(ctx, ctx->d_d, ctx->d_e, N, C, S.p.beta, S.spec[0], N, X.prop_slot, (long)C * N, ctx->d_out,
@@ -418,7 +418,7 @@ extern "C" int fkmc_chain_run_sweeps(fkmc_ctx* ctx, int n_sweeps) {
                 // Chebyshev moves never fill ed_data_: measure_energy triggers a fresh exact eigensolve
                 int rc = fkmc_launch_build_h(ctx, S.f_cur, C, S.p.U, S.p.mu_c, ctx->d_A);
                 if (rc) return rc;
-                rc = fkmc_launch_sytrd(ctx, ctx->d_A, N, C, ctx->d_d, ctx->d_e, ctx->d_tau, ctx->d_W);
+                rc = fkmc_tridiagonalize(ctx, ctx->d_A, N, C, ctx->d_d, ctx->d_e);
                 if (rc) return rc;
                 rc = fkmc_launch_tridiag_eig(ctx, ctx->d_d, ctx->d_e, N, C, S.p.beta, S.spec[0], N, nullptr, 0, ctx->d_out, nullptr, nullptr);
                 if (rc) return rc;

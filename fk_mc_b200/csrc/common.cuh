@@ -72,6 +72,9 @@ struct fkmc_ctx {
     // workspaces sized for max_batch
     double* d_A = nullptr;      // [max_batch][N][N] dense Hamiltonians (column-major, lower triangle live)
     double* d_W = nullptr;      // [max_batch][N][NB] panel workspace
+    double* d_AB = nullptr;     // [max_batch][9][N] band storage of the two-stage reduction
+    int tridiag_mode = 2;       // 1: one-stage blocked sytrd, 2: sy2sb + sb2st
+    int kpm_force_generic = 0;  // 1: always use the full-lattice-vector KPM kernel (for cross-checks)
     double* d_d = nullptr;      // [max_batch][N]
     double* d_e = nullptr;      // [max_batch][N]
     double* d_tau = nullptr;    // [max_batch][N]
@@ -127,6 +130,13 @@ int fkmc_build_lattice(fkmc_ctx* ctx);
 int fkmc_launch_build_h(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double* d_A);
 // blocked Householder tridiagonalisation, one CTA per matrix; A is overwritten
 int fkmc_launch_sytrd(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_d, double* d_e, double* d_tau, double* d_W);
+// two-stage tridiagonalisation
+int fkmc_launch_sy2sb(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_AB);
+int fkmc_launch_sb2st(fkmc_ctx* ctx, const double* d_AB, int N, int B, double* d_d, double* d_e);
+size_t fkmc_sy2sb_smem(int N);
+size_t fkmc_sb2st_smem(int N);
+// dense -> tridiagonal with the context's selected algorithm (A is overwritten)
+int fkmc_tridiagonalize(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_d, double* d_e);
 // Sturm bisection + fused logZ / energy: out[b*8 + {0: logZ, 1: E_c, 2: d2E}]
 int fkmc_launch_tridiag_eig(fkmc_ctx* ctx, const double* d_d, const double* d_e, int N, int B, double beta, double* d_evals,
                             long evals_stride, const int32_t* d_slot, long slot_stride, double* d_out, double* d_exp,

@@ -35,6 +35,7 @@ struct kpm_args {
     double* ab;             // [B][4]
     double* logz;           // [B]
     int* flag;
+    int L;                  // linear lattice size (patch variant)
     int nwarps_cols;        // warps that run the column recursion
     int vec_doubles;        // size of the shared vector region (>= 2 Nv per column warp and >= the Lanczos need)
 };
@@ -82,8 +83,13 @@ __device__ __forceinline__ double warp_ritz(const double* al, const double* be, 
     return 0.5 * (a + c);
 }
 
-template <int HALF>
-__global__ void __launch_bounds__(384, 1) kpm_kernel(kpm_args P) {
+// KIND = 0: generic stencil on full lattice vectors (any lattice, any L).
+// KIND = FKMC_CUBIC2D / FKMC_TRIANGULAR / FKMC_HONEYCOMB: local-patch variant for 2-D lattices with L >= 2 HALF + 1.
+// T_m(X) e_j is supported within m hops of site j, so the column recursion runs on the (2 HALF+1)^2 patch
+// around j, flattened with row stride 2 HALF+1 and a zero guard zone; the stencil becomes fixed offsets
+// (+-1, +-PW, +-(PW+1)) with no index table, and a warp needs 2 x 2.6 KB of shared memory instead of 2 x 8 KB.
+template <int HALF, int KIND>
+__global__ void __launch_bounds__(KIND ? 256 : 384, KIND ? 2 : 1) kpm_kernel(kpm_args P) {
     extern __shared__ double sm[];
     const int N = P.N, Z = P.Z, M = P.M, G = P.G;
     const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
@@ -204,6 +210,85 @@ __global__ void __launch_bounds__(384, 1) kpm_kernel(kpm_args P) {
     double tr[HALF + 1], d01[HALF + 1], d11[HALF + 1];
 #pragma unroll
     for (int m = 0; m <= HALF; ++m) tr[m] = d01[m] = d11[m] = 0.0;
+    if constexpr (KIND != 0) {
+        constexpr int H = HALF, PW = 2 * H + 1, PP = PW * PW, GUARD = PW + 1, PVp = (PP + 2 * GUARD + 1) & ~1, NE = (PP + 31) / 32;
+        constexpr int CEN = GUARD + H * PW + H;
+        const int L = P.L;
+        double* const vbase = vec + (size_t)warp * 2 * PVp;
+        const double svt = sv[0];                                   // nearest-neighbour hopping / a
+        const double svp = (KIND == FKMC_TRIANGULAR) ? sv[4] : 0.0;  // (x-1,y-1)/(x+1,y+1) hopping / a
+        int dyl[NE], dxl[NE];
+#pragma unroll
+        for (int i = 0; i < NE; ++i) {
+            const int kq = lane + 32 * i;
+            dyl[i] = kq / PW - H;
+            dxl[i] = kq % PW - H;
+        }
+        for (int j = warp; j < N; j += nwarps) {
+            const int y0 = j / L, x0 = j - y0 * L;
+            double* v0 = vbase;  // (the roles are swapped HALF-1 times per column: always restart from the base layout)
+            double* v1 = vbase + PVp;
+            double xdp[NE];
+#pragma unroll
+            for (int i = 0; i < NE; ++i) {
+                int yy = y0 + dyl[i], xx = x0 + dxl[i];
+                yy += (yy < 0) ? L : 0; yy -= (yy >= L) ? L : 0;
+                xx += (xx < 0) ? L : 0; xx -= (xx >= L) ? L : 0;
+                xdp[i] = (lane + 32 * i < PP) ? xd[yy * L + xx] : 0.0;
+            }
+            for (int i = lane; i < 2 * PVp; i += 32) v0[i] = 0.0;  // both buffers are contiguous
+            __syncwarp();
+            const bool jeven = ((y0 + x0) & 1) == 0;  // honeycomb: sublattice A hops up (y+1), B hops down
+            if (lane == 0) {
+                v0[CEN] = 1.0;
+                v1[CEN] = xd[j];
+                v1[CEN - 1] = svt;
+                v1[CEN + 1] = svt;
+                if (KIND == FKMC_HONEYCOMB) {
+                    v1[jeven ? CEN + PW : CEN - PW] = svt;
+                } else {
+                    v1[CEN - PW] = svt;
+                    v1[CEN + PW] = svt;
+                    if (KIND == FKMC_TRIANGULAR) { v1[CEN - PW - 1] = svp; v1[CEN + PW + 1] = svp; }
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int m = 2; m <= HALF; ++m) {
+                double s01 = 0.0, s11 = 0.0;
+                const bool need_dots = (2 * m - 1 >= HALF);
+#pragma unroll
+                for (int i = 0; i < NE; ++i) {
+                    const int kq = lane + 32 * i;
+                    if (kq < PP) {
+                        const int kk = kq + GUARD;
+                        const double c1 = v1[kk];
+                        double nb = v1[kk - 1] + v1[kk + 1];
+                        if (KIND == FKMC_HONEYCOMB) {
+                            const bool even = (((dyl[i] + dxl[i]) & 1) == 0) == jeven;
+                            nb += v1[even ? kk + PW : kk - PW];
+                        } else {
+                            nb += v1[kk - PW] + v1[kk + PW];
+                        }
+                        double sacc = fma(xdp[i], c1, svt * nb);
+                        if (KIND == FKMC_TRIANGULAR) sacc = fma(svp, v1[kk - PW - 1] + v1[kk + PW + 1], sacc);
+                        const double vn = 2. * sacc - v0[kk];
+                        v0[kk] = vn;
+                        if (need_dots) {
+                            s01 = fma(c1, vn, s01);
+                            s11 = fma(vn, vn, s11);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) tr[m] += v0[CEN];
+                d01[m] += s01;
+                d11[m] += s11;
+                double* tswap = v0; v0 = v1; v1 = tswap;
+            }
+            __syncwarp();
+        }
+    } else
     if (warp < P.nwarps_cols) {
         double* v0 = vec + (size_t)warp * 2 * Nv;
         double* v1 = v0 + Nv;
@@ -327,8 +412,35 @@ int fkmc_prepare_cheb(fkmc_ctx* ctx, int M, int G) {
     return FKMC_OK;
 }
 
+template <int HALF, int KIND>
+static int launch_kpm_patch(fkmc_ctx* ctx, kpm_args& P, int B) {
+    constexpr int PW = 2 * HALF + 1, PP = PW * PW, GUARD = PW + 1, PVp = (PP + 2 * GUARD + 1) & ~1;
+    const int N = P.N, Nv = N + 1, nw = 8;
+    const size_t lanczos_need = 3 * (size_t)Nv + 2 * KPM_KMAX + 2;
+    size_t vec_doubles = std::max((size_t)nw * 2 * PVp, lanczos_need);
+    vec_doubles += vec_doubles & 1;
+    const size_t fixed = sizeof(double) * ((size_t)N + 48 + 64 + ((P.G + 1) & ~1) + (size_t)nw * 3 * (HALF + 1));
+    const size_t smem = fixed + sizeof(double) * vec_doubles + sizeof(unsigned short) * (size_t)P.Z * N + 16;
+    if (smem > ctx->smem_optin - 1024) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: lattice too large for the shared-memory kernel");
+    P.nwarps_cols = nw;
+    P.vec_doubles = (int)vec_doubles;
+    FKMC_CUDA(ctx, cudaFuncSetAttribute(kpm_kernel<HALF, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kpm_kernel<HALF, KIND><<<B, nw * 32, smem, ctx->stream>>>(P);
+    ctx->launches++;
+    FKMC_CUDA(ctx, cudaGetLastError());
+    return FKMC_OK;
+}
+
 template <int HALF>
 static int launch_kpm_t(fkmc_ctx* ctx, kpm_args& P, int B) {
+    // local-patch variant when the lattice is 2-D and the m <= HALF hop neighbourhood does not wrap onto itself
+    if (HALF >= 2 && HALF <= 10 && P.L >= 2 * HALF + 1 && !ctx->kpm_force_generic) {
+        if constexpr (HALF >= 2 && HALF <= 10) {
+            if (ctx->kind == FKMC_CUBIC2D) return launch_kpm_patch<HALF, FKMC_CUBIC2D>(ctx, P, B);
+            if (ctx->kind == FKMC_TRIANGULAR) return launch_kpm_patch<HALF, FKMC_TRIANGULAR>(ctx, P, B);
+            if (ctx->kind == FKMC_HONEYCOMB) return launch_kpm_patch<HALF, FKMC_HONEYCOMB>(ctx, P, B);
+        }
+    }
     const int N = P.N, Nv = N + 1;
     // shared memory: fixed part + 2 vectors per column-warp; need >= 2 column warps (Lanczos uses 4 buffers)
     const size_t budget = ctx->smem_optin - 1024;
@@ -346,8 +458,8 @@ static int launch_kpm_t(fkmc_ctx* ctx, kpm_args& P, int B) {
     if (nw < 2) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: lattice too large for the shared-memory kernel");
     P.nwarps_cols = nw;
     P.vec_doubles = (int)vec_doubles;
-    FKMC_CUDA(ctx, cudaFuncSetAttribute(kpm_kernel<HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kpm_kernel<HALF><<<B, nw * 32, smem, ctx->stream>>>(P);
+    FKMC_CUDA(ctx, cudaFuncSetAttribute(kpm_kernel<HALF, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kpm_kernel<HALF, 0><<<B, nw * 32, smem, ctx->stream>>>(P);
     ctx->launches++;
     FKMC_CUDA(ctx, cudaGetLastError());
     return FKMC_OK;
@@ -360,7 +472,7 @@ int fkmc_launch_kpm(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double m
     if (ctx->N > 65535) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: N > 65535");
     fkmc_prof_scope ps(ctx, "kpm");
     kpm_args P{};
-    P.f = d_f; P.nbr_idx = ctx->d_nbr_idx; P.N = ctx->N; P.Z = ctx->Z; P.M = M; P.G = G;
+    P.f = d_f; P.nbr_idx = ctx->d_nbr_idx; P.N = ctx->N; P.Z = ctx->Z; P.M = M; P.G = G; P.L = ctx->L;
     P.U = U; P.mu_c = mu_c; P.beta = beta;
     // per-slot hopping constants (all supported stencils are uniform per slot; checked here)
     for (int z = 0; z < FKMC_MAX_Z; ++z) P.slot_val[z] = 0.0;

@@ -79,6 +79,14 @@ int fkmc_energy_from_spectrum(fkmc_ctx* ctx, const double* evals, int B, double 
  * A: [B][N][N] column-major.  d: [B][N], e: [B][N-1].  Eigen's tridiagonalization_inplace stage of
  * SelfAdjointEigenSolver (call site src/configuration.cpp:213). */
 int fkmc_sytrd_batched(fkmc_ctx* ctx, const double* A, int N, int B, double* d, double* e);
+/* Two-stage variant of the same stage (default for calc_ed): dense -> band (half-bandwidth 8, all O(N^3)
+ * work on FP64 tensor cores) -> tridiagonal (bulge chasing in shared memory).
+ * AB: [B][9][N] band storage, AB[d][c] = A(c+d, c). */
+int fkmc_sy2sb_batched(fkmc_ctx* ctx, const double* A, int N, int B, double* AB);
+int fkmc_sb2st_batched(fkmc_ctx* ctx, const double* AB, int N, int B, double* d, double* e);
+/* options: "tridiag" = 1 (one-stage blocked sytrd) | 2 (two-stage, default);
+ *          "kpm_generic" = 1 forces the full-lattice-vector KPM kernel (default 0: local-patch kernel when it applies) */
+int fkmc_set_option(fkmc_ctx* ctx, const char* name, int value);
 /* eigenvalues (ascending) of B symmetric tridiagonals by Sturm bisection */
 int fkmc_tridiag_eigvals_batched(fkmc_ctx* ctx, const double* d, const double* e, int N, int B, double* evals);
 /* device std::mt19937 + libstdc++ distributions: mode 0 raw words, 1 uniform_int(0,V-1), 2 uniform_real(0,1) */

@@ -157,3 +157,45 @@ def _():
                 np.abs(r["energies"] - se["energies"][:, ch]).max(), st["naccept"][ch], r["naccept"],
                 int((r["f_final"] != st["f"][ch]).sum())), flush=True)
         c.close()
+
+
+def band_to_dense(AB):
+    n = AB.shape[1]
+    A = np.zeros((n, n))
+    for d in range(AB.shape[0]):
+        for c in range(n - d):
+            A[c + d, c] = AB[d, c]
+            A[c, c + d] = AB[d, c]
+    return A
+
+
+@stage("two")
+def _():
+    rng = np.random.default_rng(3)
+    for n in [3, 9, 16, 17, 40, 64, 100, 256, 577, 1024]:
+        AB = rng.normal(size=(2, 9, n))
+        for d in range(9):
+            AB[:, d, n - d:] = 0
+        if n > 20:
+            AB[1, 5:, :] = 0  # narrower band
+        t0 = time.time()
+        d_, e_ = ctx8.sb2st(AB)
+        dt = time.time() - t0
+        err = 0
+        for b in range(2):
+            ref = sl.eigvalsh(band_to_dense(AB[b]))
+            got = sl.eigvalsh_tridiagonal(d_[b], e_[b])
+            err = max(err, np.abs(ref - got).max() / np.abs(ref).max())
+        print("sb2st n=%d: rel err %.2e (%.3fs)" % (n, err, dt), flush=True)
+    for n in [2, 8, 9, 16, 33, 64, 100, 256, 300]:
+        A = rng.normal(size=(2, n, n))
+        A = A + np.transpose(A, (0, 2, 1))
+        t0 = time.time()
+        AB = ctx8.sy2sb(A)
+        dt = time.time() - t0
+        err = 0
+        for b in range(2):
+            ref = sl.eigvalsh(A[b])
+            got = sl.eigvalsh(band_to_dense(AB[b]))
+            err = max(err, np.abs(ref - got).max() / np.abs(ref).max())
+        print("sy2sb n=%d: rel err %.2e (%.3fs)" % (n, err, dt), flush=True)

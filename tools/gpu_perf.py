@@ -23,6 +23,8 @@ CFG = {
 for name in cases:
     kind, L, B, U, beta, cheb = CFG[name]
     c = fk.Context(kind, L, max_batch=B)
+    if os.environ.get("FKMC_TRIDIAG"):
+        c.set_option("tridiag", int(os.environ["FKMC_TRIDIAG"]))
     N = c.N
     sweep_len = 4
     c.chain_init(B, beta, U, cheb_moves=cheb, sweep_len=sweep_len, ntherm_sweeps=1000, measure_energy=False, max_sweeps=8)
@@ -36,15 +38,21 @@ for name in cases:
     wall = time.time() - t0
     props = 2 * sweep_len * B
     line = "%s N=%d B=%d: %.1f proposals/s (wall %.3fs)" % (name, N, B, props / wall, wall)
-    for fam in ["build_h", "sytrd", "tridiag_eig", "kpm", "chain_step"]:
+    for fam in ["build_h", "sytrd", "sy2sb", "sb2st", "tridiag_eig", "kpm", "chain_step"]:
         ms, n = c.profile_get(fam)
         if n:
             line += " | %s %.3f ms/launch" % (fam, ms / n)
     print(line, flush=True)
     if not cheb:
         ms, n = c.profile_get("sytrd")
+        if n == 0:
+            ms1, n = c.profile_get("sy2sb")
+            ms2, n2 = c.profile_get("sb2st")
+            print("   sy2sb: %.2f TFLOP/s (4/3 N^3), %.0f matrices/s; sb2st %.0f matrices/s" % (
+                4.0 / 3.0 * N ** 3 * B / (ms1 / n * 1e-3) * 1e-12, B / (ms1 / n * 1e-3), B / (ms2 / n2 * 1e-3)))
+            ms = ms1 + ms2
         fl = 4.0 / 3.0 * N ** 3 * B / (ms / n * 1e-3)
-        print("   sytrd: %.2f TFLOP/s (4/3 N^3), %.0f matrices/s" % (fl * 1e-12, B / (ms / n * 1e-3)))
+        print("   tridiagonalisation: %.2f TFLOP/s (4/3 N^3), %.0f matrices/s" % (fl * 1e-12, B / (ms / n * 1e-3)))
         ms, n = c.profile_get("tridiag_eig")
         print("   tridiag_eig: %.0f matrices/s" % (B / (ms / n * 1e-3)))
     else:
