@@ -207,35 +207,43 @@ def main():
 
     # per-kernel-family device time inside the timed region (events recorded on the launching stream)
     fam = {}
-    for name in ("kpm", "sytrd", "tridiag_eig", "build_h", "chain_step"):
+    for name in ("kpm", "sytrd", "sy2sb", "sb2st", "tridiag_eig", "build_h", "chain_step"):
         tot, n = ctx.profile_get(name)
         if n:
             fam[name] = {"ms_per_launch": tot / n, "launches": n, "share": tot / ms_total}
     peaks, peak_src = measured_peaks()
-    traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["kpm" if cheb else "sytrd"]
-        traffic = tr["bytes_per_launch"] * chains / tr["units_per_launch"]
-    except Exception:
-        pass
-    if cheb:
+    # roofline of the dominant kernel (largest share of the timed region); both candidates are always reported
+    rl_kpm = rl_dense = None
+    if "kpm" in fam:
         bytes_launch = kpm_algorithmic_bytes(N, M) * chains
         achieved = bytes_launch / (fam["kpm"]["ms_per_launch"] * 1e-3) * 1e-9
-        roofline = {"kernel": "kpm_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-                    "note": "algorithmic bytes of the streaming formulation (SURVEY 8d); the kernel keeps the recursion in shared memory, "
-                            "so DRAM traffic is far below it and frac may exceed 1"}
-    else:
+        tr_k = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["kpm"]
+            tr_k = tr["bytes_per_launch"] * chains / tr["units_per_launch"]
+        except Exception:
+            pass
+        rl_kpm = {"kernel": "kpm_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                  "frac": achieved / peaks["hbm_gbs"], "traffic": tr_k, "peak_source": peak_src,
+                  "note": "algorithmic bytes of the streaming formulation (SURVEY 8d); the kernel keeps the recursion in shared memory, "
+                          "so DRAM traffic is far below it and frac exceeds 1"}
+    dense_name = "sy2sb" if "sy2sb" in fam else ("sytrd" if "sytrd" in fam else None)
+    if dense_name:
         fl = 4.0 / 3.0 * N ** 3 * chains
-        achieved = fl / (fam["sytrd"]["ms_per_launch"] * 1e-3) * 1e-12
-        roofline = {"kernel": "sytrd_lower_kernel", "bound": "tensor", "achieved": achieved, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                    "frac": achieved / DMMA_PEAK_TFLOPS, "traffic": traffic, "peak_source": "measured FP64 DMMA (tools/probe_dmma.cu)"}
-    roofline_dense = None
-    if cheb and "sytrd" in fam:
-        fl = 4.0 / 3.0 * N ** 3 * chains
-        a2 = fl / (fam["sytrd"]["ms_per_launch"] * 1e-3) * 1e-12
-        roofline_dense = {"kernel": "sytrd_lower_kernel", "bound": "tensor", "achieved": a2, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                          "frac": a2 / DMMA_PEAK_TFLOPS, "peak_source": "measured FP64 DMMA (tools/probe_dmma.cu)"}
+        a2 = fl / (fam[dense_name]["ms_per_launch"] * 1e-3) * 1e-12
+        tr_d = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))[dense_name]
+            tr_d = tr["bytes_per_launch"] * chains / tr["units_per_launch"]
+        except Exception:
+            pass
+        rl_dense = {"kernel": dense_name + "_kernel", "bound": "tensor", "achieved": a2, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                    "frac": a2 / DMMA_PEAK_TFLOPS, "traffic": tr_d, "peak_source": "measured FP64 DMMA (tools/probe_dmma.cu)",
+                    "note": "4/3 N^3 flop per matrix, all of it issued as DMMA.8x8x4 in the dense->band stage"}
+    dominant = max(fam, key=lambda k: fam[k]["share"])
+    roofline = rl_kpm if dominant == "kpm" else (rl_dense if rl_dense is not None else rl_kpm)
+    roofline_dense = rl_dense
+    roofline_kpm = rl_kpm
 
     # ---- e2e: the same sweep driven from HOST buffers through the C-ABI evaluators ----
     e2e = None
@@ -324,7 +332,8 @@ def main():
                 "config": {"workload": desc, "chains_per_gpu": chains, "sweep_len": SWEEP_LEN, "seed": SEED, "mu_c": U / 2, "mu_f": U / 2,
                            "moves": "add_remove", "M": M if cheb else None, "G": G if cheb else None,
                            "l2_flush": "256 MiB device memset between timed steps", "parallelism": "chains sharded, %d per GPU" % chains},
-                "sweeps_per_sec": value / SWEEP_LEN, "roofline": roofline, "roofline_dense": roofline_dense, "kernels": fam,
+                "sweeps_per_sec": value / SWEEP_LEN, "roofline": roofline, "roofline_dense": roofline_dense, "roofline_kpm": roofline_kpm,
+                "dominant_kernel": dominant, "kernels": fam,
                 "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks,
                 "final_gather_ms": gather_ms}
         print(json.dumps(line), flush=True)

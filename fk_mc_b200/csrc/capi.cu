@@ -69,7 +69,7 @@ int fkmc_ensure_dense_ws(fkmc_ctx* ctx) {
 }
 
 int fkmc_tridiagonalize(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_d, double* d_e) {
-    const bool two = ctx->tridiag_mode == 2 && N >= 16 && fkmc_sy2sb_smem(N) <= ctx->smem_optin && fkmc_sb2st_smem(N) <= ctx->smem_optin;
+    const bool two = ctx->tridiag_mode == 2 && N >= 16 && N <= 1024 && fkmc_sy2sb_smem(N) <= ctx->smem_optin && fkmc_sb2st_smem(N) <= ctx->smem_optin;
     if (!two) return fkmc_launch_sytrd(ctx, d_A, N, B, d_d, d_e, ctx->d_tau, ctx->d_W);
     int rc = fkmc_launch_sy2sb(ctx, d_A, N, B, ctx->d_AB);
     if (rc) return rc;

@@ -59,7 +59,7 @@ __device__ __forceinline__ refl make_reflector(double x, int i, int n) {
     return R;
 }
 
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(1024, 1)
 sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_all, double* __restrict__ e_all) {
     extern __shared__ double smem[];
     double* Wb = smem;                                         // [N + 16][16]
@@ -103,7 +103,6 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
                     if (ok) col[p - c + i] = a - vi * w;
                 }
             }
-            __syncwarp();
             // (ii) two-sided update of the diagonal block D = A(J, J): lane (i, q) owns D(i, c) for c = q, q+4
             if (tau != 0.0) {
                 double dcol[2], vc[2];
@@ -126,7 +125,6 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
                     if (i >= c) Wb[(size_t)(p + c) * WD + (i - c)] = dcol[h] - vi * uc - u * vc[h];
                 }
             }
-            __syncwarp();
             // (iii) right-apply H to the block below: A(Jn, J), Jn = rows p+8 .. p+15; lane (i, q) owns rows i, columns q, q+4
             const int pn = p + SB;
             const int nn = min(SB, N - pn);
@@ -189,7 +187,7 @@ int fkmc_launch_sb2st(fkmc_ctx* ctx, const double* d_AB, int N, int B, double* d
     if (smem > ctx->smem_optin) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sb2st: matrix too large for shared memory");
     int nwarps = (N + 23) / 24;  // ~one warp per 3 blocks of the band (the pipeline lag)
     if (nwarps < 1) nwarps = 1;
-    if (nwarps > 16) nwarps = 16;
+    if (nwarps > ((N > 640) ? 32 : 16)) nwarps = (N > 640) ? 32 : 16;  // <= 512 threads keeps two CTAs per SM for N <= 512
     FKMC_CUDA(ctx, cudaFuncSetAttribute(sb2st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     sb2st_kernel<<<B, nwarps * 32, smem, ctx->stream>>>(d_AB, N, d_d, d_e);
     ctx->launches++;

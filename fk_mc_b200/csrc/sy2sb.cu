@@ -1,17 +1,24 @@
 // Stage 1 of the two-stage tridiagonalisation: dense symmetric (lower) -> symmetric band with
-// half-bandwidth 8, one CTA per matrix, every O(N^3) flop on the FP64 tensor cores.
+// half-bandwidth 8, one CTA (8 warps) per matrix, every O(N^3) flop on the FP64 tensor cores.
 //
 // Together with sb2st.cu this replaces the tridiagonalisation stage of Eigen::SelfAdjointEigenSolver
 // as called from configuration_t::calc_ed (src/configuration.cpp:212-213).  For block column k
 // (columns k0..k0+7, trailing rows r0 = k0+8 .. N-1, m = N - r0):
 //   1. Householder QR of the m x 8 panel in shared memory  ->  V (unit lower trapezoidal), tau, R
 //   2. T (8x8, compact WY: Q = I - V T V^T) from the Gram matrix V^T V (DMMA)
-//   3. Y0 = A22 V          -- SYMM over the stored lower triangle, 32x32 warp tiles, DMMA m8n8k4;
-//                             tile tasks are paired cyclically so that no two warps add into the
-//                             same rows of Y in the same step (no atomics)
+//   3. Y0 = A22 V          -- SYMM over the stored lower triangle in 32x32 tiles
 //   4. Y = Y0 T,  X = V^T Y (DMMA),  Z = Y - 1/2 V (T^T X)
-//   5. A22 -= V Z^T + Z V^T  -- rank-16 SYR2K on the lower triangle, DMMA, operands from shared memory
+//   5. A22 -= V Z^T + Z V^T  -- rank-16 SYR2K on the lower triangle
+// Steps 3 and 5 stream the trailing matrix tile by tile: every warp owns a 32x32 shared-memory tile
+// buffer that is filled by bulk asynchronous copies (cp.async.bulk + mbarrier transaction counts, one
+// 256-byte column per lane -- SASS UBLKCP) and, in step 5, drained by bulk stores, so the tensor-core
+// warps never hold global loads in registers.  DMMA fragments are read from the tile with a column
+// stride == 4 (mod 16) doubles, which is conflict-free for both the direct and the transposed operand.
+// In step 3 the tile tasks are paired cyclically ({a, a-s}, s = 0..nt/2): a warp keeps the rows of
+// its own tiles in registers for the whole pass and adds the partner rows straight into shared
+// memory -- in one step all partner tiles are distinct, so no atomics are needed.
 // R and the diagonal blocks are emitted in band storage AB[d][c] = A(c+d, c), d = 0..8.
+// Requires N % 8 == 0 (16-byte aligned columns for the bulk copies) and N <= 1024.
 #include <cfloat>
 
 #include "common.cuh"
@@ -19,19 +26,68 @@
 namespace {
 
 constexpr int NB = 8;
+constexpr int NW = 8;       // warps per CTA
+constexpr int TS = 36;      // tile column stride in doubles (== 4 mod 16)
+constexpr int TILE = 32 * TS;
+constexpr int MAXOWN = 4;   // owned row tiles per warp: N <= 1024 -> nt <= 32 -> 4
 
 struct s1_smem {
     double* V;    // [8][ld] column-major panel / reflectors
-    double* Y;    // [8][ld] Y0 (own contributions) -> Y -> Z
-    double* Y2;   // [8][ld] Y0 (partner contributions)
+    double* Y;    // [8][ld] Y0 -> Y -> Z
     double* G;    // [64] Gram / X / scratch
     double* Tm;   // [64] T
     double* M2;   // [64] T^T X
-    double* Rs;   // [64] R
     double* tau;  // [8]
-    double* red;  // [16*64 + 72]
+    double* red;  // [NW*64 + 72]
+    double* tile; // [NW][TILE]
+    uint64_t* bar; // [NW]
     int ld;
 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FKMC_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra FKMC_DONE_%=;\n"
+        "bra FKMC_WAIT_%=;\n"
+        "FKMC_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global bulk copy (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Issue the bulk loads of tile (R, C) of the trailing matrix into this warp's buffer (whole warp calls).
+__device__ __forceinline__ void tile_load(double* buf, uint64_t* bar, const double* __restrict__ A22, int lda, int m, int R, int C,
+                                          int lane) {
+    const int nrows = min(32, m - 32 * R), ncols = min(32, m - 32 * C);
+    __syncwarp();  // every lane is done reading the previous contents
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(nrows * ncols * 8));
+    __syncwarp();
+    if (lane < ncols) bulk_g2s(buf + lane * TS, A22 + (size_t)(32 * C + lane) * lda + 32 * R, (uint32_t)(nrows * 8), bar);
+}
 
 // block-wide sum of K values per thread; result broadcast to all threads via out[0..K)
 template <int K>
@@ -71,106 +127,67 @@ __device__ __forceinline__ void gram8(const double* P, const double* Q, int ld, 
     __syncthreads();
 }
 
-// One SYMM tile task: stored tile (Rmax, Cmin) of the trailing matrix (tile coordinates relative to r0).
-// Contribution 1: Y[Rmax rows] += S V[Cmin rows];  contribution 2: Y[Cmin rows] += S^T V[Rmax rows].
-__device__ __forceinline__ void symm_tile(const double* __restrict__ A22, int lda, int m, int a, int p, const s1_smem& S, int lane) {
-    const int g = lane >> 2, t = lane & 3, ld = S.ld;
-    const bool diag = (a == p);
-    const int Rmax = a > p ? a : p, Cmin = a > p ? p : a;
-    const int rb0 = 32 * Rmax, cb0 = 32 * Cmin;
-    double accR[4][2], accC[4][2];
+// SYMM on one staged tile.  Stored tile (Rmax, Cmin), S = tile contents:
+//   accR (rows of Rmax) += S V[Cmin rows];   accC (rows of Cmin) += S^T V[Rmax rows]   (off-diagonal tiles)
+//   accR += sym(S) V[rows]                                                            (diagonal tiles)
+__device__ __forceinline__ void symm_tile(const double* __restrict__ Tb, bool diag, int rb0, int cb0, const double* __restrict__ V, int ld,
+                                          int lane, double (&accR)[4][2], double (&accC)[4][2]) {
+    const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int x = 0; x < 4; ++x) accR[x][0] = accR[x][1] = accC[x][0] = accC[x][1] = 0.0;
-    if (diag) {
-        // full symmetric tile from the stored lower triangle: element (r, c) = A[max][min]
+    for (int cb = 0; cb < 4; ++cb) {
+        const int c8 = 8 * cb;
+        const double bv0 = V[g * ld + cb0 + c8 + t], bv1 = V[g * ld + cb0 + c8 + 4 + t];
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
-            const int c8 = cb0 + 8 * cb;
-            const double bv0 = S.V[g * ld + c8 + t], bv1 = S.V[g * ld + c8 + 4 + t];
-            double a0[4], a1[4];
-#pragma unroll
-            for (int rb = 0; rb < 4; ++rb) {
-                const int r = rb0 + 8 * rb + g, c = c8 + t, c2 = c8 + 4 + t;
-                const int hi = max(r, c), lo = min(r, c), hi2 = max(r, c2), lo2 = min(r, c2);
-                a0[rb] = (hi < m) ? A22[(size_t)lo * lda + hi] : 0.0;
-                a1[rb] = (hi2 < m) ? A22[(size_t)lo2 * lda + hi2] : 0.0;
-            }
-#pragma unroll
-            for (int rb = 0; rb < 4; ++rb) {
-                dmma884(accR[rb][0], accR[rb][1], a0[rb], bv0);
-                dmma884(accR[rb][0], accR[rb][1], a1[rb], bv1);
-            }
-        }
-    } else {
-        // software pipeline over the 4 column blocks: the 16 global fragments of block cb+1 are in
-        // flight while the 16 DMMAs of block cb execute
-        double a0[4], a1[4], s0[4], s1[4];
-        auto load_cb = [&](int cb) {
-            const int c8 = cb0 + 8 * cb;
-#pragma unroll
-            for (int rb = 0; rb < 4; ++rb) {
-                const int r8 = rb0 + 8 * rb, r = r8 + g, rr0 = r8 + t, rr1 = r8 + 4 + t;
-                // contribution 1: A(g, k) = S[g][4ks + t];  contribution 2: A(g, k) = S^T[g][4ks + t] = S[4ks + t][g]
-                a0[rb] = (r < m) ? A22[(size_t)(c8 + t) * lda + r] : 0.0;
-                a1[rb] = (r < m) ? A22[(size_t)(c8 + 4 + t) * lda + r] : 0.0;
-                s0[rb] = (rr0 < m) ? A22[(size_t)(c8 + g) * lda + rr0] : 0.0;
-                s1[rb] = (rr1 < m) ? A22[(size_t)(c8 + g) * lda + rr1] : 0.0;
-            }
-        };
-        load_cb(0);
-#pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
-            const int c8 = cb0 + 8 * cb;
-            const double bv0 = S.V[g * ld + c8 + t], bv1 = S.V[g * ld + c8 + 4 + t];
-            double ca0[4], ca1[4], cs0[4], cs1[4];
-#pragma unroll
-            for (int rb = 0; rb < 4; ++rb) { ca0[rb] = a0[rb]; ca1[rb] = a1[rb]; cs0[rb] = s0[rb]; cs1[rb] = s1[rb]; }
-            if (cb < 3) load_cb(cb + 1);
-#pragma unroll
-            for (int rb = 0; rb < 4; ++rb) {
-                const int r8 = rb0 + 8 * rb;
-                dmma884(accR[rb][0], accR[rb][1], ca0[rb], bv0);
-                dmma884(accR[rb][0], accR[rb][1], ca1[rb], bv1);
-                // B(k, n) = V[r8 + 4ks + t][n = g]
-                dmma884(accC[cb][0], accC[cb][1], cs0[rb], S.V[g * ld + r8 + t]);
-                dmma884(accC[cb][0], accC[cb][1], cs1[rb], S.V[g * ld + r8 + 4 + t]);
+        for (int rb = 0; rb < 4; ++rb) {
+            const int r8 = 8 * rb;
+            if (diag) {
+                const int r = r8 + g, c = c8 + t, c2 = c8 + 4 + t;
+                const double a0 = Tb[min(r, c) * TS + max(r, c)];
+                const double a1 = Tb[min(r, c2) * TS + max(r, c2)];
+                dmma884(accR[rb][0], accR[rb][1], a0, bv0);
+                dmma884(accR[rb][0], accR[rb][1], a1, bv1);
+            } else {
+                // contribution 1: A(g, k) = S[g][4ks + t];  contribution 2: A(g, k) = S[4ks + t][g], B(k, n) = V[rb0 + r8 + 4ks + t][n = g]
+                const double a0 = Tb[(c8 + t) * TS + r8 + g], a1 = Tb[(c8 + 4 + t) * TS + r8 + g];
+                const double s0 = Tb[(c8 + g) * TS + r8 + t], s1 = Tb[(c8 + g) * TS + r8 + 4 + t];
+                dmma884(accR[rb][0], accR[rb][1], a0, bv0);
+                dmma884(accR[rb][0], accR[rb][1], a1, bv1);
+                dmma884(accC[cb][0], accC[cb][1], s0, V[g * ld + rb0 + r8 + t]);
+                dmma884(accC[cb][0], accC[cb][1], s1, V[g * ld + rb0 + r8 + 4 + t]);
             }
         }
     }
-    // accumulators: (row = 8x + g, col = 2t + h); own rows go to Y, partner rows to Y2
-    double* ownR = (diag || a == Rmax) ? S.Y : S.Y2;
-    double* ownC = (a == Rmax) ? S.Y2 : S.Y;
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            ownR[(2 * t + h) * ld + rb0 + 8 * x + g] += accR[x][h];
-            if (!diag) ownC[(2 * t + h) * ld + cb0 + 8 * x + g] += accC[x][h];
-        }
 }
 
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(NW * 32, 1)
 sy2sb_kernel(double* __restrict__ A_all, int N, double* __restrict__ AB_all) {
-    extern __shared__ double smem[];
-    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    extern __shared__ __align__(128) double smem[];
+    const int tid = threadIdx.x, T = NW * 32, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int b = blockIdx.x, lda = N;
     double* A = A_all + (size_t)b * N * N;
     double* AB = AB_all + (size_t)b * (NB + 1) * N;
-    // leading dimension of the shared panels: >= rows rounded to 32, and == 8 (mod 16) for conflict-free fragment loads
     const int mp = ((N + 31) / 32) * 32;
     s1_smem S;
-    S.ld = mp + 8;
+    S.ld = mp + 4;  // == 4 (mod 16): both fragment patterns are 2-way (optimal) on the panels
     S.V = smem;
     S.Y = S.V + 8 * S.ld;
-    S.Y2 = S.Y + 8 * S.ld;
-    S.G = S.Y2 + 8 * S.ld;
+    S.G = S.Y + 8 * S.ld;
     S.Tm = S.G + 64;
     S.M2 = S.Tm + 64;
-    S.Rs = S.M2 + 64;
-    S.tau = S.Rs + 64;
+    S.tau = S.M2 + 64;
     S.red = S.tau + 8;
+    S.tile = S.red + NW * 64 + 72;
+    S.bar = reinterpret_cast<uint64_t*>(S.tile + NW * TILE);
     const int ld = S.ld;
+    double* Tb = S.tile + warp * TILE;
+    uint64_t* bar = S.bar + warp;
+    uint32_t parity = 0;
+
+    for (int i = tid; i < NW * TILE; i += T) S.tile[i] = 0.0;
+    if (tid < NW) mbar_init(S.bar + tid, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
 
     for (int k0 = 0; k0 < N; k0 += NB) {
         const int r0 = k0 + NB, m = N - r0;
@@ -186,17 +203,25 @@ sy2sb_kernel(double* __restrict__ A_all, int N, double* __restrict__ AB_all) {
             const int j = idx / ld, i = idx % ld;
             S.V[idx] = (i < m) ? A[(size_t)(k0 + j) * lda + r0 + i] : 0.0;
             S.Y[idx] = 0.0;
-            S.Y2[idx] = 0.0;
         }
-        if (tid < 64) S.Rs[tid] = 0.0;
         __syncthreads();
         const int nref = min(NB, m);
+        bool any = false;
         for (int j = 0; j < NB; ++j) {
             double tau = 0.0;
             if (j < nref && m - j >= 2) {
-                double part = 0.0;
-                for (int i = j + 1 + tid; i < m; i += T) part = fma(S.V[j * ld + i], S.V[j * ld + i], part);
-                const double tail2 = block_sum(part, S.red);
+                // one fused reduction: pw[c] = sum_{i>j} P[i][j] P[i][c], c >= j  (c = j gives the tail norm)
+                double pw[NB];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) pw[c] = 0.0;
+                for (int i = j + 1 + tid; i < m; i += T) {
+                    const double pj = S.V[j * ld + i];
+#pragma unroll
+                    for (int c = 0; c < NB; ++c)
+                        if (c >= j) pw[c] = fma(pj, S.V[c * ld + i], pw[c]);
+                }
+                block_sum_vec<NB>(pw, S.red, S.G);
+                const double tail2 = S.G[j];
                 const double x0 = S.V[j * ld + j];
                 double beta = x0, inv = 0.0;
                 if (tail2 > DBL_MIN) {
@@ -205,43 +230,30 @@ sy2sb_kernel(double* __restrict__ A_all, int N, double* __restrict__ AB_all) {
                     inv = 1.0 / (x0 - beta);
                     tau = (beta - x0) / beta;
                 }
-                __syncthreads();  // everyone has read x0 before it is overwritten
-                // scale the reflector and form w_c = tau * (P[j][c] + sum_{i>j} v_i P[i][c]) for c > j
-                double pw[NB];
+                // w_c = tau (P[j][c] + inv * G[c]);  rows i > j: v_i = P[i][j] inv, P[i][c] -= v_i w_c
+                double w[NB];
 #pragma unroll
-                for (int c = 0; c < NB; ++c) pw[c] = 0.0;
+                for (int c = 0; c < NB; ++c) w[c] = (c > j) ? tau * fma(inv, S.G[c], S.V[c * ld + j]) : 0.0;
+                __syncthreads();  // all threads hold x0, G and row j before they change
                 for (int i = j + 1 + tid; i < m; i += T) {
                     const double vi = S.V[j * ld + i] * inv;
                     S.V[j * ld + i] = vi;
 #pragma unroll
                     for (int c = 0; c < NB; ++c)
-                        if (c > j) pw[c] = fma(vi, S.V[c * ld + i], pw[c]);
+                        if (c > j) S.V[c * ld + i] = fma(-vi, w[c], S.V[c * ld + i]);
                 }
-                block_sum_vec<NB>(pw, S.red, S.G);
-                for (int i = j + tid; i < m; i += T) {
-                    const double vi = (i == j) ? 1.0 : S.V[j * ld + i];
-#pragma unroll
-                    for (int c = 0; c < NB; ++c)
-                        if (c > j) {
-                            const double w = tau * (S.V[c * ld + j] + S.G[c]);
-                            if (i != j) S.V[c * ld + i] = fma(-vi, w, S.V[c * ld + i]);
-                        }
-                }
-                __syncthreads();
-                if (tid < NB && tid > j) S.V[tid * ld + j] -= tau * (S.V[tid * ld + j] + S.G[tid]);  // row j itself (v_j = 1)
+                if (tid < NB && tid > j) S.V[tid * ld + j] -= w[tid];  // row j itself (v_j = 1)
                 if (tid == 0) S.V[j * ld + j] = beta;
                 __syncthreads();
             }
             if (tid == 0) S.tau[j] = tau;
+            any = any || (tau != 0.0);
         }
         __syncthreads();
-        // R (upper triangle of the top 8x8) -> Rs and band storage; then make V explicit (unit lower trapezoidal)
+        // R (upper triangle of the top 8x8) -> band storage; then make V explicit (unit lower trapezoidal)
         if (tid < 64) {
             const int c = tid >> 3, i = tid & 7;
-            if (i <= c && i < m) {
-                const double r = S.V[c * ld + i];
-                AB[(size_t)(NB + i - c) * N + k0 + c] = r;
-            }
+            if (i <= c && i < m) AB[(size_t)(NB + i - c) * N + k0 + c] = S.V[c * ld + i];
         }
         __syncthreads();
         if (tid < 64) {
@@ -250,35 +262,94 @@ sy2sb_kernel(double* __restrict__ A_all, int N, double* __restrict__ AB_all) {
             else if (i == c) S.V[c * ld + i] = (i < m) ? 1.0 : 0.0;
         }
         __syncthreads();
-        bool any = false;
-        for (int j = 0; j < NB; ++j) any = any || (S.tau[j] != 0.0);
         if (!any) continue;  // nothing to apply (uniform across the block)
-        // ---- 2. T from the Gram matrix ----
+        // ---- 2. T from the Gram matrix: T(0:j, j) = -tau_j T(0:j,0:j) G(0:j, j) ----
         gram8(S.V, S.V, ld, m, S.red, S.G);
-        if (tid == 0) {
-            for (int j = 0; j < NB; ++j) {
-                const double tj = S.tau[j];
-                for (int a = 0; a < NB; ++a) S.Tm[a * 8 + j] = 0.0;
-                S.Tm[j * 8 + j] = tj;
-                // T(0:j, j) = -tau_j * T(0:j,0:j) * G(0:j, j)
-                for (int a = 0; a < j; ++a) {
-                    double s = 0.0;
-                    for (int c = a; c < j; ++c) s += S.Tm[a * 8 + c] * S.G[c * 8 + j];
-                    S.Tm[a * 8 + j] = -tj * s;
-                }
-            }
-        }
+        if (tid < 64) S.Tm[tid] = 0.0;
         __syncthreads();
-        // ---- 3. Y0 = A22 V (lower triangle stored): cyclic pairing of 32x32 tile tasks ----
-        const int nt = (m + 31) >> 5;
-        for (int wt = warp; wt < nt; wt += nwarps) symm_tile(A22, lda, m, wt, wt, S, lane);
-        for (int s = 1; s <= (nt >> 1); ++s) {
+        for (int j = 0; j < NB; ++j) {
+            if (tid < j) {
+                double s = 0.0;
+                for (int c = tid; c < j; ++c) s += S.Tm[tid * 8 + c] * S.G[c * 8 + j];
+                S.Tm[tid * 8 + j] = -S.tau[j] * s;
+            } else if (tid == j) {
+                S.Tm[j * 8 + j] = S.tau[j];
+            }
             __syncthreads();
-            const int lim = (2 * s == nt) ? (nt >> 1) : nt;
-            for (int wt = warp; wt < lim; wt += nwarps) {
-                int pt = wt - s;
-                if (pt < 0) pt += nt;
-                symm_tile(A22, lda, m, wt, pt, S, lane);
+        }
+        // ---- 3. Y0 = A22 V: cyclic pairing of tile tasks, own rows in registers, partner rows in shared memory ----
+        const int nt = (m + 31) >> 5;
+        {
+            double own[MAXOWN][4][2];
+#pragma unroll
+            for (int o = 0; o < MAXOWN; ++o)
+#pragma unroll
+                for (int x = 0; x < 4; ++x) own[o][x][0] = own[o][x][1] = 0.0;
+            const int smax = nt >> 1;
+            // prefetch the first task of this warp (its diagonal tile)
+            if (warp < nt) tile_load(Tb, bar, A22, lda, m, warp, warp, lane);
+            for (int s = 0; s <= smax; ++s) {
+                const int lim = (s > 0 && 2 * s == nt) ? (nt >> 1) : nt;
+#pragma unroll
+                for (int o = 0; o < MAXOWN; ++o) {
+                    const int a = warp + NW * o;
+                    if (a < lim) {
+                        int p = a - s;
+                        if (p < 0) p += nt;
+                        const bool diag = (s == 0);
+                        const int Rmax = max(a, p), Cmin = min(a, p);
+                        mbar_wait(bar, parity);
+                        parity ^= 1;
+                        double accR[4][2], accC[4][2];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) accR[x][0] = accR[x][1] = accC[x][0] = accC[x][1] = 0.0;
+                        symm_tile(Tb, diag, 32 * Rmax, 32 * Cmin, S.V, ld, lane, accR, accC);
+                        // prefetch this warp's next task while the results are folded
+                        {
+                            int na = a + NW, ns = s;
+                            const int nlim = lim;
+                            if (na >= nlim) {
+                                ns = s + 1;
+                                na = warp;
+                            }
+                            const int nlim2 = (ns > 0 && 2 * ns == nt) ? (nt >> 1) : nt;
+                            if (ns <= smax && na < nlim2) {
+                                int np = na - ns;
+                                if (np < 0) np += nt;
+                                tile_load(Tb, bar, A22, lda, m, max(na, np), min(na, np), lane);
+                            }
+                        }
+                        // own rows stay in registers; partner rows go to shared memory (distinct tiles within a step)
+                        if (diag || a == Rmax) {
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) { own[o][x][0] += accR[x][0]; own[o][x][1] += accR[x][1]; }
+                            if (!diag) {
+#pragma unroll
+                                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                                    for (int h = 0; h < 2; ++h) S.Y[(2 * t + h) * ld + 32 * Cmin + 8 * x + g] += accC[x][h];
+                            }
+                        } else {
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) { own[o][x][0] += accC[x][0]; own[o][x][1] += accC[x][1]; }
+#pragma unroll
+                            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) S.Y[(2 * t + h) * ld + 32 * Rmax + 8 * x + g] += accR[x][h];
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int o = 0; o < MAXOWN; ++o) {
+                const int a = warp + NW * o;
+                if (a < nt) {
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) S.Y[(2 * t + h) * ld + 32 * a + 8 * x + g] += own[o][x][h];
+                }
             }
         }
         __syncthreads();
@@ -286,14 +357,14 @@ sy2sb_kernel(double* __restrict__ A_all, int N, double* __restrict__ AB_all) {
         for (int i = tid; i < m; i += T) {
             double y0[NB], y[NB];
 #pragma unroll
-            for (int a = 0; a < NB; ++a) y0[a] = S.Y[a * ld + i] + S.Y2[a * ld + i];
+            for (int a = 0; a < NB; ++a) y0[a] = S.Y[a * ld + i];
 #pragma unroll
             for (int c = 0; c < NB; ++c) {
-                double s = 0.0;
+                double sacc = 0.0;
 #pragma unroll
                 for (int a = 0; a < NB; ++a)
-                    if (a <= c) s = fma(y0[a], S.Tm[a * 8 + c], s);
-                y[c] = s;
+                    if (a <= c) sacc = fma(y0[a], S.Tm[a * 8 + c], sacc);
+                y[c] = sacc;
             }
 #pragma unroll
             for (int c = 0; c < NB; ++c) S.Y[c * ld + i] = y[c];
@@ -302,9 +373,9 @@ sy2sb_kernel(double* __restrict__ A_all, int N, double* __restrict__ AB_all) {
         gram8(S.V, S.Y, ld, m, S.red, S.G);  // G = X = V^T Y
         if (tid < 64) {
             const int a = tid >> 3, c = tid & 7;  // M2 = T^T X
-            double s = 0.0;
-            for (int q = 0; q <= a; ++q) s += S.Tm[q * 8 + a] * S.G[q * 8 + c];
-            S.M2[a * 8 + c] = s;
+            double sacc = 0.0;
+            for (int q = 0; q <= a; ++q) sacc += S.Tm[q * 8 + a] * S.G[q * 8 + c];
+            S.M2[a * 8 + c] = sacc;
         }
         __syncthreads();
         for (int i = tid; i < m; i += T) {
@@ -313,60 +384,82 @@ sy2sb_kernel(double* __restrict__ A_all, int N, double* __restrict__ AB_all) {
             for (int a = 0; a < NB; ++a) v[a] = S.V[a * ld + i];
 #pragma unroll
             for (int c = 0; c < NB; ++c) {
-                double s = 0.0;
+                double sacc = 0.0;
 #pragma unroll
-                for (int a = 0; a < NB; ++a) s = fma(v[a], S.M2[a * 8 + c], s);
-                S.Y[c * ld + i] -= 0.5 * s;
+                for (int a = 0; a < NB; ++a) sacc = fma(v[a], S.M2[a * 8 + c], sacc);
+                S.Y[c * ld + i] -= 0.5 * sacc;
             }
         }
         __syncthreads();
-        // ---- 5. A22 -= V Z^T + Z V^T on the lower triangle (Z lives in S.Y) ----
+        // ---- 5. A22 -= V Z^T + Z V^T on the lower triangle (Z lives in S.Y): load tile, update in shared memory, bulk store ----
         const int ntl = nt * (nt + 1) / 2;
-        for (int tt = warp; tt < ntl; tt += nwarps) {
-            int R = (int)((sqrtf(8.0f * (float)tt + 1.0f) - 1.0f) * 0.5f);
+        auto decode = [](int tt, int& R, int& C) {
+            R = (int)((sqrtf(8.0f * (float)tt + 1.0f) - 1.0f) * 0.5f);
             while (R * (R + 1) / 2 > tt) --R;
             while ((R + 1) * (R + 2) / 2 <= tt) ++R;
-            const int C = tt - R * (R + 1) / 2;
+            C = tt - R * (R + 1) / 2;
+        };
+        if (warp < ntl) {
+            int R, C;
+            decode(warp, R, C);
+            tile_load(Tb, bar, A22, lda, m, R, C, lane);
+        }
+        for (int tt = warp; tt < ntl; tt += NW) {
+            int R, C;
+            decode(tt, R, C);
             const int rb0 = 32 * R, cb0 = 32 * C;
-            // the C tile is loaded straight into the accumulators (all 32 loads in flight at once) and the
-            // update is accumulated with a negated A operand: acc = C - [V Z][Z V]^T
+            // operand fragments do not depend on the tile contents: fetch them while the copy is in flight
+            double af[4][4], bf[4][4];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                // P = [V Z] (A operand, negated), Q = [Z V] (B operand); k = 4 ks + t
+                const double* Pp = (ks < 2) ? S.V : S.Y;
+                const double* Qp = (ks < 2) ? S.Y : S.V;
+                const int col = 4 * (ks & 1) + t;
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    af[ks][x] = -Pp[col * ld + rb0 + 8 * x + g];
+                    bf[ks][x] = Qp[col * ld + cb0 + 8 * x + g];
+                }
+            }
+            mbar_wait(bar, parity);
+            parity ^= 1;
             double acc[4][4][2];
 #pragma unroll
             for (int x = 0; x < 4; ++x)
 #pragma unroll
                 for (int y = 0; y < 4; ++y)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int rr = rb0 + 8 * x + g, cc = cb0 + 8 * y + 2 * t + h;
-                        acc[x][y][h] = (rr < m && cc < m && rr >= cc) ? A22[(size_t)cc * lda + rr] : 0.0;
-                    }
+                    for (int h = 0; h < 2; ++h) acc[x][y][h] = Tb[(8 * y + 2 * t + h) * TS + 8 * x + g];
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                // P = [V Z] (A operand), Q = [Z V] (B operand); k = 4 ks + t
-                const double* Pp = (ks < 2) ? S.V : S.Y;
-                const double* Qp = (ks < 2) ? S.Y : S.V;
-                const int col = 4 * (ks & 1) + t;
-                double af[4], bf[4];
-#pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    af[x] = -Pp[col * ld + rb0 + 8 * x + g];
-                    bf[x] = Qp[col * ld + cb0 + 8 * x + g];
-                }
+            for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
                 for (int x = 0; x < 4; ++x)
 #pragma unroll
-                    for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[x], bf[y]);
-            }
+                    for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[ks][x], bf[ks][y]);
 #pragma unroll
             for (int x = 0; x < 4; ++x)
 #pragma unroll
                 for (int y = 0; y < 4; ++y)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int rr = rb0 + 8 * x + g, cc = cb0 + 8 * y + 2 * t + h;
-                        if (rr < m && cc < m && rr >= cc) A22[(size_t)cc * lda + rr] = acc[x][y][h];
-                    }
+                    for (int h = 0; h < 2; ++h) Tb[(8 * y + 2 * t + h) * TS + 8 * x + g] = acc[x][y][h];
+            // drain: generic-proxy writes -> async proxy, one bulk store per column (full columns: the strictly upper part
+            // of a diagonal tile is never read by anyone)
+            fence_async_smem();
+            __syncwarp();
+            const int nrows = min(32, m - rb0), ncols = min(32, m - cb0);
+            if (lane < ncols) bulk_s2g(A22 + (size_t)(cb0 + lane) * lda + rb0, Tb + lane * TS, (uint32_t)(nrows * 8));
+            bulk_commit();
+            bulk_wait_read();  // the buffer may be overwritten once the stores have read it
+            const int tn = tt + NW;
+            if (tn < ntl) {
+                int R2, C2;
+                decode(tn, R2, C2);
+                tile_load(Tb, bar, A22, lda, m, R2, C2, lane);
+            }
         }
+        // all bulk stores of this block column must have landed before the next panel is read
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         __syncthreads();
     }
 }
@@ -374,19 +467,21 @@ sy2sb_kernel(double* __restrict__ A_all, int N, double* __restrict__ AB_all) {
 }  // namespace
 
 size_t fkmc_sy2sb_smem(int N) {
-    const size_t ld = ((N + 31) / 32) * 32 + 8;
-    return sizeof(double) * (3 * 8 * ld + 4 * 64 + 8 + 16 * 64 + 72);
+    const size_t ld = ((N + 31) / 32) * 32 + 4;
+    return sizeof(double) * (2 * 8 * ld + 3 * 64 + 8 + NW * 64 + 72 + (size_t)NW * TILE) + sizeof(uint64_t) * NW + 16;
 }
 
+int fkmc_launch_sy2sb_small(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_AB);
+
 int fkmc_launch_sy2sb(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_AB) {
+    // below N = 512 the per-block-column latency chain dominates and the register-fragment kernel is faster
+    if (N < 512 || N % 8 != 0) return fkmc_launch_sy2sb_small(ctx, d_A, N, B, d_AB);
     fkmc_prof_scope ps(ctx, "sy2sb");
+    if (N % 8 != 0 || N > 1024) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sy2sb: needs N % 8 == 0 and N <= 1024");
     const size_t smem = fkmc_sy2sb_smem(N);
     if (smem > ctx->smem_optin) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sy2sb: matrix too large for shared memory");
-    int nwarps = (N + 31) / 32;
-    if (nwarps < 2) nwarps = 2;
-    if (nwarps > 16) nwarps = 16;
     FKMC_CUDA(ctx, cudaFuncSetAttribute(sy2sb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sy2sb_kernel<<<B, nwarps * 32, smem, ctx->stream>>>(d_A, N, d_AB);
+    sy2sb_kernel<<<B, NW * 32, smem, ctx->stream>>>(d_A, N, d_AB);
     ctx->launches++;
     FKMC_CUDA(ctx, cudaGetLastError());
     return FKMC_OK;

@@ -1,0 +1,108 @@
+"""Host-side error analysis of the Monte Carlo series: log-binning, jackknife, plateau-bin estimate, specific heat.
+
+Mirrors include/fk_mc/binning.hpp:89-171 (calc_stats, bin<D>, accumulate_binning, calc_cor_length),
+include/fk_mc/jackknife.hpp:50-82 (jack, accumulate_jackknife), prog/data_save.hpp:108-122 (estimate_bin) and
+prog/data_save.hxx:158-199 (cv = beta^2 (<E^2> - <d2E> - <E>^2) / N).  A bin-stats row is (n, mean, variance, stderr)
+exactly like the reference's bin_stats_t; /stats/<obs> of the reference's HDF5 layout is that 4-vector.
+"""
+import math
+
+import numpy as np
+
+MAX_BIN_DEPTH = 15  # BINNING_RANGE in include/fk_mc/binning.hpp:18
+
+
+def calc_stats(x):
+    """(n, mean, unbiased variance, sqrt(variance / n)) -- binning.hpp:89-96."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.size
+    mean = x.sum() / n
+    var = ((x - mean) ** 2).sum() / (n - 1) if n > 1 else float("nan")
+    return (n, float(mean), float(var), float(math.sqrt(var / n)) if n > 1 else float("nan"))
+
+
+def bin_series(x, depth):
+    """Averages of 2^depth consecutive samples, incomplete tail dropped (binned_iterator, binning.hpp:26-44)."""
+    x = np.asarray(x, dtype=np.float64)
+    step = 1 << depth
+    if step > x.size:
+        raise ValueError("Can't bin with binning step(%d)> container size (%d)" % (step, x.size))  # binning.hpp:66-68
+    n = x.size // step
+    return x[: n * step].reshape(n, step).mean(axis=1)
+
+
+def bin_stats(x, depth):
+    return calc_stats(bin_series(x, depth))
+
+
+def accumulate_binning(x, max_depth):
+    """Rows for depth 0..max_depth (binning_accumulator, binning.hpp:100-128)."""
+    if max_depth > MAX_BIN_DEPTH:
+        raise ValueError("bin_depth =%d> compiled bin size" % max_depth)
+    return [bin_stats(x, d) for d in range(max_depth + 1)]
+
+
+def calc_cor_length(rows):
+    """tau_i = (2^i var_i / var_0 - 1) / 2 -- binning.hpp:163-171."""
+    s0 = rows[0][2]
+    return [0.5 * ((2.0 ** i) * r[2] / s0 - 1.0) for i, r in enumerate(rows)]
+
+
+def jack(F, series, depth=0):
+    """Jackknife of F(<x_1>, <x_2>, ...) over binned series -- jackknife.hpp:50-82.  Returns (n, value, variance, stderr)."""
+    data = [bin_series(s, depth) for s in series]
+    n = data[0].size
+    means = np.array([d.sum() / n for d in data])
+    u0 = F(*means)
+    u = np.empty(n)
+    for j in range(n):
+        loo = [(n * means[i] - data[i][j]) / (n - 1) for i in range(len(data))]
+        u[j] = F(*loo)
+    _, ubar, _, uerr = calc_stats(u)
+    u_avg = u0 - (n - 1) * (ubar - u0)
+    du = (n - 1) * uerr
+    return (n, float(u_avg), float(du * du * n), float(du))
+
+
+def accumulate_jackknife(F, series, max_depth):
+    return [jack(F, series, d) for d in range(max_depth + 1)]
+
+
+def estimate_bin(rows):
+    """Index of the bin level where the error bar has saturated -- prog/data_save.hpp:108-122."""
+    errors = np.array([r[3] for r in rows], dtype=np.float64)
+    rel_error, f, ind = 1.0, True, len(errors) - 1
+    while f and ind > 0:
+        with np.errstate(divide="ignore", invalid="ignore"):  # C++ semantics: x/0 is inf or nan, the comparisons then fail
+            cur = abs(errors[ind - 1] / errors[ind] - 1.0)
+        f = cur < 0.05 and cur < rel_error
+        rel_error = cur if f else rel_error
+        if f:
+            ind -= 1
+    return ind
+
+
+def max_bin_depth(n_samples, min_bins=4):
+    """Deepest level that still leaves `min_bins` bins, capped at the reference's compile-time depth."""
+    d = 0
+    while d < MAX_BIN_DEPTH and (n_samples >> (d + 1)) >= min_bins:
+        d += 1
+    return d
+
+
+def energy_report(energies, d2energies, beta, volume, max_depth=None):
+    """save_energy (prog/data_save.hxx:158-199): binning of E and d2E, jackknife of the specific heat.  The reference bins the
+    series in reverse order (rbegin..rend); so do we."""
+    e = np.asarray(energies, dtype=np.float64).reshape(-1)[::-1]
+    d2 = np.asarray(d2energies, dtype=np.float64).reshape(-1)[::-1]
+    if max_depth is None:
+        max_depth = max_bin_depth(e.size)
+    out = {}
+    for name, x in (("energy", e), ("d2energy", d2)):
+        rows = accumulate_binning(x, max_depth)
+        b = estimate_bin(rows)
+        out[name] = dict(binning=rows, cor_length=calc_cor_length(rows), bin=b, stats=rows[b])
+    cv_rows = accumulate_jackknife(lambda a, a2, de2: beta * beta * (a2 - de2 - a * a) / volume, [e, e * e, d2], max_depth)
+    b = estimate_bin(cv_rows)
+    out["cv"] = dict(binning=cv_rows, cor_length=calc_cor_length(cv_rows), bin=b, stats=cv_rows[b])
+    return out

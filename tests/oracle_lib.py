@@ -212,3 +212,21 @@ def bench_chains(p, nthreads, rank0=0):
     sec, nacc = C.c_double(0), C.c_long(0)
     _ck(lib().orc_bench_chains(C.byref(p), nthreads, rank0, C.byref(sec), C.byref(nacc)))
     return sec.value, nacc.value
+
+
+def binning(x, max_depth):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    rows = np.zeros((max_depth + 1, 5))
+    if lib().orc_binning(len(x), _p(x, C.c_double), max_depth, _p(rows, C.c_double)) != 0:
+        raise RuntimeError("oracle binning failed")
+    return rows
+
+
+def jackknife(series, depth):
+    d = np.ascontiguousarray(series, dtype=np.float64)
+    if d.ndim == 1:
+        d = d[None]
+    out = np.zeros(4)
+    if lib().orc_jackknife(d.shape[1], d.shape[0], _p(d, C.c_double), depth, _p(out, C.c_double)) != 0:
+        raise RuntimeError("oracle jackknife failed")
+    return out

@@ -1,0 +1,59 @@
+"""Host statistics (fk_mc_b200/stats.py) against the reference's Mathematica goldens (test/binning_test.cpp:60-63,
+test/jackknife_test.cpp:56-134) and against the oracle restatement."""
+import numpy as np
+import pytest
+
+import oracle_lib as o
+from fk_mc_b200 import stats
+
+A = np.array([0.0711992, 0.344949, 0.940913, 0.166604, 0.811305, 0.617859, 0.462844, 0.550449, 0.28126, 0.0560575, 0.0673806, 0.710085,
+              0.459742, 0.977218, 0.500193, 0.45763, 0.752903])                                   # test/binning_test.cpp:32-34
+B = np.array([0.0203252, 0.0491541, 0.0942537, 0.0815104, 0.0569245, 0.0459406, 0.0963107, 0.0170473, 0.0730589, 0.012731, 0.0571613,
+              0.0889872, 0.0771268, 0.0857561, 0.0130207, 0.0378117, 0.0690792])                 # test/jackknife_test.cpp:37-39
+
+
+def test_binning_goldens():
+    correct = [(17, 0.484035, 0.0872001, 0.07162), (8, 0.467231, 0.0422793, 0.0726974), (4, 0.467231, 0.0269458, 0.0820759),
+               (2, 0.467231, 0.00162846, 0.0285348)]
+    cor = [0, -0.0151463, 0.118023, -0.4253]
+    for rows in (stats.accumulate_binning(A, 3), [tuple(r[:4]) for r in o.binning(A, 3)]):
+        for got, want in zip(rows, correct):
+            assert got[0] == want[0] and np.allclose(got[1:], want[1:], atol=1e-5)
+    assert np.allclose(stats.calc_cor_length(stats.accumulate_binning(A, 3)), cor, atol=1e-5)
+    assert np.allclose(o.binning(A, 3)[:, 4], cor, atol=1e-5)
+    with pytest.raises(ValueError):
+        stats.bin_series(A, 6)  # binning.hpp:66-68: step 64 > 17 samples
+
+
+def test_jackknife_goldens():
+    f1 = lambda x: x  # noqa: E731
+    f2 = lambda e, e2, de2: e2 - de2 - e * e  # noqa: E731
+    for depth, want in [(0, (17, 0.484035, 0.0872002, 0.07162)), (1, (8, 0.467231, 0.0422793, 0.0726974)),
+                        (2, (4, 0.467231, 0.0269458, 0.0820759)), (3, (2, 0.467231, 0.00162846, 0.0285348))]:
+        got = stats.jack(f1, [A], depth)
+        assert got[0] == want[0] and np.allclose(got[1:], want[1:], atol=1e-5)
+        assert np.allclose(o.jackknife(A, depth), want, atol=1e-5)
+    for depth, want in [(0, (17, 0.0297767, 0.00815104, 0.0218969)), (1, (8, 0.0309895, 0.00214726, 0.0163832)),
+                        (2, (4, 0.0324411, 0.00123011, 0.0175365))]:
+        got = stats.jack(f2, [A, A * A, B], depth)
+        assert got[0] == want[0] and np.allclose(got[1:], want[1:], atol=1e-5)
+        assert np.allclose(o.jackknife(np.stack([A, A * A, B]), depth), want, atol=1e-5)
+    rows = stats.accumulate_jackknife(f1, [A], 3)
+    assert rows[3][0] == 2 and np.allclose(rows[3][1:], (0.467231, 0.00162846, 0.0285348), atol=1e-5)
+
+
+def test_estimate_bin_and_energy_report():
+    # the plateau search (data_save.hpp:108-122) walks down only while the relative change keeps shrinking and is < 5 %
+    rows = [(64, 0, 1, 0.100), (32, 0, 1, 0.101), (16, 0, 1, 0.102), (8, 0, 1, 0.103)]
+    assert stats.estimate_bin(rows) == 2
+    rows = [(64, 0, 1, 0.103), (32, 0, 1, 0.1030), (16, 0, 1, 0.10301), (8, 0, 1, 0.104)]
+    assert stats.estimate_bin(rows) == 0  # 0.96 % -> 0.0097 % -> 0 %: keeps shrinking all the way down
+    rows = [(64, 0, 1, 0.05), (32, 0, 1, 0.08), (16, 0, 1, 0.100), (8, 0, 1, 0.101)]
+    assert stats.estimate_bin(rows) == 2
+    rng = np.random.default_rng(0)
+    e = rng.normal(-50, 1, 4096)
+    d2 = np.full(4096, 0.3)
+    rep = stats.energy_report(e, d2, beta=2.0, volume=64)
+    assert abs(rep["energy"]["stats"][1] + 50) < 5 * rep["energy"]["stats"][3]
+    cv = rep["cv"]["stats"]
+    assert abs(cv[1] - 4 * (1.0 - 0.3) / 64) < 5 * cv[3]
