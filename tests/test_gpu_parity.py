@@ -372,3 +372,26 @@ def test_chain_full_batch_statistics():
     assert abs(m - np.mean(ref)) <= 5 * (s + np.std(ref) / 4)
     assert c.launch_count() > 0
     c.close()
+
+
+# ---------------- C++ host mirror of the reference API (include/fk_mc_b200/fk_mc.hpp) ----------------
+@pytest.mark.parametrize("cheb,flip", [(0, 0.0), (0, 0.5), (1, 0.5)])
+def test_cpp_host_api_matches_oracle(tmp_path, cheb, flip):
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_api_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "host_api_test.cpp"),
+                           "-o", exe, "-L" + os.path.join(root, "fk_mc_b200", "lib"), "-lfkmc_b200",
+                           "-Wl,-rpath," + os.path.join(root, "fk_mc_b200", "lib")])
+    L, beta, U, nsw, seed, rank = 8, 4.0, 4.0, 3, 32167, 2
+    out = subprocess.check_output([exe, str(L), str(beta), str(U), str(cheb), str(flip), str(nsw), str(seed), str(rank)]).decode()
+    rows = {ln.split()[0]: ln.split()[1:] for ln in out.strip().splitlines()}
+    p = o.make_params(kind=o.CUBIC2D, L=L, beta=beta, U=U, mc_flip=flip, cheb_moves=bool(cheb), seed=seed, nsweeps=nsw, sweep_len=16,
+                      ntherm_sweeps=1)
+    r = o.mc_run(p, rank=rank)
+    assert int(rows["naccept"][0]) == r["naccept"]
+    assert np.array_equal(np.array(rows["f"], dtype=np.int32), r["f_final"])
+    assert np.allclose(np.array(rows["energies"], dtype=float), r["energies"], rtol=1e-10)
+    assert np.allclose(np.array(rows["d2energies"], dtype=float), r["d2energies"], rtol=1e-9)
+    assert rows["mismatch_throws"] == ["1"] and rows["honeycomb_odd_throws"] == ["1"]
