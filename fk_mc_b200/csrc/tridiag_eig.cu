@@ -90,9 +90,22 @@ tridiag_eig_kernel(const double* __restrict__ d_all, const double* __restrict__ 
     const double scale = fmax(fabs(lo), fabs(hi));
 
     double* ev = evals_all + (size_t)b * evals_stride + (slot ? (size_t)slot[b] * slot_stride : 0);
+    // One cooperative multisection round: thread t counts the eigenvalues below its own grid point, which gives every
+    // eigenvalue a bracket of width (hi - lo) / (T + 1) for the price of one Sturm count (instead of ~log2 T bisection steps).
+    int* cnts = reinterpret_cast<int*>(red + 96);
+    const double gstep = (hi - lo) / (double)(T + 1);
+    cnts[tid] = sturm_count(de, N, lo + gstep * (double)(tid + 1));
+    __syncthreads();
     double lam = 0.0;
     for (int k = tid; k < N; k += T) {  // T >= N in practice: one eigenvalue per thread
-        double a = lo, c = hi;
+        // first grid index j with cnts[j] > k (counts are non-decreasing); the eigenvalue lies in (x_{j-1}, x_j]
+        int jl = 0, jh = T;  // search in [0, T]; index T stands for hi (count N > k)
+        while (jl < jh) {
+            const int jm = (jl + jh) >> 1;
+            if (cnts[jm] > k) jh = jm; else jl = jm + 1;
+        }
+        double a = (jl == 0) ? lo : lo + gstep * (double)jl;
+        double c = (jl >= T) ? hi : lo + gstep * (double)(jl + 1);
         int it = 0;
         for (; it < 128; ++it) {
             const double mid = 0.5 * (a + c);
@@ -167,7 +180,7 @@ int fkmc_launch_tridiag_eig(fkmc_ctx* ctx, const double* d_d, const double* d_e,
     fkmc_prof_scope ps(ctx, "tridiag_eig");
     if (N > 1024) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "tridiag_eig: N > 1024 not supported yet");
     const int T = ((N + 31) / 32) * 32;
-    const size_t smem = sizeof(double2) * N + sizeof(double) * 96;
+    const size_t smem = sizeof(double2) * N + sizeof(double) * 96 + sizeof(int) * T + 16;
     tridiag_eig_kernel<<<B, T, smem, ctx->stream>>>(d_d, d_e, N, beta, d_evals, evals_stride, d_slot, slot_stride, d_out, d_exp,
                                                     d_fermi, ctx->d_flag);
     ctx->launches++;
