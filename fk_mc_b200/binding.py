@@ -166,6 +166,30 @@ class Context:
                                                _ptr(fe, C.c_double)))
         return dict(spectrum=ev, logZ=lz, cached_exp=ex, cached_fermi=fe)
 
+    def eigh(self, f, U, mu_c, beta):
+        """configuration_t::calc_ed(true): dict(spectrum [B,N], evecs [B,N,N] with evecs[b][:, k] <-> spectrum[b][k], logZ [B])."""
+        f = self._f(f)
+        B = f.shape[0]
+        ev, lz = np.zeros((B, self.N)), np.zeros(B)
+        vec = np.zeros((B, self.N, self.N))  # column-major per matrix == [k][i]
+        self._ck(self.lib.fkmc_eigh_batched(self.h, _ptr(f, C.c_int32), B, C.c_double(U), C.c_double(mu_c), C.c_double(beta),
+                                            _ptr(ev, C.c_double), _ptr(vec, C.c_double), _ptr(lz, C.c_double)))
+        return dict(spectrum=ev, evecs=np.transpose(vec, (0, 2, 1)), logZ=lz)
+
+    def ipr(self, f, U, mu_c, beta):
+        """measure_ipr::accumulate: dict(spectrum [B,N], ipr [B,N])."""
+        f = self._f(f)
+        B = f.shape[0]
+        ev, ip = np.zeros((B, self.N)), np.zeros((B, self.N))
+        self._ck(self.lib.fkmc_ipr_batched(self.h, _ptr(f, C.c_int32), B, C.c_double(U), C.c_double(mu_c), C.c_double(beta),
+                                           _ptr(ev, C.c_double), _ptr(ip, C.c_double)))
+        return dict(spectrum=ev, ipr=ip)
+
+    def chain_ipr(self):
+        ev, ip = np.zeros((self.n_chains, self.N)), np.zeros((self.n_chains, self.N))
+        self._ck(self.lib.fkmc_chain_ipr(self.h, _ptr(ev, C.c_double), _ptr(ip, C.c_double)))
+        return dict(spectrum=ev, ipr=ip)
+
     def logz_kpm(self, f, U, mu_c, beta, M, G):
         """configuration_t::calc_chebyshev: returns dict(moments [B,M], e_min, e_max, a, b, logZ [B])."""
         f = self._f(f)

@@ -69,11 +69,25 @@ int fkmc_ensure_dense_ws(fkmc_ctx* ctx) {
 }
 
 int fkmc_tridiagonalize(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_d, double* d_e) {
-    const bool two = ctx->tridiag_mode == 2 && N >= 16 && N <= 1024 && fkmc_sy2sb_smem(N) <= ctx->smem_optin && fkmc_sb2st_smem(N) <= ctx->smem_optin;
+    const bool two = ctx->tridiag_mode == 2 && N >= 16 && N <= 1024 && fkmc_sy2sb_smem(N) <= ctx->smem_optin && fkmc_sb2st_smem(N) <= ctx->smem_optin;  // (column-major input: fkmc_launch_sy2sb converts when the tiled kernel applies)
     if (!two) return fkmc_launch_sytrd(ctx, d_A, N, B, d_d, d_e, ctx->d_tau, ctx->d_W);
     int rc = fkmc_launch_sy2sb(ctx, d_A, N, B, ctx->d_AB);
     if (rc) return rc;
     return fkmc_launch_sb2st(ctx, ctx->d_AB, N, B, d_d, d_e);
+}
+
+int fkmc_build_tridiag(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double* d_d, double* d_e) {
+    const int N = ctx->N;
+    if (ctx->tridiag_mode == 2 && fkmc_use_tiled(N) && fkmc_sy2sb_smem(N) <= ctx->smem_optin && fkmc_sb2st_smem(N) <= ctx->smem_optin) {
+        // large matrices: tiled lower-triangular layout, bulk-async dense->band, then band->tridiagonal
+        int rc = fkmc_launch_build_h_tiled(ctx, d_f, B, U, mu_c, ctx->d_A);
+        if (rc) return rc;
+        if ((rc = fkmc_launch_sy2sb_tiled(ctx, ctx->d_A, N, B, ctx->d_AB))) return rc;
+        return fkmc_launch_sb2st(ctx, ctx->d_AB, N, B, d_d, d_e);
+    }
+    int rc = fkmc_launch_build_h(ctx, d_f, B, U, mu_c, ctx->d_A);
+    if (rc) return rc;
+    return fkmc_tridiagonalize(ctx, ctx->d_A, N, B, d_d, d_e);
 }
 
 namespace {
@@ -213,8 +227,7 @@ int fkmc_logz_ed_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, doubl
     if (rc) return rc;
     if ((rc = fkmc_ensure_dense_ws(ctx))) return rc;
     const size_t N = ctx->N;
-    if ((rc = fkmc_launch_build_h(ctx, ctx->d_f, B, U, mu_c, ctx->d_A))) return rc;
-    if ((rc = fkmc_tridiagonalize(ctx, ctx->d_A, ctx->N, B, ctx->d_d, ctx->d_e))) return rc;
+    if ((rc = fkmc_build_tridiag(ctx, ctx->d_f, B, U, mu_c, ctx->d_d, ctx->d_e))) return rc;
     double* dexp = cached_exp ? ctx->d_aux : nullptr;
     double* dfer = cached_fermi ? ctx->d_aux + (size_t)ctx->max_batch * N : nullptr;
     if ((rc = fkmc_launch_tridiag_eig(ctx, ctx->d_d, ctx->d_e, ctx->N, B, beta, ctx->d_evals, N, nullptr, 0, ctx->d_out, dexp, dfer)))
@@ -228,8 +241,29 @@ int fkmc_logz_ed_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, doubl
     return check_flag(ctx);
 }
 
-int fkmc_eigh_batched(fkmc_ctx* ctx, const int32_t*, int, double, double, double, double*, double*, double*) {
-    return fkmc_set_error(ctx, FKMC_ERR_INVALID, "fkmc_eigh_batched: eigenvector path (calc_ed(true)) is not built yet");
+static int eig_common(fkmc_ctx* ctx, const int32_t* f, int B, double U, double mu_c, double beta, double* evals, double* evecs, double* ipr,
+                      double* logZ) {
+    if (!ctx) return FKMC_ERR_INVALID;
+    int rc = upload_f(ctx, f, B);
+    if (rc) return rc;
+    if ((rc = fkmc_ensure_dense_ws(ctx))) return rc;
+    const size_t N = ctx->N;
+    if ((rc = fkmc_eigvec_pipeline(ctx, ctx->d_f, B, U, mu_c, beta, ctx->d_evals, ctx->d_out, evecs, ipr, nullptr))) return rc;
+    if (evals) FKMC_CUDA(ctx, cudaMemcpyAsync(evals, ctx->d_evals, sizeof(double) * B * N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (logZ)
+        FKMC_CUDA(ctx, cudaMemcpy2DAsync(logZ, sizeof(double), ctx->d_out, 8 * sizeof(double), sizeof(double), B, cudaMemcpyDeviceToHost,
+                                         ctx->stream));
+    return check_flag(ctx);
+}
+
+int fkmc_eigh_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, double mu_c, double beta, double* evals, double* evecs, double* logZ) {
+    if (!evecs) return ctx ? fkmc_set_error(ctx, FKMC_ERR_INVALID, "evecs is NULL") : FKMC_ERR_INVALID;
+    return eig_common(ctx, f, B, U, mu_c, beta, evals, evecs, nullptr, logZ);
+}
+
+int fkmc_ipr_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, double mu_c, double beta, double* evals, double* ipr) {
+    if (!ipr) return ctx ? fkmc_set_error(ctx, FKMC_ERR_INVALID, "ipr is NULL") : FKMC_ERR_INVALID;
+    return eig_common(ctx, f, B, U, mu_c, beta, evals, nullptr, ipr, nullptr);
 }
 
 int fkmc_logz_kpm_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, double mu_c, double beta, int M, int G, double* moments,

@@ -247,9 +247,7 @@ int evaluate_proposals(fkmc_ctx* ctx, const chain_extra& X, const double** lz, i
         if (rc) return rc;
         *lz = S.logz_prop; *lz_stride = 1; *ecd2 = nullptr; *ecd2_stride = 0;
     } else {
-        int rc = fkmc_launch_build_h(ctx, S.f_prop, C, S.p.U, S.p.mu_c, ctx->d_A);
-        if (rc) return rc;
-        rc = fkmc_tridiagonalize(ctx, ctx->d_A, N, C, ctx->d_d, ctx->d_e);
+        int rc = fkmc_build_tridiag(ctx, S.f_prop, C, S.p.U, S.p.mu_c, ctx->d_d, ctx->d_e);
         if (rc) return rc;
         // spectrum of the proposal goes to the chain's non-current slot: spec[0] + slot * (C*N)
         rc = fkmc_launch_tridiag_eig(ctx, ctx->d_d, ctx->d_e, N, C, S.p.beta, S.spec[0], N, X.prop_slot, (long)C * N, ctx->d_out,
@@ -416,9 +414,7 @@ extern "C" int fkmc_chain_run_sweeps(fkmc_ctx* ctx, int n_sweeps) {
             int es = 0;
             if (S.p.measure_energy && S.p.cheb_moves) {
                 // Chebyshev moves never fill ed_data_: measure_energy triggers a fresh exact eigensolve
-                int rc = fkmc_launch_build_h(ctx, S.f_cur, C, S.p.U, S.p.mu_c, ctx->d_A);
-                if (rc) return rc;
-                rc = fkmc_tridiagonalize(ctx, ctx->d_A, N, C, ctx->d_d, ctx->d_e);
+                int rc = fkmc_build_tridiag(ctx, S.f_cur, C, S.p.U, S.p.mu_c, ctx->d_d, ctx->d_e);
                 if (rc) return rc;
                 rc = fkmc_launch_tridiag_eig(ctx, ctx->d_d, ctx->d_e, N, C, S.p.beta, S.spec[0], N, nullptr, 0, ctx->d_out, nullptr, nullptr);
                 if (rc) return rc;
@@ -502,6 +498,19 @@ extern "C" int fkmc_chain_get_trace(fkmc_ctx* ctx, int* n_steps, int32_t* move, 
     rc |= copy_out(ctx, u, S.t_u, n * 8);
     rc |= copy_out(ctx, logz_new, S.t_lz, n * 8);
     if (rc) return rc;
+    FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FKMC_OK;
+}
+
+extern "C" int fkmc_chain_ipr(fkmc_ctx* ctx, double* evals, double* ipr) {
+    if (!ctx || !ipr) return FKMC_ERR_INVALID;
+    fkmc_chain_state& S = ctx->chain;
+    if (!S.active) return fkmc_set_error(ctx, FKMC_ERR_STATE, "no chains");
+    int rc = fkmc_ensure_dense_ws(ctx);
+    if (rc) return rc;
+    const size_t C = S.n_chains, N = ctx->N;
+    if ((rc = fkmc_eigvec_pipeline(ctx, S.f_cur, (int)C, S.p.U, S.p.mu_c, S.p.beta, ctx->d_evals, ctx->d_out, nullptr, ipr, nullptr))) return rc;
+    if (evals) FKMC_CUDA(ctx, cudaMemcpyAsync(evals, ctx->d_evals, sizeof(double) * C * N, cudaMemcpyDeviceToHost, ctx->stream));
     FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FKMC_OK;
 }

@@ -135,6 +135,13 @@ int fkmc_launch_sy2sb(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_AB);
 int fkmc_launch_sb2st(fkmc_ctx* ctx, const double* d_AB, int N, int B, double* d_d, double* d_e);
 size_t fkmc_sy2sb_smem(int N);
 size_t fkmc_sb2st_smem(int N);
+int fkmc_launch_sy2sb_tiled(fkmc_ctx* ctx, double* d_At, int N, int B, double* d_AB);
+int fkmc_launch_build_h_tiled(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double* d_At);
+int fkmc_launch_to_tiled(fkmc_ctx* ctx, const double* d_A, int N, int B, double* d_At);
+size_t fkmc_tiled_stride(int N);
+bool fkmc_use_tiled(int N);
+// f -> Hamiltonian -> tridiagonal (d, e) with the context's selected algorithm and matching matrix layout
+int fkmc_build_tridiag(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double* d_d, double* d_e);
 // dense -> tridiagonal with the context's selected algorithm (A is overwritten)
 int fkmc_tridiagonalize(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_d, double* d_e);
 // Sturm bisection + fused logZ / energy: out[b*8 + {0: logZ, 1: E_c, 2: d2E}]
@@ -147,6 +154,9 @@ int fkmc_launch_energy(fkmc_ctx* ctx, const double* d_evals, long evals_stride, 
 int fkmc_prepare_cheb(fkmc_ctx* ctx, int M, int G);
 int fkmc_launch_kpm(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, int M, int G,
                     double* d_moments, double* d_ab, double* d_logz);
+// eigenvector path (measurement sweeps): evals/out on the device, eigenvectors and IPR to the host (or IPR to d_ipr)
+int fkmc_eigvec_pipeline(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, double* d_evals, double* d_out,
+                         double* h_evecs, double* h_ipr_host, double* d_ipr);
 // chains
 int fkmc_chain_free(fkmc_ctx* ctx);
 

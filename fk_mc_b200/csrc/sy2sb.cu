@@ -18,7 +18,12 @@
 // its own tiles in registers for the whole pass and adds the partner rows straight into shared
 // memory -- in one step all partner tiles are distinct, so no atomics are needed.
 // R and the diagonal blocks are emitted in band storage AB[d][c] = A(c+d, c), d = 0..8.
-// Requires N % 8 == 0 (16-byte aligned columns for the bulk copies) and N <= 1024.
+// Matrix layout ("tiled"): only the lower-triangular 32x32 tiles are stored, tile (R, C), R >= C, at offset
+// (R(R+1)/2 + C) * 1152 doubles, column-major inside the tile with the same padded column stride of 36 doubles that the
+// shared-memory copy uses -- so a tile moves with ONE 9216-byte bulk copy in each direction and lands bank-conflict-free.
+// The tile grid is fixed in global coordinates; the panels V, Y, Z are indexed by global row and are zero above the
+// trailing block, which makes the partial edge tiles of each block column come out right without masks.
+// Requires N % 8 == 0 and N <= 1024.
 #include <cfloat>
 
 #include "common.cuh"
@@ -79,15 +84,19 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Issue the bulk loads of tile (R, C) of the trailing matrix into this warp's buffer (whole warp calls).
-__device__ __forceinline__ void tile_load(double* buf, uint64_t* bar, const double* __restrict__ A22, int lda, int m, int R, int C,
-                                          int lane) {
-    const int nrows = min(32, m - 32 * R), ncols = min(32, m - 32 * C);
+__device__ __forceinline__ size_t tile_off(int R, int C) { return ((size_t)R * (R + 1) / 2 + C) * TILE; }
+
+// Issue the bulk load of global tile (R, C) into this warp's buffer (whole warp calls).
+__device__ __forceinline__ void tile_load(double* buf, uint64_t* bar, const double* __restrict__ At, int R, int C, int lane) {
     __syncwarp();  // every lane is done reading the previous contents
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(nrows * ncols * 8));
-    __syncwarp();
-    if (lane < ncols) bulk_g2s(buf + lane * TS, A22 + (size_t)(32 * C + lane) * lda + 32 * R, (uint32_t)(nrows * 8), bar);
+    if (lane == 0) {
+        mbar_expect_tx(bar, (uint32_t)(TILE * 8));
+        bulk_g2s(buf, At + tile_off(R, C), (uint32_t)(TILE * 8), bar);
+    }
 }
+
+// element (i, j), i >= j, of the tiled matrix
+__device__ __forceinline__ size_t elem_off(int i, int j) { return tile_off(i >> 5, j >> 5) + (size_t)(j & 31) * TS + (i & 31); }
 
 // block-wide sum of K values per thread; result broadcast to all threads via out[0..K)
 template <int K>
@@ -160,49 +169,52 @@ __device__ __forceinline__ void symm_tile(const double* __restrict__ Tb, bool di
 }
 
 __global__ void __launch_bounds__(NW * 32, 1)
-sy2sb_kernel(double* __restrict__ A_all, int N, double* __restrict__ AB_all) {
+sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restrict__ AB_all) {
     extern __shared__ __align__(128) double smem[];
     const int tid = threadIdx.x, T = NW * 32, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int b = blockIdx.x, lda = N;
-    double* A = A_all + (size_t)b * N * N;
+    const int b = blockIdx.x;
+    double* At = A_all + (size_t)b * a_stride;  // tiled lower-triangular storage of this matrix
     double* AB = AB_all + (size_t)b * (NB + 1) * N;
-    const int mp = ((N + 31) / 32) * 32;
-    s1_smem S;
-    S.ld = mp + 4;  // == 4 (mod 16): both fragment patterns are 2-way (optimal) on the panels
-    S.V = smem;
-    S.Y = S.V + 8 * S.ld;
-    S.G = S.Y + 8 * S.ld;
-    S.Tm = S.G + 64;
-    S.M2 = S.Tm + 64;
-    S.tau = S.M2 + 64;
-    S.red = S.tau + 8;
-    S.tile = S.red + NW * 64 + 72;
-    S.bar = reinterpret_cast<uint64_t*>(S.tile + NW * TILE);
-    const int ld = S.ld;
-    double* Tb = S.tile + warp * TILE;
-    uint64_t* bar = S.bar + warp;
+    const int mp = ((N + 31) / 32) * 32, NT = mp >> 5;
+    s1_smem S0;
+    S0.ld = mp + 4;  // == 4 (mod 16): both fragment patterns are 2-way (optimal) on the panels
+    S0.V = smem;
+    S0.Y = S0.V + 8 * S0.ld;
+    S0.G = S0.Y + 8 * S0.ld;
+    S0.Tm = S0.G + 64;
+    S0.M2 = S0.Tm + 64;
+    S0.tau = S0.M2 + 64;
+    S0.red = S0.tau + 8;
+    S0.tile = S0.red + NW * 64 + 72;
+    S0.bar = reinterpret_cast<uint64_t*>(S0.tile + NW * TILE);
+    const int ld = S0.ld;
+    double* Tb = S0.tile + warp * TILE;
+    uint64_t* bar = S0.bar + warp;
     uint32_t parity = 0;
 
-    for (int i = tid; i < NW * TILE; i += T) S.tile[i] = 0.0;
-    if (tid < NW) mbar_init(S.bar + tid, 1);
+    for (int i = tid; i < NW * TILE; i += T) S0.tile[i] = 0.0;
+    if (tid < NW) mbar_init(S0.bar + tid, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
     for (int k0 = 0; k0 < N; k0 += NB) {
         const int r0 = k0 + NB, m = N - r0;
+        const s1_smem SG = S0;  // panels indexed by global row (tile loops)
+        s1_smem S = S0;         // panels indexed by local row i = global row - r0 (QR and the thin updates)
+        S.V = S0.V + r0;
+        S.Y = S0.Y + r0;
         // ---- emit the (final) diagonal block k0 into band storage ----
         if (tid < 64) {
             const int j = tid & 7, dd = tid >> 3;
-            if (j + dd < NB && k0 + j + dd < N) AB[(size_t)dd * N + k0 + j] = A[(size_t)(k0 + j) * lda + k0 + j + dd];
+            if (j + dd < NB && k0 + j + dd < N) AB[(size_t)dd * N + k0 + j] = At[elem_off(k0 + j + dd, k0 + j)];
         }
         if (m <= 0) break;
-        double* A22 = A + (size_t)r0 * lda + r0;
-        // ---- 1. panel -> shared, Householder QR ----
+        // ---- 1. panel -> shared (global row index; zero above the trailing block), Householder QR ----
         for (int idx = tid; idx < 8 * ld; idx += T) {
-            const int j = idx / ld, i = idx % ld;
-            S.V[idx] = (i < m) ? A[(size_t)(k0 + j) * lda + r0 + i] : 0.0;
-            S.Y[idx] = 0.0;
+            const int j = idx / ld, gi = idx % ld;
+            SG.V[idx] = (gi >= r0 && gi < N) ? At[elem_off(gi, k0 + j)] : 0.0;
+            SG.Y[idx] = 0.0;
         }
         __syncthreads();
         const int nref = min(NB, m);
@@ -278,7 +290,7 @@ sy2sb_kernel(double* __restrict__ A_all, int N, double* __restrict__ AB_all) {
             __syncthreads();
         }
         // ---- 3. Y0 = A22 V: cyclic pairing of tile tasks, own rows in registers, partner rows in shared memory ----
-        const int nt = (m + 31) >> 5;
+        const int T0 = r0 >> 5, nt = NT - T0;  // tiles T0..NT-1 of the fixed global grid touch the trailing block
         {
             double own[MAXOWN][4][2];
 #pragma unroll
@@ -287,7 +299,7 @@ sy2sb_kernel(double* __restrict__ A_all, int N, double* __restrict__ AB_all) {
                 for (int x = 0; x < 4; ++x) own[o][x][0] = own[o][x][1] = 0.0;
             const int smax = nt >> 1;
             // prefetch the first task of this warp (its diagonal tile)
-            if (warp < nt) tile_load(Tb, bar, A22, lda, m, warp, warp, lane);
+            if (warp < nt) tile_load(Tb, bar, At, T0 + warp, T0 + warp, lane);
             for (int s = 0; s <= smax; ++s) {
                 const int lim = (s > 0 && 2 * s == nt) ? (nt >> 1) : nt;
 #pragma unroll
@@ -303,7 +315,7 @@ sy2sb_kernel(double* __restrict__ A_all, int N, double* __restrict__ AB_all) {
                         double accR[4][2], accC[4][2];
 #pragma unroll
                         for (int x = 0; x < 4; ++x) accR[x][0] = accR[x][1] = accC[x][0] = accC[x][1] = 0.0;
-                        symm_tile(Tb, diag, 32 * Rmax, 32 * Cmin, S.V, ld, lane, accR, accC);
+                        symm_tile(Tb, diag, 32 * (T0 + Rmax), 32 * (T0 + Cmin), SG.V, ld, lane, accR, accC);
                         // prefetch this warp's next task while the results are folded
                         {
                             int na = a + NW, ns = s;
@@ -316,7 +328,7 @@ sy2sb_kernel(double* __restrict__ A_all, int N, double* __restrict__ AB_all) {
                             if (ns <= smax && na < nlim2) {
                                 int np = na - ns;
                                 if (np < 0) np += nt;
-                                tile_load(Tb, bar, A22, lda, m, max(na, np), min(na, np), lane);
+                                tile_load(Tb, bar, At, T0 + max(na, np), T0 + min(na, np), lane);
                             }
                         }
                         // own rows stay in registers; partner rows go to shared memory (distinct tiles within a step)
@@ -327,7 +339,7 @@ sy2sb_kernel(double* __restrict__ A_all, int N, double* __restrict__ AB_all) {
 #pragma unroll
                                 for (int x = 0; x < 4; ++x)
 #pragma unroll
-                                    for (int h = 0; h < 2; ++h) S.Y[(2 * t + h) * ld + 32 * Cmin + 8 * x + g] += accC[x][h];
+                                    for (int h = 0; h < 2; ++h) SG.Y[(2 * t + h) * ld + 32 * (T0 + Cmin) + 8 * x + g] += accC[x][h];
                             }
                         } else {
 #pragma unroll
@@ -335,7 +347,7 @@ sy2sb_kernel(double* __restrict__ A_all, int N, double* __restrict__ AB_all) {
 #pragma unroll
                             for (int x = 0; x < 4; ++x)
 #pragma unroll
-                                for (int h = 0; h < 2; ++h) S.Y[(2 * t + h) * ld + 32 * Rmax + 8 * x + g] += accR[x][h];
+                                for (int h = 0; h < 2; ++h) SG.Y[(2 * t + h) * ld + 32 * (T0 + Rmax) + 8 * x + g] += accR[x][h];
                         }
                     }
                 }
@@ -348,11 +360,16 @@ sy2sb_kernel(double* __restrict__ A_all, int N, double* __restrict__ AB_all) {
 #pragma unroll
                     for (int x = 0; x < 4; ++x)
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) S.Y[(2 * t + h) * ld + 32 * a + 8 * x + g] += own[o][x][h];
+                        for (int h = 0; h < 2; ++h) SG.Y[(2 * t + h) * ld + 32 * (T0 + a) + 8 * x + g] += own[o][x][h];
                 }
             }
         }
         __syncthreads();
+        // rows of the first (edge) tile that lie above the trailing block picked up band entries: Z must be zero there
+        for (int idx = tid; idx < 8 * (r0 - 32 * T0); idx += T) {
+            const int j = idx / (r0 - 32 * T0), gi = 32 * T0 + idx % (r0 - 32 * T0);
+            SG.Y[j * ld + gi] = 0.0;
+        }
         // ---- 4. Y = Y0 T;  X = V^T Y;  Z = Y - 1/2 V (T^T X) ----
         for (int i = tid; i < m; i += T) {
             double y0[NB], y[NB];
@@ -402,19 +419,19 @@ sy2sb_kernel(double* __restrict__ A_all, int N, double* __restrict__ AB_all) {
         if (warp < ntl) {
             int R, C;
             decode(warp, R, C);
-            tile_load(Tb, bar, A22, lda, m, R, C, lane);
+            tile_load(Tb, bar, At, T0 + R, T0 + C, lane);
         }
         for (int tt = warp; tt < ntl; tt += NW) {
             int R, C;
             decode(tt, R, C);
-            const int rb0 = 32 * R, cb0 = 32 * C;
+            const int rb0 = 32 * (T0 + R), cb0 = 32 * (T0 + C);  // global rows / columns
             // operand fragments do not depend on the tile contents: fetch them while the copy is in flight
             double af[4][4], bf[4][4];
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
                 // P = [V Z] (A operand, negated), Q = [Z V] (B operand); k = 4 ks + t
-                const double* Pp = (ks < 2) ? S.V : S.Y;
-                const double* Qp = (ks < 2) ? S.Y : S.V;
+                const double* Pp = (ks < 2) ? SG.V : SG.Y;
+                const double* Qp = (ks < 2) ? SG.Y : SG.V;
                 const int col = 4 * (ks & 1) + t;
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
@@ -443,19 +460,18 @@ sy2sb_kernel(double* __restrict__ A_all, int N, double* __restrict__ AB_all) {
                 for (int y = 0; y < 4; ++y)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) Tb[(8 * y + 2 * t + h) * TS + 8 * x + g] = acc[x][y][h];
-            // drain: generic-proxy writes -> async proxy, one bulk store per column (full columns: the strictly upper part
-            // of a diagonal tile is never read by anyone)
+            // drain: generic-proxy writes -> async proxy, then one bulk store of the whole (padded) tile.  Entries outside the
+            // trailing block see a zero update (V, Z are zero there); the strictly upper part of a diagonal tile is never read.
             fence_async_smem();
             __syncwarp();
-            const int nrows = min(32, m - rb0), ncols = min(32, m - cb0);
-            if (lane < ncols) bulk_s2g(A22 + (size_t)(cb0 + lane) * lda + rb0, Tb + lane * TS, (uint32_t)(nrows * 8));
+            if (lane == 0) bulk_s2g(At + tile_off(T0 + R, T0 + C), Tb, (uint32_t)(TILE * 8));
             bulk_commit();
-            bulk_wait_read();  // the buffer may be overwritten once the stores have read it
+            bulk_wait_read();  // the buffer may be overwritten once the store has read it
             const int tn = tt + NW;
             if (tn < ntl) {
                 int R2, C2;
                 decode(tn, R2, C2);
-                tile_load(Tb, bar, A22, lda, m, R2, C2, lane);
+                tile_load(Tb, bar, At, T0 + R2, T0 + C2, lane);
             }
         }
         // all bulk stores of this block column must have landed before the next panel is read
@@ -473,16 +489,101 @@ size_t fkmc_sy2sb_smem(int N) {
 
 int fkmc_launch_sy2sb_small(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_AB);
 
-int fkmc_launch_sy2sb(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_AB) {
-    // below N = 512 the per-block-column latency chain dominates and the register-fragment kernel is faster
-    if (N < 512 || N % 8 != 0) return fkmc_launch_sy2sb_small(ctx, d_A, N, B, d_AB);
+// doubles per matrix in the tiled lower-triangular layout
+size_t fkmc_tiled_stride(int N) {
+    const size_t nt = (N + 31) / 32;
+    return nt * (nt + 1) / 2 * TILE;
+}
+bool fkmc_use_tiled(int N) { return N >= 512 && N % 8 == 0 && N <= 1024; }
+
+// dense -> band on a batch of matrices in the tiled layout (see fkmc_launch_build_h_tiled / fkmc_launch_to_tiled)
+int fkmc_launch_sy2sb_tiled(fkmc_ctx* ctx, double* d_At, int N, int B, double* d_AB) {
     fkmc_prof_scope ps(ctx, "sy2sb");
-    if (N % 8 != 0 || N > 1024) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sy2sb: needs N % 8 == 0 and N <= 1024");
+    if (!fkmc_use_tiled(N)) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sy2sb_tiled: needs 512 <= N <= 1024, N % 8 == 0");
     const size_t smem = fkmc_sy2sb_smem(N);
     if (smem > ctx->smem_optin) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sy2sb: matrix too large for shared memory");
     FKMC_CUDA(ctx, cudaFuncSetAttribute(sy2sb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sy2sb_kernel<<<B, NW * 32, smem, ctx->stream>>>(d_A, N, d_AB);
+    sy2sb_kernel<<<B, NW * 32, smem, ctx->stream>>>(d_At, fkmc_tiled_stride(N), N, d_AB);
     ctx->launches++;
     FKMC_CUDA(ctx, cudaGetLastError());
     return FKMC_OK;
+}
+
+// column-major [B][N][N] (lower triangle) -> tiled layout
+__global__ void __launch_bounds__(256) to_tiled_kernel(const double* __restrict__ A_all, int N, double* __restrict__ At_all, size_t t_stride) {
+    const int b = blockIdx.y, tile = blockIdx.x;
+    int R = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+    while (R * (R + 1) / 2 > tile) --R;
+    while ((R + 1) * (R + 2) / 2 <= tile) ++R;
+    const int C = tile - R * (R + 1) / 2;
+    const double* A = A_all + (size_t)b * N * N;
+    double* dst = At_all + (size_t)b * t_stride + (size_t)tile * TILE;
+    for (int e = threadIdx.x; e < TILE; e += blockDim.x) {
+        const int c = e / TS, r = e % TS;
+        const int i = 32 * R + r, j = 32 * C + c;
+        double v = 0.0;
+        if (r < 32 && i < N && j < N) v = A[(size_t)min(i, j) * N + max(i, j)];  // symmetric fill from the lower triangle
+        dst[e] = v;
+    }
+}
+
+int fkmc_launch_to_tiled(fkmc_ctx* ctx, const double* d_A, int N, int B, double* d_At) {
+    const int nt = (N + 31) / 32;
+    dim3 grid(nt * (nt + 1) / 2, B);
+    to_tiled_kernel<<<grid, 256, 0, ctx->stream>>>(d_A, N, d_At, fkmc_tiled_stride(N));
+    ctx->launches++;
+    FKMC_CUDA(ctx, cudaGetLastError());
+    return FKMC_OK;
+}
+
+// Hamiltonian assembly straight into the tiled layout: H = hopping + diag(U f - mu_c)
+// (configuration_t::calc_hamiltonian, src/configuration.cpp:79-91)
+__global__ void __launch_bounds__(256) build_h_tiled_kernel(const int32_t* __restrict__ f, const int* __restrict__ nbr_idx,
+                                                            const double* __restrict__ nbr_val, int N, int Z, double U, double mu_c,
+                                                            double* __restrict__ At_all, size_t t_stride) {
+    const int b = blockIdx.y, tile = blockIdx.x;
+    int R = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+    while (R * (R + 1) / 2 > tile) --R;
+    while ((R + 1) * (R + 2) / 2 <= tile) ++R;
+    const int C = tile - R * (R + 1) / 2;
+    const int32_t* fb = f + (size_t)b * N;
+    double* dst = At_all + (size_t)b * t_stride + (size_t)tile * TILE;
+    for (int e = threadIdx.x; e < TILE; e += blockDim.x) {
+        const int c = e / TS, r = e % TS;
+        const int i = 32 * R + r, j = 32 * C + c;
+        double v = 0.0;
+        if (r < 32 && i < N && j < N) {
+            if (i == j) {
+                v = U * (double)fb[i] - mu_c;
+            } else {
+                for (int z = 0; z < Z; ++z)
+                    if (nbr_idx[z * N + i] == j) v = nbr_val[z * N + i];
+            }
+        }
+        dst[e] = v;
+    }
+}
+
+int fkmc_launch_build_h_tiled(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double* d_At) {
+    fkmc_prof_scope ps(ctx, "build_h");
+    const int nt = (ctx->N + 31) / 32;
+    dim3 grid(nt * (nt + 1) / 2, B);
+    build_h_tiled_kernel<<<grid, 256, 0, ctx->stream>>>(d_f, ctx->d_nbr_idx, ctx->d_nbr_val, ctx->N, ctx->Z, U, mu_c, d_At,
+                                                       fkmc_tiled_stride(ctx->N));
+    ctx->launches++;
+    FKMC_CUDA(ctx, cudaGetLastError());
+    return FKMC_OK;
+}
+
+// column-major entry point (stage-level API and small matrices)
+int fkmc_launch_sy2sb(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_AB) {
+    if (!fkmc_use_tiled(N)) return fkmc_launch_sy2sb_small(ctx, d_A, N, B, d_AB);
+    // convert in place is not possible (layouts overlap): stage through a scratch allocation
+    double* d_At = nullptr;
+    FKMC_CUDA(ctx, cudaMalloc(&d_At, sizeof(double) * fkmc_tiled_stride(N) * (size_t)B));
+    int rc = fkmc_launch_to_tiled(ctx, d_A, N, B, d_At);
+    if (!rc) rc = fkmc_launch_sy2sb_tiled(ctx, d_At, N, B, d_AB);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_At);
+    return rc;
 }

@@ -64,6 +64,10 @@ int fkmc_logz_ed_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, doubl
 int fkmc_eigh_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, double mu_c, double beta,
                       double* evals, double* evecs, double* logZ);
 
+/* measure_ipr::accumulate, include/fk_mc/measures/ipr.hpp:39-56: calc_ed(true) + ipr_k = ||psi_k||_4 / ||psi_k||_2^2 for
+ * every eigenstate; ipr: [B][N] (ipr_k <-> evals[k]).  The eigenvectors stay on the device. */
+int fkmc_ipr_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, double mu_c, double beta, double* evals, double* ipr);
+
 /* chebyshev_eval(max_moment, grid) + calc_chebyshev, include/fk_mc/chebyshev.hpp:21-54,
  * src/configuration.cpp:94-205.  moments: [B][M] (chebyshev_cache::moments), ab: [B][4] =
  * {e_min, e_max, a, b}, logZ: [B].  M must be even. */
@@ -121,6 +125,8 @@ int fkmc_chain_get_state(fkmc_ctx* ctx, int32_t* f, double* logZ, int64_t* nacce
 /* trace: [n_steps][n_chains] each; n_steps = sweeps run * sweep_len */
 int fkmc_chain_get_trace(fkmc_ctx* ctx, int* n_steps, int32_t* move, int32_t* site_a, int32_t* site_b, int32_t* accepted,
                          double* weight, double* u, double* logz_new);
+/* measure_ipr on the chains' current configurations: evals [n_chains][N] (or NULL), ipr [n_chains][N] */
+int fkmc_chain_ipr(fkmc_ctx* ctx, double* evals, double* ipr);
 /* device pointers to the series (for the end-of-run NCCL gather): energies, d2energies, c_energies as
  * [max_sweeps][n_chains] doubles */
 int fkmc_chain_series_dev(fkmc_ctx* ctx, void** energies, void** d2energies, void** c_energies, int* ld);

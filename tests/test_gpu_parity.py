@@ -395,3 +395,58 @@ def test_cpp_host_api_matches_oracle(tmp_path, cheb, flip):
     assert np.allclose(np.array(rows["energies"], dtype=float), r["energies"], rtol=1e-10)
     assert np.allclose(np.array(rows["d2energies"], dtype=float), r["d2energies"], rtol=1e-9)
     assert rows["mismatch_throws"] == ["1"] and rows["honeycomb_odd_throws"] == ["1"]
+
+
+# ---------------- eigenvector path: calc_ed(true), measure_ipr ----------------
+@pytest.mark.parametrize("kind,L,U", [("cubic2d", 8, 4.0), ("cubic2d", 16, 2.0), ("triangular", 24, 2.0), ("cubic3d", 4, 0.37)])
+def test_eigenvectors_and_ipr(kind, L, U):
+    beta = 3.0
+    c = fk.Context(kind, L, max_batch=3)
+    n = c.N
+    fs = np.stack([o.randomize_f(32167 + i, n, n // 2)[0] for i in range(3)])
+    r = c.eigh(fs, U, U / 2, beta)
+    ri = c.ipr(fs, U, U / 2, beta)
+    for b in range(3):
+        H = o.hopping_dense(o.KINDS[kind], L) + np.diag(U * fs[b] - U / 2)
+        ev, V = r["spectrum"][b], r["evecs"][b]
+        ref = o.calc_ed(o.KINDS[kind], L, fs[b], U, U / 2, beta, vectors=True)
+        scale = np.abs(ref["spectrum"]).max()
+        assert np.abs(ev - ref["spectrum"]).max() <= TOL * scale
+        assert np.abs(H @ V - V * ev).max() <= 1e-10 * scale          # residual
+        assert np.abs(V.T @ V - np.eye(n)).max() <= 1e-9               # orthonormal columns
+        assert abs(r["logZ"][b] - ref["logZ"]) <= TOL * abs(ref["logZ"])
+        # IPR (ipr.hpp:47-53) is basis independent for non-degenerate states: compare with the oracle's eigenvectors
+        ipr_ref = o.measure_ipr(ref["evecs"])
+        gaps = np.minimum(np.diff(ev, prepend=-np.inf), np.diff(ev, append=np.inf))
+        iso = gaps > 1e-6 * scale
+        assert iso.sum() > n // 2
+        assert np.abs(ri["ipr"][b][iso] - ipr_ref[iso]).max() <= 1e-7
+        assert np.allclose(ri["ipr"][b], (np.sum(V ** 4, axis=0) ** 0.25) / np.sum(V ** 2, axis=0), rtol=1e-10)
+    c.close()
+
+
+def test_eigenvectors_degenerate_spectrum():
+    # free lattice: massively degenerate; any orthonormal basis of each eigenspace is acceptable
+    c = fk.Context("cubic2d", 8)
+    r = c.eigh(np.zeros(64, np.int32), 1.0, 0.3, 2.0)
+    H = o.hopping_dense(o.CUBIC2D, 8) - 0.3 * np.eye(64)
+    V, ev = r["evecs"][0], r["spectrum"][0]
+    assert np.abs(H @ V - V * ev).max() <= 1e-9
+    assert np.abs(V.T @ V - np.eye(64)).max() <= 1e-8
+    c.close()
+
+
+def test_chain_ipr_matches_oracle_history():
+    c = fk.Context("cubic2d", 8, max_batch=2)
+    c.chain_init(2, 4.0, 4.0, seed=32167, sweep_len=16, ntherm_sweeps=0, max_sweeps=2)
+    c.chain_run_sweeps(2)
+    got = c.chain_ipr()
+    for ch in range(2):
+        p = o.make_params(kind=o.CUBIC2D, L=8, beta=4.0, U=4.0, seed=32167, nsweeps=2, sweep_len=16, ntherm_sweeps=0, measure_ipr=True)
+        r = o.mc_run(p, rank=ch, trace=False)
+        ev = got["spectrum"][ch]
+        gaps = np.minimum(np.diff(ev, prepend=-np.inf), np.diff(ev, append=np.inf))
+        iso = gaps > 1e-6 * np.abs(ev).max()  # the IPR is basis dependent inside (near-)degenerate subspaces
+        assert iso.sum() > 32
+        assert np.abs(got["ipr"][ch][iso] - r["ipr_history"][-1][iso]).max() <= 1e-7
+    c.close()

@@ -199,3 +199,17 @@ def _():
             got = sl.eigvalsh(band_to_dense(AB[b]))
             err = max(err, np.abs(ref - got).max() / np.abs(ref).max())
         print("sy2sb n=%d: rel err %.2e (%.3fs)" % (n, err, dt), flush=True)
+
+
+@stage("tiled")
+def _():
+    rng = np.random.default_rng(3)
+    for n in [512, 520, 576, 1024]:
+        A = rng.normal(size=(2, n, n))
+        A = A + np.transpose(A, (0, 2, 1))
+        AB = ctx8.sy2sb(A)
+        err = 0
+        for b in range(2):
+            ref = sl.eigvalsh(A[b])
+            err = max(err, np.abs(ref - sl.eigvalsh(band_to_dense(AB[b]))).max() / np.abs(ref).max())
+        print("sy2sb tiled n=%d: rel err %.2e" % (n, err), flush=True)
