@@ -159,6 +159,7 @@ int fkmc_create(fkmc_ctx** out, int device, int lattice_kind, int L, double t, d
     if (cudaMalloc(&ctx->d_flag, sizeof(int)) != cudaSuccess) return fail("cudaMalloc");
     if (cudaMalloc(&ctx->d_moments, sizeof(double) * B * 2 * FKMC_MAX_HALF) != cudaSuccess) return fail("cudaMalloc");
     if (cudaMalloc(&ctx->d_ab, sizeof(double) * B * 4) != cudaSuccess) return fail("cudaMalloc");
+    if (cudaMalloc(&ctx->d_kpm_steps, sizeof(int) * B) != cudaSuccess) return fail("cudaMalloc");
     cudaMemcpy(ctx->d_nbr_idx, ctx->h_nbr_idx.data(), sizeof(int) * Z * N, cudaMemcpyHostToDevice);
     cudaMemcpy(ctx->d_nbr_val, ctx->h_nbr_val.data(), sizeof(double) * Z * N, cudaMemcpyHostToDevice);
     cudaMemset(ctx->d_flag, 0, sizeof(int));
@@ -175,7 +176,7 @@ int fkmc_destroy(fkmc_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     fkmc_profile_resolve(ctx);
     fkmc_chain_free(ctx);
-    cudaFree(ctx->d_AB);
+    cudaFree(ctx->d_AB); cudaFree(ctx->d_kpm_steps);
     cudaFree(ctx->d_nbr_idx); cudaFree(ctx->d_nbr_val); cudaFree(ctx->d_A); cudaFree(ctx->d_W); cudaFree(ctx->d_d);
     cudaFree(ctx->d_e); cudaFree(ctx->d_tau); cudaFree(ctx->d_evals); cudaFree(ctx->d_out); cudaFree(ctx->d_f);
     cudaFree(ctx->d_flag); cudaFree(ctx->d_moments); cudaFree(ctx->d_ab); cudaFree(ctx->d_aux);
@@ -392,6 +393,13 @@ int fkmc_tridiag_eigvals_batched(fkmc_ctx* ctx, const double* d, const double* e
     }
     cudaFree(dd); cudaFree(de); cudaFree(dv); cudaFree(dout);
     return rc;
+}
+
+int fkmc_kpm_last_steps(fkmc_ctx* ctx, int B, int32_t* steps) {
+    if (!ctx || !steps || B < 1 || B > ctx->max_batch) return FKMC_ERR_INVALID;
+    FKMC_CUDA(ctx, cudaMemcpyAsync(steps, ctx->d_kpm_steps, sizeof(int) * B, cudaMemcpyDeviceToHost, ctx->stream));
+    FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FKMC_OK;
 }
 
 int64_t fkmc_launch_count(const fkmc_ctx* ctx) { return ctx ? ctx->launches : -1; }

@@ -84,6 +84,7 @@ struct fkmc_ctx {
     int* d_flag = nullptr;      // non-convergence flag
     double* d_moments = nullptr;  // [max_batch][2*FKMC_MAX_HALF]
     double* d_ab = nullptr;       // [max_batch][4]
+    int* d_kpm_steps = nullptr;   // [max_batch] Lanczos steps of the last KPM launch (diagnostics)
     double* d_aux = nullptr;      // [max_batch][2][N] cached_exp / cached_fermi staging
 
     // Chebyshev tables for the (M, G) last used

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
 
 #include "common.cuh"
 
@@ -35,44 +36,61 @@ struct kpm_args {
     double* ab;             // [B][4]
     double* logz;           // [B]
     int* flag;
+    int* steps;             // [B] Lanczos steps taken (diagnostics), may be null
     int L;                  // linear lattice size (patch variant)
     int nwarps_cols;        // warps that run the column recursion
     int vec_doubles;        // size of the shared vector region (>= 2 Nv per column warp and >= the Lanczos need)
 };
 
-// number of eigenvalues of the k x k Lanczos tridiagonal (al[0..k-1], off-diagonals be[1..k-1]) below x
-__device__ __forceinline__ int lanczos_sturm(const double* al, const double* be, int k, double x) {
-    double pm1 = 1.0, p = al[0] - x;
+// number of eigenvalues of the k x k Lanczos tridiagonal below x.  ab[i] = (alpha_i, beta_i^2) with beta_0 = 0
+// (beta_i couples rows i-1 and i).  Rows are fetched eight at a time so that the shared-memory latency is paid once
+// per chunk and only the dependent FMA chain remains.
+__device__ __forceinline__ int lanczos_sturm(const double2* __restrict__ ab, int k, double x) {
+    double pm1 = 1.0, p = ab[0].x - x;
     if (p == 0.0) p = -DBL_EPSILON;
     bool neg = p < 0.0;
     int cnt = neg ? 1 : 0;
-    for (int i = 1; i < k; ++i) {
-        const double bb = be[i];
-        double pn = fma(al[i] - x, p, -(bb * bb * pm1));
+    int i = 1;
+    for (; i + 8 <= k; i += 8) {
+        double2 q[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) q[u] = ab[i + u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            double pn = fma(q[u].x - x, p, -(q[u].y * pm1));
+            if (pn == 0.0) pn = -DBL_EPSILON * p;
+            const bool nneg = pn < 0.0;
+            cnt += (nneg != neg) ? 1 : 0;
+            neg = nneg;
+            pm1 = p;
+            p = pn;
+        }
+        const double m = fmax(fabs(p), fabs(pm1));
+        if (m > 1.157920892373162e77) { p *= 8.636168555094445e-78; pm1 *= 8.636168555094445e-78; }
+        else if (m < 8.636168555094445e-78) { p *= 1.157920892373162e77; pm1 *= 1.157920892373162e77; }
+    }
+    for (; i < k; ++i) {
+        const double2 q = ab[i];
+        double pn = fma(q.x - x, p, -(q.y * pm1));
         if (pn == 0.0) pn = -DBL_EPSILON * p;
         const bool nneg = pn < 0.0;
         cnt += (nneg != neg) ? 1 : 0;
         neg = nneg;
         pm1 = p;
         p = pn;
-        if ((i & 7) == 0) {
-            const double m = fmax(fabs(p), fabs(pm1));
-            if (m > 1.157920892373162e77) { p *= 8.636168555094445e-78; pm1 *= 8.636168555094445e-78; }
-            else if (m < 8.636168555094445e-78) { p *= 1.157920892373162e77; pm1 *= 1.157920892373162e77; }
-        }
     }
     return cnt;
 }
 
 // idx-th eigenvalue of the Lanczos tridiagonal by 32-way multisection (whole warp participates)
-__device__ __forceinline__ double warp_ritz(const double* al, const double* be, int k, int idx, double lo, double hi, int lane) {
+__device__ __forceinline__ double warp_ritz(const double2* __restrict__ ab, int k, int idx, double lo, double hi, int lane) {
     const double pad = 8.0 * DBL_EPSILON * fmax(fabs(lo), fabs(hi)) + DBL_MIN;
     double a = lo - pad, c = hi + pad;
     for (int round = 0; round < 14; ++round) {
         const double h = (c - a) * (1.0 / 33.0);
         if (!(h > 2.0 * DBL_EPSILON * fmax(fabs(a), fabs(c)) * (1.0 / 33.0))) break;
         const double x = a + h * (double)(lane + 1);
-        const bool above = lanczos_sturm(al, be, k, x) > idx;
+        const bool above = lanczos_sturm(ab, k, x) > idx;
         const unsigned mask = __ballot_sync(0xffffffffu, above);
         const int first = mask ? (__ffs(mask) - 1) : 32;
         const double na = first > 0 ? a + h * (double)first : a;
@@ -109,52 +127,96 @@ __global__ void __launch_bounds__(KIND ? 256 : 384, KIND ? 2 : 1) kpm_kernel(kpm
     __syncthreads();
 
     // =========================== 1. Lanczos for e_min / e_max ===========================
-    // vectors live in the first three column buffers; alpha/beta in the fourth
-    double* lv = vec;            // v_k
-    double* lp = vec + Nv;       // v_{k-1}
-    double* lw = vec + 2 * Nv;   // w
-    double* al = vec + 3 * Nv;   // [KPM_KMAX]
-    double* be = al + KPM_KMAX;  // [KPM_KMAX + 1]
+    // v_k is kept twice: in registers (own elements, together with v_{k-1} and w) and in a ping-pong pair of shared
+    // vectors for the neighbour reads of the stencil.  One fused reduction per step gives alpha = v.Hv' and |w|^2,
+    // beta^2 = |w|^2 - alpha^2 (recomputed directly when it cancels), so a step costs two barriers.
+    constexpr int LE = 8;                // own elements per thread (N <= 8 * blockDim)
+    double* vb0 = vec;                   // v_k, ping
+    double* vb1 = vec + Nv;              // v_k, pong
+    double2* ab = reinterpret_cast<double2*>((reinterpret_cast<uintptr_t>(vec + 3 * Nv) + 15) & ~(uintptr_t)15);  // [KPM_KMAX + 1] (alpha_i, beta_i^2)
+    double* redp = red;                  // [2][nwarps][2] ping-pong partial sums (nwarps <= 12 -> 48 doubles)
+    double vr[LE], pr[LE], wr[LE];
+    double hv[FKMC_MAX_Z];  // per-slot hopping constants in registers
+#pragma unroll
+    for (int z = 0; z < FKMC_MAX_Z; ++z) hv[z] = (z < Z) ? P.slot_val[z] : 0.0;
     {
         double part = 0.0;
-        for (int i = tid; i < Nv; i += T) {
+#pragma unroll
+        for (int q = 0; q < LE; ++q) {
+            const int i = tid + q * T;
             double v = 0.0;
             if (i < N) {
                 unsigned h = (unsigned)i * 2654435761u + 0x9e3779b9u;
                 h ^= h >> 15; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
                 v = (double)h * (1.0 / 4294967296.0) - 0.5;
             }
-            lv[i] = v; lp[i] = 0.0; lw[i] = 0.0;
+            vr[q] = v; pr[q] = 0.0; wr[q] = 0.0;
             part = fma(v, v, part);
         }
-        const double nrm = sqrt(block_sum(part, red));
-        for (int i = tid; i < N; i += T) lv[i] /= nrm;
-        if (tid == 0) be[0] = 0.0;
+        if (tid == 0) { vb0[N] = 0.0; vb1[N] = 0.0; ab[0].y = 0.0; }  // zero slots
+        const double nrm = sqrt(block_sum(part, msc));
+#pragma unroll
+        for (int q = 0; q < LE; ++q) {
+            const int i = tid + q * T;
+            vr[q] /= nrm;
+            if (i < N) vb0[i] = vr[q];
+        }
         __syncthreads();
     }
+#ifdef FKMC_KPM_TIMING
+    long long t_ritz = 0, t_start = clock64(), t_tmp = 0;
+#endif
     const int kcap = min(KPM_KMAX, N);
-    double e_min = 0.0, e_max = 0.0, prev_min = 0.0, prev_max = 0.0, gl = DBL_MAX, gh = -DBL_MAX, hscale = 0.0;
-    bool have_prev = false, converged = false;
+    double e_min = 0.0, e_max = 0.0, gl = DBL_MAX, gh = -DBL_MAX, hscale = 0.0;
+    bool converged = false;
     int k = 0;
     double beta_k = 0.0;
     while (k < kcap) {
-        double part = 0.0;
-        for (int i = tid; i < N; i += T) {
-            double s = xd[i] * lv[i];
-            for (int z = 0; z < Z; ++z) s = fma(P.slot_val[z], lv[nidx[z * N + i]], s);
-            s = fma(-beta_k, lp[i], s);
-            lw[i] = s;
-            part = fma(s, lv[i], part);
+        const double* lv = (k & 1) ? vb1 : vb0;
+        double* lvn = (k & 1) ? vb0 : vb1;
+        double* rp = redp + (k & 1) * 2 * nwarps;
+        double pa = 0.0;
+#pragma unroll
+        for (int q = 0; q < LE; ++q) {
+            const int i = tid + q * T;
+            if (i < N) {
+                // all neighbour indices first, then the gathers: the loads of different slots overlap
+                int nb[FKMC_MAX_Z];
+#pragma unroll
+                for (int z = 0; z < FKMC_MAX_Z; ++z) nb[z] = (z < Z) ? nidx[z * N + i] : N;
+                double sacc = xd[i] * vr[q];
+#pragma unroll
+                for (int z = 0; z < FKMC_MAX_Z; ++z)
+                    if (z < Z) sacc = fma(hv[z], lv[nb[z]], sacc);
+                sacc = fma(-beta_k, pr[q], sacc);
+                wr[q] = sacc;
+                pa = fma(sacc, vr[q], pa);
+            }
         }
-        const double alpha = block_sum(part, red);
-        part = 0.0;
-        for (int i = tid; i < N; i += T) {
-            const double s = fma(-alpha, lv[i], lw[i]);
-            lw[i] = s;
-            part = fma(s, s, part);
+        pa = warp_sum(pa);
+        if (lane == 0) rp[2 * warp] = pa;
+        __syncthreads();
+        double alpha = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < 12; ++ww)
+            if (ww < nwarps) alpha += rp[2 * ww];
+        // classical two-reduction form (the one-reduction shortcut |w|^2 - alpha^2 lets the normalisation error grow
+        // like (alpha/beta)^2 per step): w -= alpha v, then its norm
+        double pb = 0.0;
+#pragma unroll
+        for (int q = 0; q < LE; ++q) {
+            wr[q] = fma(-alpha, vr[q], wr[q]);
+            pb = fma(wr[q], wr[q], pb);
         }
-        const double nb = sqrt(block_sum(part, red));
-        if (tid == 0) { al[k] = alpha; be[k + 1] = nb; }
+        pb = warp_sum(pb);
+        if (lane == 0) rp[2 * warp + 1] = pb;
+        __syncthreads();
+        double nb2 = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < 12; ++ww)
+            if (ww < nwarps) nb2 += rp[2 * ww + 1];
+        const double nb = sqrt(fmax(nb2, 0.0));
+        if (tid == 0) { ab[k].x = alpha; ab[k + 1].y = nb * nb; }
         // Gershgorin enclosure of the Lanczos tridiagonal (all threads keep it in registers)
         gl = fmin(gl, alpha - beta_k - nb);
         gh = fmax(gh, alpha + beta_k + nb);
@@ -163,36 +225,47 @@ __global__ void __launch_bounds__(KIND ? 256 : 384, KIND ? 2 : 1) kpm_kernel(kpm
         const bool breakdown = nb <= 1e-13 * hscale;
         if (!breakdown) {
             const double inv = 1.0 / nb;
-            for (int i = tid; i < N; i += T) {
-                const double s = lw[i] * inv;
-                lw[i] = lp[i];  // recycled as scratch next step
-                lp[i] = lv[i];
-                lv[i] = s;
+#pragma unroll
+            for (int q = 0; q < LE; ++q) {
+                const int i = tid + q * T;
+                const double vn = wr[q] * inv;
+                pr[q] = vr[q];
+                vr[q] = vn;
+                if (i < N) lvn[i] = vn;
             }
         }
         beta_k = nb;
         __syncthreads();
         const bool last = breakdown || k == kcap;
-        if (last || (k >= 32 && (k & 15) == 0)) {
-            // the enclosure must not count the (dropped) last off-diagonal: be[k] is outside T_k
-            if (warp == 0) {
-                const double v = warp_ritz(al, be, k, 0, gl, gh, lane);
-                if (lane == 0) msc[0] = v;
-            } else if (warp == 1) {
-                const double v = warp_ritz(al, be, k, k - 1, gl, gh, lane);
-                if (lane == 0) msc[1] = v;
+        if (last || (k >= 96 && (k & 31) == 0)) {
+            // Ritz values of T_k and of T_{k-16} (four independent multisections spread over the warps); converged when
+            // both ends have stopped moving.  beta_k is outside T_k, which only loosens the Gershgorin enclosure.
+            const int kprev = k > 16 ? k - 16 : k;
+#ifdef FKMC_KPM_TIMING
+            t_tmp = clock64();
+#endif
+            for (int task = warp; task < 4; task += nwarps) {
+                const int kk = (task < 2) ? k : kprev;
+                const double v = warp_ritz(ab, kk, (task & 1) ? kk - 1 : 0, gl, gh, lane);
+                if (lane == 0) msc[task] = v;
             }
             __syncthreads();
             e_min = msc[0];
             e_max = msc[1];
             const double tol = 8.0 * DBL_EPSILON * hscale;
-            if (have_prev && fabs(e_min - prev_min) <= tol && fabs(e_max - prev_max) <= tol) converged = true;
-            prev_min = e_min; prev_max = e_max; have_prev = true;
+            if (k > 16 && fabs(e_min - msc[2]) <= tol && fabs(e_max - msc[3]) <= tol) converged = true;
             __syncthreads();
+#ifdef FKMC_KPM_TIMING
+            t_ritz += clock64() - t_tmp;
+#endif
             if (converged || last) break;
         }
     }
+#ifdef FKMC_KPM_TIMING
+    const long long t_lanczos_end = clock64();
+#endif
     if (!converged && k == kcap && k < N && tid == 0) atomicOr(P.flag, 2);
+    if (P.steps && tid == 0) P.steps[b] = k;
 
     // =========================== 2. moments ===========================
     const double a = (e_max - e_min) / 2., bsh = (e_max + e_min) / 2.;
@@ -211,82 +284,96 @@ __global__ void __launch_bounds__(KIND ? 256 : 384, KIND ? 2 : 1) kpm_kernel(kpm
 #pragma unroll
     for (int m = 0; m <= HALF; ++m) tr[m] = d01[m] = d11[m] = 0.0;
     if constexpr (KIND != 0) {
-        constexpr int H = HALF, PW = 2 * H + 1, PP = PW * PW, GUARD = PW + 1, PVp = (PP + 2 * GUARD + 1) & ~1, NE = (PP + 31) / 32;
-        constexpr int CEN = GUARD + H * PW + H;
+        // Local-patch recursion.  The patch (PW x PW, flattened with row stride PW) is split into 32 contiguous runs of R
+        // elements, one per lane (R odd -> conflict-free shared-memory access); lane 31 also owns the last element when
+        // 32 R = PP - 1.  A lane keeps its runs of T_{m-1} e_j and T_{m-2} e_j in registers, so the +-1 neighbours come from
+        // registers (run ends: one shuffle) and only the +-PW (+-(PW+1)) neighbours are read from shared memory.
+        constexpr int H = HALF, PW = 2 * H + 1, PP = PW * PW, GUARD = PW + 1, PVp = (PP + 2 * GUARD + 1) & ~1;
+        constexpr int R0 = (PP - 1 + 31) / 32, R = (R0 % 2) ? R0 : R0 + 1;   // run length (odd)
+        constexpr bool TAIL = (32 * R == PP - 1);                             // one extra element for lane 31
+        constexpr int RE = R + (TAIL ? 1 : 0);
+        constexpr int KC = H * PW + H, LANE_C = KC / R, E_C = KC % R;         // the centre of the patch
         const int L = P.L;
-        double* const vbase = vec + (size_t)warp * 2 * PVp;
+        double* const sb0 = vec + (size_t)warp * 2 * PVp + GUARD;  // shared copies, index k in [0, PP), zero guard zones around
+        double* const sb1 = sb0 + PVp;
         const double svt = sv[0];                                   // nearest-neighbour hopping / a
         const double svp = (KIND == FKMC_TRIANGULAR) ? sv[4] : 0.0;  // (x-1,y-1)/(x+1,y+1) hopping / a
-        int dyl[NE], dxl[NE];
-#pragma unroll
-        for (int i = 0; i < NE; ++i) {
-            const int kq = lane + 32 * i;
-            dyl[i] = kq / PW - H;
-            dxl[i] = kq % PW - H;
-        }
+        for (int i = lane; i < 2 * PVp; i += 32) sb0[i - GUARD] = 0.0;  // both buffers incl. guards (contiguous), once
+        __syncwarp();
+        const int kbase = R * lane;
         for (int j = warp; j < N; j += nwarps) {
             const int y0 = j / L, x0 = j - y0 * L;
-            double* v0 = vbase;  // (the roles are swapped HALF-1 times per column: always restart from the base layout)
-            double* v1 = vbase + PVp;
-            double xdp[NE];
+            const bool jeven = ((y0 + x0) & 1) == 0;  // honeycomb: sublattice A hops up (y+1), B hops down
+            double xdp[RE], va[RE], vb[RE];           // diagonal of X on the patch; T_{m-2} e_j (va) and T_{m-1} e_j (vb)
+            bool up[RE];                              // honeycomb: this site's vertical bond goes to +PW
 #pragma unroll
-            for (int i = 0; i < NE; ++i) {
-                int yy = y0 + dyl[i], xx = x0 + dxl[i];
+            for (int e = 0; e < RE; ++e) {
+                const int kq = kbase + e;
+                const bool live = (e < R) ? (kq < PP) : (TAIL && lane == 31);
+                const int dy = kq / PW - H, dx = kq % PW - H;
+                int yy = y0 + dy, xx = x0 + dx;
                 yy += (yy < 0) ? L : 0; yy -= (yy >= L) ? L : 0;
                 xx += (xx < 0) ? L : 0; xx -= (xx >= L) ? L : 0;
-                xdp[i] = (lane + 32 * i < PP) ? xd[yy * L + xx] : 0.0;
-            }
-            for (int i = lane; i < 2 * PVp; i += 32) v0[i] = 0.0;  // both buffers are contiguous
-            __syncwarp();
-            const bool jeven = ((y0 + x0) & 1) == 0;  // honeycomb: sublattice A hops up (y+1), B hops down
-            if (lane == 0) {
-                v0[CEN] = 1.0;
-                v1[CEN] = xd[j];
-                v1[CEN - 1] = svt;
-                v1[CEN + 1] = svt;
-                if (KIND == FKMC_HONEYCOMB) {
-                    v1[jeven ? CEN + PW : CEN - PW] = svt;
-                } else {
-                    v1[CEN - PW] = svt;
-                    v1[CEN + PW] = svt;
-                    if (KIND == FKMC_TRIANGULAR) { v1[CEN - PW - 1] = svp; v1[CEN + PW + 1] = svp; }
+                xdp[e] = live ? xd[yy * L + xx] : 0.0;
+                up[e] = (((dy + dx) & 1) == 0) == jeven;
+                // v0 = e_j, v1 = X e_j (column j of the symmetric X)
+                const int off = kq - KC;
+                va[e] = (live && off == 0) ? 1.0 : 0.0;
+                double v1 = 0.0;
+                if (live) {
+                    if (off == 0) v1 = xd[j];
+                    else if (off == 1 || off == -1) v1 = svt;
+                    else if (KIND == FKMC_HONEYCOMB) { if (off == (jeven ? PW : -PW)) v1 = svt; }
+                    else if (off == PW || off == -PW) v1 = svt;
+                    else if (KIND == FKMC_TRIANGULAR && (off == PW + 1 || off == -PW - 1)) v1 = svp;
                 }
+                vb[e] = v1;
+                if (live) sb1[kq] = v1;
             }
             __syncwarp();
+            // one recursion step: vold <- 2 X vcur - vold (in registers), published to the shared buffer snew
+            auto step = [&](double (&vold)[RE], const double (&vcur)[RE], const double* __restrict__ scur, double* __restrict__ snew,
+                            bool need_dots, double& s01, double& s11, double& centre) {
+                // run-end neighbours from the adjacent lanes
+                double left = __shfl_up_sync(0xffffffffu, vcur[R - 1], 1);
+                double right = __shfl_down_sync(0xffffffffu, vcur[0], 1);
+                if (lane == 0) left = 0.0;
+                if (lane == 31) right = TAIL ? vcur[RE - 1] : 0.0;
 #pragma unroll
-            for (int m = 2; m <= HALF; ++m) {
-                double s01 = 0.0, s11 = 0.0;
-                const bool need_dots = (2 * m - 1 >= HALF);
-#pragma unroll
-                for (int i = 0; i < NE; ++i) {
-                    const int kq = lane + 32 * i;
-                    if (kq < PP) {
-                        const int kk = kq + GUARD;
-                        const double c1 = v1[kk];
-                        double nb = v1[kk - 1] + v1[kk + 1];
-                        if (KIND == FKMC_HONEYCOMB) {
-                            const bool even = (((dyl[i] + dxl[i]) & 1) == 0) == jeven;
-                            nb += v1[even ? kk + PW : kk - PW];
-                        } else {
-                            nb += v1[kk - PW] + v1[kk + PW];
-                        }
-                        double sacc = fma(xdp[i], c1, svt * nb);
-                        if (KIND == FKMC_TRIANGULAR) sacc = fma(svp, v1[kk - PW - 1] + v1[kk + PW + 1], sacc);
-                        const double vn = 2. * sacc - v0[kk];
-                        v0[kk] = vn;
+                for (int e = 0; e < RE; ++e) {
+                    const int kq = kbase + e;
+                    const bool live = (e < R) ? (kq < PP) : (TAIL && lane == 31);
+                    if (live) {
+                        const double c1 = vcur[e];
+                        const double lft = (e == 0) ? left : vcur[e - 1];
+                        const double rgt = (e == R - 1) ? right : ((e < R - 1) ? vcur[e + 1] : 0.0);
+                        double nb = lft + rgt;
+                        if (KIND == FKMC_HONEYCOMB) nb += scur[up[e] ? kq + PW : kq - PW];
+                        else nb += scur[kq - PW] + scur[kq + PW];
+                        double sacc = fma(xdp[e], c1, svt * nb);
+                        if (KIND == FKMC_TRIANGULAR) sacc = fma(svp, scur[kq - PW - 1] + scur[kq + PW + 1], sacc);
+                        const double vn = 2. * sacc - vold[e];
+                        vold[e] = vn;
+                        snew[kq] = vn;
                         if (need_dots) {
                             s01 = fma(c1, vn, s01);
                             s11 = fma(vn, vn, s11);
                         }
                     }
                 }
+                centre = (lane == LANE_C) ? vold[E_C] : 0.0;
                 __syncwarp();
-                if (lane == 0) tr[m] += v0[CEN];
+            };
+#pragma unroll
+            for (int m = 2; m <= HALF; ++m) {
+                double s01 = 0.0, s11 = 0.0, centre = 0.0;
+                const bool need_dots = (2 * m - 1 >= HALF);
+                if ((m & 1) == 0) step(va, vb, sb1, sb0, need_dots, s01, s11, centre);   // va <- T_m e_j
+                else step(vb, va, sb0, sb1, need_dots, s01, s11, centre);                 // vb <- T_m e_j
+                tr[m] += centre;
                 d01[m] += s01;
                 d11[m] += s11;
-                double* tswap = v0; v0 = v1; v1 = tswap;
             }
-            __syncwarp();
         }
     } else
     if (warp < P.nwarps_cols) {
@@ -341,6 +428,11 @@ __global__ void __launch_bounds__(KIND ? 256 : 384, KIND ? 2 : 1) kpm_kernel(kpm
         }
     }
     __syncthreads();
+#ifdef FKMC_KPM_TIMING
+    if (tid == 0 && b == 0)
+        printf("kpm timing (cycles): lanczos total %lld (ritz %lld, steps %d) moments %lld\n", t_lanczos_end - t_start, t_ritz, k,
+               (long long)clock64() - t_lanczos_end);
+#endif
     // =========================== 3. coefficients and logZ ===========================
     double* mom = msc + 8;  // [M] (M <= 32)
     if (tid == 0) {
@@ -416,12 +508,13 @@ template <int HALF, int KIND>
 static int launch_kpm_patch(fkmc_ctx* ctx, kpm_args& P, int B) {
     constexpr int PW = 2 * HALF + 1, PP = PW * PW, GUARD = PW + 1, PVp = (PP + 2 * GUARD + 1) & ~1;
     const int N = P.N, Nv = N + 1, nw = 8;
-    const size_t lanczos_need = 3 * (size_t)Nv + 2 * KPM_KMAX + 2;
+    const size_t lanczos_need = 3 * (size_t)Nv + 2 * KPM_KMAX + 6;
     size_t vec_doubles = std::max((size_t)nw * 2 * PVp, lanczos_need);
     vec_doubles += vec_doubles & 1;
     const size_t fixed = sizeof(double) * ((size_t)N + 48 + 64 + ((P.G + 1) & ~1) + (size_t)nw * 3 * (HALF + 1));
     const size_t smem = fixed + sizeof(double) * vec_doubles + sizeof(unsigned short) * (size_t)P.Z * N + 16;
     if (smem > ctx->smem_optin - 1024) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: lattice too large for the shared-memory kernel");
+    if (N > 8 * nw * 32) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: lattice too large for the Lanczos register tiling");
     P.nwarps_cols = nw;
     P.vec_doubles = (int)vec_doubles;
     FKMC_CUDA(ctx, cudaFuncSetAttribute(kpm_kernel<HALF, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -446,7 +539,7 @@ static int launch_kpm_t(fkmc_ctx* ctx, kpm_args& P, int B) {
     const size_t budget = ctx->smem_optin - 1024;
     int nw = 12;
     size_t smem = 0, vec_doubles = 0;
-    const size_t lanczos_need = 3 * (size_t)Nv + 2 * KPM_KMAX + 2;
+    const size_t lanczos_need = 3 * (size_t)Nv + 2 * KPM_KMAX + 6;
     for (; nw >= 2; --nw) {
         const size_t fixed = sizeof(double) * ((size_t)N + 48 + 64 + ((P.G + 1) & ~1) + (size_t)nw * 3 * (HALF + 1));
         vec_doubles = std::max((size_t)nw * 2 * Nv, lanczos_need);
@@ -456,6 +549,7 @@ static int launch_kpm_t(fkmc_ctx* ctx, kpm_args& P, int B) {
         if (smem <= budget) break;
     }
     if (nw < 2) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: lattice too large for the shared-memory kernel");
+    if (N > 8 * nw * 32) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: lattice too large for the Lanczos register tiling");
     P.nwarps_cols = nw;
     P.vec_doubles = (int)vec_doubles;
     FKMC_CUDA(ctx, cudaFuncSetAttribute(kpm_kernel<HALF, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -486,7 +580,7 @@ int fkmc_launch_kpm(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double m
         }
     }
     P.chebt = ctx->d_chebt; P.lobatto = ctx->d_lobatto; P.dtheta = ctx->d_dtheta;
-    P.moments = d_moments; P.ab = d_ab; P.logz = d_logz; P.flag = ctx->d_flag;
+    P.moments = d_moments; P.ab = d_ab; P.logz = d_logz; P.flag = ctx->d_flag; P.steps = ctx->d_kpm_steps;
     switch (M / 2) {
 #define FKMC_KPM_CASE(H) case H: return launch_kpm_t<H>(ctx, P, B);
         FKMC_KPM_CASE(1) FKMC_KPM_CASE(2) FKMC_KPM_CASE(3) FKMC_KPM_CASE(4) FKMC_KPM_CASE(5) FKMC_KPM_CASE(6)

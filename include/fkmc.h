@@ -132,6 +132,8 @@ int fkmc_chain_ipr(fkmc_ctx* ctx, double* evals, double* ipr);
 int fkmc_chain_series_dev(fkmc_ctx* ctx, void** energies, void** d2energies, void** c_energies, int* ld);
 
 /* ---- instrumentation -------------------------------------------------------------------- */
+/* Lanczos steps each of the last B KPM evaluations needed for e_min / e_max (the reference's ARPACK iteration count analogue) */
+int fkmc_kpm_last_steps(fkmc_ctx* ctx, int B, int32_t* steps);
 /* number of kernels this context has launched since creation */
 int64_t fkmc_launch_count(const fkmc_ctx* ctx);
 /* CUDA-event timing on the context's stream: begin/end a region, read milliseconds */
