@@ -42,6 +42,39 @@ __device__ __forceinline__ int sturm_count(const double2* __restrict__ de, int n
     return cnt;
 }
 
+// Sturm count plus the characteristic polynomial p_n(x) and its derivative (same recurrence, differentiated:
+// p'_i = (d_i - x) p'_{i-1} - p_{i-1} - e_{i-1}^2 p'_{i-2}), jointly rescaled, for a safeguarded Newton step.
+__device__ __forceinline__ int sturm_newton(const double2* __restrict__ de, int n, double x, double& pn_out, double& dpn_out) {
+    double pm1 = 1.0, p = de[0].x - x, dpm1 = 0.0, dp = -1.0;
+    if (p == 0.0) p = -DBL_EPSILON;
+    bool neg = p < 0.0;
+    int cnt = neg ? 1 : 0;
+    for (int i0 = 1; i0 < n; i0 += 8) {
+        const int i1 = min(i0 + 8, n);
+        for (int i = i0; i < i1; ++i) {
+            const double2 q = de[i];
+            const double t = q.x - x;
+            double pn = fma(t, p, -(q.y * pm1));
+            const double dpn = fma(t, dp, -fma(q.y, dpm1, p));
+            if (pn == 0.0) pn = -DBL_EPSILON * p;
+            const bool nneg = pn < 0.0;
+            cnt += (nneg != neg) ? 1 : 0;
+            neg = nneg;
+            pm1 = p; p = pn;
+            dpm1 = dp; dp = dpn;
+        }
+        const double m = fmax(fmax(fabs(p), fabs(pm1)), fmax(fabs(dp), fabs(dpm1)) * 0x1p-60);
+        if (m > 1.157920892373162e77) {
+            p *= 8.636168555094445e-78; pm1 *= 8.636168555094445e-78; dp *= 8.636168555094445e-78; dpm1 *= 8.636168555094445e-78;
+        } else if (m < 8.636168555094445e-78) {
+            p *= 1.157920892373162e77; pm1 *= 1.157920892373162e77; dp *= 1.157920892373162e77; dpm1 *= 1.157920892373162e77;
+        }
+    }
+    pn_out = p;
+    dpn_out = dp;
+    return cnt;
+}
+
 // shared-memory block: de[Np] (double2), red[40]
 __global__ void __launch_bounds__(1024)
 tridiag_eig_kernel(const double* __restrict__ d_all, const double* __restrict__ e_all, int N, double beta,
@@ -106,14 +139,56 @@ tridiag_eig_kernel(const double* __restrict__ d_all, const double* __restrict__ 
         }
         double a = (jl == 0) ? lo : lo + gstep * (double)jl;
         double c = (jl >= T) ? hi : lo + gstep * (double)(jl + 1);
+        int ca = (jl == 0) ? 0 : cnts[jl - 1];   // eigenvalues below a (<= k)
+        int cc = (jl >= T) ? N : cnts[jl];        // eigenvalues below c (> k)
+        const double tolw = 2.0 * DBL_EPSILON * scale;
         int it = 0;
-        for (; it < 128; ++it) {
+        // (1) a fixed number of bisection steps for every lane (keeps the warp in lockstep on the cheap count-only
+        //     recurrence and leaves all but ~0.03 % of the eigenvalues isolated), then more only while not isolated
+        for (; it < 128 && (it < 12 || cc - ca > 1); ++it) {
             const double mid = 0.5 * (a + c);
-            if (mid <= a || mid >= c) break;
-            if (c - a <= 2.0 * DBL_EPSILON * scale) break;
-            if (sturm_count(de, N, mid) > k) c = mid; else a = mid;
+            if (mid <= a || mid >= c || c - a <= tolw) break;
+            const int cm = sturm_count(de, N, mid);
+            if (cm > k) { c = mid; cc = cm; } else { a = mid; ca = cm; }
+        }
+        // (2) safeguarded Newton on the characteristic polynomial: every evaluation also shrinks the bracket through its
+        //     Sturm count, a step that leaves the bracket (or a non-finite one) is replaced by bisection
+        double x = 0.5 * (a + c);
+        bool done = !(c - a > tolw);
+        int nnewt = 0;
+        double prev_step = DBL_MAX;
+        for (; it < 128 && !done; ++it) {
+            double pv, dpv;
+            const int cm = sturm_newton(de, N, x, pv, dpv);
+            if (cm > k) c = x; else a = x;
+            const double dn = -pv / dpv;
+            double xn = x + dn;
+            const bool isolated = (cc - ca == 1);
+            // a correction at working precision means x already is the eigenvalue (the count may put it on either side of x)
+            if (isolated && fabs(dn) <= 4.0 * tolw) {
+                a = x; c = x;
+                done = true;
+                break;
+            }
+            // Newton only for an isolated root, inside the bracket (also rejects NaN); after 8 Newton steps every other step
+            // is a bisection so that an ill-conditioned root cannot stall the iteration
+            const bool ok = isolated && (xn > a) && (xn < c) && (nnewt < 8 || (nnewt & 1));
+            ++nnewt;
+            if (!ok) xn = 0.5 * (a + c);
+            // also stop when the correction has stopped contracting (rounding floor of p/p' near the root)
+            const double stepn = fabs(xn - x);
+            const bool floor_hit = ok && nnewt >= 3 && stepn <= 64.0 * tolw && stepn >= 0.25 * prev_step;
+            if (floor_hit || !(c - a > tolw) || xn <= a || xn >= c) {
+                if (ok) { a = xn; c = xn; }
+                done = true;
+            }
+            prev_step = ok ? stepn : DBL_MAX;
+            x = xn;
         }
         if (it >= 128) atomicOr(flag, 1);
+#ifdef FKMC_TRIDIAG_DEBUG
+        if (fermi_all) fermi_all[(size_t)b * N + k] = (double)(it * 1000 + nnewt);
+#endif
         lam = 0.5 * (a + c) * sc;
         ev[k] = lam;
     }
@@ -132,7 +207,9 @@ tridiag_eig_kernel(const double* __restrict__ d_all, const double* __restrict__ 
         ec = x / (1.0 + ex);
         d2 = x * x / (1.0 + 0.5 * (ex + 1.0 / ex));
         if (exp_all) exp_all[(size_t)b * N + k] = ex;
+#ifndef FKMC_TRIDIAG_DEBUG
         if (fermi_all) fermi_all[(size_t)b * N + k] = 1.0 / (1.0 + ex);
+#endif
     }
     lz = block_sum(lz, red);
     ec = block_sum(ec, red);
