@@ -16,6 +16,9 @@
 
 namespace {
 
+#ifndef FKMC_SB2ST_SLEEP
+#define FKMC_SB2ST_SLEEP 20
+#endif
 constexpr int SB = 8;     // half bandwidth
 constexpr int WD = 16;    // stored sub-diagonals per column
 
@@ -81,7 +84,7 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
         int n = min(SB, N - p);         // its size
         // ---- step 0: annihilate column j below the sub-diagonal ----
         if (j > 0) {
-            while (prog[j - 1] < 3) { }
+            while (prog[j - 1] < 3) { __nanosleep(FKMC_SB2ST_SLEEP); }
             __threadfence_block();
         }
         double x = Wb[(size_t)j * WD + 1 + i];  // rows p..p+7 of column j (zero beyond the matrix)
@@ -155,7 +158,7 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
             if (lane == 0) prog[j] = s;
             if (!(n == SB && nn >= 2)) break;
             if (j > 0) {
-                while (prog[j - 1] < s + 3) { }
+                while (prog[j - 1] < s + 3) { __nanosleep(FKMC_SB2ST_SLEEP); }
                 __threadfence_block();
             }
             // reflector from the first column of the block below (rows pn.., column p); re-read after the wait is not

@@ -106,3 +106,33 @@ def energy_report(energies, d2energies, beta, volume, max_depth=None):
     b = estimate_bin(cv_rows)
     out["cv"] = dict(binning=cv_rows, cor_length=calc_cor_length(cv_rows), bin=b, stats=cv_rows[b])
     return out
+
+
+# ---- plaintext twin of the reference output (prog/data_save.hxx:9-30, prog/data_save.hpp:124-156, README.md:42-43) ----
+def savetxt(fname, rows):
+    """gftools-style plaintext: scientific notation, space separated, one row per line (README example:
+    `5.000000e+01 -2.474323e-01 1.207943e-28 1.554312e-15`)."""
+    rows = np.atleast_2d(np.asarray(rows, dtype=np.float64))
+    with open(fname, "w") as fh:
+        for r in rows:
+            fh.write(" ".join("%e" % v for v in r) + "\n")
+
+
+def save_binning_plaintext(outdir, name, rows):
+    """save_binning(..., save_plaintext=true): <name>_binning.dat = nbins x 5 [n, mean, variance, stderr, tau_int] and, at the bin
+    chosen by estimate_bin, <name>_error.dat = [n, mean, variance, stderr] (== /binning/<name> and /stats/<name> of the HDF5 file)."""
+    import os
+    cor = calc_cor_length(rows)
+    table = [list(r) + [c] for r, c in zip(rows, cor)]
+    savetxt(os.path.join(outdir, name + "_binning.dat"), table)
+    b = estimate_bin(rows)
+    savetxt(os.path.join(outdir, name + "_error.dat"), [list(rows[b])])
+    return b
+
+
+def save_energy_plaintext(outdir, energies, d2energies, beta, volume, max_depth=None):
+    """The energy part of data_saver::save_all (prog/data_save.hxx:158-199) in the --plaintext layout."""
+    rep = energy_report(energies, d2energies, beta, volume, max_depth)
+    for name in ("energy", "d2energy", "cv"):
+        save_binning_plaintext(outdir, name, rep[name]["binning"])
+    return rep

@@ -215,3 +215,82 @@ void mc_run(const mc_params& p, int rank, mc_result& res, mc_trace* trace) {
 }
 
 }  // namespace orc
+
+namespace orc {
+
+// include/fk_mc/measures/stiffness.hpp:69-187 (2-D hypercubic, t_ = 1): T = -pi sum_k (V^T Tm V)_kk f_k,
+// V = sum_{i>j, |e_i-e_j|>1e-12, |sigma|>1e-13} 2 pi (f_j - f_i) mJ_ji mJ_ij / (e_i - e_j), stiffness = (T + V) / N;
+// conductivity sigma(w) = sum of Lorentzians of the resonant terms.
+double measure_stiffness(const lattice& lat, const ed_result& ed, double beta, double offset, const std::vector<double>* wgrid,
+                         std::vector<double>* cond) {
+    (void)beta;
+    const int n = lat.N, L = lat.L;
+    if (lat.ndim < 2) throw std::logic_error("no stiffness in 1-D");
+    const std::vector<double>& V = ed.evecs;
+    // left / right neighbours along dimension 0 (the first coordinate)
+    std::vector<int> left(n), right(n);
+    for (int i = 0; i < n; ++i) {
+        auto pos = lat.index_to_pos(i);
+        auto pl = pos, pr = pos;
+        pl[0] = ((pos[0] - 1) + L) % L;
+        pr[0] = ((pos[0] + 1) + L) % L;
+        left[i] = lat.pos_to_index(pl);
+        right[i] = lat.pos_to_index(pr);
+    }
+    // TV = Tm V, JV = Jm V with Tm(i,left)=Tm(i,right)=-1, Jm(i,left)=-1, Jm(i,right)=+1
+    std::vector<double> TV((size_t)n * n), JV((size_t)n * n);
+    for (int k = 0; k < n; ++k)
+        for (int i = 0; i < n; ++i) {
+            const double vl = V[(size_t)k * n + left[i]], vr = V[(size_t)k * n + right[i]];
+            TV[(size_t)k * n + i] = -vl - vr;
+            JV[(size_t)k * n + i] = -vl + vr;
+        }
+    double T = 0;
+    for (int k = 0; k < n; ++k) {
+        double d = 0;
+        for (int i = 0; i < n; ++i) d += V[(size_t)k * n + i] * TV[(size_t)k * n + i];
+        T += d * ed.cached_fermi[k];
+    }
+    T *= -M_PI;
+    double Vsum = 0;
+    std::vector<std::pair<double, double>> terms;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j) {
+            if (!(std::fabs(ed.spectrum[i] - ed.spectrum[j]) > 1e-12)) continue;
+            double mji = 0, mij = 0;  // mJ(j,i) = v_j . (Jm v_i)
+            for (int r = 0; r < n; ++r) {
+                mji += V[(size_t)j * n + r] * JV[(size_t)i * n + r];
+                mij += V[(size_t)i * n + r] * JV[(size_t)j * n + r];
+            }
+            const double sigma_v = M_PI * (ed.cached_fermi[j] - ed.cached_fermi[i]) * mji * mij;
+            if (std::fabs(sigma_v) > 1e-13) {
+                Vsum += 2. * sigma_v / (ed.spectrum[i] - ed.spectrum[j]);
+                terms.push_back({ed.spectrum[j] - ed.spectrum[i], sigma_v});
+                terms.push_back({ed.spectrum[i] - ed.spectrum[j], -sigma_v});
+            }
+        }
+    if (wgrid && cond) {
+        cond->assign(wgrid->size(), 0.0);
+        for (size_t w = 0; w < wgrid->size(); ++w)
+            for (auto& t : terms) {
+                const double x = (*wgrid)[w] + t.first;
+                (*cond)[w] += offset / M_PI / (x * x + offset * offset) * t.second;
+            }
+    }
+    return (Vsum + T) / n;
+}
+
+}  // namespace orc
+
+extern "C" int orc_stiffness(int kind, int L, double t, const int* f, double U, double mu_c, double beta, double offset, int nw,
+                             const double* wgrid, double* cond, double* stiffness) {
+    try {
+        orc::lattice l = orc::make_lattice(kind, L, t, 1.0);
+        orc::ed_result ed;
+        orc::calc_ed(l, std::vector<int>(f, f + l.N), U, mu_c, beta, true, ed);
+        std::vector<double> wg(wgrid, wgrid + nw), cd;
+        *stiffness = orc::measure_stiffness(l, ed, beta, offset, &wg, &cd);
+        for (int i = 0; i < nw; ++i) cond[i] = cd[i];
+    } catch (std::exception&) { return -1; }
+    return 0;
+}

@@ -230,3 +230,14 @@ def jackknife(series, depth):
     if lib().orc_jackknife(d.shape[1], d.shape[0], _p(d, C.c_double), depth, _p(out, C.c_double)) != 0:
         raise RuntimeError("oracle jackknife failed")
     return out
+
+
+def stiffness(kind, L, f, U, mu_c, beta, offset=0.05, wgrid=(0.0,), t=1.0):
+    f = np.ascontiguousarray(f, dtype=np.int32)
+    wg = np.ascontiguousarray(wgrid, dtype=np.float64)
+    cond = np.zeros(len(wg))
+    st = C.c_double(0)
+    if lib().orc_stiffness(kind, L, C.c_double(t), _p(f, C.c_int), C.c_double(U), C.c_double(mu_c), C.c_double(beta), C.c_double(offset),
+                           len(wg), _p(wg, C.c_double), _p(cond, C.c_double), C.byref(st)) != 0:
+        raise RuntimeError("oracle stiffness failed")
+    return st.value, cond

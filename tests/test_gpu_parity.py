@@ -450,3 +450,21 @@ def test_chain_ipr_matches_oracle_history():
         assert iso.sum() > 32
         assert np.abs(got["ipr"][ch][iso] - r["ipr_history"][-1][iso]).max() <= 1e-7
     c.close()
+
+
+# ---------------- stiffness: the reference's only golden values that involve eigenvectors (test/stiffness_test.cpp:60-63) ----------------
+F5 = [0, 1, 0, 1, 1, 0, 1, 0, 0, 1, 0, 0, 1, 0, 1, 0, 1, 1, 1, 0, 1, 1, 0, 1, 1]
+F7 = [0, 1, 0, 0, 0, 0, 1, 1, 0, 1, 1, 0, 0, 1, 1, 0, 1, 1, 0, 1, 1, 0, 1, 0, 0, 0, 1, 1, 0, 1, 1, 1, 1, 1, 0, 1, 1, 0, 1, 1, 1, 1, 0, 0, 0, 1, 0, 1, 1]
+
+
+@pytest.mark.parametrize("U,f,golden", [(0.0, F5, 1.31597), (2.0, F5, 0.287547), (6.0, F5, 0.00260831), (0.37, F7, 1.26046)])
+def test_stiffness_reference_goldens(U, f, golden):
+    from fk_mc_b200 import measures
+    L = int(round(len(f) ** 0.5))
+    c = fk.Context("cubic2d", L)
+    st, cond = measures.stiffness(c, np.array(f, np.int32), U, U / 2, 1000.0)
+    assert st[0] == pytest.approx(golden, abs=1e-3)           # the reference's tolerance
+    ref, cref = o.stiffness(o.CUBIC2D, L, np.array(f, np.int32), U, U / 2, 1000.0)
+    assert st[0] == pytest.approx(ref, abs=1e-8)
+    assert cond[0, 0] == pytest.approx(cref[0], rel=1e-6, abs=1e-9)
+    c.close()

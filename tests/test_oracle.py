@@ -222,3 +222,16 @@ def test_ipr_of_plane_waves():
     ed = o.calc_ed(o.CUBIC1D, 12, np.zeros(12, np.int32), 1.0, 0.0, 1.0, vectors=True)
     ipr = o.measure_ipr(ed["evecs"])
     assert ipr[0] == pytest.approx((12 * (1 / 12) ** 2) ** 0.25, rel=1e-12)  # uniform ground state
+
+
+F5 = [0, 1, 0, 1, 1, 0, 1, 0, 0, 1, 0, 0, 1, 0, 1, 0, 1, 1, 1, 0, 1, 1, 0, 1, 1]
+F7 = [0, 1, 0, 0, 0, 0, 1, 1, 0, 1, 1, 0, 0, 1, 1, 0, 1, 1, 0, 1, 1, 0, 1, 0, 0, 0, 1, 1, 0, 1, 1, 1, 1, 1, 0, 1, 1, 0, 1, 1, 1, 1, 0, 0, 0, 1, 0, 1, 1]
+
+
+@pytest.mark.parametrize("U,f,golden", [(0.0, F5, 1.31597), (2.0, F5, 0.287547), (6.0, F5, 0.00260831), (0.37, F7, 1.26046)])
+def test_stiffness_reference_goldens(U, f, golden):
+    # test/stiffness_test.cpp:60-63: the reference's only known answers that go through eigenvalues AND eigenvectors (+-1e-3)
+    L = int(round(len(f) ** 0.5))
+    st, _ = o.stiffness(o.CUBIC2D, L, np.array(f, np.int32), U, U / 2, 1000.0)
+    assert st == pytest.approx(golden, abs=1e-3)
+    assert st == pytest.approx(golden, rel=2e-5)  # agrees to the printed digits

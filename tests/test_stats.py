@@ -57,3 +57,17 @@ def test_estimate_bin_and_energy_report():
     assert abs(rep["energy"]["stats"][1] + 50) < 5 * rep["energy"]["stats"][3]
     cv = rep["cv"]["stats"]
     assert abs(cv[1] - 4 * (1.0 - 0.3) / 64) < 5 * cv[3]
+
+
+def test_plaintext_layout(tmp_path):
+    # README.md:42-43: "<obs>_error.dat" holds 4 numbers in scientific notation, space separated
+    rng = np.random.default_rng(1)
+    e = rng.normal(-0.25 * 64, 0.5, 256)
+    d2 = rng.normal(0.1, 0.01, 256)
+    rep = stats.save_energy_plaintext(str(tmp_path), e, d2, beta=1.0, volume=64)
+    err = open(tmp_path / "energy_error.dat").read().split()
+    assert len(err) == 4 and all("e" in x for x in err)
+    assert float(err[0]) == rep["energy"]["stats"][0] and float(err[1]) == pytest.approx(rep["energy"]["stats"][1], rel=1e-6)
+    table = np.loadtxt(tmp_path / "cv_binning.dat")
+    assert table.shape == (len(rep["cv"]["binning"]), 5)
+    assert table[0, 0] == 256 and table[1, 0] == 128
