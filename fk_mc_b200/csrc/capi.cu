@@ -176,7 +176,7 @@ int fkmc_destroy(fkmc_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     fkmc_profile_resolve(ctx);
     fkmc_chain_free(ctx);
-    cudaFree(ctx->d_AB); cudaFree(ctx->d_kpm_steps);
+    cudaFree(ctx->d_AB); cudaFree(ctx->d_kpm_steps); cudaFree(ctx->d_s1_scratch);
     cudaFree(ctx->d_nbr_idx); cudaFree(ctx->d_nbr_val); cudaFree(ctx->d_A); cudaFree(ctx->d_W); cudaFree(ctx->d_d);
     cudaFree(ctx->d_e); cudaFree(ctx->d_tau); cudaFree(ctx->d_evals); cudaFree(ctx->d_out); cudaFree(ctx->d_f);
     cudaFree(ctx->d_flag); cudaFree(ctx->d_moments); cudaFree(ctx->d_ab); cudaFree(ctx->d_aux);

@@ -73,6 +73,8 @@ struct fkmc_ctx {
     double* d_A = nullptr;      // [max_batch][N][N] dense Hamiltonians (column-major, lower triangle live)
     double* d_W = nullptr;      // [max_batch][N][NB] panel workspace
     double* d_AB = nullptr;     // [max_batch][9][N] band storage of the two-stage reduction
+    double* d_s1_scratch = nullptr;  // sy2sb: fragment-ordered panel records, one slot per matrix
+    size_t s1_scratch_cap = 0;       // doubles
     int tridiag_mode = 2;       // 1: one-stage blocked sytrd, 2: sy2sb + sb2st
     int kpm_force_generic = 0;  // 1: always use the full-lattice-vector KPM kernel (for cross-checks)
     double* d_d = nullptr;      // [max_batch][N]
@@ -135,6 +137,7 @@ int fkmc_launch_sytrd(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_d, dou
 int fkmc_launch_sy2sb(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_AB);
 int fkmc_launch_sb2st(fkmc_ctx* ctx, const double* d_AB, int N, int B, double* d_d, double* d_e);
 size_t fkmc_sy2sb_smem(int N);
+size_t fkmc_sy2sb_scratch(int N);
 size_t fkmc_sb2st_smem(int N);
 int fkmc_launch_sy2sb_tiled(fkmc_ctx* ctx, double* d_At, int N, int B, double* d_AB);
 int fkmc_launch_build_h_tiled(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double* d_At);

@@ -2,25 +2,34 @@
 // half-bandwidth 8, one CTA (8 warps) per matrix, every O(N^3) flop on the FP64 tensor cores.
 //
 // Together with sb2st.cu this replaces the tridiagonalisation stage of Eigen::SelfAdjointEigenSolver
-// as called from configuration_t::calc_ed (src/configuration.cpp:212-213).  For block column k
-// (columns k0..k0+7, trailing rows r0 = k0+8 .. N-1, m = N - r0):
-//   1. Householder QR of the m x 8 panel in shared memory  ->  V (unit lower trapezoidal), tau, R
-//   2. T (8x8, compact WY: Q = I - V T V^T) from the Gram matrix V^T V (DMMA)
-//   3. Y0 = A22 V          -- SYMM over the stored lower triangle in 32x32 tiles
-//   4. Y = Y0 T,  X = V^T Y (DMMA),  Z = Y - 1/2 V (T^T X)
-//   5. A22 -= V Z^T + Z V^T  -- rank-16 SYR2K on the lower triangle
-// Steps 3 and 5 stream the trailing matrix tile by tile: every warp owns a 32x32 shared-memory tile
-// buffer that is filled by bulk asynchronous copies (cp.async.bulk + mbarrier transaction counts, one
-// 256-byte column per lane -- SASS UBLKCP) and, in step 5, drained by bulk stores, so the tensor-core
-// warps never hold global loads in registers.  DMMA fragments are read from the tile with a column
-// stride == 4 (mod 16) doubles, which is conflict-free for both the direct and the transposed operand.
-// In step 3 the tile tasks are paired cyclically ({a, a-s}, s = 0..nt/2): a warp keeps the rows of
-// its own tiles in registers for the whole pass and adds the partner rows straight into shared
-// memory -- in one step all partner tiles are distinct, so no atomics are needed.
+// as called from configuration_t::calc_ed (src/configuration.cpp:212-213).
+//
+// Look-ahead formulation: the trailing matrix is streamed through the SM ONCE per block column (one read,
+// one write) instead of three times.  For block column k (columns k0..k0+7, trailing rows r0 = k0+8..N-1):
+//   build   P_k = columns k0..k0+7 of A with the rank-16 update of block column k-1 applied on the fly
+//           (thin, CUDA cores); the finished 8x8 diagonal block goes to band storage
+//   QR      Householder QR of the m x 8 panel in shared memory -> V_k (unit lower trapezoidal), tau, R;
+//           T_k (compact WY: Q = I - V T V^T) from the DMMA Gram matrix V^T V
+//   export  V_k to global scratch in DMMA-fragment order (stays in L2: 320 KB per CTA)
+//   pass    for every lower 32x32 tile of the trailing matrix, ONE visit:
+//               A_tile -= V_{k-1} Z_{k-1}^T + Z_{k-1} V_{k-1}^T      (rank-16 SYR2K, DMMA)
+//               store the tile
+//               Y0_k(rows R) += A_tile V_k(rows C),  Y0_k(rows C) += A_tile^T V_k(rows R)   (SYMM, DMMA)
+//   final   Y = Y0 T,  X = V^T Y (DMMA),  Z_k = Y - 1/2 V (T^T X);  export Z_k in fragment order
+// The DMMA operands of the pass come from the fragment-ordered records in global memory (128-bit loads, L2 hits),
+// which frees the shared memory the panels used to occupy for tile buffers: every warp owns TWO 8 KB tile
+// buffers (16 tiles in flight per SM), filled by bulk asynchronous copies (cp.async.bulk + mbarrier transaction
+// counts -- SASS UBLKCP) and drained by bulk stores, so the tensor-core warps never hold global loads of matrix
+// data in registers and the next tile is in flight while the current one is in the tensor pipe.
+// SYMM tile tasks are paired cyclically ({a, a-s}, s = 0..nt/2): a warp keeps the rows of its own tiles in
+// registers for the whole pass and adds the partner rows straight into shared memory -- in one step all partner
+// tiles are distinct, so no atomics are needed.
 // R and the diagonal blocks are emitted in band storage AB[d][c] = A(c+d, c), d = 0..8.
+//
 // Matrix layout ("tiled"): only the lower-triangular 32x32 tiles are stored, tile (R, C), R >= C, at offset
-// (R(R+1)/2 + C) * 1152 doubles, column-major inside the tile with the same padded column stride of 36 doubles that the
-// shared-memory copy uses -- so a tile moves with ONE 9216-byte bulk copy in each direction and lands bank-conflict-free.
+// (R(R+1)/2 + C) * 1024 doubles, column-major inside the tile with an XOR swizzle of the row index
+// (element (r, c) at c*32 + (r ^ 4*((c ^ c>>2) & 3))) -- unpadded, so a tile moves with ONE 8192-byte bulk copy in each
+// direction, and all three fragment patterns (accumulator, direct operand, transposed operand) are bank-conflict-free.
 // The tile grid is fixed in global coordinates; the panels V, Y, Z are indexed by global row and are zero above the
 // trailing block, which makes the partial edge tiles of each block column come out right without masks.
 // Requires N % 8 == 0 and N <= 1024.
@@ -31,23 +40,15 @@
 namespace {
 
 constexpr int NB = 8;
-constexpr int NW = 8;       // warps per CTA
-constexpr int TS = 36;      // tile column stride in doubles (== 4 mod 16)
-constexpr int TILE = 32 * TS;
-constexpr int MAXOWN = 4;   // owned row tiles per warp: N <= 1024 -> nt <= 32 -> 4
+constexpr int NW = 8;        // warps per CTA
+constexpr int TILE = 1024;   // doubles per tile (no padding)
+constexpr int MAXOWN = 4;    // owned row tiles per warp: N <= 1024 -> nt <= 32 -> 4
+constexpr int QR = 4;        // panel rows per thread during the QR: m <= 1016 -> 4
 
-struct s1_smem {
-    double* V;    // [8][ld] column-major panel / reflectors
-    double* Y;    // [8][ld] Y0 -> Y -> Z
-    double* G;    // [64] Gram / X / scratch
-    double* Tm;   // [64] T
-    double* M2;   // [64] T^T X
-    double* tau;  // [8]
-    double* red;  // [NW*64 + 72]
-    double* tile; // [NW][TILE]
-    uint64_t* bar; // [NW]
-    int ld;
-};
+// column swizzle of tile row r: 4 * bitswap2(r & 3)
+__host__ __device__ __forceinline__ int csw(int r) { return ((r & 1) << 3) | ((r & 2) << 1); }
+// position of element (r, c) inside a tile (row-major, swizzled columns)
+__host__ __device__ __forceinline__ int tix(int r, int c) { return (r << 5) + (c ^ csw(r)); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -56,6 +57,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -84,49 +88,38 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ size_t tile_off(int R, int C) { return ((size_t)R * (R + 1) / 2 + C) * TILE; }
+// DMMA without the volatile qualifier: a pure function of its operands, so ptxas may interleave independent accumulators
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
-// Issue the bulk load of global tile (R, C) into this warp's buffer (whole warp calls).
+__host__ __device__ __forceinline__ size_t tile_off(int R, int C) { return ((size_t)R * (R + 1) / 2 + C) * TILE; }
+// element (i, j), i >= j, of the tiled matrix
+__device__ __forceinline__ size_t elem_off(int i, int j) { return tile_off(i >> 5, j >> 5) + (size_t)tix(i & 31, j & 31); }
+
+// Issue the bulk load of global tile (R, C) into a tile buffer (whole warp calls).
 __device__ __forceinline__ void tile_load(double* buf, uint64_t* bar, const double* __restrict__ At, int R, int C, int lane) {
-    __syncwarp();  // every lane is done reading the previous contents
+    __syncwarp();  // every lane is done with the previous contents
     if (lane == 0) {
         mbar_expect_tx(bar, (uint32_t)(TILE * 8));
         bulk_g2s(buf, At + tile_off(R, C), (uint32_t)(TILE * 8), bar);
     }
 }
 
-// element (i, j), i >= j, of the tiled matrix
-__device__ __forceinline__ size_t elem_off(int i, int j) { return tile_off(i >> 5, j >> 5) + (size_t)(j & 31) * TS + (i & 31); }
-
-// block-wide sum of K values per thread; result broadcast to all threads via out[0..K)
-template <int K>
-__device__ __forceinline__ void block_sum_vec(double (&v)[K], double* red, double* out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const double s = warp_sum(v[k]);
-        if (lane == 0) red[warp * K + k] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < K) {
-        double s = 0.0;
-        for (int w = 0; w < nw; ++w) s += red[w * K + threadIdx.x];
-        out[threadIdx.x] = s;
-    }
-    __syncthreads();
-}
-
-// C(8x8) = P^T Q over rows [0, m): P, Q column-major [8][ld] in shared memory.  Each warp accumulates a
+// C(8x8) = P^T Q over rows [0, m): P, Q column-major [8][ld] (shared or global memory).  Each warp accumulates a
 // slice of rows with DMMA, partial tiles are summed through red[nwarps][64]; result in out[a*8 + c].
-__device__ __forceinline__ void gram8(const double* P, const double* Q, int ld, int m, double* red, double* out) {
+__device__ __forceinline__ void gram8(const double* P, int ldp, const double* Q, int ldq, int m, double* red, double* out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, g = lane >> 2, t = lane & 3;
-    double c0 = 0.0, c1 = 0.0;
-    for (int r = 4 * warp; r < m; r += 4 * nw) {
+    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+    int r = 4 * warp;
+    for (; r + 4 * nw < m; r += 8 * nw) {
         // A(g, k=t) = P[r+t][g], B(k=t, n=g) = Q[r+t][g]   (rows >= m are zero-padded)
-        dmma884(c0, c1, P[g * ld + r + t], Q[g * ld + r + t]);
+        dmma(c0, c1, P[g * ldp + r + t], Q[g * ldq + r + t]);
+        dmma(d0, d1, P[g * ldp + r + 4 * nw + t], Q[g * ldq + r + 4 * nw + t]);
     }
-    red[warp * 64 + g * 8 + 2 * t] = c0;
-    red[warp * 64 + g * 8 + 2 * t + 1] = c1;
+    if (r < m) dmma(c0, c1, P[g * ldp + r + t], Q[g * ldq + r + t]);
+    red[warp * 64 + g * 8 + 2 * t] = c0 + d0;
+    red[warp * 64 + g * 8 + 2 * t + 1] = c1 + d1;
     __syncthreads();
     if (threadIdx.x < 64) {
         double s = 0.0;
@@ -136,40 +129,110 @@ __device__ __forceinline__ void gram8(const double* P, const double* Q, int ld, 
     __syncthreads();
 }
 
-// SYMM on one staged tile.  Stored tile (Rmax, Cmin), S = tile contents:
-//   accR (rows of Rmax) += S V[Cmin rows];   accC (rows of Cmin) += S^T V[Rmax rows]   (off-diagonal tiles)
-//   accR += sym(S) V[rows]                                                            (diagonal tiles)
-__device__ __forceinline__ void symm_tile(const double* __restrict__ Tb, bool diag, int rb0, int cb0, const double* __restrict__ V, int ld,
-                                          int lane, double (&accR)[4][2], double (&accC)[4][2]) {
+// one 64-byte fragment record (8 doubles per lane) from global memory
+struct rec8 {
+    double v[8];
+};
+__device__ __forceinline__ rec8 load_rec(const double* __restrict__ base, int R, int lane) {
+    const double2* p = reinterpret_cast<const double2*>(base + ((size_t)(R * 32 + lane) << 3));
+    rec8 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double2 x = p[i];
+        r.v[2 * i] = x.x;
+        r.v[2 * i + 1] = x.y;
+    }
+    return r;
+}
+
+// One visit of a staged tile S = (Rmax, Cmin):
+//   S -= V_R Z_C^T + Z_R V_C^T                      (upd; records x[4q + blk] = X[32T + 8 blk + g][4q + t])
+//   accR (rows of Rmax) += S V'[Cmin rows]          (accumulator fragments reused as A operands; vCp[2 blk + h] = V'[32C + 8 blk + 2t + h][g])
+// Diagonal tiles hold both triangles, so this is all they need.
+template <bool UPD>
+__device__ __forceinline__ void tile_update_symm(double* __restrict__ Tb, const rec8& uvR, const rec8& uzR, const rec8& uvC, const rec8& uzC,
+                                                 const rec8& vCp, int lane, double (&accR)[4][2]) {
     const int g = lane >> 2, t = lane & 3;
+    const int cs = csw(g);
 #pragma unroll
-    for (int cb = 0; cb < 4; ++cb) {
-        const int c8 = 8 * cb;
-        const double bv0 = V[g * ld + cb0 + c8 + t], bv1 = V[g * ld + cb0 + c8 + 4 + t];
+    for (int half = 0; half < 2; ++half) {
+        double acc[4][2][2];
 #pragma unroll
-        for (int rb = 0; rb < 4; ++rb) {
-            const int r8 = 8 * rb;
-            if (diag) {
-                const int r = r8 + g, c = c8 + t, c2 = c8 + 4 + t;
-                const double a0 = Tb[min(r, c) * TS + max(r, c)];
-                const double a1 = Tb[min(r, c2) * TS + max(r, c2)];
-                dmma884(accR[rb][0], accR[rb][1], a0, bv0);
-                dmma884(accR[rb][0], accR[rb][1], a1, bv1);
-            } else {
-                // contribution 1: A(g, k) = S[g][4ks + t];  contribution 2: A(g, k) = S[4ks + t][g], B(k, n) = V[rb0 + r8 + 4ks + t][n = g]
-                const double a0 = Tb[(c8 + t) * TS + r8 + g], a1 = Tb[(c8 + 4 + t) * TS + r8 + g];
-                const double s0 = Tb[(c8 + g) * TS + r8 + t], s1 = Tb[(c8 + g) * TS + r8 + 4 + t];
-                dmma884(accR[rb][0], accR[rb][1], a0, bv0);
-                dmma884(accR[rb][0], accR[rb][1], a1, bv1);
-                dmma884(accC[cb][0], accC[cb][1], s0, V[g * ld + rb0 + r8 + t]);
-                dmma884(accC[cb][0], accC[cb][1], s1, V[g * ld + rb0 + r8 + 4 + t]);
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int yy = 0; yy < 2; ++yy) {
+                const double2 v = *reinterpret_cast<const double2*>(Tb + ((8 * x + g) << 5) + ((8 * (2 * half + yy) + 2 * t) ^ cs));
+                acc[x][yy][0] = v.x;
+                acc[x][yy][1] = v.y;
             }
+        if (UPD) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int yy = 0; yy < 2; ++yy) dmma(acc[x][yy][0], acc[x][yy][1], -uvR.v[4 * q + x], uzC.v[4 * q + 2 * half + yy]);
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int yy = 0; yy < 2; ++yy) dmma(acc[x][yy][0], acc[x][yy][1], -uzR.v[4 * q + x], uvC.v[4 * q + 2 * half + yy]);
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int yy = 0; yy < 2; ++yy)
+                    *reinterpret_cast<double2*>(Tb + ((8 * x + g) << 5) + ((8 * (2 * half + yy) + 2 * t) ^ cs)) = make_double2(acc[x][yy][0], acc[x][yy][1]);
         }
+#pragma unroll
+        for (int yy = 0; yy < 2; ++yy)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int x = 0; x < 4; ++x) dmma(accR[x][0], accR[x][1], acc[x][yy][h], vCp.v[2 * (2 * half + yy) + h]);
     }
 }
 
+// accC (rows of Cmin) += S^T V'[Rmax rows]   (off-diagonal tiles; vRq[2 blk + h] = V'[32R + 8 blk + 4h + t][g])
+__device__ __forceinline__ void tile_symm_t(const double* __restrict__ Tb, const rec8& vRq, int lane, double (&accC)[4][2]) {
+    const int g = lane >> 2, t = lane & 3;
+    const int cs = csw(t);
+#pragma unroll
+    for (int rb = 0; rb < 4; ++rb)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const double* row = Tb + ((8 * rb + 4 * h + t) << 5);
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) dmma(accC[cb][0], accC[cb][1], row[(8 * cb + g) ^ cs], vRq.v[2 * rb + h]);
+        }
+}
+
+// next task (s, o) of this warp in the cyclic pairing schedule; false when the pass is exhausted
+__device__ __forceinline__ bool next_task(int& s, int& o, int warp, int nt, int smax) {
+    ++o;
+    while (s <= smax) {
+        const int lim = (s > 0 && 2 * s == nt) ? (nt >> 1) : nt;
+        if (warp + NW * o < lim) return true;
+        ++s;
+        o = 0;
+    }
+    return false;
+}
+__device__ __forceinline__ void task_tile(int s, int o, int warp, int nt, int& a, int& Rmax, int& Cmin) {
+    a = warp + NW * o;
+    int p = a - s;
+    if (p < 0) p += nt;
+    Rmax = max(a, p);
+    Cmin = min(a, p);
+}
+
+// scratch layout per matrix (doubles): Vcm [8][ld] | recVp [NT][32][8] | recVq [NT][32][8] | recAV [2][NT][32][8] | recAZ [NT][32][8]
+__host__ __device__ __forceinline__ size_t scratch_doubles(int N) {
+    const size_t mp = ((N + 31) / 32) * 32, nt = mp / 32;
+    return 8 * (mp + 4) + 32 + 5 * nt * 256;
+}
+
 __global__ void __launch_bounds__(NW * 32, 1)
-sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restrict__ AB_all) {
+sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restrict__ AB_all, double* __restrict__ scr_all) {
     extern __shared__ __align__(128) double smem[];
     const int tid = threadIdx.x, T = NW * 32, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -177,182 +240,352 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
     double* At = A_all + (size_t)b * a_stride;  // tiled lower-triangular storage of this matrix
     double* AB = AB_all + (size_t)b * (NB + 1) * N;
     const int mp = ((N + 31) / 32) * 32, NT = mp >> 5;
-    s1_smem S0;
-    S0.ld = mp + 4;  // == 4 (mod 16): both fragment patterns are 2-way (optimal) on the panels
-    S0.V = smem;
-    S0.Y = S0.V + 8 * S0.ld;
-    S0.G = S0.Y + 8 * S0.ld;
-    S0.Tm = S0.G + 64;
-    S0.M2 = S0.Tm + 64;
-    S0.tau = S0.M2 + 64;
-    S0.red = S0.tau + 8;
-    S0.tile = S0.red + NW * 64 + 72;
-    S0.bar = reinterpret_cast<uint64_t*>(S0.tile + NW * TILE);
-    const int ld = S0.ld;
-    double* Tb = S0.tile + warp * TILE;
-    uint64_t* bar = S0.bar + warp;
-    uint32_t parity = 0;
+    const int ld = mp + 4;    // V staging (X) and its global copy
+    const int ldy = mp + 18;  // == 2 (mod 16): the accumulator-fragment adds into Y are bank-conflict-free
+    const int xsz = max(8 * ld, NW * TILE);
+    // shared memory: tile buffers 0 | X (V staging around the QR, tile buffers 1 during the pass) | Y | small stuff
+    double* TB0 = smem;
+    double* X = TB0 + NW * TILE;
+    double* Y = X + xsz;
+    double* G = Y + 8 * ldy;
+    double* Tm = G + 64;
+    double* M2 = Tm + 64;
+    double* red = M2 + 64;                      // [NW*64] gram partials; QR: [2][NW][8] partials + [2][8] pivot row
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + NW * 64);
+    uint64_t* stepbar = bars + 2 * NW;
+    // global scratch
+    double* Vcm = scr_all + (size_t)b * scratch_doubles(N);
+    double* recVp = Vcm + 8 * ld + 32;
+    double* recVq = recVp + NT * 256;
+    double* recAV = recVq + NT * 256;
+    double* recAZ = recAV + 2 * NT * 256;
 
-    for (int i = tid; i < NW * TILE; i += T) S0.tile[i] = 0.0;
-    if (tid < NW) mbar_init(S0.bar + tid, 1);
+    double* buf0 = TB0 + warp * TILE;
+    double* buf1 = X + warp * TILE;
+    uint64_t* bar0 = bars + 2 * warp;
+    uint64_t* bar1 = bar0 + 1;
+    uint32_t ph0 = 0, ph1 = 0;
+    uint32_t steps_done = 0;  // completed phases of stepbar (same in every warp)
+    int par = 0;
+
+    for (int i = tid; i < 8 * ldy; i += T) Y[i] = 0.0;
+    for (int i = tid; i < xsz; i += T) X[i] = 0.0;
+    if (tid < 2 * NW) mbar_init(bars + tid, 1);
+    if (tid == 0) mbar_init(stepbar, NW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
     for (int k0 = 0; k0 < N; k0 += NB) {
         const int r0 = k0 + NB, m = N - r0;
-        const s1_smem SG = S0;  // panels indexed by global row (tile loops)
-        s1_smem S = S0;         // panels indexed by local row i = global row - r0 (QR and the thin updates)
-        S.V = S0.V + r0;
-        S.Y = S0.Y + r0;
-        // ---- emit the (final) diagonal block k0 into band storage ----
-        if (tid < 64) {
-            const int j = tid & 7, dd = tid >> 3;
-            if (j + dd < NB && k0 + j + dd < N) AB[(size_t)dd * N + k0 + j] = At[elem_off(k0 + j + dd, k0 + j)];
-        }
-        if (m <= 0) break;
-        // ---- 1. panel -> shared (global row index; zero above the trailing block), Householder QR ----
-        for (int idx = tid; idx < 8 * ld; idx += T) {
-            const int j = idx / ld, gi = idx % ld;
-            SG.V[idx] = (gi >= r0 && gi < N) ? At[elem_off(gi, k0 + j)] : 0.0;
-            SG.Y[idx] = 0.0;
+        // ---- build the panel in registers: columns k0..k0+7 of A, rows >= k0, minus the pending update of block column k-1.
+        //      Thread tid owns local rows i = tid + 256 q (global row r0 + i); threads 0..7 also finish the diagonal block. ----
+        if (k0 > 0 && tid < 64) {
+            const int c = tid >> 3, j = tid & 7;  // rows k0+c of V_{k-1}, Z_{k-1}
+            G[tid] = Vcm[j * ld + k0 + c];
+            M2[tid] = Y[j * ldy + k0 + c];
         }
         __syncthreads();
-        const int nref = min(NB, m);
-        bool any = false;
+        double p[QR][NB];
+        {
+            double dg[NB];
+#pragma unroll
+            for (int c = 0; c < NB; ++c) dg[c] = 0.0;
+            const int gd = k0 + tid;  // diagonal-block row (tid < 8)
+            if (tid < NB) {
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (c <= tid) dg[c] = __ldcg(At + elem_off(gd, k0 + c));
+            }
+#pragma unroll
+            for (int q = 0; q < QR; ++q) {
+                const int gi = r0 + tid + T * q;
+#pragma unroll
+                for (int c = 0; c < NB; ++c) p[q][c] = (gi < N) ? __ldcg(At + elem_off(gi, k0 + c)) : 0.0;
+            }
+            if (k0 > 0) {
+#pragma unroll
+                for (int q = 0; q < QR; ++q) {
+                    const int gi = r0 + tid + T * q;
+                    if (gi < N) {
+                        double vi[NB], zi[NB];
+#pragma unroll
+                        for (int j = 0; j < NB; ++j) {
+                            vi[j] = Vcm[j * ld + gi];
+                            zi[j] = Y[j * ldy + gi];
+                        }
+#pragma unroll
+                        for (int c = 0; c < NB; ++c) {
+                            double s = 0.0;
+#pragma unroll
+                            for (int j = 0; j < NB; ++j) s = fma(vi[j], M2[c * 8 + j], fma(zi[j], G[c * 8 + j], s));
+                            p[q][c] -= s;
+                        }
+                    }
+                }
+                if (tid < NB) {
+                    double vi[NB], zi[NB];
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        vi[j] = Vcm[j * ld + gd];
+                        zi[j] = Y[j * ldy + gd];
+                    }
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int j = 0; j < NB; ++j) s = fma(vi[j], M2[c * 8 + j], fma(zi[j], G[c * 8 + j], s));
+                        dg[c] -= s;
+                    }
+                }
+            }
+            // finished diagonal block -> band storage
+            if (tid < NB) {
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (c <= tid) AB[(size_t)(tid - c) * N + k0 + c] = dg[c];
+            }
+        }
+        if (m <= 0) break;
+        // ---- Householder QR of the panel, rows in registers, one block barrier per column ----
+        double tauv[NB];
+#pragma unroll
         for (int j = 0; j < NB; ++j) {
-            double tau = 0.0;
-            if (j < nref && m - j >= 2) {
-                // one fused reduction: pw[c] = sum_{i>j} P[i][j] P[i][c], c >= j  (c = j gives the tail norm)
+            double* rbuf = red + (j & 1) * (NW * 8 + 8);
+            tauv[j] = 0.0;
+            if (m - j >= 2) {  // uniform
+                // pw[c] = sum_{i>j} P[i][j] P[i][c], c >= j  (c = j gives the tail norm)
                 double pw[NB];
 #pragma unroll
                 for (int c = 0; c < NB; ++c) pw[c] = 0.0;
-                for (int i = j + 1 + tid; i < m; i += T) {
-                    const double pj = S.V[j * ld + i];
 #pragma unroll
-                    for (int c = 0; c < NB; ++c)
-                        if (c >= j) pw[c] = fma(pj, S.V[c * ld + i], pw[c]);
+                for (int q = 0; q < QR; ++q) {
+                    const int i = tid + T * q;
+                    if (i > j && i < m) {
+#pragma unroll
+                        for (int c = 0; c < NB; ++c)
+                            if (c >= j) pw[c] = fma(p[q][j], p[q][c], pw[c]);
+                    }
                 }
-                block_sum_vec<NB>(pw, S.red, S.G);
-                const double tail2 = S.G[j];
-                const double x0 = S.V[j * ld + j];
-                double beta = x0, inv = 0.0;
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (c >= j) {
+                        const double s = warp_sum(pw[c]);
+                        if (lane == 0) rbuf[warp * 8 + c] = s;
+                    }
+                if (tid == j) {
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) rbuf[NW * 8 + c] = p[0][c];  // pivot row j: x0 and P[j][c]
+                }
+                __syncthreads();
+                double Gs[NB];
+#pragma unroll
+                for (int c = 0; c < NB; ++c) {
+                    Gs[c] = 0.0;
+                    if (c >= j) {
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) Gs[c] += rbuf[w * 8 + c];
+                    }
+                }
+                const double tail2 = Gs[j];
+                const double x0 = rbuf[NW * 8 + j];
+                double beta = x0, inv = 0.0, tau = 0.0;
                 if (tail2 > DBL_MIN) {
                     beta = sqrt(fma(x0, x0, tail2));
                     if (x0 >= 0.0) beta = -beta;
                     inv = 1.0 / (x0 - beta);
                     tau = (beta - x0) / beta;
                 }
+                tauv[j] = tau;
                 // w_c = tau (P[j][c] + inv * G[c]);  rows i > j: v_i = P[i][j] inv, P[i][c] -= v_i w_c
                 double w[NB];
 #pragma unroll
-                for (int c = 0; c < NB; ++c) w[c] = (c > j) ? tau * fma(inv, S.G[c], S.V[c * ld + j]) : 0.0;
-                __syncthreads();  // all threads hold x0, G and row j before they change
-                for (int i = j + 1 + tid; i < m; i += T) {
-                    const double vi = S.V[j * ld + i] * inv;
-                    S.V[j * ld + i] = vi;
+                for (int c = 0; c < NB; ++c) w[c] = (c > j) ? tau * fma(inv, Gs[c], rbuf[NW * 8 + c]) : 0.0;
+#pragma unroll
+                for (int q = 0; q < QR; ++q) {
+                    const int i = tid + T * q;
+                    if (i > j && i < m) {
+                        const double vi = p[q][j] * inv;
+                        p[q][j] = vi;
+#pragma unroll
+                        for (int c = 0; c < NB; ++c)
+                            if (c > j) p[q][c] = fma(-vi, w[c], p[q][c]);
+                    }
+                }
+                if (tid == j) {  // row j itself (v_j = 1)
 #pragma unroll
                     for (int c = 0; c < NB; ++c)
-                        if (c > j) S.V[c * ld + i] = fma(-vi, w[c], S.V[c * ld + i]);
+                        if (c > j) p[0][c] -= w[c];
+                    p[0][j] = beta;
                 }
-                if (tid < NB && tid > j) S.V[tid * ld + j] -= w[tid];  // row j itself (v_j = 1)
-                if (tid == 0) S.V[j * ld + j] = beta;
-                __syncthreads();
             }
-            if (tid == 0) S.tau[j] = tau;
-            any = any || (tau != 0.0);
         }
-        __syncthreads();
-        // R (upper triangle of the top 8x8) -> band storage; then make V explicit (unit lower trapezoidal)
-        if (tid < 64) {
-            const int c = tid >> 3, i = tid & 7;
-            if (i <= c && i < m) AB[(size_t)(NB + i - c) * N + k0 + c] = S.V[c * ld + i];
+        // R (upper triangle of the top 8x8) -> band storage; V explicit (unit lower trapezoidal) -> X staging
+        if (tid < NB && tid < m) {
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+                if (tid <= c) AB[(size_t)(NB + tid - c) * N + k0 + c] = p[0][c];
+                if (tid < c) p[0][c] = 0.0;
+                else if (tid == c) p[0][c] = 1.0;
+            }
         }
-        __syncthreads();
-        if (tid < 64) {
-            const int c = tid >> 3, i = tid & 7;
-            if (i < c) S.V[c * ld + i] = 0.0;
-            else if (i == c) S.V[c * ld + i] = (i < m) ? 1.0 : 0.0;
+#pragma unroll
+        for (int q = 0; q < QR; ++q) {
+            const int gi = r0 + tid + T * q;
+            if (gi < ld) {
+#pragma unroll
+                for (int c = 0; c < NB; ++c) X[c * ld + gi] = (gi < N) ? p[q][c] : 0.0;
+            }
         }
+        // rows above the trailing block are zero in X: they were zeroed at start-up / by the previous export and only rows >= r0 are written
         __syncthreads();
-        if (!any) continue;  // nothing to apply (uniform across the block)
-        // ---- 2. T from the Gram matrix: T(0:j, j) = -tau_j T(0:j,0:j) G(0:j, j) ----
-        gram8(S.V, S.V, ld, m, S.red, S.G);
-        if (tid < 64) S.Tm[tid] = 0.0;
-        __syncthreads();
-        for (int j = 0; j < NB; ++j) {
-            if (tid < j) {
+        // ---- T from the Gram matrix: T(0:j, j) = -tau_j T(0:j,0:j) G(0:j, j); lane i of warp 0 owns row i ----
+        gram8(X + r0, ld, X + r0, ld, m, red, G);
+        if (tid < NB) {
+            double tr[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
                 double s = 0.0;
-                for (int c = tid; c < j; ++c) s += S.Tm[tid * 8 + c] * S.G[c * 8 + j];
-                S.Tm[tid * 8 + j] = -S.tau[j] * s;
-            } else if (tid == j) {
-                S.Tm[j * 8 + j] = S.tau[j];
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (c < j) s = (c >= tid) ? fma(tr[c], G[c * 8 + j], s) : s;
+                tr[j] = (j == tid) ? tauv[j] : ((j > tid) ? -tauv[j] * s : 0.0);
             }
-            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < NB; ++j) Tm[tid * 8 + j] = tr[j];
         }
-        // ---- 3. Y0 = A22 V: cyclic pairing of tile tasks, own rows in registers, partner rows in shared memory ----
+        // ---- export V: column-major copy + the fragment orders; clear Y for the new Y0; clear the X rows that die ----
         const int T0 = r0 >> 5, nt = NT - T0;  // tiles T0..NT-1 of the fixed global grid touch the trailing block
+        for (int i = tid; i < 8 * ld; i += T) Vcm[i] = X[i];
+        for (int i = tid; i < 8 * ldy; i += T) Y[i] = 0.0;
         {
+            double* rA = recAV + (size_t)par * NT * 256;
+            for (int idx = T0 * 256 + tid; idx < NT * 256; idx += T) {
+                const int e = idx & 7, ln = (idx >> 3) & 31, R = idx >> 8, gg = ln >> 2, tt = ln & 3;
+                // SYMM B operands: V[32R + 8 blk + 2t + h][g] (pair order) and V[32R + 8 blk + 4h + t][g] (quad order), e = 2 blk + h
+                recVp[idx] = X[gg * ld + 32 * R + 8 * (e >> 1) + 2 * tt + (e & 1)];
+                recVq[idx] = X[gg * ld + 32 * R + 8 * (e >> 1) + 4 * (e & 1) + tt];
+                // SYR2K A/B operand: V[32R + 8 blk + g][4q + t], e = 4q + blk
+                rA[idx] = X[(4 * (e >> 2) + tt) * ld + 32 * R + 8 * (e & 3) + gg];
+            }
+        }
+        fence_async_smem();  // generic-proxy accesses to X are ordered before the bulk copies that reuse it
+        __syncthreads();
+        // ---- the pass: pending SYR2K of block column k-1 fused with the SYMM of block column k ----
+        {
+            const bool upd = k0 > 0;
+            const double* uV = recAV + (size_t)(par ^ 1) * NT * 256;
             double own[MAXOWN][4][2];
 #pragma unroll
             for (int o = 0; o < MAXOWN; ++o)
 #pragma unroll
                 for (int x = 0; x < 4; ++x) own[o][x][0] = own[o][x][1] = 0.0;
             const int smax = nt >> 1;
-            // prefetch the first task of this warp (its diagonal tile)
-            if (warp < nt) tile_load(Tb, bar, At, T0 + warp, T0 + warp, lane);
+            // task cursors: c = current, n1 = next; loads are issued two tasks ahead
+            int cs = 0, co = -1;
+            bool cv = next_task(cs, co, warp, nt, smax);
+            int n1s = cs, n1o = co;
+            bool n1v = cv && next_task(n1s, n1o, warp, nt, smax);
+            int slot = 0;
+            if (cv) {
+                int a, R, C;
+                task_tile(cs, co, warp, nt, a, R, C);
+                tile_load(buf0, bar0, At, T0 + R, T0 + C, lane);
+            }
+            if (n1v) {
+                int a, R, C;
+                task_tile(n1s, n1o, warp, nt, a, R, C);
+                tile_load(buf1, bar1, At, T0 + R, T0 + C, lane);
+            }
             for (int s = 0; s <= smax; ++s) {
-                const int lim = (s > 0 && 2 * s == nt) ? (nt >> 1) : nt;
+                bool waited = (s == 0);
 #pragma unroll
                 for (int o = 0; o < MAXOWN; ++o) {
-                    const int a = warp + NW * o;
-                    if (a < lim) {
-                        int p = a - s;
-                        if (p < 0) p += nt;
+                    if (cv && cs == s && co == o) {
+                        int a, Rmax, Cmin;
+                        task_tile(s, o, warp, nt, a, Rmax, Cmin);
                         const bool diag = (s == 0);
-                        const int Rmax = max(a, p), Cmin = min(a, p);
-                        mbar_wait(bar, parity);
-                        parity ^= 1;
+                        double* Tb = slot ? buf1 : buf0;
+                        uint64_t* bar = slot ? bar1 : bar0;
+                        // operand records do not depend on the tile contents: fetch them while the copy is in flight
+                        rec8 uvR, uzR, uvC, uzC;
+                        if (upd) {
+                            uvR = load_rec(uV, T0 + Rmax, lane);
+                            uzR = load_rec(recAZ, T0 + Rmax, lane);
+                            uvC = load_rec(uV, T0 + Cmin, lane);
+                            uzC = load_rec(recAZ, T0 + Cmin, lane);
+                        }
+                        const rec8 vCp = load_rec(recVp, T0 + Cmin, lane);
+                        if (slot) {
+                            mbar_wait(bar, ph1);
+                            ph1 ^= 1;
+                        } else {
+                            mbar_wait(bar, ph0);
+                            ph0 ^= 1;
+                        }
                         double accR[4][2], accC[4][2];
 #pragma unroll
                         for (int x = 0; x < 4; ++x) accR[x][0] = accR[x][1] = accC[x][0] = accC[x][1] = 0.0;
-                        symm_tile(Tb, diag, 32 * (T0 + Rmax), 32 * (T0 + Cmin), SG.V, ld, lane, accR, accC);
-                        // prefetch this warp's next task while the results are folded
-                        {
-                            int na = a + NW, ns = s;
-                            const int nlim = lim;
-                            if (na >= nlim) {
-                                ns = s + 1;
-                                na = warp;
-                            }
-                            const int nlim2 = (ns > 0 && 2 * ns == nt) ? (nt >> 1) : nt;
-                            if (ns <= smax && na < nlim2) {
-                                int np = na - ns;
-                                if (np < 0) np += nt;
-                                tile_load(Tb, bar, At, T0 + max(na, np), T0 + min(na, np), lane);
-                            }
+                        if (upd) {
+                            tile_update_symm<true>(Tb, uvR, uzR, uvC, uzC, vCp, lane, accR);
+                            // drain: generic-proxy writes -> async proxy, then one bulk store of the whole tile.  Entries outside the
+                            // trailing block see a zero update (V, Z are zero there).
+                            fence_async_smem();
+                            __syncwarp();
+                            if (lane == 0) bulk_s2g(At + tile_off(T0 + Rmax, T0 + Cmin), Tb, (uint32_t)(TILE * 8));
+                            bulk_commit();
+                        } else {
+                            tile_update_symm<false>(Tb, uvR, uzR, uvC, uzC, vCp, lane, accR);
                         }
-                        // own rows stay in registers; partner rows go to shared memory (distinct tiles within a step)
+                        if (!diag) {
+                            const rec8 vRq = load_rec(recVq, T0 + Rmax, lane);
+                            tile_symm_t(Tb, vRq, lane, accC);
+                        }
+                        // refill this buffer with the task after next once the store has read it
+                        {
+                            int n2s = n1s, n2o = n1o;
+                            const bool n2v = n1v && next_task(n2s, n2o, warp, nt, smax);
+                            if (upd) bulk_wait_read();
+                            if (n2v) {
+                                int a2, R2, C2;
+                                task_tile(n2s, n2o, warp, nt, a2, R2, C2);
+                                tile_load(Tb, bar, At, T0 + R2, T0 + C2, lane);
+                            }
+                            cs = n1s; co = n1o; cv = n1v;
+                            n1s = n2s; n1o = n2o; n1v = n2v;
+                            slot ^= 1;
+                        }
+                        // own rows stay in registers; partner rows go to shared memory (distinct tiles within a step, and every
+                        // warp has finished the adds of the previous step)
                         if (diag || a == Rmax) {
 #pragma unroll
                             for (int x = 0; x < 4; ++x) { own[o][x][0] += accR[x][0]; own[o][x][1] += accR[x][1]; }
                             if (!diag) {
+                                if (!waited) { mbar_wait(stepbar, (steps_done - 1) & 1); waited = true; }
 #pragma unroll
                                 for (int x = 0; x < 4; ++x)
 #pragma unroll
-                                    for (int h = 0; h < 2; ++h) SG.Y[(2 * t + h) * ld + 32 * (T0 + Cmin) + 8 * x + g] += accC[x][h];
+                                    for (int h = 0; h < 2; ++h) Y[(2 * t + h) * ldy + 32 * (T0 + Cmin) + 8 * x + g] += accC[x][h];
                             }
                         } else {
 #pragma unroll
                             for (int x = 0; x < 4; ++x) { own[o][x][0] += accC[x][0]; own[o][x][1] += accC[x][1]; }
+                            if (!waited) { mbar_wait(stepbar, (steps_done - 1) & 1); waited = true; }
 #pragma unroll
                             for (int x = 0; x < 4; ++x)
 #pragma unroll
-                                for (int h = 0; h < 2; ++h) SG.Y[(2 * t + h) * ld + 32 * (T0 + Rmax) + 8 * x + g] += accR[x][h];
+                                for (int h = 0; h < 2; ++h) Y[(2 * t + h) * ldy + 32 * (T0 + Rmax) + 8 * x + g] += accR[x][h];
                         }
                     }
                 }
-                __syncthreads();
+                // this warp's adds of step s are done.  A warp never arrives twice in one phase: it first sees the previous step complete.
+                if (!waited) mbar_wait(stepbar, (steps_done - 1) & 1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(stepbar);
+                ++steps_done;
             }
+            // all bulk stores of this pass must have landed before the next panel is read
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            mbar_wait(stepbar, (steps_done - 1) & 1);  // every warp's partner adds are in
 #pragma unroll
             for (int o = 0; o < MAXOWN; ++o) {
                 const int a = warp + NW * o;
@@ -360,132 +593,74 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
 #pragma unroll
                     for (int x = 0; x < 4; ++x)
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) SG.Y[(2 * t + h) * ld + 32 * (T0 + a) + 8 * x + g] += own[o][x][h];
+                        for (int h = 0; h < 2; ++h) Y[(2 * t + h) * ldy + 32 * (T0 + a) + 8 * x + g] += own[o][x][h];
                 }
             }
         }
         __syncthreads();
-        // rows of the first (edge) tile that lie above the trailing block picked up band entries: Z must be zero there
+        // ---- Y = Y0 T;  X = V^T Y;  Z = Y - 1/2 V (T^T X)   (V from its global copy: the staging buffer held tiles).
+        //      Rows of the first (edge) tile above the trailing block picked up band entries: Z must be zero there. ----
+        double* YV = Y + r0;
         for (int idx = tid; idx < 8 * (r0 - 32 * T0); idx += T) {
             const int j = idx / (r0 - 32 * T0), gi = 32 * T0 + idx % (r0 - 32 * T0);
-            SG.Y[j * ld + gi] = 0.0;
+            Y[j * ldy + gi] = 0.0;
         }
-        // ---- 4. Y = Y0 T;  X = V^T Y;  Z = Y - 1/2 V (T^T X) ----
         for (int i = tid; i < m; i += T) {
             double y0[NB], y[NB];
 #pragma unroll
-            for (int a = 0; a < NB; ++a) y0[a] = S.Y[a * ld + i];
+            for (int a = 0; a < NB; ++a) y0[a] = YV[a * ldy + i];
 #pragma unroll
             for (int c = 0; c < NB; ++c) {
                 double sacc = 0.0;
 #pragma unroll
                 for (int a = 0; a < NB; ++a)
-                    if (a <= c) sacc = fma(y0[a], S.Tm[a * 8 + c], sacc);
+                    if (a <= c) sacc = fma(y0[a], Tm[a * 8 + c], sacc);
                 y[c] = sacc;
             }
 #pragma unroll
-            for (int c = 0; c < NB; ++c) S.Y[c * ld + i] = y[c];
+            for (int c = 0; c < NB; ++c) YV[c * ldy + i] = y[c];
         }
         __syncthreads();
-        gram8(S.V, S.Y, ld, m, S.red, S.G);  // G = X = V^T Y
+        gram8(Vcm + r0, ld, YV, ldy, m, red, G);  // G = X = V^T Y
         if (tid < 64) {
             const int a = tid >> 3, c = tid & 7;  // M2 = T^T X
             double sacc = 0.0;
-            for (int q = 0; q <= a; ++q) sacc += S.Tm[q * 8 + a] * S.G[q * 8 + c];
-            S.M2[a * 8 + c] = sacc;
+            for (int q = 0; q <= a; ++q) sacc += Tm[q * 8 + a] * G[q * 8 + c];
+            M2[a * 8 + c] = sacc;
         }
         __syncthreads();
         for (int i = tid; i < m; i += T) {
             double v[NB];
 #pragma unroll
-            for (int a = 0; a < NB; ++a) v[a] = S.V[a * ld + i];
+            for (int a = 0; a < NB; ++a) v[a] = Vcm[a * ld + r0 + i];
 #pragma unroll
             for (int c = 0; c < NB; ++c) {
                 double sacc = 0.0;
 #pragma unroll
-                for (int a = 0; a < NB; ++a) sacc = fma(v[a], S.M2[a * 8 + c], sacc);
-                S.Y[c * ld + i] -= 0.5 * sacc;
+                for (int a = 0; a < NB; ++a) sacc = fma(v[a], M2[a * 8 + c], sacc);
+                YV[c * ldy + i] -= 0.5 * sacc;
             }
         }
         __syncthreads();
-        // ---- 5. A22 -= V Z^T + Z V^T on the lower triangle (Z lives in S.Y): load tile, update in shared memory, bulk store ----
-        const int ntl = nt * (nt + 1) / 2;
-        auto decode = [](int tt, int& R, int& C) {
-            R = (int)((sqrtf(8.0f * (float)tt + 1.0f) - 1.0f) * 0.5f);
-            while (R * (R + 1) / 2 > tt) --R;
-            while ((R + 1) * (R + 2) / 2 <= tt) ++R;
-            C = tt - R * (R + 1) / 2;
-        };
-        if (warp < ntl) {
-            int R, C;
-            decode(warp, R, C);
-            tile_load(Tb, bar, At, T0 + R, T0 + C, lane);
+        // export Z in SYR2K fragment order; X rows that leave the trailing block must read as zero from now on
+        for (int idx = T0 * 256 + tid; idx < NT * 256; idx += T) {
+            const int e = idx & 7, ln = (idx >> 3) & 31, R = idx >> 8, gg = ln >> 2, tt = ln & 3;
+            recAZ[idx] = Y[(4 * (e >> 2) + tt) * ldy + 32 * R + 8 * (e & 3) + gg];
         }
-        for (int tt = warp; tt < ntl; tt += NW) {
-            int R, C;
-            decode(tt, R, C);
-            const int rb0 = 32 * (T0 + R), cb0 = 32 * (T0 + C);  // global rows / columns
-            // operand fragments do not depend on the tile contents: fetch them while the copy is in flight
-            double af[4][4], bf[4][4];
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                // P = [V Z] (A operand, negated), Q = [Z V] (B operand); k = 4 ks + t
-                const double* Pp = (ks < 2) ? SG.V : SG.Y;
-                const double* Qp = (ks < 2) ? SG.Y : SG.V;
-                const int col = 4 * (ks & 1) + t;
-#pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    af[ks][x] = -Pp[col * ld + rb0 + 8 * x + g];
-                    bf[ks][x] = Qp[col * ld + cb0 + 8 * x + g];
-                }
-            }
-            mbar_wait(bar, parity);
-            parity ^= 1;
-            double acc[4][4][2];
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) acc[x][y][h] = Tb[(8 * y + 2 * t + h) * TS + 8 * x + g];
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) dmma884(acc[x][y][0], acc[x][y][1], af[ks][x], bf[ks][y]);
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) Tb[(8 * y + 2 * t + h) * TS + 8 * x + g] = acc[x][y][h];
-            // drain: generic-proxy writes -> async proxy, then one bulk store of the whole (padded) tile.  Entries outside the
-            // trailing block see a zero update (V, Z are zero there); the strictly upper part of a diagonal tile is never read.
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) bulk_s2g(At + tile_off(T0 + R, T0 + C), Tb, (uint32_t)(TILE * 8));
-            bulk_commit();
-            bulk_wait_read();  // the buffer may be overwritten once the store has read it
-            const int tn = tt + NW;
-            if (tn < ntl) {
-                int R2, C2;
-                decode(tn, R2, C2);
-                tile_load(Tb, bar, At, T0 + R2, T0 + C2, lane);
-            }
-        }
-        // all bulk stores of this block column must have landed before the next panel is read
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        __syncthreads();
+        for (int i = tid; i < xsz; i += T) X[i] = 0.0;
+        par ^= 1;
+        // (the __syncthreads after the staging of G/M2 at the top of the next iteration orders these writes)
     }
 }
 
 }  // namespace
 
 size_t fkmc_sy2sb_smem(int N) {
-    const size_t ld = ((N + 31) / 32) * 32 + 4;
-    return sizeof(double) * (2 * 8 * ld + 3 * 64 + 8 + NW * 64 + 72 + (size_t)NW * TILE) + sizeof(uint64_t) * NW + 16;
+    const size_t mp = ((N + 31) / 32) * 32, ld = mp + 4;
+    const size_t xsz = std::max<size_t>(8 * ld, (size_t)NW * TILE);
+    return sizeof(double) * ((size_t)NW * TILE + xsz + 8 * (mp + 18) + 3 * 64 + NW * 64) + sizeof(uint64_t) * (2 * NW + 1) + 16;
 }
+size_t fkmc_sy2sb_scratch(int N) { return scratch_doubles(N); }
 
 int fkmc_launch_sy2sb_small(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_AB);
 
@@ -502,27 +677,45 @@ int fkmc_launch_sy2sb_tiled(fkmc_ctx* ctx, double* d_At, int N, int B, double* d
     if (!fkmc_use_tiled(N)) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sy2sb_tiled: needs 512 <= N <= 1024, N % 8 == 0");
     const size_t smem = fkmc_sy2sb_smem(N);
     if (smem > ctx->smem_optin) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sy2sb: matrix too large for shared memory");
+    // fragment-ordered panel records, one slot per matrix (zero-initialised: rows outside the trailing block stay zero)
+    const size_t need = fkmc_sy2sb_scratch(N) * (size_t)B;
+    if (need > ctx->s1_scratch_cap) {
+        if (ctx->d_s1_scratch) {
+            FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_s1_scratch);
+            ctx->d_s1_scratch = nullptr;
+            ctx->s1_scratch_cap = 0;
+        }
+        FKMC_CUDA(ctx, cudaMalloc(&ctx->d_s1_scratch, sizeof(double) * need));
+        ctx->s1_scratch_cap = need;
+        FKMC_CUDA(ctx, cudaMemsetAsync(ctx->d_s1_scratch, 0, sizeof(double) * need, ctx->stream));
+    }
     FKMC_CUDA(ctx, cudaFuncSetAttribute(sy2sb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sy2sb_kernel<<<B, NW * 32, smem, ctx->stream>>>(d_At, fkmc_tiled_stride(N), N, d_AB);
+    sy2sb_kernel<<<B, NW * 32, smem, ctx->stream>>>(d_At, fkmc_tiled_stride(N), N, d_AB, ctx->d_s1_scratch);
     ctx->launches++;
     FKMC_CUDA(ctx, cudaGetLastError());
     return FKMC_OK;
 }
 
+__device__ __forceinline__ void tile_decode(int tile, int& R, int& C) {
+    R = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+    while (R * (R + 1) / 2 > tile) --R;
+    while ((R + 1) * (R + 2) / 2 <= tile) ++R;
+    C = tile - R * (R + 1) / 2;
+}
+
 // column-major [B][N][N] (lower triangle) -> tiled layout
 __global__ void __launch_bounds__(256) to_tiled_kernel(const double* __restrict__ A_all, int N, double* __restrict__ At_all, size_t t_stride) {
     const int b = blockIdx.y, tile = blockIdx.x;
-    int R = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
-    while (R * (R + 1) / 2 > tile) --R;
-    while ((R + 1) * (R + 2) / 2 <= tile) ++R;
-    const int C = tile - R * (R + 1) / 2;
+    int R, C;
+    tile_decode(tile, R, C);
     const double* A = A_all + (size_t)b * N * N;
     double* dst = At_all + (size_t)b * t_stride + (size_t)tile * TILE;
     for (int e = threadIdx.x; e < TILE; e += blockDim.x) {
-        const int c = e / TS, r = e % TS;
+        const int r = e >> 5, c = (e & 31) ^ csw(r);
         const int i = 32 * R + r, j = 32 * C + c;
         double v = 0.0;
-        if (r < 32 && i < N && j < N) v = A[(size_t)min(i, j) * N + max(i, j)];  // symmetric fill from the lower triangle
+        if (i < N && j < N) v = A[(size_t)min(i, j) * N + max(i, j)];  // symmetric fill from the lower triangle
         dst[e] = v;
     }
 }
@@ -542,22 +735,22 @@ __global__ void __launch_bounds__(256) build_h_tiled_kernel(const int32_t* __res
                                                             const double* __restrict__ nbr_val, int N, int Z, double U, double mu_c,
                                                             double* __restrict__ At_all, size_t t_stride) {
     const int b = blockIdx.y, tile = blockIdx.x;
-    int R = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
-    while (R * (R + 1) / 2 > tile) --R;
-    while ((R + 1) * (R + 2) / 2 <= tile) ++R;
-    const int C = tile - R * (R + 1) / 2;
+    int R, C;
+    tile_decode(tile, R, C);
     const int32_t* fb = f + (size_t)b * N;
     double* dst = At_all + (size_t)b * t_stride + (size_t)tile * TILE;
     for (int e = threadIdx.x; e < TILE; e += blockDim.x) {
-        const int c = e / TS, r = e % TS;
+        const int r = e >> 5, c = (e & 31) ^ csw(r);
         const int i = 32 * R + r, j = 32 * C + c;
         double v = 0.0;
-        if (r < 32 && i < N && j < N) {
+        if (i < N && j < N) {
             if (i == j) {
                 v = U * (double)fb[i] - mu_c;
             } else {
+                // the lower triangle is the live one (as in the reference); diagonal tiles carry its mirror image
+                const int lo = max(i, j), up = min(i, j);
                 for (int z = 0; z < Z; ++z)
-                    if (nbr_idx[z * N + i] == j) v = nbr_val[z * N + i];
+                    if (nbr_idx[z * N + lo] == up) v = nbr_val[z * N + lo];
             }
         }
         dst[e] = v;
