@@ -34,6 +34,8 @@
 // trailing block, which makes the partial edge tiles of each block column come out right without masks.
 // Requires N % 8 == 0 and N <= 1024.
 #include <cfloat>
+#include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -74,19 +76,51 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// L2 eviction policies: the matrix tiles stream through L2 once per block column (evict first), the fragment records of the
+// current block column are re-read by every tile task (evict last)
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 // global -> shared bulk copy, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-                 "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
                  : "memory");
 }
 // shared -> global bulk copy (bulk async-group completion)
-__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes),
+                 "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void st_keep(double* p, double v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ double2 ld_keep2(const double2* p, uint64_t pol) {
+    double2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol) : "memory");
+    return v;
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ int ld_acquire_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_s32(int* p, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
 
 // DMMA without the volatile qualifier: a pure function of its operands, so ptxas may interleave independent accumulators
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -98,11 +132,26 @@ __host__ __device__ __forceinline__ size_t tile_off(int R, int C) { return ((siz
 __device__ __forceinline__ size_t elem_off(int i, int j) { return tile_off(i >> 5, j >> 5) + (size_t)tix(i & 31, j & 31); }
 
 // Issue the bulk load of global tile (R, C) into a tile buffer (whole warp calls).
-__device__ __forceinline__ void tile_load(double* buf, uint64_t* bar, const double* __restrict__ At, int R, int C, int lane) {
+__device__ __forceinline__ void tile_load(double* buf, uint64_t* bar, const double* __restrict__ At, int R, int C, int lane, uint64_t pol) {
     __syncwarp();  // every lane is done with the previous contents
     if (lane == 0) {
         mbar_expect_tx(bar, (uint32_t)(TILE * 8));
-        bulk_g2s(buf, At + tile_off(R, C), (uint32_t)(TILE * 8), bar);
+        bulk_g2s(buf, At + tile_off(R, C), (uint32_t)(TILE * 8), bar, pol);
+    }
+}
+
+// eight consecutive columns c0..c0+7 (c0 % 8 == 0) of row i of the tiled matrix, straight from L2 (four 128-bit loads)
+__device__ __forceinline__ void load_row8(const double* __restrict__ At, int i, int c0, double (&out)[8]) {
+    const int r = i & 31, cl = c0 & 31;
+    const double* base = At + tile_off(i >> 5, c0 >> 5) + (r << 5);
+#pragma unroll
+    for (int hq = 0; hq < 2; ++hq) {
+        const double2* q = reinterpret_cast<const double2*>(base + ((cl + 4 * hq) ^ csw(r)));
+        const double2 a = __ldcg(q), b = __ldcg(q + 1);
+        out[4 * hq] = a.x;
+        out[4 * hq + 1] = a.y;
+        out[4 * hq + 2] = b.x;
+        out[4 * hq + 3] = b.y;
     }
 }
 
@@ -111,13 +160,21 @@ __device__ __forceinline__ void tile_load(double* buf, uint64_t* bar, const doub
 __device__ __forceinline__ void gram8(const double* P, int ldp, const double* Q, int ldq, int m, double* red, double* out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, g = lane >> 2, t = lane & 3;
     double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
-    int r = 4 * warp;
-    for (; r + 4 * nw < m; r += 8 * nw) {
-        // A(g, k=t) = P[r+t][g], B(k=t, n=g) = Q[r+t][g]   (rows >= m are zero-padded)
-        dmma(c0, c1, P[g * ldp + r + t], Q[g * ldq + r + t]);
-        dmma(d0, d1, P[g * ldp + r + 4 * nw + t], Q[g * ldq + r + 4 * nw + t]);
+    // A(g, k=t) = P[r+t][g], B(k=t, n=g) = Q[r+t][g]   (rows >= m are zero-padded); operands fetched eight row groups at a time
+    for (int r0 = 4 * warp; r0 < m; r0 += 32 * nw) {
+        double pa[8], qa[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = r0 + 4 * nw * i;
+            pa[i] = (r < m) ? P[g * ldp + r + t] : 0.0;
+            qa[i] = (r < m) ? Q[g * ldq + r + t] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            dmma(c0, c1, pa[i], qa[i]);
+            dmma(d0, d1, pa[i + 1], qa[i + 1]);
+        }
     }
-    if (r < m) dmma(c0, c1, P[g * ldp + r + t], Q[g * ldq + r + t]);
     red[warp * 64 + g * 8 + 2 * t] = c0 + d0;
     red[warp * 64 + g * 8 + 2 * t + 1] = c1 + d1;
     __syncthreads();
@@ -133,15 +190,15 @@ __device__ __forceinline__ void gram8(const double* P, int ldp, const double* Q,
 struct rec8 {
     double v[8];
 };
-__device__ __forceinline__ rec8 load_rec(const double* __restrict__ base, int R, int lane) {
-    const double2* p = reinterpret_cast<const double2*>(base + ((size_t)(R * 32 + lane) << 3));
+__device__ __forceinline__ rec8 load_rec(const double* __restrict__ base, int R, int lane, uint64_t pol) {
+    const double* p = base + ((size_t)(R * 32 + lane) << 3);
     rec8 r;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const double2 x = p[i];
-        r.v[2 * i] = x.x;
-        r.v[2 * i + 1] = x.y;
-    }
+    for (int i = 0; i < 2; ++i)
+        asm volatile("ld.global.L2::cache_hint.v4.f64 {%0, %1, %2, %3}, [%4], %5;"
+                     : "=d"(r.v[4 * i]), "=d"(r.v[4 * i + 1]), "=d"(r.v[4 * i + 2]), "=d"(r.v[4 * i + 3])
+                     : "l"(p + 4 * i), "l"(pol)
+                     : "memory");
     return r;
 }
 
@@ -193,7 +250,7 @@ __device__ __forceinline__ void tile_update_symm(double* __restrict__ Tb, const 
 }
 
 // accC (rows of Cmin) += S^T V'[Rmax rows]   (off-diagonal tiles; vRq[2 blk + h] = V'[32R + 8 blk + 4h + t][g])
-__device__ __forceinline__ void tile_symm_t(const double* __restrict__ Tb, const rec8& vRq, int lane, double (&accC)[4][2]) {
+__device__ __forceinline__ void tile_symm_t(const double* __restrict__ Tb, const rec8& vRq, int lane, double (&accC)[2][4][2]) {
     const int g = lane >> 2, t = lane & 3;
     const int cs = csw(t);
 #pragma unroll
@@ -202,28 +259,60 @@ __device__ __forceinline__ void tile_symm_t(const double* __restrict__ Tb, const
         for (int h = 0; h < 2; ++h) {
             const double* row = Tb + ((8 * rb + 4 * h + t) << 5);
 #pragma unroll
-            for (int cb = 0; cb < 4; ++cb) dmma(accC[cb][0], accC[cb][1], row[(8 * cb + g) ^ cs], vRq.v[2 * rb + h]);
+            for (int cb = 0; cb < 4; ++cb) dmma(accC[h][cb][0], accC[h][cb][1], row[(8 * cb + g) ^ cs], vRq.v[2 * rb + h]);
         }
 }
 
-// next task (s, o) of this warp in the cyclic pairing schedule; false when the pass is exhausted
-__device__ __forceinline__ bool next_task(int& s, int& o, int warp, int nt, int smax) {
-    ++o;
-    while (s <= smax) {
-        const int lim = (s > 0 && 2 * s == nt) ? (nt >> 1) : nt;
-        if (warp + NW * o < lim) return true;
-        ++s;
-        o = 0;
+// The pass schedule.  Step s = 0..nt/2 pairs row block a with p = a - s (mod nt): tile (max, min).  Row blocks a < base = 8*(nt/8)
+// are OWNED by warp a % 8 (their sums stay in its registers for the whole pass); the nt % 8 left-over blocks are FLOATING: their
+// tasks rotate over the warps (at most one per warp and step, always last in the warp's step), and both halves of their result go
+// to shared memory.  That keeps the tile count per warp and step equal to within one.
+struct sched {
+    int warp, nt, smax, nown, base, rem;
+    __device__ __forceinline__ int lim(int s) const { return (s > 0 && 2 * s == nt) ? (nt >> 1) : nt; }
+    // row block of slot o in step s, or -1
+    __device__ __forceinline__ int row(int s, int o) const {
+        int a;
+        if (o < nown) {
+            a = warp + NW * o;
+        } else if (o == nown) {
+            const int k = (warp - s * rem) & 7;
+            if (k >= rem) return -1;
+            a = base + k;
+        } else {
+            return -1;
+        }
+        return a < lim(s) ? a : -1;
     }
-    return false;
-}
-__device__ __forceinline__ void task_tile(int s, int o, int warp, int nt, int& a, int& Rmax, int& Cmin) {
-    a = warp + NW * o;
-    int p = a - s;
-    if (p < 0) p += nt;
-    Rmax = max(a, p);
-    Cmin = min(a, p);
-}
+    // advance (s, o) to this warp's next task; false when the pass is exhausted
+    __device__ __forceinline__ bool next(int& s, int& o) const {
+        ++o;
+        while (s <= smax) {
+            while (o <= nown) {
+                if (row(s, o) >= 0) return true;
+                ++o;
+            }
+            ++s;
+            o = 0;
+        }
+        return false;
+    }
+    __device__ __forceinline__ void tile(int s, int o, int& a, int& Rmax, int& Cmin) const {
+        a = row(s, o);
+        int p = a - s;
+        if (p < 0) p += nt;
+        Rmax = max(a, p);
+        Cmin = min(a, p);
+    }
+    __device__ __forceinline__ bool half_step(int s) const { return s > 0 && 2 * s == nt; }
+    // number of shared-memory adds into row block b that precede its partner add / its floating own add of step s
+    __device__ __forceinline__ int before_partner(int b, int s) const { return b >= base ? 2 * s - 1 : s - 1; }
+    __device__ __forceinline__ int before_own(int b, int s) const {
+        if (s == 0) return 0;
+        const bool has_partner = !half_step(s) || b >= (nt >> 1);
+        return 2 * s - 1 + (has_partner ? 1 : 0);
+    }
+};
 
 // scratch layout per matrix (doubles): Vcm [8][ld] | recVp [NT][32][8] | recVq [NT][32][8] | recAV [2][NT][32][8] | recAZ [NT][32][8]
 __host__ __device__ __forceinline__ size_t scratch_doubles(int N) {
@@ -231,8 +320,15 @@ __host__ __device__ __forceinline__ size_t scratch_doubles(int N) {
     return 8 * (mp + 4) + 32 + 5 * nt * 256;
 }
 
+// DBG: cycle counters of CTA 0 (developer instrumentation, FKMC_S1_TIMING=1): dbg[0..7] phase totals of thread 0,
+// dbg[8 + 8 w + i] pass sub-phase totals of warp w
+#define S1_T(var) \
+    long long var = 0; \
+    if (DBG) var = clock64();
+template <bool DBG>
 __global__ void __launch_bounds__(NW * 32, 1)
-sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restrict__ AB_all, double* __restrict__ scr_all) {
+sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restrict__ AB_all, double* __restrict__ scr_all, long long* dbg) {
+    long long ph_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ps_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, spin_t = 0;
     extern __shared__ __align__(128) double smem[];
     const int tid = threadIdx.x, T = NW * 32, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -252,9 +348,12 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
     double* M2 = Tm + 64;
     double* red = M2 + 64;                      // [NW*64] gram partials; QR: [2][NW][8] partials + [2][8] pivot row
     uint64_t* bars = reinterpret_cast<uint64_t*>(red + NW * 64);
-    uint64_t* stepbar = bars + 2 * NW;
+    int* blkstep = reinterpret_cast<int*>(bars + 2 * NW);  // [32] last step whose partner add into row block p is complete
     // global scratch
-    double* Vcm = scr_all + (size_t)b * scratch_doubles(N);
+    // one scratch slot per SM (a single CTA fits on an SM): the records of the block column in flight stay hot in L2
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    double* Vcm = scr_all + (size_t)smid * scratch_doubles(N);
     double* recVp = Vcm + 8 * ld + 32;
     double* recVq = recVp + NT * 256;
     double* recAV = recVq + NT * 256;
@@ -265,18 +364,31 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
     uint64_t* bar0 = bars + 2 * warp;
     uint64_t* bar1 = bar0 + 1;
     uint32_t ph0 = 0, ph1 = 0;
-    uint32_t steps_done = 0;  // completed phases of stepbar (same in every warp)
+    const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
     int par = 0;
 
     for (int i = tid; i < 8 * ldy; i += T) Y[i] = 0.0;
     for (int i = tid; i < xsz; i += T) X[i] = 0.0;
     if (tid < 2 * NW) mbar_init(bars + tid, 1);
-    if (tid == 0) mbar_init(stepbar, NW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
+    // raw panel rows (loaded ahead of time: before the loop for the first panel, right after the pass for the others)
+    double p[QR][NB], dg[NB];
+#pragma unroll
+    for (int c = 0; c < NB; ++c) dg[c] = 0.0;
+    if (tid < NB) load_row8(At, tid, 0, dg);
+#pragma unroll
+    for (int q = 0; q < QR; ++q) {
+        const int gi = NB + tid + T * q;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) p[q][c] = 0.0;
+        if (gi < N) load_row8(At, gi, 0, p[q]);
+    }
+
     for (int k0 = 0; k0 < N; k0 += NB) {
         const int r0 = k0 + NB, m = N - r0;
+        S1_T(t_a)
         // ---- build the panel in registers: columns k0..k0+7 of A, rows >= k0, minus the pending update of block column k-1.
         //      Thread tid owns local rows i = tid + 256 q (global row r0 + i); threads 0..7 also finish the diagonal block. ----
         if (k0 > 0 && tid < 64) {
@@ -285,23 +397,8 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
             M2[tid] = Y[j * ldy + k0 + c];
         }
         __syncthreads();
-        double p[QR][NB];
         {
-            double dg[NB];
-#pragma unroll
-            for (int c = 0; c < NB; ++c) dg[c] = 0.0;
             const int gd = k0 + tid;  // diagonal-block row (tid < 8)
-            if (tid < NB) {
-#pragma unroll
-                for (int c = 0; c < NB; ++c)
-                    if (c <= tid) dg[c] = __ldcg(At + elem_off(gd, k0 + c));
-            }
-#pragma unroll
-            for (int q = 0; q < QR; ++q) {
-                const int gi = r0 + tid + T * q;
-#pragma unroll
-                for (int c = 0; c < NB; ++c) p[q][c] = (gi < N) ? __ldcg(At + elem_off(gi, k0 + c)) : 0.0;
-            }
             if (k0 > 0) {
 #pragma unroll
                 for (int q = 0; q < QR; ++q) {
@@ -346,6 +443,7 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
             }
         }
         if (m <= 0) break;
+        S1_T(t_b)
         // ---- Householder QR of the panel, rows in registers, one block barrier per column ----
         double tauv[NB];
 #pragma unroll
@@ -438,6 +536,7 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
         }
         // rows above the trailing block are zero in X: they were zeroed at start-up / by the previous export and only rows >= r0 are written
         __syncthreads();
+        S1_T(t_c)
         // ---- T from the Gram matrix: T(0:j, j) = -tau_j T(0:j,0:j) G(0:j, j); lane i of warp 0 owns row i ----
         gram8(X + r0, ld, X + r0, ld, m, red, G);
         if (tid < NB) {
@@ -455,21 +554,23 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
         }
         // ---- export V: column-major copy + the fragment orders; clear Y for the new Y0; clear the X rows that die ----
         const int T0 = r0 >> 5, nt = NT - T0;  // tiles T0..NT-1 of the fixed global grid touch the trailing block
-        for (int i = tid; i < 8 * ld; i += T) Vcm[i] = X[i];
+        for (int i = tid; i < 8 * ld; i += T) st_keep(Vcm + i, X[i], pol_keep);
         for (int i = tid; i < 8 * ldy; i += T) Y[i] = 0.0;
         {
             double* rA = recAV + (size_t)par * NT * 256;
             for (int idx = T0 * 256 + tid; idx < NT * 256; idx += T) {
                 const int e = idx & 7, ln = (idx >> 3) & 31, R = idx >> 8, gg = ln >> 2, tt = ln & 3;
                 // SYMM B operands: V[32R + 8 blk + 2t + h][g] (pair order) and V[32R + 8 blk + 4h + t][g] (quad order), e = 2 blk + h
-                recVp[idx] = X[gg * ld + 32 * R + 8 * (e >> 1) + 2 * tt + (e & 1)];
-                recVq[idx] = X[gg * ld + 32 * R + 8 * (e >> 1) + 4 * (e & 1) + tt];
+                st_keep(recVp + idx, X[gg * ld + 32 * R + 8 * (e >> 1) + 2 * tt + (e & 1)], pol_keep);
+                st_keep(recVq + idx, X[gg * ld + 32 * R + 8 * (e >> 1) + 4 * (e & 1) + tt], pol_keep);
                 // SYR2K A/B operand: V[32R + 8 blk + g][4q + t], e = 4q + blk
-                rA[idx] = X[(4 * (e >> 2) + tt) * ld + 32 * R + 8 * (e & 3) + gg];
+                st_keep(rA + idx, X[(4 * (e >> 2) + tt) * ld + 32 * R + 8 * (e & 3) + gg], pol_keep);
             }
         }
+        if (tid < 32) blkstep[tid] = 0;
         fence_async_smem();  // generic-proxy accesses to X are ordered before the bulk copies that reuse it
         __syncthreads();
+        S1_T(t_d)
         // ---- the pass: pending SYR2K of block column k-1 fused with the SYMM of block column k ----
         {
             const bool upd = k0 > 0;
@@ -479,122 +580,198 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
             for (int o = 0; o < MAXOWN; ++o)
 #pragma unroll
                 for (int x = 0; x < 4; ++x) own[o][x][0] = own[o][x][1] = 0.0;
-            const int smax = nt >> 1;
-            // task cursors: c = current, n1 = next; loads are issued two tasks ahead
-            int cs = 0, co = -1;
-            bool cv = next_task(cs, co, warp, nt, smax);
-            int n1s = cs, n1o = co;
-            bool n1v = cv && next_task(n1s, n1o, warp, nt, smax);
-            int slot = 0;
-            if (cv) {
-                int a, R, C;
-                task_tile(cs, co, warp, nt, a, R, C);
-                tile_load(buf0, bar0, At, T0 + R, T0 + C, lane);
-            }
-            if (n1v) {
-                int a, R, C;
-                task_tile(n1s, n1o, warp, nt, a, R, C);
-                tile_load(buf1, bar1, At, T0 + R, T0 + C, lane);
-            }
-            for (int s = 0; s <= smax; ++s) {
-                bool waited = (s == 0);
-#pragma unroll
-                for (int o = 0; o < MAXOWN; ++o) {
-                    if (cv && cs == s && co == o) {
-                        int a, Rmax, Cmin;
-                        task_tile(s, o, warp, nt, a, Rmax, Cmin);
-                        const bool diag = (s == 0);
-                        double* Tb = slot ? buf1 : buf0;
-                        uint64_t* bar = slot ? bar1 : bar0;
-                        // operand records do not depend on the tile contents: fetch them while the copy is in flight
-                        rec8 uvR, uzR, uvC, uzC;
-                        if (upd) {
-                            uvR = load_rec(uV, T0 + Rmax, lane);
-                            uzR = load_rec(recAZ, T0 + Rmax, lane);
-                            uvC = load_rec(uV, T0 + Cmin, lane);
-                            uzC = load_rec(recAZ, T0 + Cmin, lane);
-                        }
-                        const rec8 vCp = load_rec(recVp, T0 + Cmin, lane);
-                        if (slot) {
-                            mbar_wait(bar, ph1);
-                            ph1 ^= 1;
-                        } else {
-                            mbar_wait(bar, ph0);
-                            ph0 ^= 1;
-                        }
-                        double accR[4][2], accC[4][2];
-#pragma unroll
-                        for (int x = 0; x < 4; ++x) accR[x][0] = accR[x][1] = accC[x][0] = accC[x][1] = 0.0;
-                        if (upd) {
-                            tile_update_symm<true>(Tb, uvR, uzR, uvC, uzC, vCp, lane, accR);
-                            // drain: generic-proxy writes -> async proxy, then one bulk store of the whole tile.  Entries outside the
-                            // trailing block see a zero update (V, Z are zero there).
-                            fence_async_smem();
-                            __syncwarp();
-                            if (lane == 0) bulk_s2g(At + tile_off(T0 + Rmax, T0 + Cmin), Tb, (uint32_t)(TILE * 8));
-                            bulk_commit();
-                        } else {
-                            tile_update_symm<false>(Tb, uvR, uzR, uvC, uzC, vCp, lane, accR);
-                        }
-                        if (!diag) {
-                            const rec8 vRq = load_rec(recVq, T0 + Rmax, lane);
-                            tile_symm_t(Tb, vRq, lane, accC);
-                        }
-                        // refill this buffer with the task after next once the store has read it
-                        {
-                            int n2s = n1s, n2o = n1o;
-                            const bool n2v = n1v && next_task(n2s, n2o, warp, nt, smax);
-                            if (upd) bulk_wait_read();
-                            if (n2v) {
-                                int a2, R2, C2;
-                                task_tile(n2s, n2o, warp, nt, a2, R2, C2);
-                                tile_load(Tb, bar, At, T0 + R2, T0 + C2, lane);
-                            }
-                            cs = n1s; co = n1o; cv = n1v;
-                            n1s = n2s; n1o = n2o; n1v = n2v;
-                            slot ^= 1;
-                        }
-                        // own rows stay in registers; partner rows go to shared memory (distinct tiles within a step, and every
-                        // warp has finished the adds of the previous step)
-                        if (diag || a == Rmax) {
-#pragma unroll
-                            for (int x = 0; x < 4; ++x) { own[o][x][0] += accR[x][0]; own[o][x][1] += accR[x][1]; }
-                            if (!diag) {
-                                if (!waited) { mbar_wait(stepbar, (steps_done - 1) & 1); waited = true; }
-#pragma unroll
-                                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                                    for (int h = 0; h < 2; ++h) Y[(2 * t + h) * ldy + 32 * (T0 + Cmin) + 8 * x + g] += accC[x][h];
-                            }
-                        } else {
-#pragma unroll
-                            for (int x = 0; x < 4; ++x) { own[o][x][0] += accC[x][0]; own[o][x][1] += accC[x][1]; }
-                            if (!waited) { mbar_wait(stepbar, (steps_done - 1) & 1); waited = true; }
-#pragma unroll
-                            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                                for (int h = 0; h < 2; ++h) Y[(2 * t + h) * ldy + 32 * (T0 + Rmax) + 8 * x + g] += accR[x][h];
-                        }
+            sched sc;
+            sc.warp = warp;
+            sc.nt = nt;
+            sc.smax = nt >> 1;
+            sc.nown = nt >> 3;
+            sc.base = sc.nown * NW;
+            sc.rem = nt - sc.base;
+            // this warp's task list, packed (s | o << 5 | a << 8 | Rmax << 13 | Cmin << 18), task i in lane i % 32 of d[i / 32]
+            int d0 = 0, d1 = 0, d2 = 0, ntasks = 0;
+            for (int s = 0; s <= sc.smax; ++s)
+                for (int o = 0; o <= sc.nown; ++o) {
+                    const int a = sc.row(s, o);
+                    if (a >= 0) {
+                        int p = a - s;
+                        if (p < 0) p += nt;
+                        const int pk = s | (o << 5) | (a << 8) | (max(a, p) << 13) | (min(a, p) << 18);
+                        if (ntasks == lane) d0 = pk;
+                        if (ntasks == lane + 32) d1 = pk;
+                        if (ntasks == lane + 64) d2 = pk;
+                        ++ntasks;
                     }
                 }
-                // this warp's adds of step s are done.  A warp never arrives twice in one phase: it first sees the previous step complete.
-                if (!waited) mbar_wait(stepbar, (steps_done - 1) & 1);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(stepbar);
-                ++steps_done;
+            auto task = [&](int i) { return __shfl_sync(0xffffffffu, i < 32 ? d0 : (i < 64 ? d1 : d2), i & 31); };
+            // tile loads are issued two tasks ahead, operand records one task ahead
+            uint32_t phb = ph0 | (ph1 << 1);
+            rec8 uvR, uzR, uvC, uzC, vCp;
+            if (ntasks > 0) {
+                const int D = task(0), R = (D >> 13) & 31, C = (D >> 18) & 31;
+                tile_load(buf0, bar0, At, T0 + R, T0 + C, lane, pol_stream);
+                if (upd) {
+                    uvR = load_rec(uV, T0 + R, lane, pol_keep);
+                    uzR = load_rec(recAZ, T0 + R, lane, pol_keep);
+                    uvC = load_rec(uV, T0 + C, lane, pol_keep);
+                    uzC = load_rec(recAZ, T0 + C, lane, pol_keep);
+                }
+                vCp = load_rec(recVp, T0 + C, lane, pol_keep);
             }
+            if (ntasks > 1) {
+                const int D = task(1);
+                tile_load(buf1, bar1, At, T0 + ((D >> 13) & 31), T0 + ((D >> 18) & 31), lane, pol_stream);
+            }
+            for (int i = 0; i < ntasks; ++i) {
+                const int D = task(i);
+                const int s = D & 31, o = (D >> 5) & 7, a = (D >> 8) & 31, Rmax = (D >> 13) & 31, Cmin = (D >> 18) & 31;
+                const int slot = i & 1;
+                const bool diag = (s == 0);
+                double* Tb = slot ? buf1 : buf0;
+                uint64_t* bar = slot ? bar1 : bar0;
+                rec8 vRq;
+                if (!diag) vRq = load_rec(recVq, T0 + Rmax, lane, pol_keep);
+                S1_T(q0)
+                mbar_wait(bar, (phb >> slot) & 1);
+                phb ^= 1u << slot;
+                S1_T(q1)
+                double accR[4][2], accC[2][4][2];
+#pragma unroll
+                for (int x = 0; x < 4; ++x) accR[x][0] = accR[x][1] = accC[0][x][0] = accC[0][x][1] = accC[1][x][0] = accC[1][x][1] = 0.0;
+                if (upd) {
+                    tile_update_symm<true>(Tb, uvR, uzR, uvC, uzC, vCp, lane, accR);
+                    // drain: generic-proxy writes -> async proxy, then one bulk store of the whole tile.  Entries outside the
+                    // trailing block see a zero update (V, Z are zero there).
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) bulk_s2g(At + tile_off(T0 + Rmax, T0 + Cmin), Tb, (uint32_t)(TILE * 8), pol_stream);
+                    bulk_commit();
+                } else {
+                    tile_update_symm<false>(Tb, uvR, uzR, uvC, uzC, vCp, lane, accR);
+                }
+                S1_T(q2)
+                // the operand records of the next task travel while this one finishes
+                if (i + 1 < ntasks) {
+                    const int D1 = task(i + 1), n1R = (D1 >> 13) & 31, n1C = (D1 >> 18) & 31;
+                    if (upd) {
+                        uvR = load_rec(uV, T0 + n1R, lane, pol_keep);
+                        uzR = load_rec(recAZ, T0 + n1R, lane, pol_keep);
+                        uvC = load_rec(uV, T0 + n1C, lane, pol_keep);
+                        uzC = load_rec(recAZ, T0 + n1C, lane, pol_keep);
+                    }
+                    vCp = load_rec(recVp, T0 + n1C, lane, pol_keep);
+                }
+                S1_T(q3)
+                if (!diag) tile_symm_t(Tb, vRq, lane, accC);
+                S1_T(q4)
+                // refill this buffer with the task after next once the store has read it
+                {
+                    S1_T(w0)
+                    if (upd) bulk_wait_read();
+                    if (DBG) ps_t[7] += clock64() - w0;
+                    if (i + 2 < ntasks) {
+                        const int D2 = task(i + 2);
+                        tile_load(Tb, bar, At, T0 + ((D2 >> 13) & 31), T0 + ((D2 >> 18) & 31), lane, pol_stream);
+                    }
+                }
+                S1_T(q5)
+                // owned rows stay in registers; everything else goes to shared memory.  The adds into one row block happen in a fixed
+                // order (per step: partner add, then the floating own add), enforced with a per-block counter: deterministic sums.
+                const bool fl = (o == sc.nown);
+                double ow[4][2];
+                if (diag) {
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) { ow[x][0] = accR[x][0]; ow[x][1] = accR[x][1]; }
+                } else {
+                    const bool ownR = (a == Rmax);
+                    const int pblk = ownR ? Cmin : Rmax;
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const double c0 = accC[0][x][0] + accC[1][x][0], c1 = accC[0][x][1] + accC[1][x][1];
+                        ow[x][0] = ownR ? accR[x][0] : c0;
+                        ow[x][1] = ownR ? accR[x][1] : c1;
+                        accR[x][0] = ownR ? c0 : accR[x][0];
+                        accR[x][1] = ownR ? c1 : accR[x][1];
+                    }
+                    const int need = sc.before_partner(pblk, s);
+                    S1_T(sp0)
+                    while (ld_acquire_s32(blkstep + pblk) < need) {
+                    }
+                    if (DBG) spin_t += clock64() - sp0;
+                    double* yp = Y + 32 * (T0 + pblk) + g + 2 * t * ldy;
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) yp[h * ldy + 8 * x] += accR[x][h];
+                    __syncwarp();
+                    if (lane == 0) st_release_s32(blkstep + pblk, need + 1);
+                }
+                if (!fl) {
+#pragma unroll
+                    for (int oo = 0; oo < MAXOWN; ++oo)
+                        if (oo == o) {
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) { own[oo][x][0] += ow[x][0]; own[oo][x][1] += ow[x][1]; }
+                        }
+                } else {
+                    const int need2 = sc.before_own(a, s);
+                    while (ld_acquire_s32(blkstep + a) < need2) {
+                    }
+                    double* yo = Y + 32 * (T0 + a) + g + 2 * t * ldy;
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) yo[h * ldy + 8 * x] += ow[x][h];
+                    __syncwarp();
+                    if (lane == 0) st_release_s32(blkstep + a, need2 + 1);
+                }
+                if (DBG) {
+                    const long long q6 = clock64();
+                    ps_t[0] += q1 - q0;  // wait for the tile
+                    ps_t[1] += q2 - q1;  // update + accR + store issue
+                    ps_t[2] += q3 - q2;  // next-record issue
+                    ps_t[3] += q4 - q3;  // transposed SYMM
+                    ps_t[4] += q5 - q4;  // store-read wait + refill
+                    ps_t[5] += q6 - q5;  // adds
+                    ps_t[6] += 1;
+                }
+            }
+            ph0 = phb & 1;
+            ph1 = (phb >> 1) & 1;
             // all bulk stores of this pass must have landed before the next panel is read
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-            mbar_wait(stepbar, (steps_done - 1) & 1);  // every warp's partner adds are in
+            S1_T(t_e0)
+            __syncthreads();  // every warp's partner adds are in
+            S1_T(t_e)
+            if (DBG) {
+                ph_t[0] += t_b - t_a;
+                ph_t[1] += t_c - t_b;
+                ph_t[2] += t_d - t_c;
+                ph_t[3] += t_e - t_d;
+                ph_t[5] += t_e - t_e0;
+                ph_t[6] = t_e;
+            }
 #pragma unroll
             for (int o = 0; o < MAXOWN; ++o) {
                 const int a = warp + NW * o;
-                if (a < nt) {
+                if (o < (nt >> 3)) {
 #pragma unroll
                     for (int x = 0; x < 4; ++x)
 #pragma unroll
                         for (int h = 0; h < 2; ++h) Y[(2 * t + h) * ldy + 32 * (T0 + a) + 8 * x + g] += own[o][x][h];
                 }
+            }
+        }
+        // ---- raw rows of the next panel (columns r0..r0+7): in flight while Z is finished ----
+        {
+#pragma unroll
+            for (int c = 0; c < NB; ++c) dg[c] = 0.0;
+            if (tid < NB) load_row8(At, r0 + tid, r0, dg);
+#pragma unroll
+            for (int q = 0; q < QR; ++q) {
+                const int gi = r0 + NB + tid + T * q;
+#pragma unroll
+                for (int c = 0; c < NB; ++c) p[q][c] = 0.0;
+                if (gi < N) load_row8(At, gi, r0, p[q]);
             }
         }
         __syncthreads();
@@ -645,11 +822,19 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
         // export Z in SYR2K fragment order; X rows that leave the trailing block must read as zero from now on
         for (int idx = T0 * 256 + tid; idx < NT * 256; idx += T) {
             const int e = idx & 7, ln = (idx >> 3) & 31, R = idx >> 8, gg = ln >> 2, tt = ln & 3;
-            recAZ[idx] = Y[(4 * (e >> 2) + tt) * ldy + 32 * R + 8 * (e & 3) + gg];
+            st_keep(recAZ + idx, Y[(4 * (e >> 2) + tt) * ldy + 32 * R + 8 * (e & 3) + gg], pol_keep);
         }
         for (int i = tid; i < xsz; i += T) X[i] = 0.0;
         par ^= 1;
+        if (DBG) ph_t[4] += clock64() - ph_t[6], ph_t[6] = 0;
         // (the __syncthreads after the staging of G/M2 at the top of the next iteration orders these writes)
+    }
+    if (DBG && blockIdx.x == 0) {
+        if (tid == 0)
+            for (int i = 0; i < 8; ++i) dbg[i] = ph_t[i];
+        if (lane == 0)
+            for (int i = 0; i < 8; ++i) dbg[8 + 8 * warp + i] = (i == 2) ? ps_t[i] : ps_t[i];
+        if (lane == 0) dbg[72 + warp] = spin_t;
     }
 }
 
@@ -658,11 +843,17 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
 size_t fkmc_sy2sb_smem(int N) {
     const size_t mp = ((N + 31) / 32) * 32, ld = mp + 4;
     const size_t xsz = std::max<size_t>(8 * ld, (size_t)NW * TILE);
-    return sizeof(double) * ((size_t)NW * TILE + xsz + 8 * (mp + 18) + 3 * 64 + NW * 64) + sizeof(uint64_t) * (2 * NW + 1) + 16;
+    return sizeof(double) * ((size_t)NW * TILE + xsz + 8 * (mp + 18) + 3 * 64 + NW * 64) + sizeof(uint64_t) * 2 * NW + sizeof(int) * 32 + 16;
 }
 size_t fkmc_sy2sb_scratch(int N) { return scratch_doubles(N); }
 
 int fkmc_launch_sy2sb_small(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_AB);
+
+__global__ void nsmid_kernel(unsigned* out) {
+    unsigned n;
+    asm volatile("mov.u32 %0, %%nsmid;" : "=r"(n));
+    *out = n;
+}
 
 // doubles per matrix in the tiled lower-triangular layout
 size_t fkmc_tiled_stride(int N) {
@@ -677,8 +868,18 @@ int fkmc_launch_sy2sb_tiled(fkmc_ctx* ctx, double* d_At, int N, int B, double* d
     if (!fkmc_use_tiled(N)) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sy2sb_tiled: needs 512 <= N <= 1024, N % 8 == 0");
     const size_t smem = fkmc_sy2sb_smem(N);
     if (smem > ctx->smem_optin) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sy2sb: matrix too large for shared memory");
-    // fragment-ordered panel records, one slot per matrix (zero-initialised: rows outside the trailing block stay zero)
-    const size_t need = fkmc_sy2sb_scratch(N) * (size_t)B;
+    // fragment-ordered panel records, one slot per SM
+    if (ctx->nsmid == 0) {
+        unsigned* d_n = nullptr;
+        unsigned h_n = 0;
+        FKMC_CUDA(ctx, cudaMalloc(&d_n, sizeof(unsigned)));
+        nsmid_kernel<<<1, 1, 0, ctx->stream>>>(d_n);
+        FKMC_CUDA(ctx, cudaMemcpyAsync(&h_n, d_n, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+        FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_n);
+        ctx->nsmid = (int)h_n;
+    }
+    const size_t need = fkmc_sy2sb_scratch(N) * (size_t)ctx->nsmid;
     if (need > ctx->s1_scratch_cap) {
         if (ctx->d_s1_scratch) {
             FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -690,8 +891,27 @@ int fkmc_launch_sy2sb_tiled(fkmc_ctx* ctx, double* d_At, int N, int B, double* d
         ctx->s1_scratch_cap = need;
         FKMC_CUDA(ctx, cudaMemsetAsync(ctx->d_s1_scratch, 0, sizeof(double) * need, ctx->stream));
     }
-    FKMC_CUDA(ctx, cudaFuncSetAttribute(sy2sb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sy2sb_kernel<<<B, NW * 32, smem, ctx->stream>>>(d_At, fkmc_tiled_stride(N), N, d_AB, ctx->d_s1_scratch);
+    if (getenv("FKMC_S1_TIMING")) {
+        long long* d_dbg = nullptr;
+        long long h[80];
+        FKMC_CUDA(ctx, cudaMalloc(&d_dbg, sizeof(h)));
+        FKMC_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, sizeof(h), ctx->stream));
+        FKMC_CUDA(ctx, cudaFuncSetAttribute(sy2sb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sy2sb_kernel<true><<<B, NW * 32, smem, ctx->stream>>>(d_At, fkmc_tiled_stride(N), N, d_AB, ctx->d_s1_scratch, d_dbg);
+        FKMC_CUDA(ctx, cudaMemcpyAsync(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_dbg);
+        fprintf(stderr, "[s1 timing, CTA 0, cycles] build %lld  qr %lld  T+export %lld  pass %lld (end barrier %lld)  final %lld\n", h[0], h[1], h[2],
+                h[3], h[5], h[4]);
+        for (int w = 0; w < NW; ++w)
+            fprintf(stderr, "  warp %d: tasks %lld | tile wait %lld  update %lld  rec issue %lld  symm_t %lld  refill %lld (store-read wait %lld)  adds %lld (spin %lld)\n", w,
+                    h[8 + 8 * w + 6], h[8 + 8 * w], h[8 + 8 * w + 1], h[8 + 8 * w + 2], h[8 + 8 * w + 3], h[8 + 8 * w + 4], h[8 + 8 * w + 7],
+                    h[8 + 8 * w + 5], h[72 + w]);
+        ctx->launches++;
+        return FKMC_OK;
+    }
+    FKMC_CUDA(ctx, cudaFuncSetAttribute(sy2sb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sy2sb_kernel<false><<<B, NW * 32, smem, ctx->stream>>>(d_At, fkmc_tiled_stride(N), N, d_AB, ctx->d_s1_scratch, nullptr);
     ctx->launches++;
     FKMC_CUDA(ctx, cudaGetLastError());
     return FKMC_OK;
