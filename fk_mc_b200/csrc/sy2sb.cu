@@ -113,13 +113,19 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ int ld_acquire_s32(const int* p) {
+// Per-block progress counters in shared memory.  Writer: Y adds (all lanes), __syncwarp, counter store (lane 0); reader: counter load,
+// then Y adds.  Both sides are plain shared-memory accesses of one SM, which the LSU performs in issue order, so volatile accesses with
+// compiler barriers are enough -- a release/acquire pair would also wait for the global operand loads that are in flight on purpose.
+__device__ __forceinline__ int ld_flag(const int* p) {
     int v;
-    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_s32(int* p, int v) {
-    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+__device__ __forceinline__ void st_flag(int* p, int v) {
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream2(double* p, double a, double b, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(a), "d"(b), "l"(pol) : "memory");
 }
 
 // DMMA without the volatile qualifier: a pure function of its operands, so ptxas may interleave independent accumulators
@@ -207,8 +213,8 @@ __device__ __forceinline__ rec8 load_rec(const double* __restrict__ base, int R,
 //   accR (rows of Rmax) += S V'[Cmin rows]          (accumulator fragments reused as A operands; vCp[2 blk + h] = V'[32C + 8 blk + 2t + h][g])
 // Diagonal tiles hold both triangles, so this is all they need.
 template <bool UPD>
-__device__ __forceinline__ void tile_update_symm(double* __restrict__ Tb, const rec8& uvR, const rec8& uzR, const rec8& uvC, const rec8& uzC,
-                                                 const rec8& vCp, int lane, double (&accR)[4][2]) {
+__device__ __forceinline__ void tile_update_symm(double* __restrict__ Tb, double* __restrict__ gT, uint64_t pol, const rec8& uvR, const rec8& uzR,
+                                                 const rec8& uvC, const rec8& uzC, const rec8& vCp, int lane, double (&accR)[4][2]) {
     const int g = lane >> 2, t = lane & 3;
     const int cs = csw(g);
 #pragma unroll
@@ -238,7 +244,11 @@ __device__ __forceinline__ void tile_update_symm(double* __restrict__ Tb, const 
             for (int x = 0; x < 4; ++x)
 #pragma unroll
                 for (int yy = 0; yy < 2; ++yy)
-                    *reinterpret_cast<double2*>(Tb + ((8 * x + g) << 5) + ((8 * (2 * half + yy) + 2 * t) ^ cs)) = make_double2(acc[x][yy][0], acc[x][yy][1]);
+                {
+                    const int off = ((8 * x + g) << 5) + ((8 * (2 * half + yy) + 2 * t) ^ cs);
+                    *reinterpret_cast<double2*>(Tb + off) = make_double2(acc[x][yy][0], acc[x][yy][1]);  // for the transposed reads
+                    st_stream2(gT + off, acc[x][yy][0], acc[x][yy][1], pol);                             // the tile itself, straight from registers
+                }
         }
 #pragma unroll
         for (int yy = 0; yy < 2; ++yy)
@@ -568,7 +578,8 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
             }
         }
         if (tid < 32) blkstep[tid] = 0;
-        fence_async_smem();  // generic-proxy accesses to X are ordered before the bulk copies that reuse it
+        // generic-proxy accesses to X and the tile stores of the previous pass are ordered before the bulk copies of this pass
+        asm volatile("fence.proxy.async;" ::: "memory");
         __syncthreads();
         S1_T(t_d)
         // ---- the pass: pending SYR2K of block column k-1 fused with the SYMM of block column k ----
@@ -637,16 +648,12 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
                 double accR[4][2], accC[2][4][2];
 #pragma unroll
                 for (int x = 0; x < 4; ++x) accR[x][0] = accR[x][1] = accC[0][x][0] = accC[0][x][1] = accC[1][x][0] = accC[1][x][1] = 0.0;
+                // entries outside the trailing block see a zero update (V, Z are zero there)
                 if (upd) {
-                    tile_update_symm<true>(Tb, uvR, uzR, uvC, uzC, vCp, lane, accR);
-                    // drain: generic-proxy writes -> async proxy, then one bulk store of the whole tile.  Entries outside the
-                    // trailing block see a zero update (V, Z are zero there).
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) bulk_s2g(At + tile_off(T0 + Rmax, T0 + Cmin), Tb, (uint32_t)(TILE * 8), pol_stream);
-                    bulk_commit();
+                    tile_update_symm<true>(Tb, At + tile_off(T0 + Rmax, T0 + Cmin), pol_stream, uvR, uzR, uvC, uzC, vCp, lane, accR);
+                    __syncwarp();  // the transposed reads below see every lane's writes
                 } else {
-                    tile_update_symm<false>(Tb, uvR, uzR, uvC, uzC, vCp, lane, accR);
+                    tile_update_symm<false>(Tb, nullptr, pol_stream, uvR, uzR, uvC, uzC, vCp, lane, accR);
                 }
                 S1_T(q2)
                 // the operand records of the next task travel while this one finishes
@@ -665,9 +672,6 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
                 S1_T(q4)
                 // refill this buffer with the task after next once the store has read it
                 {
-                    S1_T(w0)
-                    if (upd) bulk_wait_read();
-                    if (DBG) ps_t[7] += clock64() - w0;
                     if (i + 2 < ntasks) {
                         const int D2 = task(i + 2);
                         tile_load(Tb, bar, At, T0 + ((D2 >> 13) & 31), T0 + ((D2 >> 18) & 31), lane, pol_stream);
@@ -694,7 +698,7 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
                     }
                     const int need = sc.before_partner(pblk, s);
                     S1_T(sp0)
-                    while (ld_acquire_s32(blkstep + pblk) < need) {
+                    while (ld_flag(blkstep + pblk) < need) {
                     }
                     if (DBG) spin_t += clock64() - sp0;
                     double* yp = Y + 32 * (T0 + pblk) + g + 2 * t * ldy;
@@ -703,7 +707,7 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
 #pragma unroll
                         for (int h = 0; h < 2; ++h) yp[h * ldy + 8 * x] += accR[x][h];
                     __syncwarp();
-                    if (lane == 0) st_release_s32(blkstep + pblk, need + 1);
+                    if (lane == 0) st_flag(blkstep + pblk, need + 1);
                 }
                 if (!fl) {
 #pragma unroll
@@ -714,7 +718,7 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
                         }
                 } else {
                     const int need2 = sc.before_own(a, s);
-                    while (ld_acquire_s32(blkstep + a) < need2) {
+                    while (ld_flag(blkstep + a) < need2) {
                     }
                     double* yo = Y + 32 * (T0 + a) + g + 2 * t * ldy;
 #pragma unroll
@@ -722,7 +726,7 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
 #pragma unroll
                         for (int h = 0; h < 2; ++h) yo[h * ldy + 8 * x] += ow[x][h];
                     __syncwarp();
-                    if (lane == 0) st_release_s32(blkstep + a, need2 + 1);
+                    if (lane == 0) st_flag(blkstep + a, need2 + 1);
                 }
                 if (DBG) {
                     const long long q6 = clock64();
@@ -737,8 +741,6 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
             }
             ph0 = phb & 1;
             ph1 = (phb >> 1) & 1;
-            // all bulk stores of this pass must have landed before the next panel is read
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             S1_T(t_e0)
             __syncthreads();  // every warp's partner adds are in
             S1_T(t_e)
