@@ -47,8 +47,10 @@ constexpr int TILE = 1024;   // doubles per tile (no padding)
 constexpr int MAXOWN = 4;    // owned row tiles per warp: N <= 1024 -> nt <= 32 -> 4
 constexpr int QR = 4;        // panel rows per thread during the QR: m <= 1016 -> 4
 
-// column swizzle of tile row r: 4 * bitswap2(r & 3)
-__host__ __device__ __forceinline__ int csw(int r) { return ((r & 1) << 3) | ((r & 2) << 1); }
+// column swizzle of tile row r: 4 * f(r & 7), f = (0, 2, 1, 3, 2, 0, 3, 1): rows {0,2,4,6} and {1,3,5,7} each get four different values
+// (transposed operand reads of rows 2t + h are conflict-free) and rows 2j, 2j+1 differ in the high bit (so are the 128-bit
+// accumulator-fragment accesses)
+__host__ __device__ __forceinline__ int csw(int r) { return ((((r >> 1) & 3) + 2 * (r & 1)) & 3) << 2; }
 // position of element (r, c) inside a tile (row-major, swizzled columns)
 __host__ __device__ __forceinline__ int tix(int r, int c) { return (r << 5) + (c ^ csw(r)); }
 
@@ -259,17 +261,18 @@ __device__ __forceinline__ void tile_update_symm(double* __restrict__ Tb, double
     }
 }
 
-// accC (rows of Cmin) += S^T V'[Rmax rows]   (off-diagonal tiles; vRq[2 blk + h] = V'[32R + 8 blk + 4h + t][g])
-__device__ __forceinline__ void tile_symm_t(const double* __restrict__ Tb, const rec8& vRq, int lane, double (&accC)[2][4][2]) {
+// accC (rows of Cmin) += S^T V'[Rmax rows]   (off-diagonal tiles; same pair-order record: vRp[2 blk + h] = V'[32R + 8 blk + 2t + h][g])
+__device__ __forceinline__ void tile_symm_t(const double* __restrict__ Tb, const rec8& vRp, int lane, double (&accC)[2][4][2]) {
     const int g = lane >> 2, t = lane & 3;
-    const int cs = csw(t);
 #pragma unroll
     for (int rb = 0; rb < 4; ++rb)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const double* row = Tb + ((8 * rb + 4 * h + t) << 5);
+            const int r = 8 * rb + 2 * t + h;
+            const double* row = Tb + (r << 5);
+            const int cs = csw(2 * t + h);
 #pragma unroll
-            for (int cb = 0; cb < 4; ++cb) dmma(accC[h][cb][0], accC[h][cb][1], row[(8 * cb + g) ^ cs], vRq.v[2 * rb + h]);
+            for (int cb = 0; cb < 4; ++cb) dmma(accC[h][cb][0], accC[h][cb][1], row[(8 * cb + g) ^ cs], vRp.v[2 * rb + h]);
         }
 }
 
@@ -324,10 +327,10 @@ struct sched {
     }
 };
 
-// scratch layout per matrix (doubles): Vcm [8][ld] | recVp [NT][32][8] | recVq [NT][32][8] | recAV [2][NT][32][8] | recAZ [NT][32][8]
+// scratch layout per SM (doubles): Vcm [8][ld] | recVp [NT][32][8] | recAV [2][NT][32][8] | recAZ [NT][32][8]
 __host__ __device__ __forceinline__ size_t scratch_doubles(int N) {
     const size_t mp = ((N + 31) / 32) * 32, nt = mp / 32;
-    return 8 * (mp + 4) + 32 + 5 * nt * 256;
+    return 8 * (mp + 4) + 32 + 4 * nt * 256;
 }
 
 // DBG: cycle counters of CTA 0 (developer instrumentation, FKMC_S1_TIMING=1): dbg[0..7] phase totals of thread 0,
@@ -365,8 +368,7 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     double* Vcm = scr_all + (size_t)smid * scratch_doubles(N);
     double* recVp = Vcm + 8 * ld + 32;
-    double* recVq = recVp + NT * 256;
-    double* recAV = recVq + NT * 256;
+    double* recAV = recVp + NT * 256;
     double* recAZ = recAV + 2 * NT * 256;
 
     double* buf0 = TB0 + warp * TILE;
@@ -570,9 +572,8 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
             double* rA = recAV + (size_t)par * NT * 256;
             for (int idx = T0 * 256 + tid; idx < NT * 256; idx += T) {
                 const int e = idx & 7, ln = (idx >> 3) & 31, R = idx >> 8, gg = ln >> 2, tt = ln & 3;
-                // SYMM B operands: V[32R + 8 blk + 2t + h][g] (pair order) and V[32R + 8 blk + 4h + t][g] (quad order), e = 2 blk + h
+                // SYMM B operand (pair order): V[32R + 8 blk + 2t + h][g], e = 2 blk + h
                 st_keep(recVp + idx, X[gg * ld + 32 * R + 8 * (e >> 1) + 2 * tt + (e & 1)], pol_keep);
-                st_keep(recVq + idx, X[gg * ld + 32 * R + 8 * (e >> 1) + 4 * (e & 1) + tt], pol_keep);
                 // SYR2K A/B operand: V[32R + 8 blk + g][4q + t], e = 4q + blk
                 st_keep(rA + idx, X[(4 * (e >> 2) + tt) * ld + 32 * R + 8 * (e & 3) + gg], pol_keep);
             }
@@ -640,7 +641,7 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
                 double* Tb = slot ? buf1 : buf0;
                 uint64_t* bar = slot ? bar1 : bar0;
                 rec8 vRq;
-                if (!diag) vRq = load_rec(recVq, T0 + Rmax, lane, pol_keep);
+                if (!diag) vRq = load_rec(recVp, T0 + Rmax, lane, pol_keep);
                 S1_T(q0)
                 mbar_wait(bar, (phb >> slot) & 1);
                 phb ^= 1u << slot;
