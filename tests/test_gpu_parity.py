@@ -100,6 +100,54 @@ def test_sytrd_preserves_spectrum(ctx8, n):
         assert abs((d[b] ** 2).sum() + 2 * (e[b] ** 2).sum() - (A[b] ** 2).sum()) <= 1e-10 * (A[b] ** 2).sum() + 1e-12
 
 
+def _band_eigvals(AB):
+    # AB[d][c] = A(c+d, c): scipy's lower band form
+    return sl.eig_banded(AB, lower=True, eigvals_only=True)
+
+
+@pytest.mark.parametrize("n", [8, 16, 33, 100, 256, 512, 520, 576, 1024])
+def test_two_stage_reduction_preserves_spectrum(ctx8, n):
+    """dense -> band (sy2sb, half-bandwidth 8) -> tridiagonal (sb2st) against LAPACK; n >= 512 runs the tiled look-ahead kernel."""
+    rng = np.random.default_rng(n)
+    A = rng.normal(size=(3, n, n))
+    A = A + np.transpose(A, (0, 2, 1))
+    A[2] = np.diag(rng.normal(size=n)) + np.diag(np.ones(n - 1), 1) + np.diag(np.ones(n - 1), -1)  # already tridiagonal: trivial reflectors
+    AB = ctx8.sy2sb(np.tril(A) + 7.0 * np.triu(np.ones((n, n)), 1))  # only the lower triangle may be read
+    d, e = ctx8.sb2st(AB)
+    for b in range(3):
+        ref = sl.eigvalsh(A[b])
+        scale = max(1.0, np.abs(ref).max())
+        assert np.abs(_band_eigvals(AB[b]) - ref).max() <= 1e-12 * scale
+        assert np.abs(sl.eigvalsh_tridiagonal(d[b], e[b]) - ref).max() <= 1e-12 * scale
+        assert abs(AB[b, 0].sum() - np.trace(A[b])) <= 1e-11 * scale * n
+        fro = (AB[b, 0] ** 2).sum() + 2 * (AB[b, 1:] ** 2).sum()
+        assert abs(fro - (A[b] ** 2).sum()) <= 1e-10 * (A[b] ** 2).sum()
+
+
+def test_two_stage_full_size_batch():
+    """BASELINE config 5's measurement eigensolve at more than two waves of CTAs (the per-SM scratch slots of sy2sb are reused):
+    size-independent invariants for every matrix, oracle spot checks for a few."""
+    B, L, U, beta = 333, 32, 2.0, 20.0
+    c = fk.Context("cubic2d", L, max_batch=B)
+    n = c.N
+    rng = np.random.default_rng(5)
+    fs = (rng.random((B, n)) < 0.5).astype(np.int32)
+    ev = c.logz_ed(fs, U, U / 2, beta)["spectrum"]
+    assert (np.diff(ev, axis=1) >= 0).all()
+    nf = fs.sum(axis=1)
+    assert np.abs(ev.sum(axis=1) - (U * nf - U / 2 * n)).max() < 1e-9
+    assert np.abs((ev ** 2).sum(axis=1) - (4 * n + ((U * fs - U / 2) ** 2).sum(axis=1))).max() < 1e-8
+    r2 = c.logz_ed(1 - fs[:4], U, U / 2, beta)  # particle-hole symmetry on the bipartite lattice
+    assert np.abs(r2["spectrum"] + ev[:4, ::-1]).max() < 1e-11
+    for b in (0, 147, 148, 332):
+        ref = o.calc_ed(o.CUBIC2D, L, fs[b], U, U / 2, beta)
+        assert np.abs(ref["spectrum"] - ev[b]).max() <= TOL * np.abs(ref["spectrum"]).max()
+    # bit-reproducible: the shared-memory accumulation order of the tile pass is fixed
+    ev2 = c.logz_ed(fs[:160], U, U / 2, beta)["spectrum"]
+    assert np.array_equal(ev2, ev[:160])
+    c.close()
+
+
 # ---------------- calc_ed ----------------
 ED_CASES = [("cubic2d", 8, 1.0, 1.0), ("cubic2d", 16, 2.0, 10.0), ("cubic3d", 8, 4.0, 5.0), ("triangular", 24, 2.0, 10.0),
             ("honeycomb", 24, 2.0, 10.0), ("honeycomb_ref_lower", 24, 2.0, 10.0), ("cubic2d", 32, 2.0, 20.0), ("cubic1d", 12, 1.5, 3.0),
