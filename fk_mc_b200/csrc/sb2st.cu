@@ -7,9 +7,14 @@
 // Storage: Wb[c][d] = A(c+d, c), d = 0..15 (band 0..8 plus room for the transient fill 9..15), i.e. each
 // matrix column from its diagonal downward in 16 consecutive doubles.  Sweep j annihilates column j below
 // the sub-diagonal with an 8-row reflector and chases the resulting bulge down the band in blocks of 8
-// (Murata-Horikoshi / Lang).  Each warp owns whole sweeps; sweep j+1 may execute its step s once sweep j
-// has finished step s+2, which is tracked with per-sweep progress counters in shared memory, so up to
-// nwarps sweeps are in flight along the band.
+// (Murata-Horikoshi / Lang).  Sweep j+1 may execute its step s once sweep j has finished step s+2.
+//
+// Work decomposition: EIGHT LANES PER SWEEP, four consecutive sweeps per warp.  Every lane keeps the whole
+// reflector (8 doubles) in registers and owns one column (left update of the previous block, two-sided update of
+// the diagonal block) or one row (right update of the block below) of the 8x8 blocks, so all contractions with v
+// run inside a lane; per step a group needs only two 8-value broadcasts and two 8-lane sums.  The four groups of
+// a warp run in lockstep three steps apart -- exactly the lag the data dependence asks for -- so only the first
+// group of a warp has to watch another warp's progress counter.
 #include <cfloat>
 
 #include "common.cuh"
@@ -21,48 +26,39 @@ namespace {
 #endif
 constexpr int SB = 8;     // half bandwidth
 constexpr int WD = 16;    // stored sub-diagonals per column
+constexpr int LAG = 3;    // steps between consecutive sweeps
+
+// sum over the 8 lanes of a group (m: the group's lane mask)
+__device__ __forceinline__ double gsum8(double x, unsigned m) {
+    x += __shfl_xor_sync(m, x, 1);
+    x += __shfl_xor_sync(m, x, 2);
+    x += __shfl_xor_sync(m, x, 4);
+    return x;
+}
 
 struct refl {
-    double v;    // lane i (0..7 within every group of 8) holds v_i; v_0 = 1
+    double v;    // lane l of the group holds v_l; v_0 = 1
     double tau;
     double beta;
 };
 
-// sum over the 8 lanes that share (lane >> 3)
-__device__ __forceinline__ double sum8(double x) {
-    x += __shfl_xor_sync(0xffffffffu, x, 1);
-    x += __shfl_xor_sync(0xffffffffu, x, 2);
-    x += __shfl_xor_sync(0xffffffffu, x, 4);
-    return x;
-}
-// sum over the 4 groups (lanes with equal lane & 7)
-__device__ __forceinline__ double sum4g(double x) {
-    x += __shfl_xor_sync(0xffffffffu, x, 8);
-    x += __shfl_xor_sync(0xffffffffu, x, 16);
-    return x;
-}
-
-// Householder reflector for x (x_i in lane i of each group, i < n; zero beyond n)
-__device__ __forceinline__ refl make_reflector(double x, int i, int n) {
+// Householder reflector for x (x_l in lane l of the group, l < n; zero beyond n)
+__device__ __forceinline__ refl make_reflector(double x, int l, int n, unsigned m, int gbase) {
     refl R;
-    const double tail2 = sum8((i >= 1 && i < n) ? x * x : 0.0);
-    const double x0 = __shfl_sync(0xffffffffu, x, (threadIdx.x & 24));  // lane 0 of this group
-    if (tail2 <= DBL_MIN) {
-        R.tau = 0.0;
-        R.beta = x0;
-        R.v = (i == 0) ? 1.0 : 0.0;
-    } else {
-        double beta = sqrt(fma(x0, x0, tail2));
-        if (x0 >= 0.0) beta = -beta;
-        R.beta = beta;
-        R.tau = (beta - x0) / beta;
-        const double inv = 1.0 / (x0 - beta);
-        R.v = (i == 0) ? 1.0 : ((i < n) ? x * inv : 0.0);
-    }
+    const double tail2 = gsum8((l >= 1 && l < n) ? x * x : 0.0, m);
+    const double x0 = __shfl_sync(m, x, gbase);
+    const bool triv = tail2 <= DBL_MIN;
+    double beta = sqrt(fma(x0, x0, triv ? 1.0 : tail2));
+    if (x0 >= 0.0) beta = -beta;
+    const double tau = (beta - x0) / beta;
+    const double inv = 1.0 / (x0 - beta);
+    R.beta = triv ? x0 : beta;
+    R.tau = triv ? 0.0 : tau;
+    R.v = (l == 0) ? 1.0 : ((l < n && !triv) ? x * inv : 0.0);
     return R;
 }
 
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(512, 1)
 sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_all, double* __restrict__ e_all) {
     extern __shared__ double smem[];
     double* Wb = smem;                                         // [N + 16][16]
@@ -77,99 +73,120 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
     for (int j = tid; j < N; j += T) prog[j] = 0;
     __syncthreads();
 
-    const int i = lane & 7, q = lane >> 3;  // i: row index inside a block of 8, q: column group
+    const int l = lane & 7, q = lane >> 3, gbase = lane & 24;
+    const unsigned gmask = 0xffu << gbase;
     const int nsweeps = N - 2;
-    for (int j = warp; j < nsweeps; j += nwarps) {
+    for (int jb = 4 * warp; jb < nsweeps; jb += 4 * nwarps) {
+        const int j = jb + q;
         int p = j + 1;                  // first row of the current reflector's index set
         int n = min(SB, N - p);         // its size
-        // ---- step 0: annihilate column j below the sub-diagonal ----
-        if (j > 0) {
-            while (prog[j - 1] < 3) { __nanosleep(FKMC_SB2ST_SLEEP); }
-            __threadfence_block();
-        }
-        double x = Wb[(size_t)j * WD + 1 + i];  // rows p..p+7 of column j (zero beyond the matrix)
-        refl R = make_reflector(x, i, n);
-        if (q == 0 && i < n) Wb[(size_t)j * WD + 1 + i] = (i == 0) ? R.beta : 0.0;
-        int s = 0;
-        while (true) {
-            const double vi = R.v, tau = R.tau;
-            // (i) [s >= 1] left-apply H to the other 7 columns of the bulge block A(J, p-8+1 .. p-1)
-            if (s >= 1 && tau != 0.0) {
+        int s = -LAG * q;               // step of this group (negative: not started)
+        bool done = j >= nsweeps;
+        double v[SB], vl = 0.0, tau = 0.0;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int cc = 1 + q + 4 * h;  // column offset inside the previous block, 1..8 (8 is out of range)
-                    const bool ok = cc < SB;
-                    const int c = p - SB + (ok ? cc : 1);
-                    double* col = Wb + (size_t)c * WD;
-                    const double a = ok ? col[p - c + i] : 0.0;
-                    const double w = tau * sum8(vi * a);
-                    if (ok) col[p - c + i] = a - vi * w;
-                }
-            }
-            // (ii) two-sided update of the diagonal block D = A(J, J): lane (i, q) owns D(i, c) for c = q, q+4
-            if (tau != 0.0) {
-                double dcol[2], vc[2];
-                double part = 0.0;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int c = q + 4 * h;
-                    const int hi = max(i, c), lo = min(i, c);
-                    dcol[h] = Wb[(size_t)(p + lo) * WD + (hi - lo)];
-                    vc[h] = __shfl_sync(0xffffffffu, vi, (lane & 24) + c);
-                    part = fma(dcol[h], vc[h], part);
-                }
-                double u = tau * sum4g(part);                  // u_i = tau * (D v)_i
-                const double alpha = -0.5 * tau * sum8(u * vi);
-                u = fma(alpha, vi, u);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int c = q + 4 * h;
-                    const double uc = __shfl_sync(0xffffffffu, u, (lane & 24) + c);
-                    if (i >= c) Wb[(size_t)(p + c) * WD + (i - c)] = dcol[h] - vi * uc - u * vc[h];
-                }
-            }
-            // (iii) right-apply H to the block below: A(Jn, J), Jn = rows p+8 .. p+15; lane (i, q) owns rows i, columns q, q+4
-            const int pn = p + SB;
-            const int nn = min(SB, N - pn);
-            double xnext = 0.0;
-            if (n == SB && nn > 0) {
-                double bel[2], vc[2];
-                double part = 0.0;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int c = q + 4 * h;
-                    bel[h] = Wb[(size_t)(p + c) * WD + (SB + i - c)];
-                    vc[h] = __shfl_sync(0xffffffffu, vi, (lane & 24) + c);
-                    part = fma(bel[h], vc[h], part);
-                }
-                const double z = tau * sum4g(part);            // z_i = tau * sum_c B(i, c) v_c
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int c = q + 4 * h;
-                    bel[h] = fma(-z, vc[h], bel[h]);
-                    if (tau != 0.0) Wb[(size_t)(p + c) * WD + (SB + i - c)] = bel[h];
-                }
-                xnext = __shfl_sync(0xffffffffu, bel[0], i);   // column 0 of the block lives in group q = 0, h = 0
+        for (int i = 0; i < SB; ++i) v[i] = 0.0;
+        while (!__all_sync(0xffffffffu, done)) {
+            const bool act = !done && s >= 0;
+            // only the first sweep of the warp depends on another warp: sweep jb-1 must have finished step s+2
+            if (q == 0 && act && jb > 0) {
+                while (prog[jb - 1] < s + LAG) { __nanosleep(FKMC_SB2ST_SLEEP); }
             }
             __syncwarp();
-            // publish progress, then move to the next block
             __threadfence_block();
-            ++s;
-            if (lane == 0) prog[j] = s;
-            if (!(n == SB && nn >= 2)) break;
-            if (j > 0) {
-                while (prog[j - 1] < s + 3) { __nanosleep(FKMC_SB2ST_SLEEP); }
-                __threadfence_block();
+            if (act) {
+                if (s == 0) {
+                    // ---- step 0: annihilate column j below the sub-diagonal ----
+                    const double x = Wb[(size_t)j * WD + 1 + l];  // rows p..p+7 of column j (zero beyond the matrix)
+                    const refl R = make_reflector(x, l, n, gmask, gbase);
+                    if (l < n) Wb[(size_t)j * WD + 1 + l] = (l == 0) ? R.beta : 0.0;
+                    vl = R.v;
+                    tau = R.tau;
+#pragma unroll
+                    for (int i = 0; i < SB; ++i) v[i] = __shfl_sync(gmask, vl, gbase + i);
+                }
+                // One step = three independent block updates with the same reflector (tau = 0 makes all of them the identity):
+                //   (i)   [s >= 1] left-apply H to columns p-7 .. p-1 of the bulge block A(J, .): lane l owns column p-8+l
+                //   (ii)  two-sided update of the diagonal block D = A(J, J): lane l owns its (symmetric) column l
+                //   (iii) right-apply H to the block below, A(Jn, J), Jn = rows p+8 .. p+15: lane l owns row l
+                // All loads first, then the arithmetic in one basic block (the three FMA chains and the next reflector's
+                // sqrt / divisions interleave), then the stores.
+                const int pn = p + SB;
+                const int nn = min(SB, N - pn);
+                const bool c1 = (s >= 1) && (l >= 1);
+                const bool c3 = (n == SB) && (nn > 0);
+                double* col = Wb + (size_t)(c1 ? (p - SB + l) : p) * WD + (SB - l);
+                double* D0 = Wb + (size_t)p * WD;
+                double* B0 = Wb + (size_t)p * WD + SB + l;
+                double a[SB], dcol[SB], bel[SB];
+#pragma unroll
+                for (int i = 0; i < SB; ++i) {
+                    bel[i] = c3 ? B0[i * (WD - 1)] : 0.0;
+                    dcol[i] = D0[min(i, l) * (WD - 1) + max(i, l)];
+                    a[i] = c1 ? col[i] : 0.0;
+                }
+                // (iii) first: the next reflector hangs on it
+                double z0 = 0.0, z1 = 0.0;
+#pragma unroll
+                for (int c = 0; c < SB; c += 2) {
+                    z0 = fma(bel[c], v[c], z0);
+                    z1 = fma(bel[c + 1], v[c + 1], z1);
+                }
+                const double z = tau * (z0 + z1);
+#pragma unroll
+                for (int c = 0; c < SB; ++c) bel[c] = fma(-z, v[c], bel[c]);
+                const bool more = (n == SB && nn >= 2);
+                // next reflector from the first column of the block below (rows pn.., column p): only this sweep touches it now
+                const refl R = make_reflector(bel[0], l, nn, gmask, gbase);
+                // (i)
+                double w0 = 0.0, w1 = 0.0;
+#pragma unroll
+                for (int i = 0; i < SB; i += 2) {
+                    w0 = fma(v[i], a[i], w0);
+                    w1 = fma(v[i + 1], a[i + 1], w1);
+                }
+                const double w = tau * (w0 + w1);
+#pragma unroll
+                for (int i = 0; i < SB; ++i) a[i] = fma(-v[i], w, a[i]);
+                // (ii)
+                double u0 = 0.0, u1 = 0.0;
+#pragma unroll
+                for (int i = 0; i < SB; i += 2) {
+                    u0 = fma(dcol[i], v[i], u0);
+                    u1 = fma(dcol[i + 1], v[i + 1], u1);
+                }
+                double u = tau * (u0 + u1);                        // u_l = tau (D v)_l
+                const double alpha = -0.5 * tau * gsum8(u * vl, gmask);
+                u = fma(alpha, vl, u);
+#pragma unroll
+                for (int i = 0; i < SB; ++i) {
+                    const double ui = __shfl_sync(gmask, u, gbase + i);
+                    dcol[i] = dcol[i] - v[i] * u - ui * vl;
+                }
+                // stores
+#pragma unroll
+                for (int i = 0; i < SB; ++i) {
+                    if (c1) col[i] = a[i];
+                    if (i >= l) D0[l * (WD - 1) + i] = dcol[i];
+                    if (c3) B0[i * (WD - 1)] = bel[i];
+                }
+                if (more) {
+                    if (l < nn) Wb[(size_t)p * WD + SB + l] = (l == 0) ? R.beta : 0.0;
+                    vl = R.v;
+                    tau = R.tau;
+#pragma unroll
+                    for (int i = 0; i < SB; ++i) v[i] = __shfl_sync(gmask, vl, gbase + i);
+                    p = pn;
+                    n = nn;
+                } else {
+                    done = true;
+                }
             }
-            // reflector from the first column of the block below (rows pn.., column p); re-read after the wait is not
-            // needed: that column is only ever touched by this sweep at this point
-            R = make_reflector(xnext, i, nn);
-            if (q == 0 && i < nn) Wb[(size_t)p * WD + SB + i] = (i == 0) ? R.beta : 0.0;
-            p = pn;
-            n = nn;
+            // publish progress: the writes of this step are visible before the counter moves
+            __syncwarp();
+            __threadfence_block();
+            if (act && l == 0) prog[j] = done ? (1 << 30) : s + 1;
+            ++s;
         }
-        __threadfence_block();
-        if (lane == 0) prog[j] = 1 << 30;
     }
     __syncthreads();
     double* dd = d_all + (size_t)b * N;
@@ -188,9 +205,10 @@ int fkmc_launch_sb2st(fkmc_ctx* ctx, const double* d_AB, int N, int B, double* d
     fkmc_prof_scope ps(ctx, "sb2st");
     const size_t smem = fkmc_sb2st_smem(N);
     if (smem > ctx->smem_optin) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sb2st: matrix too large for shared memory");
-    int nwarps = (N + 23) / 24;  // ~one warp per 3 blocks of the band (the pipeline lag)
-    if (nwarps < 1) nwarps = 1;
-    if (nwarps > ((N > 640) ? 32 : 16)) nwarps = (N > 640) ? 32 : 16;  // <= 512 threads keeps two CTAs per SM for N <= 512
+    // sweeps in flight <= blocks along the band / lag, four sweeps per warp
+    const int nblk = (N + SB - 1) / SB;
+    int nwarps = ((nblk + LAG - 1) / LAG + 3) / 4 + 1;
+    if (nwarps > 16) nwarps = 16;
     FKMC_CUDA(ctx, cudaFuncSetAttribute(sb2st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     sb2st_kernel<<<B, nwarps * 32, smem, ctx->stream>>>(d_AB, N, d_d, d_e);
     ctx->launches++;
