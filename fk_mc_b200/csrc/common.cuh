@@ -77,6 +77,7 @@ struct fkmc_ctx {
     size_t s1_scratch_cap = 0;       // doubles
     int nsmid = 0;                   // %nsmid of the device (scratch slots of sy2sb)
     int tridiag_mode = 2;       // 1: one-stage blocked sytrd, 2: sy2sb + sb2st
+    int sb2st_warps = 0;        // 0: automatic
     int kpm_force_generic = 0;  // 1: always use the full-lattice-vector KPM kernel (for cross-checks)
     double* d_d = nullptr;      // [max_batch][N]
     double* d_e = nullptr;      // [max_batch][N]

@@ -207,8 +207,10 @@ int fkmc_launch_sb2st(fkmc_ctx* ctx, const double* d_AB, int N, int B, double* d
     if (smem > ctx->smem_optin) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sb2st: matrix too large for shared memory");
     // sweeps in flight <= blocks along the band / lag, four sweeps per warp
     const int nblk = (N + SB - 1) / SB;
-    int nwarps = ((nblk + LAG - 1) / LAG + 3) / 4 + 1;
-    if (nwarps > 16) nwarps = 16;
+    int nwarps = ((nblk + LAG - 1) / LAG + 3) / 4;  // measured: N=1024 flat from 8 to 12 warps, N=256 best at 3 (several CTAs share an SM)
+    if (nwarps < 1) nwarps = 1;
+    if (nwarps > 12) nwarps = 12;
+    if (ctx->sb2st_warps > 0) nwarps = ctx->sb2st_warps;  // tuning override (fkmc_set_option "sb2st_warps")
     FKMC_CUDA(ctx, cudaFuncSetAttribute(sb2st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     sb2st_kernel<<<B, nwarps * 32, smem, ctx->stream>>>(d_AB, N, d_d, d_e);
     ctx->launches++;
