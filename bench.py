@@ -211,6 +211,11 @@ def main():
         tot, n = ctx.profile_get(name)
         if n:
             fam[name] = {"ms_per_launch": tot / n, "launches": n, "share": tot / ms_total}
+    sub = {}  # the two kernels inside one "kpm" evaluation (csrc/kpm2d.cu); their time is already counted in fam["kpm"]
+    for name in ("kpm_lanczos", "kpm_moments"):
+        tot, n = ctx.profile_get(name)
+        if n:
+            sub[name] = {"ms_per_launch": tot / n, "launches": n, "share": tot / ms_total, "part_of": "kpm"}
     peaks, peak_src = measured_peaks()
     # roofline of the dominant kernel (largest share of the timed region); both candidates are always reported
     rl_kpm = rl_dense = None
@@ -223,7 +228,7 @@ def main():
             tr_k = tr["bytes_per_launch"] * chains / tr["units_per_launch"]
         except Exception:
             pass
-        rl_kpm = {"kernel": "kpm_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        rl_kpm = {"kernel": "lanczos2d_kernel + kpm_moments2d_kernel" if sub else "kpm_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                   "frac": achieved / peaks["hbm_gbs"], "traffic": tr_k, "peak_source": peak_src,
                   "note": "algorithmic bytes of the streaming formulation (SURVEY 8d); the kernel keeps the recursion in shared memory, "
                           "so DRAM traffic is far below it and frac exceeds 1"}
@@ -333,7 +338,7 @@ def main():
                            "moves": "add_remove", "M": M if cheb else None, "G": G if cheb else None,
                            "l2_flush": "256 MiB device memset between timed steps", "parallelism": "chains sharded, %d per GPU" % chains},
                 "sweeps_per_sec": value / SWEEP_LEN, "roofline": roofline, "roofline_dense": roofline_dense, "roofline_kpm": roofline_kpm,
-                "dominant_kernel": dominant, "kernels": fam,
+                "dominant_kernel": dominant, "kernels": {**fam, **sub},
                 "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks,
                 "final_gather_ms": gather_ms}
         print(json.dumps(line), flush=True)

@@ -9,7 +9,7 @@ import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
-LIB_PATH = os.path.join(PKG_DIR, "lib", "libfkmc_b200.so")
+LIB_PATH = os.environ.get("FKMC_LIB", os.path.join(PKG_DIR, "lib", "libfkmc_b200.so"))  # FKMC_LIB: developer builds (instrumented kernels)
 HEADER = os.path.join(ROOT, "include", "fkmc.h")
 
 KINDS = {"cubic1d": 1, "cubic2d": 2, "cubic3d": 3, "triangular": 4, "honeycomb": 5, "honeycomb_ref_lower": 7}

@@ -79,6 +79,11 @@ struct fkmc_ctx {
     int tridiag_mode = 2;       // 1: one-stage blocked sytrd, 2: sy2sb + sb2st
     int sb2st_warps = 0;        // 0: automatic
     int kpm_force_generic = 0;  // 1: always use the full-lattice-vector KPM kernel (for cross-checks)
+    int kpm_force_v1 = 0;       // 1: single-kernel KPM (kpm.cu) even where the two-kernel 2-D path (kpm2d.cu) applies
+    int kpm2_H = 0;             // radius of the cached patch tables of kpm2d.cu
+    int* d_kpm2_cnt = nullptr;
+    int* d_kpm2_off = nullptr;
+    unsigned short* d_kpm2_nb = nullptr;
     double* d_d = nullptr;      // [max_batch][N]
     double* d_e = nullptr;      // [max_batch][N]
     double* d_tau = nullptr;    // [max_batch][N]
@@ -160,6 +165,10 @@ int fkmc_launch_energy(fkmc_ctx* ctx, const double* d_evals, long evals_stride, 
 int fkmc_prepare_cheb(fkmc_ctx* ctx, int M, int G);
 int fkmc_launch_kpm(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, int M, int G,
                     double* d_moments, double* d_ab, double* d_logz);
+// two-kernel variant for the regular 2-D lattices (kpm2d.cu); slot_val = per-slot hopping constants
+bool fkmc_kpm2d_applicable(const fkmc_ctx* ctx, int M);
+int fkmc_launch_kpm2d(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, int M, int G, const double* slot_val,
+                      double* d_moments, double* d_ab, double* d_logz);
 // eigenvector path (measurement sweeps): evals/out on the device, eigenvectors and IPR to the host (or IPR to d_ipr)
 int fkmc_eigvec_pipeline(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, double* d_evals, double* d_out,
                          double* h_evecs, double* h_ipr_host, double* d_ipr);

@@ -1,0 +1,795 @@
+// Two-kernel Chebyshev / KPM weight evaluation for the regular 2-D lattices (cubic2d, triangular, honeycomb brick wall).
+//
+// Same contract as kpm.cu (configuration_t::calc_chebyshev, src/configuration.cpp:94-205; chebyshev_eval,
+// include/fk_mc/chebyshev.hpp:21-54), split by what bounds each half:
+//
+//   lanczos2d_kernel   e_min / e_max of H (reference: two ARPACK solves, configuration.cpp:99-100).  Latency-bound, so the
+//                      CTA is small (128 threads, one 1 x 8 strip of the lattice per thread) and many proposals share an SM.
+//                      The stencil reads whole neighbour strips with 128-bit shared-memory loads, x neighbours stay in
+//                      registers.  Ritz values of the Lanczos tridiagonal come from Laguerre's iteration on the
+//                      characteristic polynomial (monotone from outside the spectrum, cubic convergence), confirmed and
+//                      rounded by one 32-point Sturm count around the result; the multisection of kpm.cu is the fallback.
+//   kpm_moments2d_kernel  exact full-trace moments mu_m = Tr T_m(X)/N by the column recursion (configuration.cpp:117-194).
+//                      T_m(X) e_j lives on the sites within m hops of j, so the sites of the H-hop neighbourhood are numbered
+//                      ring by ring (element e of a patch = lane e % 32, slot e / 32) and step m only touches the
+//                      slots below cnt(m): 18 warp-wide element updates per column for H = 8 instead of 70 for the
+//                      (2H+1)^2 square.  Neighbour positions come from a per-lattice table built on the host from the
+//                      context's own stencil, so one kernel serves all three lattices.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <queue>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int LZ_KMAX = 384;      // Lanczos step cap (as kpm.cu)
+constexpr int LZ_T = 128;         // threads per proposal
+constexpr int LZ_FIRST = 64;      // first Ritz evaluation
+constexpr int LZ_EVERY = 16;      // then every LZ_EVERY steps, compared with the previous evaluation
+
+struct lz_args {
+    const int32_t* f;
+    int N, L;
+    double U, mu_c, ht, hp;
+    double* ab;   // [B][4]: e_min, e_max written here
+    int* flag;
+    int* steps;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Sturm count of the k x k Lanczos tridiagonal: number of eigenvalues below x.  ab[i] = (alpha_i, beta_i^2), beta_0 = 0.
+__device__ __forceinline__ int sturm_below(const double2* __restrict__ ab, int k, double x) {
+    // p_{i+1} = (alpha_i - x) p_i - beta_i^2 p_{i-1}; an exact zero counts as negative (the next value then has the sign
+    // opposite to the previous one, so the number of sign changes comes out right) -- the sign logic stays off the FMA chain
+    double pm1 = 1.0, p = ab[0].x - x;
+    bool neg = !(p > 0.0);
+    int cnt = neg ? 1 : 0;
+    int i = 1;
+    for (; i + 8 <= k; i += 8) {
+        double2 q[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) q[u] = ab[i + u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double pn = fma(q[u].x - x, p, -(q[u].y * pm1));
+            const bool nneg = !(pn > 0.0);
+            cnt += (nneg != neg) ? 1 : 0;
+            neg = nneg;
+            pm1 = p;
+            p = pn;
+        }
+        const double m = fmax(fabs(p), fabs(pm1));
+        if (m > 1.157920892373162e77) { p *= 8.636168555094445e-78; pm1 *= 8.636168555094445e-78; }
+        else if (m < 8.636168555094445e-78) { p *= 1.157920892373162e77; pm1 *= 1.157920892373162e77; }
+    }
+    for (; i < k; ++i) {
+        const double2 q = ab[i];
+        const double pn = fma(q.x - x, p, -(q.y * pm1));
+        const bool nneg = !(pn > 0.0);
+        cnt += (nneg != neg) ? 1 : 0;
+        neg = nneg;
+        pm1 = p;
+        p = pn;
+    }
+    return cnt;
+}
+
+// idx-th eigenvalue by 32-way multisection inside [lo, hi] (whole warp; the rigorous fallback)
+__device__ __forceinline__ double warp_multisect(const double2* __restrict__ ab, int k, int idx, double lo, double hi, int lane) {
+    const double pad = 8.0 * DBL_EPSILON * fmax(fabs(lo), fabs(hi)) + DBL_MIN;
+    double a = lo - pad, c = hi + pad;
+    for (int round = 0; round < 14; ++round) {
+        const double h = (c - a) * (1.0 / 33.0);
+        if (!(h > 2.0 * DBL_EPSILON * fmax(fabs(a), fabs(c)) * (1.0 / 33.0))) break;
+        const double x = a + h * (double)(lane + 1);
+        const bool above = sturm_below(ab, k, x) > idx;
+        const unsigned mask = __ballot_sync(0xffffffffu, above);
+        const int first = mask ? (__ffs(mask) - 1) : 32;
+        const double na = first > 0 ? a + h * (double)first : a;
+        const double nc = first < 32 ? a + h * (double)(first + 1) : c;
+        a = na;
+        c = nc;
+    }
+    return 0.5 * (a + c);
+}
+
+// p(x) = det(T_k - x) with p', p'' by a warp-wide product of 2x2 transfer matrices: (p_i, p_{i-1})^T = M_i (p_{i-1}, p_{i-2})^T,
+// M_i = [[alpha_{i-1} - x, -beta_{i-1}^2], [1, 0]].  Lane l multiplies its chunk of rows, a butterfly over the lanes multiplies the
+// chunks in order (the partner with the higher lane index holds the later rows = the left factor).  The triple (P, P', P'') is
+// rescaled by a power of two after every stage: only the ratios p'/p and p''/p are used.
+struct tm3 {
+    double p[4], d[4], s[4];  // row-major 2x2: P, dP/dx, d2P/dx2
+};
+__device__ __forceinline__ void mm2(const double* A, const double* B, double* C) {  // C = A B
+    C[0] = fma(A[0], B[0], A[1] * B[2]);
+    C[1] = fma(A[0], B[1], A[1] * B[3]);
+    C[2] = fma(A[2], B[0], A[3] * B[2]);
+    C[3] = fma(A[2], B[1], A[3] * B[3]);
+}
+__device__ __forceinline__ void mm2acc(const double* A, const double* B, double* C, double w) {  // C += w A B
+    C[0] = fma(w * A[0], B[0], fma(w * A[1], B[2], C[0]));
+    C[1] = fma(w * A[0], B[1], fma(w * A[1], B[3], C[1]));
+    C[2] = fma(w * A[2], B[0], fma(w * A[3], B[2], C[2]));
+    C[3] = fma(w * A[2], B[1], fma(w * A[3], B[3], C[3]));
+}
+__device__ __forceinline__ void warp_charpoly3(const double2* __restrict__ ab, int k, double x, int lane, double& p, double& dp, double& ddp) {
+    const int c = (k + 31) >> 5;
+    tm3 t;
+    t.p[0] = 1.0; t.p[1] = 0.0; t.p[2] = 0.0; t.p[3] = 1.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t.d[i] = t.s[i] = 0.0;
+    const int r0 = lane * c, r1 = min(k, r0 + c);
+    for (int i = r0; i < r1; ++i) {
+        const double2 q = ab[i];
+        const double a = q.x - x, b = q.y;
+        // X <- M X;  X' <- M X' - E11 X;  X'' <- M X'' - 2 E11 X'
+        const double s0 = fma(a, t.s[0], fma(-b, t.s[2], -2.0 * t.d[0])), s1 = fma(a, t.s[1], fma(-b, t.s[3], -2.0 * t.d[1]));
+        t.s[2] = t.s[0]; t.s[3] = t.s[1]; t.s[0] = s0; t.s[1] = s1;
+        const double d0 = fma(a, t.d[0], fma(-b, t.d[2], -t.p[0])), d1 = fma(a, t.d[1], fma(-b, t.d[3], -t.p[1]));
+        t.d[2] = t.d[0]; t.d[3] = t.d[1]; t.d[0] = d0; t.d[1] = d1;
+        const double p0 = fma(a, t.p[0], -(b * t.p[2])), p1 = fma(a, t.p[1], -(b * t.p[3]));
+        t.p[2] = t.p[0]; t.p[3] = t.p[1]; t.p[0] = p0; t.p[1] = p1;
+    }
+#pragma unroll
+    for (int mask = 1; mask < 32; mask <<= 1) {
+        tm3 o;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            o.p[i] = __shfl_xor_sync(0xffffffffu, t.p[i], mask);
+            o.d[i] = __shfl_xor_sync(0xffffffffu, t.d[i], mask);
+            o.s[i] = __shfl_xor_sync(0xffffffffu, t.s[i], mask);
+        }
+        const bool high = (lane & mask) != 0;  // own chunk holds the later rows
+        tm3 H, Lo;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            H.p[i] = high ? t.p[i] : o.p[i]; H.d[i] = high ? t.d[i] : o.d[i]; H.s[i] = high ? t.s[i] : o.s[i];
+            Lo.p[i] = high ? o.p[i] : t.p[i]; Lo.d[i] = high ? o.d[i] : t.d[i]; Lo.s[i] = high ? o.s[i] : t.s[i];
+        }
+        mm2(H.p, Lo.p, t.p);
+        mm2(H.d, Lo.p, t.d);
+        mm2acc(H.p, Lo.d, t.d, 1.0);
+        mm2(H.s, Lo.p, t.s);
+        mm2acc(H.d, Lo.d, t.s, 2.0);
+        mm2acc(H.p, Lo.s, t.s, 1.0);
+        double m = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m = fmax(m, fmax(fabs(t.p[i]), fmax(fabs(t.d[i]), fabs(t.s[i]))));
+        const int ex = (__double2hiint(m) >> 20) & 0x7ff;
+        const double sc = __hiloint2double(min(max(2046 - ex, 1), 2046) << 20, 0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { t.p[i] *= sc; t.d[i] *= sc; t.s[i] *= sc; }
+    }
+    p = t.p[0];
+    dp = t.d[0];
+    ddp = t.s[0];
+}
+
+// Laguerre's iteration on p(x) = det(T_k - x) from a start outside the spectrum (x0 below every eigenvalue for the lower
+// end, above for the upper end): the iterates move monotonically towards the nearest root and never pass it.  Whole warp.
+__device__ __forceinline__ double laguerre_end(const double2* __restrict__ ab, int k, double x, double tol, int lane, int& iters) {
+    const double n = (double)k;
+    for (int it = 0; it < 24; ++it) {
+        ++iters;
+        double p1, d1, s1;
+        warp_charpoly3(ab, k, x, lane, p1, d1, s1);
+        if (p1 == 0.0) return x;
+        const double Gq = d1 / p1, Hq = Gq * Gq - s1 / p1;
+        double disc = (n - 1.0) * (n * Hq - Gq * Gq);
+        disc = disc > 0.0 ? sqrt(disc) : 0.0;
+        const double den = Gq >= 0.0 ? Gq + disc : Gq - disc;
+        if (den == 0.0) return x;
+        const double a = n / den;
+        x -= a;
+        if (fabs(a) <= tol) break;
+    }
+    return x;
+}
+
+// Ritz value at one end of T_k (upper = false: smallest, true: largest), whole warp.  gl / gh enclose the spectrum.
+// With a previous value (of a leading sub-matrix: interlacing puts it inside the new spectrum, next to the wanted end) the
+// iteration starts there and typically needs two steps; a start outside the spectrum is the safe restart.  Either way the
+// result is accepted only when 32 Sturm counts around it bracket the wanted eigenvalue; the multisection is the last resort.
+__device__ __noinline__ double warp_ritz_end(const double2* __restrict__ ab, int k, bool upper, double gl, double gh, double hscale,
+                                             int lane, bool have_prev, double prev, int& iters, int& fallbacks) {
+    const double pad = 8.0 * DBL_EPSILON * fmax(fabs(gl), fabs(gh)) + DBL_MIN;
+    const double delta = 2.0 * DBL_EPSILON * hscale;
+    const int idx = upper ? k - 1 : 0;
+    for (int attempt = have_prev ? 0 : 1; attempt < 2; ++attempt) {
+        const double x0 = attempt == 0 ? prev : (upper ? gh + pad : gl - pad);
+        const double xs = __shfl_sync(0xffffffffu, laguerre_end(ab, k, x0, 1e-9 * hscale, lane, iters), 0);
+        // the eigenvalue sits between the last point with count <= idx and the first with count > idx
+        const double x = xs + delta * ((double)lane - 15.5);
+        const bool above = sturm_below(ab, k, x) > idx;
+        const unsigned mask = __ballot_sync(0xffffffffu, above);
+        if (mask != 0u && mask != 0xffffffffu) {
+            const int first = __ffs(mask) - 1;  // counts are monotone in x: lanes >= first are above
+            return xs + delta * ((double)first - 16.0);
+        }
+        ++fallbacks;
+    }
+    return warp_multisect(ab, k, idx, gl, gh, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Lanczos for e_min / e_max.  Thread t owns the strip (y, 8 sx .. 8 sx + 7), t = y (L/8) + sx; site index = y L + x
+// (hypercubic_lattice::pos_to_index: last coordinate fastest).
+template <int KIND>
+__global__ void __launch_bounds__(LZ_T, 4) lanczos2d_kernel(lz_args P) {
+    extern __shared__ __align__(16) double sm[];
+    const int N = P.N, L = P.L;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARP = LZ_T / 32;
+    double* vb0 = sm;                                         // [N] v_k, ping
+    double* vb1 = vb0 + N;                                    // [N] v_k, pong
+    double2* ab = reinterpret_cast<double2*>(vb1 + N);        // [LZ_KMAX + 1] (alpha_i, beta_i^2)
+    double* rpA = reinterpret_cast<double*>(ab + LZ_KMAX + 2);  // [NWARP]
+    double* rpB = rpA + NWARP;                                // [NWARP]
+    double* msc = rpB + NWARP;                                // [8]
+
+    const int nstrip = L >> 3, NS = N >> 3;
+    const bool active = tid < NS;
+    const int y = active ? tid / nstrip : 0, sx = active ? tid - y * nstrip : 0, x0 = sx << 3;
+    // shared vectors are strip-major: element e of strip t at e * NS + t, so that a warp's accesses are consecutive words
+    const int tu = (y + 1 == L) ? sx : tid + nstrip, td = (y == 0) ? tid + NS - nstrip : tid - nstrip;     // strips above / below
+    const int sl = (sx == 0) ? nstrip - 1 : -1, sr = (sx + 1 == nstrip) ? 1 - nstrip : 1;                      // strip offsets left / right
+    const int base = y * L + x0;
+    const bool yodd = (y & 1) != 0;
+
+    double xd[8], vr[8], pr[8];
+    {
+        const int4* fp = reinterpret_cast<const int4*>(P.f + (size_t)b * N + base);
+        int fv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (active) {
+            const int4 a = fp[0], c = fp[1];
+            fv[0] = a.x; fv[1] = a.y; fv[2] = a.z; fv[3] = a.w; fv[4] = c.x; fv[5] = c.y; fv[6] = c.z; fv[7] = c.w;
+        }
+        double part = 0.0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            xd[e] = P.U * (double)fv[e] - P.mu_c;
+            double v = 0.0;
+            if (active) {
+                unsigned h = (unsigned)(base + e) * 2654435761u + 0x9e3779b9u;
+                h ^= h >> 15; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+                v = (double)h * (1.0 / 4294967296.0) - 0.5;
+            }
+            vr[e] = v;
+            pr[e] = 0.0;
+            part = fma(v, v, part);
+        }
+        part = warp_sum(part);
+        if (lane == 0) rpA[warp] = part;
+        if (tid == 0) ab[0].y = 0.0;
+        __syncthreads();
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) s += rpA[w];
+        const double inv = rsqrt(s);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) vr[e] *= inv;
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) vb0[e * NS + tid] = vr[e];
+        }
+        __syncthreads();
+    }
+
+    const int kcap = min(LZ_KMAX, N);
+    double e_min = 0.0, e_max = 0.0, gl = DBL_MAX, gh = -DBL_MAX, hscale = 0.0;
+    double prev_min = 0.0, prev_max = 0.0;
+    bool have_prev = false, converged = false;
+    int k = 0;
+    double beta_k = 0.0;
+    const double ht = P.ht, hp = P.hp;
+#ifdef FKMC_LZ_TIMING
+    long long t_ritz = 0, t_start = clock64();
+#endif
+    int lag_iters = 0, lag_fallbacks = 0, nchecks = 0;
+    while (k < kcap) {
+        const double* lv = (k & 1) ? vb1 : vb0;
+        double* lvn = (k & 1) ? vb0 : vb1;
+        double pa = 0.0;
+        if (active) {
+            double u[9], d[9];  // u[e] = v(y+1, x0+e), e = 0..8;  d[e + 1] = v(y-1, x0+e), d[0] = v(y-1, x0-1)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                u[e] = lv[e * NS + tu];
+                d[e + 1] = lv[e * NS + td];
+            }
+            const double left = lv[7 * NS + tid + sl], right = lv[tid + sr];
+            if (KIND == FKMC_TRIANGULAR) {
+                u[8] = lv[tu + sr];
+                d[0] = lv[7 * NS + td + sl];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const double lf = (e == 0) ? left : vr[e - 1];
+                const double rg = (e == 7) ? right : vr[e + 1];
+                double nb = lf + rg;
+                if (KIND == FKMC_HONEYCOMB) {
+                    // sublattice A ((y + x) even) hops up, B hops down; x0 is a multiple of 8
+                    const bool odd = ((e & 1) != 0) != yodd;
+                    nb += odd ? d[e + 1] : u[e];
+                } else {
+                    nb += u[e] + d[e + 1];
+                }
+                double sacc = fma(xd[e], vr[e], ht * nb);
+                if (KIND == FKMC_TRIANGULAR) sacc = fma(hp, d[e] + u[e + 1], sacc);
+                sacc = fma(-beta_k, pr[e], sacc);
+                pr[e] = sacc;  // w (v_{k-1} is not needed any more)
+                pa = fma(sacc, vr[e], pa);
+            }
+        }
+        pa = warp_sum(pa);
+        if (lane == 0) rpA[warp] = pa;
+        __syncthreads();
+        double alpha = 0.0;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) alpha += rpA[w];
+        double pb = 0.0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            pr[e] = fma(-alpha, vr[e], pr[e]);
+            pb = fma(pr[e], pr[e], pb);
+        }
+        pb = warp_sum(pb);
+        if (lane == 0) rpB[warp] = pb;
+        __syncthreads();
+        double nb2 = 0.0;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) nb2 += rpB[w];
+        nb2 = fmax(nb2, 0.0);
+        const double rinv = nb2 > 0.0 ? rsqrt(nb2) : 0.0;
+        const double nbv = nb2 * rinv;
+        if (tid == 0) { ab[k].x = alpha; ab[k + 1].y = nb2; }
+        gl = fmin(gl, alpha - beta_k - nbv);
+        gh = fmax(gh, alpha + beta_k + nbv);
+        hscale = fmax(hscale, fabs(alpha) + nbv);
+        ++k;
+        const bool breakdown = nbv <= 1e-13 * hscale;
+        if (!breakdown) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const double vn = pr[e] * rinv;
+                pr[e] = vr[e];
+                vr[e] = vn;
+            }
+            if (active) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) lvn[e * NS + tid] = vr[e];
+            }
+        }
+        beta_k = nbv;
+        __syncthreads();
+        const bool last = breakdown || k == kcap;
+        if (last || (k >= LZ_FIRST && ((k - LZ_FIRST) % LZ_EVERY) == 0)) {
+            // extreme Ritz values of T_k (beta_k is outside T_k, which only loosens the Gershgorin enclosure); converged
+            // when both ends have stopped moving since the previous evaluation
+#ifdef FKMC_LZ_TIMING
+            const long long t_r0 = clock64();
+#endif
+            ++nchecks;
+            if (warp < 2) {
+                const double v = warp_ritz_end(ab, k, warp == 1, gl, gh, hscale, lane, have_prev, warp == 1 ? prev_max : prev_min, lag_iters, lag_fallbacks);
+                if (lane == 0) msc[warp] = v;
+            }
+            __syncthreads();
+            e_min = msc[0];
+            e_max = msc[1];
+            const double tol = 8.0 * DBL_EPSILON * hscale;
+            if (have_prev && fabs(e_min - prev_min) <= tol && fabs(e_max - prev_max) <= tol) converged = true;
+            prev_min = e_min;
+            prev_max = e_max;
+            have_prev = true;
+            __syncthreads();
+#ifdef FKMC_LZ_TIMING
+            t_ritz += clock64() - t_r0;
+#endif
+            if (converged || last) break;
+        }
+    }
+#ifdef FKMC_LZ_TIMING
+    if ((tid == 0 || tid == 32) && b < 4)
+        printf("lanczos2d b=%d warp=%d: total %lld cycles, ritz %lld, steps %d, checks %d, laguerre iterations %d, fallbacks %d\n", b, warp,
+               (long long)clock64() - t_start, t_ritz, k, nchecks, lag_iters, lag_fallbacks);
+#endif
+    if (tid == 0) {
+        if (!converged && k == kcap && k < N) atomicOr(P.flag, 2);
+        if (P.steps) P.steps[b] = k;
+        P.ab[(size_t)b * 4 + 0] = e_min;
+        P.ab[(size_t)b * 4 + 1] = e_max;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Moments.  Patch tables (device, built by the host from the context's stencil), per parity class c:
+//   cnt[c][m]           number of patch elements within m hops of the centre, m = 0..H (element 0 is the centre)
+//   off[c][e]           (dy + 128) << 8 | (dx + 128) of element e, e < EP = 32 S
+//   nb[c][z][e]         patch element reached through stencil slot z, or EP (the zero slot)
+struct mom_args {
+    const int32_t* f;
+    int N, L, M, G, ncls;
+    double U, mu_c, beta;
+    double slot_val[FKMC_MAX_Z];
+    const int* cnt;
+    const int* off;
+    const unsigned short* nb;
+    const double* chebt;    // [M][G]
+    const double* lobatto;  // [G]
+    const double* dtheta;   // [G-1]
+    double* moments;        // [B][M]
+    double* ab;             // [B][4] e_min, e_max in; a, b out
+    double* logz;           // [B]
+};
+
+constexpr int MOM_WARPS = 8;
+
+template <int HALF, int Z, int S>
+__global__ void __launch_bounds__(MOM_WARPS * 32, 2) kpm_moments2d_kernel(mom_args P) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int EP = 32 * S, PV = EP + 16;  // per-buffer doubles: the patch + 16 zero words (one per bank pair)
+    const int N = P.N, L = P.L, M = P.M, G = P.G;
+    const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    double* xd = sm;                           // [N] diagonal of X
+    double* red = xd + N;                      // [48]
+    double* msc = red + 48;                    // [64]
+    double* Fg = msc + 64;                     // [G]
+    double* acc = Fg + ((G + 1) & ~1);         // [MOM_WARPS][3][HALF+1]
+    double* vec = acc + MOM_WARPS * 3 * (HALF + 1);  // [MOM_WARPS][2][PV]
+
+    const double e_min = P.ab[(size_t)b * 4 + 0], e_max = P.ab[(size_t)b * 4 + 1];
+    const double a = (e_max - e_min) / 2., bsh = (e_max + e_min) / 2.;
+    const int32_t* f = P.f + (size_t)b * N;
+    double part = 0.0;
+    for (int i = tid; i < N; i += T) {
+        const double x = ((P.U * (double)f[i] - P.mu_c) - bsh) / a;
+        xd[i] = x;
+        part += x;
+    }
+    const double trx = block_sum(part, red);
+    double sv2[Z];
+#pragma unroll
+    for (int z = 0; z < Z; ++z) sv2[z] = 2.0 * (P.slot_val[z] / a);
+
+    double* const s0 = vec + (size_t)warp * 2 * PV;  // T_even
+    double* const s1 = s0 + PV;                      // T_odd
+    if (lane < 16) { s0[EP + lane] = 0.0; s1[EP + lane] = 0.0; }
+
+    double tr[HALF + 1], d01[HALF + 1], d11[HALF + 1];
+#pragma unroll
+    for (int m = 0; m <= HALF; ++m) tr[m] = d01[m] = d11[m] = 0.0;
+
+    for (int cls = 0; cls < P.ncls; ++cls) {
+        // this lane's elements: e = 32 s + lane
+        int dyx[S], nbi[Z][S], cnt[HALF + 1];
+        double h1 = 0.0;  // (X e_j)(e) for the radius-1 elements of slot 0 (hopping / a, doubled above: halve)
+#pragma unroll
+        for (int m = 0; m <= HALF; ++m) cnt[m] = P.cnt[cls * (HALF + 1) + m];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int e = 32 * s + lane;
+            dyx[s] = P.off[cls * EP + e];
+#pragma unroll
+            for (int z = 0; z < Z; ++z) nbi[z][s] = P.nb[((size_t)cls * Z + z) * EP + e];
+        }
+#pragma unroll
+        for (int z = 0; z < Z; ++z)
+            if (nbi[z][0] == 0 && lane != 0) h1 += 0.5 * sv2[z];
+        for (int j = warp; j < N; j += MOM_WARPS) {
+            const int y0 = j / L, x0 = j - y0 * L;
+            if (P.ncls > 1 && ((y0 + x0) & 1) != cls) continue;
+            double xd2[S], va[S], vb[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                int yy = y0 + (dyx[s] >> 8) - 128, xx = x0 + (dyx[s] & 255) - 128;
+                yy += (yy < 0) ? L : 0; yy -= (yy >= L) ? L : 0;
+                xx += (xx < 0) ? L : 0; xx -= (xx >= L) ? L : 0;
+                xd2[s] = (32 * s + lane < cnt[HALF]) ? 2.0 * xd[yy * L + xx] : 0.0;
+                va[s] = 0.0;
+                vb[s] = 0.0;
+                s0[32 * s + lane] = 0.0;
+                if (s > 0) s1[32 * s + lane] = 0.0;
+            }
+            // T_0 e_j = e_j (element 0), T_1 e_j = X e_j
+            va[0] = (lane == 0) ? 1.0 : 0.0;
+            vb[0] = (lane == 0) ? 0.5 * xd2[0] : ((lane < cnt[1]) ? h1 : 0.0);
+            s1[lane] = vb[0];
+            __syncwarp();
+            // one recursion step: vold <- 2 X vcur - vold, published to snew
+            auto step = [&](double (&vold)[S], const double (&vcur)[S], const double* __restrict__ scur, double* __restrict__ snew,
+                            const int cm, const bool need_dots, double& q01, double& q11) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    if (32 * s < cm) {  // warp-uniform
+                        double vn = fma(xd2[s], vcur[s], -vold[s]);
+#pragma unroll
+                        for (int z = 0; z < Z; ++z) vn = fma(sv2[z], scur[nbi[z][s]], vn);
+                        vn = (32 * s + lane < cm) ? vn : 0.0;
+                        vold[s] = vn;
+                        snew[32 * s + lane] = vn;
+                        if (need_dots) {
+                            q01 = fma(vcur[s], vn, q01);
+                            q11 = fma(vn, vn, q11);
+                        }
+                    }
+                }
+                __syncwarp();
+            };
+#pragma unroll
+            for (int m = 2; m <= HALF; ++m) {
+                const bool need_dots = (2 * m - 1 >= HALF);
+                if ((m & 1) == 0) {
+                    step(va, vb, s1, s0, cnt[m], need_dots, d01[m], d11[m]);  // va <- T_m e_j
+                    tr[m] += (lane == 0) ? va[0] : 0.0;
+                } else {
+                    step(vb, va, s0, s1, cnt[m], need_dots, d01[m], d11[m]);  // vb <- T_m e_j
+                    tr[m] += (lane == 0) ? vb[0] : 0.0;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 2; m <= HALF; ++m) {
+        const double a0 = warp_sum(tr[m]), a1 = warp_sum(d01[m]), a2 = warp_sum(d11[m]);
+        if (lane == 0) {
+            acc[(warp * 3 + 0) * (HALF + 1) + m] = a0;
+            acc[(warp * 3 + 1) * (HALF + 1) + m] = a1;
+            acc[(warp * 3 + 2) * (HALF + 1) + m] = a2;
+        }
+    }
+    __syncthreads();
+    // coefficients and logZ (configuration.cpp:198-202, chebyshev.hpp:36-54)
+    double* mom = msc + 8;  // [M] (M <= 32)
+    if (tid == 0) {
+        bool is_set[2 * FKMC_MAX_HALF];
+        for (int m = 0; m < M; ++m) { is_set[m] = false; mom[m] = 0.0; }
+        mom[0] = 1.0; is_set[0] = true;
+        mom[1] = trx / N; is_set[1] = true;
+        for (int m = 2; m <= HALF; ++m) {
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+            for (int w = 0; w < MOM_WARPS; ++w) {
+                t0 += acc[(w * 3 + 0) * (HALF + 1) + m];
+                t1 += acc[(w * 3 + 1) * (HALF + 1) + m];
+                t2 += acc[(w * 3 + 2) * (HALF + 1) + m];
+            }
+            if (!is_set[m]) { mom[m] = t0 / N; is_set[m] = true; }
+            int kk = 2 * m - 1;
+            if (kk < M && kk >= HALF) {
+                mom[kk] = (t1 * 2. - trx) / N; is_set[kk] = true;
+                if (kk != M - 1) { ++kk; mom[kk] = (t2 / N * 2. - 1.0); is_set[kk] = true; }
+            }
+        }
+    }
+    for (int i = tid; i < G; i += T) Fg[i] = N * log(1. + exp(-P.beta * (a * P.lobatto[i] + bsh)));
+    __syncthreads();
+    if (tid < M) {
+        const double* Tm = P.chebt + (size_t)tid * G;
+        double s = 0.0;
+        for (int i = 0; i < G - 1; ++i) s += (Fg[i + 1] * Tm[i + 1] + Fg[i] * Tm[i]) * P.dtheta[i];
+        acc[tid] = s * 0.5;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double s = acc[0];
+        for (int m = 1; m < M; ++m) s += 2. * acc[m] * mom[m];
+        P.logz[b] = s;
+        P.ab[(size_t)b * 4 + 2] = a;
+        P.ab[(size_t)b * 4 + 3] = bsh;
+    }
+    if (tid < M && P.moments) P.moments[(size_t)b * M + tid] = mom[tid];
+}
+
+// number of sites within H hops on the infinite lattice (upper bound for the honeycomb brick wall)
+constexpr int patch_elems(int kind, int H) { return kind == FKMC_TRIANGULAR ? 3 * H * H + 3 * H + 1 : 2 * H * H + 2 * H + 1; }
+
+}  // namespace
+
+// Build (or reuse) the ring-ordered patch tables for radius H.
+static int prepare_patch_tables(fkmc_ctx* ctx, int H, int S) {
+    if (ctx->kpm2_H == H && ctx->d_kpm2_cnt) return FKMC_OK;
+    const int N = ctx->N, L = ctx->L, Z = ctx->Z, EP = 32 * S;
+    const int ncls = (ctx->kind == FKMC_HONEYCOMB) ? 2 : 1;
+    std::vector<int> cnt((size_t)ncls * (H + 1)), off((size_t)ncls * EP, (128 << 8) | 128);
+    std::vector<unsigned short> nb((size_t)ncls * Z * EP, (unsigned short)EP);
+    for (int c = 0; c < ncls; ++c) {
+        const int y0 = L / 2, x0 = ((y0 + L / 2) & 1) == c ? L / 2 : L / 2 - 1;
+        const int j0 = y0 * L + x0;
+        std::vector<int> dist(N, -1), order;
+        std::queue<int> q;
+        dist[j0] = 0;
+        q.push(j0);
+        while (!q.empty()) {
+            const int s = q.front();
+            q.pop();
+            order.push_back(s);
+            if (dist[s] == H) continue;
+            for (int z = 0; z < Z; ++z) {
+                const int t = ctx->h_nbr_idx[(size_t)z * N + s];
+                if (t < N && dist[t] < 0) { dist[t] = dist[s] + 1; q.push(t); }
+            }
+        }
+        // the centre sits in the middle of the lattice and L >= 2H+1, so the patch never crosses the periodic boundary
+        auto rel = [&](int s, int& dy, int& dx) {
+            dy = s / L - y0;
+            dx = s % L - x0;
+        };
+        // ring order, by angle inside a ring: neighbouring lanes then read neighbouring shared-memory words
+        std::stable_sort(order.begin(), order.end(), [&](int s, int t) {
+            if (dist[s] != dist[t]) return dist[s] < dist[t];
+            int ay, ax, by, bx;
+            rel(s, ay, ax);
+            rel(t, by, bx);
+            return std::atan2((double)ay, (double)ax) < std::atan2((double)by, (double)bx);
+        });
+        const int E = (int)order.size();
+        if (E > EP || E > 65000) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: patch larger than its table");
+        std::vector<int> cn(H + 1);
+        for (int m = 0; m <= H; ++m) {
+            int n = 0;
+            for (int e = 0; e < E; ++e) n += dist[order[e]] <= m;
+            cn[m] = n;
+            cnt[(size_t)c * (H + 1) + m] = n;
+        }
+        // Shared-memory bank conflicts of the neighbour gathers depend only on the numbering inside the rings, which is
+        // free: anneal it.  A 64-bit warp request is served half-warp by half-warp, one wavefront per distinct word in the
+        // busiest bank (word mod 16); slot s is visited by every step m with cnt(m) > 32 s.  Neighbours outside the patch
+        // read one of 16 zero words (EP + lane % 16).
+        std::vector<int> elem(N, -1);
+        auto neighbour = [&](int e, int z) {
+            if (e >= E) return EP + (e & 15);
+            const int t = ctx->h_nbr_idx[(size_t)z * N + order[e]];
+            return (t < N && elem[t] >= 0) ? elem[t] : EP + (e & 15);
+        };
+        auto cost = [&]() {
+            for (int e = 0; e < E; ++e) elem[order[e]] = e;
+            long total = 0;
+            for (int sl = 0; sl < S; ++sl) {
+                int visits = 0;
+                for (int m = 2; m <= H; ++m) visits += cn[m] > 32 * sl;
+                if (!visits) continue;
+                for (int z = 0; z < Z; ++z)
+                    for (int half = 0; half < 2; ++half) {
+                        int words[16], nw = 0, load[16] = {0};
+                        for (int l = 0; l < 16; ++l) {
+                            const int w = neighbour(32 * sl + 16 * half + l, z);
+                            bool seen = false;
+                            for (int i = 0; i < nw; ++i) seen |= words[i] == w;
+                            if (!seen) { words[nw++] = w; ++load[w & 15]; }
+                        }
+                        int worst = 1;
+                        for (int i = 0; i < 16; ++i) worst = std::max(worst, load[i]);
+                        total += (long)visits * worst;
+                    }
+            }
+            return total;
+        };
+        {
+            uint64_t rng = 0x9e3779b97f4a7c15ull + (uint64_t)c;
+            auto next = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+            long cur = cost();
+            const long first = cur;
+            const int iters = 40000;
+            for (int it = 0; it < iters && E > 2; ++it) {
+                const int r = 1 + (int)(next() % (uint64_t)H);
+                const int lo = cn[r - 1], n = cn[r] - cn[r - 1];
+                if (n < 2) continue;
+                const int i = lo + (int)(next() % (uint64_t)n), j = lo + (int)(next() % (uint64_t)n);
+                if (i == j) continue;
+                std::swap(order[i], order[j]);
+                const long nc = cost();
+                // accept improvements, and small deteriorations early on
+                const double temp = 2.0 * (1.0 - (double)it / iters);
+                const bool accept = nc <= cur || (double)(next() % 1000000) * 1e-6 < std::exp(-(double)(nc - cur) / std::max(temp, 1e-3));
+                if (accept) cur = nc;
+                else std::swap(order[i], order[j]);
+            }
+            for (int e = 0; e < E; ++e) elem[order[e]] = e;
+            if (getenv("FKMC_KPM_DEBUG")) fprintf(stderr, "kpm2d patch tables: class %d, %d elements, gather wavefronts per column %ld -> %ld\n", c, E, first, cur);
+        }
+        for (int e = 0; e < EP; ++e) {
+            if (e < E) {
+                int dy, dx;
+                rel(order[e], dy, dx);
+                if (std::abs(dy) > H || std::abs(dx) > H) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: patch wraps around the lattice");
+                off[(size_t)c * EP + e] = ((dy + 128) << 8) | (dx + 128);
+            }
+            for (int z = 0; z < Z; ++z) nb[((size_t)c * Z + z) * EP + e] = (unsigned short)neighbour(e, z);
+        }
+    }
+    if (ctx->d_kpm2_cnt) { cudaFree(ctx->d_kpm2_cnt); cudaFree(ctx->d_kpm2_off); cudaFree(ctx->d_kpm2_nb); ctx->d_kpm2_cnt = nullptr; }
+    FKMC_CUDA(ctx, cudaMalloc(&ctx->d_kpm2_cnt, sizeof(int) * cnt.size()));
+    FKMC_CUDA(ctx, cudaMalloc(&ctx->d_kpm2_off, sizeof(int) * off.size()));
+    FKMC_CUDA(ctx, cudaMalloc(&ctx->d_kpm2_nb, sizeof(unsigned short) * nb.size()));
+    FKMC_CUDA(ctx, cudaMemcpyAsync(ctx->d_kpm2_cnt, cnt.data(), sizeof(int) * cnt.size(), cudaMemcpyHostToDevice, ctx->stream));
+    FKMC_CUDA(ctx, cudaMemcpyAsync(ctx->d_kpm2_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, ctx->stream));
+    FKMC_CUDA(ctx, cudaMemcpyAsync(ctx->d_kpm2_nb, nb.data(), sizeof(unsigned short) * nb.size(), cudaMemcpyHostToDevice, ctx->stream));
+    FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->kpm2_H = H;
+    return FKMC_OK;
+}
+
+template <int KIND>
+static int launch_lanczos2d(fkmc_ctx* ctx, const lz_args& P, int B) {
+    const size_t smem = sizeof(double) * (2 * (size_t)P.N + 2 * (LZ_KMAX + 2) + 2 * (LZ_T / 32) + 8);
+    FKMC_CUDA(ctx, cudaFuncSetAttribute(lanczos2d_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lanczos2d_kernel<KIND><<<B, LZ_T, smem, ctx->stream>>>(P);
+    ctx->launches++;
+    FKMC_CUDA(ctx, cudaGetLastError());
+    return FKMC_OK;
+}
+
+template <int HALF, int KIND>
+static int launch_moments2d(fkmc_ctx* ctx, mom_args& P, int B) {
+    constexpr int Z = (KIND == FKMC_TRIANGULAR) ? 6 : (KIND == FKMC_HONEYCOMB ? 3 : 4);
+    constexpr int S = (patch_elems(KIND, HALF) + 31) / 32;
+    int rc = prepare_patch_tables(ctx, HALF, S);
+    if (rc) return rc;
+    P.cnt = ctx->d_kpm2_cnt;
+    P.off = ctx->d_kpm2_off;
+    P.nb = ctx->d_kpm2_nb;
+    const size_t smem = sizeof(double) * ((size_t)P.N + 48 + 64 + ((P.G + 1) & ~1) + (size_t)MOM_WARPS * 3 * (HALF + 1) +
+                                          (size_t)MOM_WARPS * 2 * (32 * S + 16));
+    if (smem > ctx->smem_optin - 1024) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: lattice too large for the shared-memory kernel");
+    FKMC_CUDA(ctx, cudaFuncSetAttribute(kpm_moments2d_kernel<HALF, Z, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kpm_moments2d_kernel<HALF, Z, S><<<B, MOM_WARPS * 32, smem, ctx->stream>>>(P);
+    ctx->launches++;
+    FKMC_CUDA(ctx, cudaGetLastError());
+    return FKMC_OK;
+}
+
+template <int KIND>
+static int launch_moments2d_half(fkmc_ctx* ctx, mom_args& P, int B, int half) {
+    switch (half) {
+        case 2: return launch_moments2d<2, KIND>(ctx, P, B);
+        case 3: return launch_moments2d<3, KIND>(ctx, P, B);
+        case 4: return launch_moments2d<4, KIND>(ctx, P, B);
+        case 5: return launch_moments2d<5, KIND>(ctx, P, B);
+        case 6: return launch_moments2d<6, KIND>(ctx, P, B);
+        case 7: return launch_moments2d<7, KIND>(ctx, P, B);
+        case 8: return launch_moments2d<8, KIND>(ctx, P, B);
+        case 9: return launch_moments2d<9, KIND>(ctx, P, B);
+        case 10: return launch_moments2d<10, KIND>(ctx, P, B);
+    }
+    return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: unsupported M for the 2-D kernels");
+}
+
+// true when (lattice, M) is served by the two-kernel path
+bool fkmc_kpm2d_applicable(const fkmc_ctx* ctx, int M) {
+    const int half = M / 2;
+    if (ctx->kpm_force_generic || ctx->kpm_force_v1) return false;
+    if (ctx->kind != FKMC_CUBIC2D && ctx->kind != FKMC_TRIANGULAR && ctx->kind != FKMC_HONEYCOMB) return false;
+    if (ctx->L % 8 != 0 || ctx->N > 8 * LZ_T) return false;
+    return half >= 2 && half <= 10 && ctx->L >= 2 * half + 1;
+}
+
+int fkmc_launch_kpm2d(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, int M, int G, const double* slot_val,
+                      double* d_moments, double* d_ab, double* d_logz) {
+    lz_args Q{};
+    Q.f = d_f; Q.N = ctx->N; Q.L = ctx->L; Q.U = U; Q.mu_c = mu_c;
+    Q.ht = slot_val[0];
+    Q.hp = (ctx->kind == FKMC_TRIANGULAR) ? slot_val[4] : 0.0;
+    Q.ab = d_ab; Q.flag = ctx->d_flag; Q.steps = ctx->d_kpm_steps;
+    int rc;
+    {
+        fkmc_prof_scope ps(ctx, "kpm_lanczos");
+        if (ctx->kind == FKMC_CUBIC2D) rc = launch_lanczos2d<FKMC_CUBIC2D>(ctx, Q, B);
+        else if (ctx->kind == FKMC_TRIANGULAR) rc = launch_lanczos2d<FKMC_TRIANGULAR>(ctx, Q, B);
+        else rc = launch_lanczos2d<FKMC_HONEYCOMB>(ctx, Q, B);
+    }
+    if (rc) return rc;
+    mom_args P{};
+    P.f = d_f; P.N = ctx->N; P.L = ctx->L; P.M = M; P.G = G; P.ncls = (ctx->kind == FKMC_HONEYCOMB) ? 2 : 1;
+    P.U = U; P.mu_c = mu_c; P.beta = beta;
+    for (int z = 0; z < FKMC_MAX_Z; ++z) P.slot_val[z] = slot_val[z];
+    P.chebt = ctx->d_chebt; P.lobatto = ctx->d_lobatto; P.dtheta = ctx->d_dtheta;
+    P.moments = d_moments; P.ab = d_ab; P.logz = d_logz;
+    fkmc_prof_scope ps(ctx, "kpm_moments");
+    if (ctx->kind == FKMC_CUBIC2D) return launch_moments2d_half<FKMC_CUBIC2D>(ctx, P, B, M / 2);
+    if (ctx->kind == FKMC_TRIANGULAR) return launch_moments2d_half<FKMC_TRIANGULAR>(ctx, P, B, M / 2);
+    return launch_moments2d_half<FKMC_HONEYCOMB>(ctx, P, B, M / 2);
+}

@@ -272,6 +272,33 @@ def test_calc_chebyshev_matches_oracle(kind, L, U, beta):
     c.close()
 
 
+@pytest.mark.parametrize("kind,L,U,beta,M", [("cubic2d", 32, 2.0, 20.0, 16), ("cubic2d", 16, 2.0, 10.0, 12), ("cubic2d", 24, 4.0, 5.0, 4),
+                                             ("cubic2d", 32, 2.0, 5.0, 20), ("triangular", 24, 2.0, 10.0, 14),
+                                             ("honeycomb", 24, 2.0, 10.0, 14), ("honeycomb", 16, 4.0, 5.0, 12)])
+def test_kpm_two_kernel_path_matches_single_kernel_and_oracle(kind, L, U, beta, M):
+    """kpm2d.cu (strip Lanczos + Laguerre Ritz values, ring-ordered patch recursion) against kpm.cu on a batch with
+    empty / full / random configurations, and against the oracle on two of them (configuration.cpp:94-205)."""
+    B = 40
+    c = fk.Context(kind, L, max_batch=B)
+    n = c.N
+    rng = np.random.default_rng(7)
+    fs = (rng.random((B, n)) < rng.random((B, 1))).astype(np.int32)
+    fs[0], fs[1] = 0, 1
+    r2 = c.logz_kpm(fs, U, U / 2, beta, M, 2 * M)
+    c.set_option("kpm_v1", 1)
+    r1 = c.logz_kpm(fs, U, U / 2, beta, M, 2 * M)
+    c.set_option("kpm_v1", 0)
+    scale = np.maximum(np.abs(r1["e_min"]), np.abs(r1["e_max"]))
+    assert (np.abs(r1["e_min"] - r2["e_min"]) <= 1e-12 * scale).all() and (np.abs(r1["e_max"] - r2["e_max"]) <= 1e-12 * scale).all()
+    assert np.abs(r1["moments"] - r2["moments"]).max() <= 1e-12
+    assert (np.abs(r1["logZ"] - r2["logZ"]) <= 1e-12 * np.maximum(1.0, np.abs(r1["logZ"]))).all()
+    for b in (1, 5):
+        ref = o.calc_chebyshev(o.KINDS[kind], L, fs[b], U, U / 2, beta, M, 2 * M, emode=0)
+        assert np.abs(r2["moments"][b] - ref["moments"]).max() <= TOL
+        assert abs(r2["logZ"][b] - ref["logZ"]) <= TOL * max(1.0, abs(ref["logZ"]))
+    c.close()
+
+
 def test_calc_chebyshev_golden_and_other_sizes(golden):
     for cse in golden["spectra"]["cases"]:
         if "kpm" not in cse:
