@@ -1,0 +1,90 @@
+"""HDF5 output writer (fk_mc_b200/h5out.py): the reader is pinned on a file written by the real HDF5 library, the writer
+is checked through that reader, and save_all_data against the reference layout (prog/data_save.hxx:33-151)."""
+import glob
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from fk_mc_b200 import h5out, stats
+
+
+def _real_hdf5_fixture():
+    import scipy.io
+    hits = glob.glob(os.path.join(os.path.dirname(scipy.io.__file__), "matlab", "tests", "data", "testhdf5_7.4_GLNX86.mat"))
+    return hits[0] if hits else None
+
+
+def test_reader_parses_a_file_written_by_libhdf5():
+    fn = _real_hdf5_fixture()
+    if fn is None:
+        pytest.skip("scipy's HDF5 fixture is not installed")
+    r = h5out.H5Reader(fn)
+    assert r.base == 512 and (r.leaf_k, r.internal_k) == (4, 16)          # MATLAB user block, library default K values
+    t = r.tree()
+    assert list(t) == ["/testdouble"]
+    assert np.allclose(t["/testdouble"].ravel(), np.arange(9) * np.pi / 4)  # the fixture's content (scipy test_mio.py)
+
+
+def test_writer_round_trip_and_structure(tmp_path):
+    w = h5out.H5Writer()
+    rng = np.random.default_rng(0)
+    big = rng.standard_normal((7, 33))
+    w["/mc_data/energies"] = np.arange(10.0)
+    w["/mc_data/ipr_history"] = big
+    w["/mc_data/empty"] = np.zeros(0)
+    w["/stats/energy"] = np.array([50, -0.2474323, 1.207943e-28, 1.554312e-15])
+    w["/parameters/beta"] = 10.0
+    w["/parameters/L"] = 32
+    w["/parameters/seed"] = np.int64(2 ** 40 + 3)
+    w["/parameters/cheb_moves"] = True
+    w["/parameters/output"] = "output.h5"
+    for i in range(40):                       # more members than one symbol-table node holds (2 * LEAF_K = 8)
+        w["/many/p%02d" % i] = float(i)
+    fn = str(tmp_path / "t.h5")
+    size = w.save(fn)
+    raw = open(fn, "rb").read()
+    assert len(raw) == size and raw[:8] == b"\x89HDF\r\n\x1a\n"
+    assert struct.unpack("<Q", raw[40:48])[0] == size                      # end-of-file address in the superblock
+    r = h5out.H5Reader(fn)
+    t = r.tree()
+    assert np.array_equal(t["/mc_data/energies"], np.arange(10.0)) and np.array_equal(t["/mc_data/ipr_history"], big)
+    assert t["/mc_data/empty"].shape == (0,)
+    assert t["/parameters/beta"] == 10.0 and t["/parameters/L"] == 32 and t["/parameters/seed"] == 2 ** 40 + 3
+    assert t["/parameters/cheb_moves"] == 1 and t["/parameters/output"] == "output.h5"
+    assert [t["/many/p%02d" % i] for i in range(40)] == [float(i) for i in range(40)]
+    assert sorted(r["/"]) == ["many", "mc_data", "parameters", "stats"]
+    # the float64 datatype message is byte-identical to the one libhdf5 writes (taken from the fixture above)
+    fx = _real_hdf5_fixture()
+    if fx:
+        rr = h5out.H5Reader(fx)
+        theirs = [d for t_, d in rr._messages(rr.members()["testdouble"]) if t_ == 3][0]
+        ours = [d for t_, d in r._messages(r["/mc_data"]["energies"]) if t_ == 3][0]
+        assert ours == theirs
+    with pytest.raises(KeyError):
+        r["/nope"]
+
+
+def test_save_all_data_layout(tmp_path):
+    rng = np.random.default_rng(1)
+    n, beta, vol = 256, 10.0, 64
+    e = -0.25 + 0.01 * rng.standard_normal(n)
+    d2 = 0.02 + 0.001 * rng.standard_normal(n)
+    ce = e + 0.5
+    fn = str(tmp_path / "output.h5")
+    params = dict(beta=beta, U=1.0, L=8, mu_c=0.5, mu_f=0.5, nsweeps=n, sweep_len=16, cheb_moves=False, output="output.h5")
+    out = h5out.save_all_data(fn, params, e, d2, ce, beta, vol, histories={"ipr_history": rng.random((64, 4))})
+    t = h5out.H5Reader(fn).tree()
+    assert {"/mc_data/energies", "/mc_data/d2energies", "/mc_data/c_energies", "/mc_data/ipr_history", "/parameters/beta",
+            "/stats/energy", "/stats/d2energy", "/stats/c_energy", "/stats/cv", "/binning/energy", "/binning/cv"} <= set(t)
+    assert np.array_equal(t["/mc_data/energies"], e)
+    rep = stats.energy_report(e, d2, beta, vol)
+    assert t["/stats/energy"].shape == (4,) and np.allclose(t["/stats/energy"], rep["energy"]["stats"])
+    assert np.allclose(t["/stats/cv"], rep["cv"]["stats"])
+    assert t["/binning/energy"].shape == (len(rep["energy"]["binning"]), 5)          # [n, mean, variance, stderr, tau_int]
+    assert np.allclose(t["/binning/energy"][:, 4], rep["energy"]["cor_length"])
+    assert np.allclose(out["cv"][1], t["/stats/cv"])
+    # consumer convention (scripts/parse/parse_thermod.py:48-49): (nbins, value, disp, error) = h5["stats"][obs]
+    nb, val, disp, err = t["/stats/energy"]
+    assert nb >= 4 and abs(val - e.mean()) < 1e-12 and err > 0
