@@ -16,8 +16,9 @@
 
 namespace {
 
-// number of eigenvalues < x.  de[i] = (d_i, e_{i-1}^2), e_{-1} = 0.
-__device__ __forceinline__ int sturm_count(const double2* __restrict__ de, int n, double x) {
+// number of eigenvalues < x.  de[i] = (d_i, e_{i-1}^2), e_{-1} = 0.  Guarded form: an exact zero is nudged off zero, so the
+// recurrence survives e_i = 0 (a decoupled block) right after a zero.  Slow path of sturm_count below.
+__device__ __noinline__ int sturm_count_guarded(const double2* __restrict__ de, int n, double x) {
     double pm1 = 1.0, p = de[0].x - x;
     if (p == 0.0) p = -DBL_EPSILON;
     bool neg = p < 0.0;
@@ -42,9 +43,38 @@ __device__ __forceinline__ int sturm_count(const double2* __restrict__ de, int n
     return cnt;
 }
 
+// Fast form: three FP64 instructions per row (subtract, multiply, FMA), signs counted on the integer pipe from the high words.
+// An isolated exact zero needs no care (p_{i+1} = -e_i^2 p_{i-1} then has the sign opposite to p_{i-1}: one sign change whichever
+// sign the zero is given); only a zero followed by e_i = 0 sticks, which shows as p = p_{-1} = 0 at the next rescaling check and is
+// sent to the guarded form.
+__device__ __forceinline__ int sturm_count(const double2* __restrict__ de, int n, double x) {
+    double pm1 = 1.0, p = de[0].x - x;
+    int sprev = __double2hiint(p);
+    int cnt = (int)((unsigned)sprev >> 31);
+    for (int i0 = 1; i0 < n; i0 += 8) {
+        const int i1 = min(i0 + 8, n);
+        for (int i = i0; i < i1; ++i) {
+            const double2 q = de[i];
+            const double pn = fma(q.x - x, p, -(q.y * pm1));
+            const int sn = __double2hiint(pn);
+            cnt += (int)((unsigned)(sn ^ sprev) >> 31);
+            sprev = sn;
+            pm1 = p;
+            p = pn;
+        }
+        const double m = fmax(fabs(p), fabs(pm1));
+        if (m > 1.157920892373162e77) { p *= 8.636168555094445e-78; pm1 *= 8.636168555094445e-78; }
+        else if (m < 8.636168555094445e-78) {
+            if (m == 0.0) return sturm_count_guarded(de, n, x);
+            p *= 1.157920892373162e77; pm1 *= 1.157920892373162e77;
+        }
+    }
+    return cnt;
+}
+
 // Sturm count plus the characteristic polynomial p_n(x) and its derivative (same recurrence, differentiated:
-// p'_i = (d_i - x) p'_{i-1} - p_{i-1} - e_{i-1}^2 p'_{i-2}), jointly rescaled, for a safeguarded Newton step.
-__device__ __forceinline__ int sturm_newton(const double2* __restrict__ de, int n, double x, double& pn_out, double& dpn_out) {
+// p'_i = (d_i - x) p'_{i-1} - p_{i-1} - e_{i-1}^2 p'_{i-2}), jointly rescaled, for a safeguarded Newton step.  Guarded form.
+__device__ __noinline__ int sturm_newton_guarded(const double2* __restrict__ de, int n, double x, double& pn_out, double& dpn_out) {
     double pm1 = 1.0, p = de[0].x - x, dpm1 = 0.0, dp = -1.0;
     if (p == 0.0) p = -DBL_EPSILON;
     bool neg = p < 0.0;
@@ -64,6 +94,38 @@ __device__ __forceinline__ int sturm_newton(const double2* __restrict__ de, int 
             dpm1 = dp; dp = dpn;
         }
         const double m = fmax(fmax(fabs(p), fabs(pm1)), fmax(fabs(dp), fabs(dpm1)) * 0x1p-60);
+        if (m > 1.157920892373162e77) {
+            p *= 8.636168555094445e-78; pm1 *= 8.636168555094445e-78; dp *= 8.636168555094445e-78; dpm1 *= 8.636168555094445e-78;
+        } else if (m < 8.636168555094445e-78) {
+            p *= 1.157920892373162e77; pm1 *= 1.157920892373162e77; dp *= 1.157920892373162e77; dpm1 *= 1.157920892373162e77;
+        }
+    }
+    pn_out = p;
+    dpn_out = dp;
+    return cnt;
+}
+
+// Fast form of the above (same treatment of zeros as sturm_count).
+__device__ __forceinline__ int sturm_newton(const double2* __restrict__ de, int n, double x, double& pn_out, double& dpn_out) {
+    double pm1 = 1.0, p = de[0].x - x, dpm1 = 0.0, dp = -1.0;
+    int sprev = __double2hiint(p);
+    int cnt = (int)((unsigned)sprev >> 31);
+    for (int i0 = 1; i0 < n; i0 += 8) {
+        const int i1 = min(i0 + 8, n);
+        for (int i = i0; i < i1; ++i) {
+            const double2 q = de[i];
+            const double t = q.x - x;
+            const double pn = fma(t, p, -(q.y * pm1));
+            const double dpn = fma(t, dp, -fma(q.y, dpm1, p));
+            const int sn = __double2hiint(pn);
+            cnt += (int)((unsigned)(sn ^ sprev) >> 31);
+            sprev = sn;
+            pm1 = p; p = pn;
+            dpm1 = dp; dp = dpn;
+        }
+        const double mp = fmax(fabs(p), fabs(pm1));
+        if (mp == 0.0) return sturm_newton_guarded(de, n, x, pn_out, dpn_out);
+        const double m = fmax(mp, fmax(fabs(dp), fabs(dpm1)) * 0x1p-60);
         if (m > 1.157920892373162e77) {
             p *= 8.636168555094445e-78; pm1 *= 8.636168555094445e-78; dp *= 8.636168555094445e-78; dpm1 *= 8.636168555094445e-78;
         } else if (m < 8.636168555094445e-78) {
