@@ -48,9 +48,12 @@ __device__ __forceinline__ refl make_reflector(double x, int l, int n, unsigned 
     const double tail2 = gsum8((l >= 1 && l < n) ? x * x : 0.0, m);
     const double x0 = __shfl_sync(m, x, gbase);
     const bool triv = tail2 <= DBL_MIN;
-    double beta = sqrt(fma(x0, x0, triv ? 1.0 : tail2));
-    if (x0 >= 0.0) beta = -beta;
-    const double tau = (beta - x0) / beta;
+    // |beta| = sqrt(x0^2 + tail2) through one reciprocal square root; tau = (beta - x0) / beta = 1 + |x0| / |beta| needs no division
+    const double s2 = fma(x0, x0, triv ? 1.0 : tail2);
+    const double rs = rsqrt(s2);
+    const double nrm = s2 * rs;
+    const double beta = (x0 >= 0.0) ? -nrm : nrm;
+    const double tau = fma(fabs(x0), rs, 1.0);
     const double inv = 1.0 / (x0 - beta);
     R.beta = triv ? x0 : beta;
     R.tau = triv ? 0.0 : tau;
