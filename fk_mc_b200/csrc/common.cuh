@@ -84,6 +84,8 @@ struct fkmc_ctx {
     int* d_kpm2_cnt = nullptr;
     int* d_kpm2_off = nullptr;
     unsigned short* d_kpm2_nb = nullptr;
+    double* d_kpm2_part = nullptr;   // [max_batch][2][3][FKMC_MAX_HALF+1] per-CTA partial traces of the moments kernel
+    int* d_kpm2_arrived = nullptr;   // [max_batch]
     double* d_d = nullptr;      // [max_batch][N]
     double* d_e = nullptr;      // [max_batch][N]
     double* d_tau = nullptr;    // [max_batch][N]

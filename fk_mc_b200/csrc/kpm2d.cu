@@ -425,16 +425,20 @@ struct mom_args {
     double* moments;        // [B][M]
     double* ab;             // [B][4] e_min, e_max in; a, b out
     double* logz;           // [B]
+    double* part;           // [B][MOM_SPLIT][3][FKMC_MAX_HALF + 1] partial traces of the CTAs of one proposal
+    int* arrived;           // [B] CTAs of the proposal that have delivered their partial traces (self-resetting)
 };
 
 constexpr int MOM_WARPS = 8;
+constexpr int MOM_SPLIT = 2;  // CTAs per proposal (the columns are dealt out round robin): 2 B CTAs fill the last wave much better than B
 
 template <int HALF, int Z, int S>
 __global__ void __launch_bounds__(MOM_WARPS * 32, 2) kpm_moments2d_kernel(mom_args P) {
     extern __shared__ __align__(16) double sm[];
     constexpr int EP = 32 * S, PV = EP + 16;  // per-buffer doubles: the patch + 16 zero words (one per bank pair)
     const int N = P.N, L = P.L, M = P.M, G = P.G;
-    const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x / MOM_SPLIT, cta_part = blockIdx.x % MOM_SPLIT;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
     double* xd = sm;                           // [N] diagonal of X
     double* red = xd + N;                      // [48]
     double* msc = red + 48;                    // [64]
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(MOM_WARPS * 32, 2) kpm_moments2d_kernel(mom_ar
 #pragma unroll
         for (int z = 0; z < Z; ++z)
             if (nbi[z][0] == 0 && lane != 0) h1 += 0.5 * sv2[z];
-        for (int j = warp; j < N; j += MOM_WARPS) {
+        for (int j = warp + MOM_WARPS * cta_part; j < N; j += MOM_WARPS * MOM_SPLIT) {
             const int y0 = j / L, x0 = j - y0 * L;
             if (P.ncls > 1 && ((y0 + x0) & 1) != cls) continue;
             double xd2[S], va[S], vb[S];
@@ -543,6 +547,27 @@ __global__ void __launch_bounds__(MOM_WARPS * 32, 2) kpm_moments2d_kernel(mom_ar
         }
     }
     __syncthreads();
+    // this CTA's traces (warps summed in a fixed order) -> global; the CTA that delivers last finishes the proposal
+    if (MOM_SPLIT > 1) {
+        double* mine = P.part + ((size_t)b * MOM_SPLIT + cta_part) * 3 * (FKMC_MAX_HALF + 1);
+        if (tid < 3 * (HALF + 1)) {
+            const int q = tid / (HALF + 1), m = tid % (HALF + 1);
+            double t = 0.0;
+            for (int w = 0; w < MOM_WARPS; ++w) t += acc[(w * 3 + q) * (HALF + 1) + m];
+            __stcg(mine + q * (FKMC_MAX_HALF + 1) + m, t);
+        }
+        __threadfence();
+        __syncthreads();
+        __shared__ int last_flag;
+        if (tid == 0) {
+            const int seen = atomicAdd(P.arrived + b, 1);
+            last_flag = (seen == MOM_SPLIT - 1);
+            if (last_flag) P.arrived[b] = 0;  // ready for the next launch
+        }
+        __syncthreads();
+        if (!last_flag) return;
+        __threadfence();
+    }
     // coefficients and logZ (configuration.cpp:198-202, chebyshev.hpp:36-54)
     double* mom = msc + 8;  // [M] (M <= 32)
     if (tid == 0) {
@@ -552,10 +577,19 @@ __global__ void __launch_bounds__(MOM_WARPS * 32, 2) kpm_moments2d_kernel(mom_ar
         mom[1] = trx / N; is_set[1] = true;
         for (int m = 2; m <= HALF; ++m) {
             double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-            for (int w = 0; w < MOM_WARPS; ++w) {
-                t0 += acc[(w * 3 + 0) * (HALF + 1) + m];
-                t1 += acc[(w * 3 + 1) * (HALF + 1) + m];
-                t2 += acc[(w * 3 + 2) * (HALF + 1) + m];
+            if (MOM_SPLIT > 1) {
+                for (int c = 0; c < MOM_SPLIT; ++c) {
+                    const double* pc = P.part + ((size_t)b * MOM_SPLIT + c) * 3 * (FKMC_MAX_HALF + 1);
+                    t0 += __ldcg(pc + m);
+                    t1 += __ldcg(pc + (FKMC_MAX_HALF + 1) + m);
+                    t2 += __ldcg(pc + 2 * (FKMC_MAX_HALF + 1) + m);
+                }
+            } else {
+                for (int w = 0; w < MOM_WARPS; ++w) {
+                    t0 += acc[(w * 3 + 0) * (HALF + 1) + m];
+                    t1 += acc[(w * 3 + 1) * (HALF + 1) + m];
+                    t2 += acc[(w * 3 + 2) * (HALF + 1) + m];
+                }
             }
             if (!is_set[m]) { mom[m] = t0 / N; is_set[m] = true; }
             int kk = 2 * m - 1;
@@ -736,7 +770,14 @@ static int launch_moments2d(fkmc_ctx* ctx, mom_args& P, int B) {
                                           (size_t)MOM_WARPS * 2 * (32 * S + 16));
     if (smem > ctx->smem_optin - 1024) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: lattice too large for the shared-memory kernel");
     FKMC_CUDA(ctx, cudaFuncSetAttribute(kpm_moments2d_kernel<HALF, Z, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kpm_moments2d_kernel<HALF, Z, S><<<B, MOM_WARPS * 32, smem, ctx->stream>>>(P);
+    if (!ctx->d_kpm2_part) {
+        FKMC_CUDA(ctx, cudaMalloc(&ctx->d_kpm2_part, sizeof(double) * (size_t)ctx->max_batch * MOM_SPLIT * 3 * (FKMC_MAX_HALF + 1)));
+        FKMC_CUDA(ctx, cudaMalloc(&ctx->d_kpm2_arrived, sizeof(int) * (size_t)ctx->max_batch));
+        FKMC_CUDA(ctx, cudaMemsetAsync(ctx->d_kpm2_arrived, 0, sizeof(int) * (size_t)ctx->max_batch, ctx->stream));
+    }
+    P.part = ctx->d_kpm2_part;
+    P.arrived = ctx->d_kpm2_arrived;
+    kpm_moments2d_kernel<HALF, Z, S><<<B * MOM_SPLIT, MOM_WARPS * 32, smem, ctx->stream>>>(P);
     ctx->launches++;
     FKMC_CUDA(ctx, cudaGetLastError());
     return FKMC_OK;
