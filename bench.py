@@ -38,6 +38,7 @@ WORKLOADS = {
 }
 SWEEP_LEN = 16      # src/mc_metropolis.cpp:14
 SEED = 32167        # test/fast_update_test.cpp:48, benchmark/fast_update.cpp:152
+CPU_SWEEPS = 8      # sweeps per chain in one CPU sample (about 10 s of work per host thread at c5)
 DMMA_PEAK_TFLOPS = 37.0  # measured on this pool's B200 by tools/probe_dmma.cu (profiles/r01_probe_dmma.txt)
 
 
@@ -104,7 +105,7 @@ def run_reference(args, wl, rank, world):
     import oracle_lib as o
     kind, L, beta, U, cheb, chains, desc = wl
     cores = os.cpu_count() or 1
-    p = o.make_params(kind=o.KINDS[kind], L=L, beta=beta, U=U, cheb_moves=cheb, emode=1, seed=SEED, nsweeps=1, sweep_len=SWEEP_LEN,
+    p = o.make_params(kind=o.KINDS[kind], L=L, beta=beta, U=U, cheb_moves=cheb, emode=1, seed=SEED, nsweeps=CPU_SWEEPS, sweep_len=SWEEP_LEN,
                       ntherm_sweeps=0, measure_energy=True)
     times = []
     for it in range(args.warmup + args.steps):
@@ -112,13 +113,13 @@ def run_reference(args, wl, rank, world):
         if it >= args.warmup:
             times.append(sec)
     ms = 1e3 * float(np.mean(times))
-    value = cores * SWEEP_LEN / (ms * 1e-3)
+    value = cores * SWEEP_LEN * CPU_SWEEPS / (ms * 1e-3)
     line = {"impl": "reference", "metric": "metropolis_proposals_per_sec", "value": value, "unit": "proposals/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "chains": cores, "sweep_len": SWEEP_LEN, "seed": SEED},
             "cpu_baseline": {"value": value, "unit": "proposals/s", "cores": cores, "kind": "port",
-                             "sample": "%d chains x 1 sweep (16 proposals + 1 measurement) per step, one chain per host thread" % cores},
+                             "sample": "%d chains x %d sweeps (16 proposals + 1 measurement each) per step, one chain per host thread" % (cores, CPU_SWEEPS)},
             "e2e": {"value": value, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -324,11 +325,12 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib as o
         cores = os.cpu_count() or 1
-        p = o.make_params(kind=o.KINDS[kind], L=L, beta=beta, U=U, cheb_moves=cheb, emode=1, seed=SEED, nsweeps=1, sweep_len=SWEEP_LEN,
-                          ntherm_sweeps=0, measure_energy=True)
+        p = o.make_params(kind=o.KINDS[kind], L=L, beta=beta, U=U, cheb_moves=cheb, emode=1, seed=SEED, nsweeps=CPU_SWEEPS,
+                          sweep_len=SWEEP_LEN, ntherm_sweeps=0, measure_energy=True)
         sec, _ = o.bench_chains(p, cores)
-        cpu_baseline = {"value": cores * SWEEP_LEN / sec, "unit": "proposals/s", "cores": cores, "kind": "port",
-                        "sample": "%d chains x 1 sweep (16 proposals + 1 measurement), one chain per host thread, %.1f s" % (cores, sec)}
+        cpu_baseline = {"value": cores * SWEEP_LEN * CPU_SWEEPS / sec, "unit": "proposals/s", "cores": cores, "kind": "port",
+                        "sample": "%d chains x %d sweeps (16 proposals + 1 measurement each), one chain per host thread, %.1f s"
+                                  % (cores, CPU_SWEEPS, sec)}
 
     if rank == 0:
         line = {"metric": "metropolis_proposals_per_sec", "value": value, "unit": "proposals/s", "n_gpus": world, "steps": args.steps,
