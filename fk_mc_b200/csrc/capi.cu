@@ -181,7 +181,7 @@ int fkmc_destroy(fkmc_ctx* ctx) {
     cudaFree(ctx->d_e); cudaFree(ctx->d_tau); cudaFree(ctx->d_evals); cudaFree(ctx->d_out); cudaFree(ctx->d_f);
     cudaFree(ctx->d_flag); cudaFree(ctx->d_moments); cudaFree(ctx->d_ab); cudaFree(ctx->d_aux);
     cudaFree(ctx->d_chebt); cudaFree(ctx->d_lobatto); cudaFree(ctx->d_dtheta);
-    cudaFree(ctx->d_kpm2_cnt); cudaFree(ctx->d_kpm2_off); cudaFree(ctx->d_kpm2_nb);
+    cudaFree(ctx->d_kpm2_tabi); cudaFree(ctx->d_kpm2_h1); cudaFree(ctx->d_kpm2_off); cudaFree(ctx->d_kpm2_nb);
     cudaFree(ctx->d_kpm2_part); cudaFree(ctx->d_kpm2_arrived);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -375,6 +375,10 @@ int fkmc_set_option(fkmc_ctx* ctx, const char* name, int value) {
     }
     if (std::string(name) == "kpm_generic") {
         ctx->kpm_force_generic = value != 0;
+        return FKMC_OK;
+    }
+    if (std::string(name) == "kpm_generic_schedule") {
+        ctx->kpm_no_sched = value != 0;
         return FKMC_OK;
     }
     if (std::string(name) == "kpm_v1") {

@@ -81,7 +81,11 @@ struct fkmc_ctx {
     int kpm_force_generic = 0;  // 1: always use the full-lattice-vector KPM kernel (for cross-checks)
     int kpm_force_v1 = 0;       // 1: single-kernel KPM (kpm.cu) even where the two-kernel 2-D path (kpm2d.cu) applies
     int kpm2_H = 0;             // radius of the cached patch tables of kpm2d.cu
-    int* d_kpm2_cnt = nullptr;
+    unsigned long long kpm2_sched = 0;        // slots per step of the cached tables, four bits per step
+    int kpm_no_sched = 0;                     // 1: never use the schedule-specialised moments kernel (cross-checks)
+    int kpm2_S = 0, kpm2_PV = 0, kpm2_P = 0;  // slots per lane, cells per buffer, row pitch of the patch array
+    int* d_kpm2_tabi = nullptr;
+    double* d_kpm2_h1 = nullptr;
     int* d_kpm2_off = nullptr;
     unsigned short* d_kpm2_nb = nullptr;
     double* d_kpm2_part = nullptr;   // [max_batch][2][3][FKMC_MAX_HALF+1] per-CTA partial traces of the moments kernel

@@ -407,18 +407,27 @@ __global__ void __launch_bounds__(LZ_T, 4) lanczos2d_kernel(lz_args P) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Moments.  Patch tables (device, built by the host from the context's stencil), per parity class c:
-//   cnt[c][m]           number of patch elements within m hops of the centre, m = 0..H (element 0 is the centre)
-//   off[c][e]           (dy + 128) << 8 | (dx + 128) of element e, e < EP = 32 S
-//   nb[c][z][e]         patch element reached through stencil slot z, or EP (the zero slot)
+// Moments.  The patch of column j (the sites within H hops of j) is kept in shared memory as a (2H+3) x P array addressed
+// by relative position, a(dy, dx) = (dy + H + 1) P + (dx + H + 1), with a ring of cells around it that stay zero, so a neighbour
+// is always "own address + constant" and nothing outside the patch needs a special case.  Every patch element is owned by one
+// (slot, lane): elements are dealt out by increasing hop distance so that step m only has to visit the first ns(m) slots, and
+// the lane inside a half-warp IS the address modulo 16 -- sixteen lanes of a half-warp therefore hit sixteen different bank
+// pairs for their own cell and, shifted by the same constant, for every neighbour: no bank conflicts by construction.
+// Tables (device, built by the host from the context's stencil), per parity class c, EP = 32 S entries (index 32 slot + lane):
+//   tabi[c][m], m = 0..H    ns(m): slots that hold elements within m hops;   tabi[c][H+1] = lane of the centre,
+//   tabi[c][H+2] = P,  tabi[c][H+3] = cells per buffer
+//   off[c][e]               (hops << 16) | (dy + 128) << 8 | (dx + 128); hops = 255 for an unused (slot, lane)
+//   nb[c][z][e], z < Z      cell of the neighbour through stencil slot z;   nb[c][Z][e] = own cell
+//   h1[c][lane]             hopping from the centre to the slot-0 element of this lane (0 if they are not neighbours)
 struct mom_args {
     const int32_t* f;
     int N, L, M, G, ncls;
     double U, mu_c, beta;
     double slot_val[FKMC_MAX_Z];
-    const int* cnt;
+    const int* tabi;
     const int* off;
     const unsigned short* nb;
+    const double* h1;
     const double* chebt;    // [M][G]
     const double* lobatto;  // [G]
     const double* dtheta;   // [G-1]
@@ -432,15 +441,19 @@ struct mom_args {
 constexpr int MOM_WARPS = 8;
 constexpr int MOM_SPLIT = 2;  // CTAs per proposal (the columns are dealt out round robin): 2 B CTAs fill the last wave much better than B
 
-template <int HALF, int Z, int S>
+// SCHED != 0: the slots per step are compile-time constants (four bits per step, m = 2 first), which turns the slot loop of a step
+// into straight-line code whose loads and FMA chains interleave; UNI: all hoppings are equal (one multiplication per element).
+template <int HALF, int Z, int S, unsigned long long SCHED, bool UNI>
 __global__ void __launch_bounds__(MOM_WARPS * 32, 2) kpm_moments2d_kernel(mom_args P) {
     extern __shared__ __align__(16) double sm[];
-    constexpr int EP = 32 * S, PV = EP + 16;  // per-buffer doubles: the patch + 16 zero words (one per bank pair)
+    constexpr int EP = 32 * S, NT = HALF + 4;
     const int N = P.N, L = P.L, M = P.M, G = P.G;
     const int b = blockIdx.x / MOM_SPLIT, cta_part = blockIdx.x % MOM_SPLIT;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    double* xd = sm;                           // [N] diagonal of X
-    double* red = xd + N;                      // [48]
+    const int PW = P.tabi[HALF + 2], PV = P.tabi[HALF + 3];
+    const int PX = L + (((PW - L) % 16) + 16) % 16;  // row pitch of the diagonal: same residue structure as the patch array
+    double* xd = sm;                           // [L][PX] diagonal of X
+    double* red = xd + L * PX;                 // [48]
     double* msc = red + 48;                    // [64]
     double* Fg = msc + 64;                     // [G]
     double* acc = Fg + ((G + 1) & ~1);         // [MOM_WARPS][3][HALF+1]
@@ -452,7 +465,8 @@ __global__ void __launch_bounds__(MOM_WARPS * 32, 2) kpm_moments2d_kernel(mom_ar
     double part = 0.0;
     for (int i = tid; i < N; i += T) {
         const double x = ((P.U * (double)f[i] - P.mu_c) - bsh) / a;
-        xd[i] = x;
+        const int y = i / L;
+        xd[y * PX + (i - y * L)] = x;
         part += x;
     }
     const double trx = block_sum(part, red);
@@ -462,60 +476,71 @@ __global__ void __launch_bounds__(MOM_WARPS * 32, 2) kpm_moments2d_kernel(mom_ar
 
     double* const s0 = vec + (size_t)warp * 2 * PV;  // T_even
     double* const s1 = s0 + PV;                      // T_odd
-    if (lane < 16) { s0[EP + lane] = 0.0; s1[EP + lane] = 0.0; }
+    for (int i = lane; i < 2 * PV; i += 32) s0[i] = 0.0;  // the cells outside the patch stay zero for good
+    __syncwarp();
 
     double tr[HALF + 1], d01[HALF + 1], d11[HALF + 1];
 #pragma unroll
     for (int m = 0; m <= HALF; ++m) tr[m] = d01[m] = d11[m] = 0.0;
 
     for (int cls = 0; cls < P.ncls; ++cls) {
-        // this lane's elements: e = 32 s + lane
-        int dyx[S], nbi[Z][S], cnt[HALF + 1];
-        double h1 = 0.0;  // (X e_j)(e) for the radius-1 elements of slot 0 (hopping / a, doubled above: halve)
+        // this lane's elements: table index 32 s + lane
+        int dyx[S], nbi[Z + 1][S], ns[HALF + 1];
 #pragma unroll
-        for (int m = 0; m <= HALF; ++m) cnt[m] = P.cnt[cls * (HALF + 1) + m];
+        for (int m = 0; m <= HALF; ++m) ns[m] = P.tabi[cls * NT + m];
+        const int lc = P.tabi[cls * NT + HALF + 1];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             const int e = 32 * s + lane;
             dyx[s] = P.off[cls * EP + e];
 #pragma unroll
-            for (int z = 0; z < Z; ++z) nbi[z][s] = P.nb[((size_t)cls * Z + z) * EP + e];
+            for (int z = 0; z <= Z; ++z) nbi[z][s] = P.nb[((size_t)cls * (Z + 1) + z) * EP + e];
         }
-#pragma unroll
-        for (int z = 0; z < Z; ++z)
-            if (nbi[z][0] == 0 && lane != 0) h1 += 0.5 * sv2[z];
+        const double h1 = P.h1[cls * 32 + lane] / a;  // (X e_j)(e) for the slot-0 element next to the centre
         for (int j = warp + MOM_WARPS * cta_part; j < N; j += MOM_WARPS * MOM_SPLIT) {
             const int y0 = j / L, x0 = j - y0 * L;
             if (P.ncls > 1 && ((y0 + x0) & 1) != cls) continue;
             double xd2[S], va[S], vb[S];
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-                int yy = y0 + (dyx[s] >> 8) - 128, xx = x0 + (dyx[s] & 255) - 128;
+                int yy = y0 + ((dyx[s] >> 8) & 255) - 128, xx = x0 + (dyx[s] & 255) - 128;
                 yy += (yy < 0) ? L : 0; yy -= (yy >= L) ? L : 0;
                 xx += (xx < 0) ? L : 0; xx -= (xx >= L) ? L : 0;
-                xd2[s] = (32 * s + lane < cnt[HALF]) ? 2.0 * xd[yy * L + xx] : 0.0;
+                xd2[s] = ((dyx[s] >> 16) <= HALF) ? 2.0 * xd[yy * PX + xx] : 0.0;
                 va[s] = 0.0;
                 vb[s] = 0.0;
-                s0[32 * s + lane] = 0.0;
-                if (s > 0) s1[32 * s + lane] = 0.0;
+                s0[nbi[Z][s]] = 0.0;   // what the previous column left in the patch
+                s1[nbi[Z][s]] = 0.0;
             }
-            // T_0 e_j = e_j (element 0), T_1 e_j = X e_j
-            va[0] = (lane == 0) ? 1.0 : 0.0;
-            vb[0] = (lane == 0) ? 0.5 * xd2[0] : ((lane < cnt[1]) ? h1 : 0.0);
-            s1[lane] = vb[0];
+            // T_0 e_j = e_j (the centre), T_1 e_j = X e_j
+            va[0] = (lane == lc) ? 1.0 : 0.0;
+            vb[0] = (lane == lc) ? 0.5 * xd2[0] : h1;
+            s1[nbi[Z][0]] = vb[0];
             __syncwarp();
             // one recursion step: vold <- 2 X vcur - vold, published to snew
             auto step = [&](double (&vold)[S], const double (&vcur)[S], const double* __restrict__ scur, double* __restrict__ snew,
-                            const int cm, const bool need_dots, double& q01, double& q11) {
+                            const int m, const bool need_dots, double& q01, double& q11) {
 #pragma unroll
                 for (int s = 0; s < S; ++s) {
-                    if (32 * s < cm) {  // warp-uniform
+                    const int nsm = SCHED ? (int)((SCHED >> (4 * (m - 2))) & 15) : ns[m];
+                    if (s < nsm) {  // warp-uniform
                         double vn = fma(xd2[s], vcur[s], -vold[s]);
+                        if (UNI) {
+                            double nbs[Z];
 #pragma unroll
-                        for (int z = 0; z < Z; ++z) vn = fma(sv2[z], scur[nbi[z][s]], vn);
-                        vn = (32 * s + lane < cm) ? vn : 0.0;
+                            for (int z = 0; z < Z; ++z) nbs[z] = scur[nbi[z][s]];
+#pragma unroll
+                            for (int w = 1; w < Z; w *= 2)
+#pragma unroll
+                                for (int z = 0; z + w < Z; z += 2 * w) nbs[z] += nbs[z + w];
+                            vn = fma(sv2[0], nbs[0], vn);
+                        } else {
+#pragma unroll
+                            for (int z = 0; z < Z; ++z) vn = fma(sv2[z], scur[nbi[z][s]], vn);
+                        }
+                        vn = ((dyx[s] >> 16) <= m) ? vn : 0.0;
                         vold[s] = vn;
-                        snew[32 * s + lane] = vn;
+                        snew[nbi[Z][s]] = vn;
                         if (need_dots) {
                             q01 = fma(vcur[s], vn, q01);
                             q11 = fma(vn, vn, q11);
@@ -528,11 +553,11 @@ __global__ void __launch_bounds__(MOM_WARPS * 32, 2) kpm_moments2d_kernel(mom_ar
             for (int m = 2; m <= HALF; ++m) {
                 const bool need_dots = (2 * m - 1 >= HALF);
                 if ((m & 1) == 0) {
-                    step(va, vb, s1, s0, cnt[m], need_dots, d01[m], d11[m]);  // va <- T_m e_j
-                    tr[m] += (lane == 0) ? va[0] : 0.0;
+                    step(va, vb, s1, s0, m, need_dots, d01[m], d11[m]);  // va <- T_m e_j
+                    tr[m] += (lane == lc) ? va[0] : 0.0;
                 } else {
-                    step(vb, va, s0, s1, cnt[m], need_dots, d01[m], d11[m]);  // vb <- T_m e_j
-                    tr[m] += (lane == 0) ? vb[0] : 0.0;
+                    step(vb, va, s0, s1, m, need_dots, d01[m], d11[m]);  // vb <- T_m e_j
+                    tr[m] += (lane == lc) ? vb[0] : 0.0;
                 }
             }
         }
@@ -623,127 +648,140 @@ constexpr int patch_elems(int kind, int H) { return kind == FKMC_TRIANGULAR ? 3 
 
 }  // namespace
 
-// Build (or reuse) the ring-ordered patch tables for radius H.
-static int prepare_patch_tables(fkmc_ctx* ctx, int H, int S) {
-    if (ctx->kpm2_H == H && ctx->d_kpm2_cnt) return FKMC_OK;
-    const int N = ctx->N, L = ctx->L, Z = ctx->Z, EP = 32 * S;
+// Build (or reuse) the patch tables for radius H (see the comment above mom_args).  *S_out = slots per lane.
+static int prepare_patch_tables(fkmc_ctx* ctx, int H, int* S_out) {
+    if (ctx->kpm2_H == H && ctx->d_kpm2_tabi) { *S_out = ctx->kpm2_S; return FKMC_OK; }
+    const int N = ctx->N, L = ctx->L, Z = ctx->Z, NT = H + 4;
     const int ncls = (ctx->kind == FKMC_HONEYCOMB) ? 2 : 1;
-    std::vector<int> cnt((size_t)ncls * (H + 1)), off((size_t)ncls * EP, (128 << 8) | 128);
-    std::vector<unsigned short> nb((size_t)ncls * Z * EP, (unsigned short)EP);
+    struct site { int s, dy, dx, hops; };
+    std::vector<std::vector<site>> patch(ncls);
+    std::vector<int> centre(ncls);
     for (int c = 0; c < ncls; ++c) {
+        // the centre sits in the middle of the lattice and L >= 2H+1, so the patch never crosses the periodic boundary
         const int y0 = L / 2, x0 = ((y0 + L / 2) & 1) == c ? L / 2 : L / 2 - 1;
         const int j0 = y0 * L + x0;
-        std::vector<int> dist(N, -1), order;
+        centre[c] = j0;
+        std::vector<int> dist(N, -1);
         std::queue<int> q;
         dist[j0] = 0;
         q.push(j0);
         while (!q.empty()) {
             const int s = q.front();
             q.pop();
-            order.push_back(s);
+            patch[c].push_back({s, s / L - y0, s % L - x0, dist[s]});
             if (dist[s] == H) continue;
             for (int z = 0; z < Z; ++z) {
                 const int t = ctx->h_nbr_idx[(size_t)z * N + s];
                 if (t < N && dist[t] < 0) { dist[t] = dist[s] + 1; q.push(t); }
             }
         }
-        // the centre sits in the middle of the lattice and L >= 2H+1, so the patch never crosses the periodic boundary
-        auto rel = [&](int s, int& dy, int& dx) {
-            dy = s / L - y0;
-            dx = s % L - x0;
-        };
-        // ring order, by angle inside a ring: neighbouring lanes then read neighbouring shared-memory words
-        std::stable_sort(order.begin(), order.end(), [&](int s, int t) {
-            if (dist[s] != dist[t]) return dist[s] < dist[t];
-            int ay, ax, by, bx;
-            rel(s, ay, ax);
-            rel(t, by, bx);
-            return std::atan2((double)ay, (double)ax) < std::atan2((double)by, (double)bx);
+        for (auto& e : patch[c])
+            if (std::abs(e.dy) > H || std::abs(e.dx) > H) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: patch wraps around the lattice");
+        std::stable_sort(patch[c].begin(), patch[c].end(), [](const site& a, const site& b2) {
+            if (a.hops != b2.hops) return a.hops < b2.hops;
+            return std::atan2((double)a.dy, (double)a.dx) < std::atan2((double)b2.dy, (double)b2.dx);
         });
-        const int E = (int)order.size();
-        if (E > EP || E > 65000) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: patch larger than its table");
-        std::vector<int> cn(H + 1);
-        for (int m = 0; m <= H; ++m) {
-            int n = 0;
-            for (int e = 0; e < E; ++e) n += dist[order[e]] <= m;
-            cn[m] = n;
-            cnt[(size_t)c * (H + 1) + m] = n;
+    }
+    // deal the elements out, nearest first: an element goes to the first slot whose half-warps still have its lane
+    // (= cell address mod 16) free.  The row pitch P decides the residues; take the one that needs the fewest slot visits.
+    auto cell = [&](int P, int dy, int dx) { return (dy + H + 1) * P + (dx + H + 1); };
+    struct plan { long visits; int S; std::vector<std::vector<int>> where; std::vector<std::vector<int>> ns; };  // where[c][e] = 32 slot + lane
+    auto make_plan = [&](int P) {
+        plan pl;
+        pl.visits = 0;
+        pl.S = 0;
+        pl.where.resize(ncls);
+        pl.ns.assign(ncls, std::vector<int>(H + 1, 1));
+        for (int c = 0; c < ncls; ++c) {
+            std::vector<char> used;  // [slot][half][residue]
+            for (const site& e : patch[c]) {
+                const int r = cell(P, e.dy, e.dx) & 15;
+                int sl = 0, half = -1;
+                for (;; ++sl) {
+                    if ((int)used.size() < 32 * (sl + 1)) used.resize(32 * (sl + 1), 0);
+                    if (!used[32 * sl + r]) { half = 0; break; }
+                    if (!used[32 * sl + 16 + r]) { half = 1; break; }
+                }
+                used[32 * sl + 16 * half + r] = 1;
+                pl.where[c].push_back(32 * sl + 16 * half + r);
+                for (int m = e.hops; m <= H; ++m) pl.ns[c][m] = std::max(pl.ns[c][m], sl + 1);
+                pl.S = std::max(pl.S, sl + 1);
+            }
+            for (int m = 2; m <= H; ++m) pl.visits += pl.ns[c][m];
         }
-        // Shared-memory bank conflicts of the neighbour gathers depend only on the numbering inside the rings, which is
-        // free: anneal it.  A 64-bit warp request is served half-warp by half-warp, one wavefront per distinct word in the
-        // busiest bank (word mod 16); slot s is visited by every step m with cnt(m) > 32 s.  Neighbours outside the patch
-        // read one of 16 zero words (EP + lane % 16).
-        std::vector<int> elem(N, -1);
-        auto neighbour = [&](int e, int z) {
-            if (e >= E) return EP + (e & 15);
-            const int t = ctx->h_nbr_idx[(size_t)z * N + order[e]];
-            return (t < N && elem[t] >= 0) ? elem[t] : EP + (e & 15);
-        };
-        auto cost = [&]() {
-            for (int e = 0; e < E; ++e) elem[order[e]] = e;
-            long total = 0;
-            for (int sl = 0; sl < S; ++sl) {
-                int visits = 0;
-                for (int m = 2; m <= H; ++m) visits += cn[m] > 32 * sl;
-                if (!visits) continue;
-                for (int z = 0; z < Z; ++z)
-                    for (int half = 0; half < 2; ++half) {
-                        int words[16], nw = 0, load[16] = {0};
-                        for (int l = 0; l < 16; ++l) {
-                            const int w = neighbour(32 * sl + 16 * half + l, z);
-                            bool seen = false;
-                            for (int i = 0; i < nw; ++i) seen |= words[i] == w;
-                            if (!seen) { words[nw++] = w; ++load[w & 15]; }
-                        }
-                        int worst = 1;
-                        for (int i = 0; i < 16; ++i) worst = std::max(worst, load[i]);
-                        total += (long)visits * worst;
-                    }
+        return pl;
+    };
+    int P = 2 * H + 3;
+    plan best = make_plan(P);
+    for (int cand = 2 * H + 4; cand < 2 * H + 3 + 16; ++cand) {
+        plan pl = make_plan(cand);
+        if (pl.visits < best.visits || (pl.visits == best.visits && pl.S < best.S)) { best = pl; P = cand; }
+    }
+    const int S = best.S, EP = 32 * S;
+    int PV = (2 * H + 3) * P;
+    PV += PV & 1;
+    if (PV > 65000) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: patch larger than its table");
+    std::vector<int> tabi((size_t)ncls * NT, 0), off((size_t)ncls * EP, (255 << 16) | (128 << 8) | 128);
+    std::vector<unsigned short> nb((size_t)ncls * (Z + 1) * EP);
+    std::vector<double> h1((size_t)ncls * 32, 0.0);
+    for (int c = 0; c < ncls; ++c) {
+        for (int m = 0; m <= H; ++m) tabi[(size_t)c * NT + m] = best.ns[c][m];
+        tabi[(size_t)c * NT + H + 2] = P;
+        tabi[(size_t)c * NT + H + 3] = PV;
+        // unused (slot, lane): a cell of the first row (outside the patch) with the lane's residue, so that it stays conflict-free
+        for (int e = 0; e < EP; ++e)
+            for (int z = 0; z <= Z; ++z) nb[((size_t)c * (Z + 1) + z) * EP + e] = (unsigned short)(e & 15);
+        for (size_t i = 0; i < patch[c].size(); ++i) {
+            const site& e = patch[c][i];
+            const int w = best.where[c][i];
+            off[(size_t)c * EP + w] = (e.hops << 16) | ((e.dy + 128) << 8) | (e.dx + 128);
+            nb[((size_t)c * (Z + 1) + Z) * EP + w] = (unsigned short)cell(P, e.dy, e.dx);
+            for (int z = 0; z < Z; ++z) {
+                const int t = ctx->h_nbr_idx[(size_t)z * N + e.s];
+                // a padding slot of the stencil (no neighbour): any cell that stays zero, keep the residue
+                int cw = cell(P, e.dy, e.dx) & 15;
+                if (t < N && t != e.s) {
+                    int ty = t / L - centre[c] / L, tx = t % L - centre[c] % L;  // minimal image: a neighbour just outside the patch may wrap
+                    ty += (ty < -(H + 1)) ? L : 0; ty -= (ty > H + 1) ? L : 0;
+                    tx += (tx < -(H + 1)) ? L : 0; tx -= (tx > H + 1) ? L : 0;
+                    if (std::abs(ty) > H + 1 || std::abs(tx) > H + 1) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: neighbour outside the patch array");
+                    cw = cell(P, ty, tx);
+                }
+                nb[((size_t)c * (Z + 1) + z) * EP + w] = (unsigned short)cw;
+                if (t == centre[c] && w < 32) h1[(size_t)c * 32 + w] += ctx->h_nbr_val[(size_t)z * N + e.s];
             }
-            return total;
-        };
-        {
-            uint64_t rng = 0x9e3779b97f4a7c15ull + (uint64_t)c;
-            auto next = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
-            long cur = cost();
-            const long first = cur;
-            const int iters = 40000;
-            for (int it = 0; it < iters && E > 2; ++it) {
-                const int r = 1 + (int)(next() % (uint64_t)H);
-                const int lo = cn[r - 1], n = cn[r] - cn[r - 1];
-                if (n < 2) continue;
-                const int i = lo + (int)(next() % (uint64_t)n), j = lo + (int)(next() % (uint64_t)n);
-                if (i == j) continue;
-                std::swap(order[i], order[j]);
-                const long nc = cost();
-                // accept improvements, and small deteriorations early on
-                const double temp = 2.0 * (1.0 - (double)it / iters);
-                const bool accept = nc <= cur || (double)(next() % 1000000) * 1e-6 < std::exp(-(double)(nc - cur) / std::max(temp, 1e-3));
-                if (accept) cur = nc;
-                else std::swap(order[i], order[j]);
-            }
-            for (int e = 0; e < E; ++e) elem[order[e]] = e;
-            if (getenv("FKMC_KPM_DEBUG")) fprintf(stderr, "kpm2d patch tables: class %d, %d elements, gather wavefronts per column %ld -> %ld\n", c, E, first, cur);
+            if (e.hops == 0) tabi[(size_t)c * NT + H + 1] = w;
+            if (e.hops <= 1 && w >= 32) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: first ring does not fit the first slot");
         }
-        for (int e = 0; e < EP; ++e) {
-            if (e < E) {
-                int dy, dx;
-                rel(order[e], dy, dx);
-                if (std::abs(dy) > H || std::abs(dx) > H) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: patch wraps around the lattice");
-                off[(size_t)c * EP + e] = ((dy + 128) << 8) | (dx + 128);
-            }
-            for (int z = 0; z < Z; ++z) nb[((size_t)c * Z + z) * EP + e] = (unsigned short)neighbour(e, z);
+        if (getenv("FKMC_KPM_DEBUG")) {
+            fprintf(stderr, "kpm2d patch tables: class %d, %zu elements, pitch %d, %d slots, slots per step:", c, patch[c].size(), P, S);
+            for (int m = 2; m <= H; ++m) fprintf(stderr, " %d", best.ns[c][m]);
+            fprintf(stderr, "\n");
         }
     }
-    if (ctx->d_kpm2_cnt) { cudaFree(ctx->d_kpm2_cnt); cudaFree(ctx->d_kpm2_off); cudaFree(ctx->d_kpm2_nb); ctx->d_kpm2_cnt = nullptr; }
-    FKMC_CUDA(ctx, cudaMalloc(&ctx->d_kpm2_cnt, sizeof(int) * cnt.size()));
+    if (ctx->d_kpm2_tabi) {
+        cudaFree(ctx->d_kpm2_tabi); cudaFree(ctx->d_kpm2_off); cudaFree(ctx->d_kpm2_nb); cudaFree(ctx->d_kpm2_h1);
+        ctx->d_kpm2_tabi = nullptr;
+    }
+    FKMC_CUDA(ctx, cudaMalloc(&ctx->d_kpm2_tabi, sizeof(int) * tabi.size()));
     FKMC_CUDA(ctx, cudaMalloc(&ctx->d_kpm2_off, sizeof(int) * off.size()));
     FKMC_CUDA(ctx, cudaMalloc(&ctx->d_kpm2_nb, sizeof(unsigned short) * nb.size()));
-    FKMC_CUDA(ctx, cudaMemcpyAsync(ctx->d_kpm2_cnt, cnt.data(), sizeof(int) * cnt.size(), cudaMemcpyHostToDevice, ctx->stream));
+    FKMC_CUDA(ctx, cudaMalloc(&ctx->d_kpm2_h1, sizeof(double) * h1.size()));
+    FKMC_CUDA(ctx, cudaMemcpyAsync(ctx->d_kpm2_tabi, tabi.data(), sizeof(int) * tabi.size(), cudaMemcpyHostToDevice, ctx->stream));
     FKMC_CUDA(ctx, cudaMemcpyAsync(ctx->d_kpm2_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, ctx->stream));
     FKMC_CUDA(ctx, cudaMemcpyAsync(ctx->d_kpm2_nb, nb.data(), sizeof(unsigned short) * nb.size(), cudaMemcpyHostToDevice, ctx->stream));
+    FKMC_CUDA(ctx, cudaMemcpyAsync(ctx->d_kpm2_h1, h1.data(), sizeof(double) * h1.size(), cudaMemcpyHostToDevice, ctx->stream));
     FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->kpm2_sched = 0;
+    for (int m = 2; m <= H && m <= 17; ++m) ctx->kpm2_sched |= (unsigned long long)(best.ns[0][m] & 15) << (4 * (m - 2));
+    for (int c = 1; c < ncls; ++c)
+        for (int m = 2; m <= H; ++m)
+            if (best.ns[c][m] != best.ns[0][m]) ctx->kpm2_sched = ~0ull;
     ctx->kpm2_H = H;
+    ctx->kpm2_S = S;
+    ctx->kpm2_PV = PV;
+    ctx->kpm2_P = P;
+    *S_out = S;
     return FKMC_OK;
 }
 
@@ -757,19 +795,38 @@ static int launch_lanczos2d(fkmc_ctx* ctx, const lz_args& P, int B) {
     return FKMC_OK;
 }
 
+template <int HALF, int Z, int S, unsigned long long SCHED, bool UNI>
+static int launch_moments2d_s(fkmc_ctx* ctx, mom_args& P, int B) {
+    const int PW = ctx->kpm2_P, PX = P.L + (((PW - P.L) % 16) + 16) % 16;
+    const size_t smem = sizeof(double) * ((size_t)P.L * PX + 48 + 64 + ((P.G + 1) & ~1) + (size_t)MOM_WARPS * 3 * (HALF + 1) +
+                                          (size_t)MOM_WARPS * 2 * ctx->kpm2_PV);
+    if (smem > ctx->smem_optin - 1024) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: lattice too large for the shared-memory kernel");
+    FKMC_CUDA(ctx, cudaFuncSetAttribute(kpm_moments2d_kernel<HALF, Z, S, SCHED, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kpm_moments2d_kernel<HALF, Z, S, SCHED, UNI><<<B * MOM_SPLIT, MOM_WARPS * 32, smem, ctx->stream>>>(P);
+    ctx->launches++;
+    FKMC_CUDA(ctx, cudaGetLastError());
+    return FKMC_OK;
+}
+
+// slots per step of the square lattice's diamond patch, m = 2, 3, ... (what prepare_patch_tables finds; checked at launch)
+constexpr unsigned long long cubic2d_sched(int H) {
+    constexpr int ns[9] = {1, 1, 2, 3, 3, 4, 5, 6, 8};
+    unsigned long long v = 0;
+    for (int m = 2; m <= H && m <= 10; ++m) v |= (unsigned long long)ns[m - 2] << (4 * (m - 2));
+    return v;
+}
+
 template <int HALF, int KIND>
 static int launch_moments2d(fkmc_ctx* ctx, mom_args& P, int B) {
     constexpr int Z = (KIND == FKMC_TRIANGULAR) ? 6 : (KIND == FKMC_HONEYCOMB ? 3 : 4);
-    constexpr int S = (patch_elems(KIND, HALF) + 31) / 32;
-    int rc = prepare_patch_tables(ctx, HALF, S);
+    constexpr int S0 = (patch_elems(KIND, HALF) + 31) / 32;  // slots if every slot could be filled completely
+    int S = 0;
+    int rc = prepare_patch_tables(ctx, HALF, &S);
     if (rc) return rc;
-    P.cnt = ctx->d_kpm2_cnt;
+    P.tabi = ctx->d_kpm2_tabi;
     P.off = ctx->d_kpm2_off;
     P.nb = ctx->d_kpm2_nb;
-    const size_t smem = sizeof(double) * ((size_t)P.N + 48 + 64 + ((P.G + 1) & ~1) + (size_t)MOM_WARPS * 3 * (HALF + 1) +
-                                          (size_t)MOM_WARPS * 2 * (32 * S + 16));
-    if (smem > ctx->smem_optin - 1024) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: lattice too large for the shared-memory kernel");
-    FKMC_CUDA(ctx, cudaFuncSetAttribute(kpm_moments2d_kernel<HALF, Z, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    P.h1 = ctx->d_kpm2_h1;
     if (!ctx->d_kpm2_part) {
         FKMC_CUDA(ctx, cudaMalloc(&ctx->d_kpm2_part, sizeof(double) * (size_t)ctx->max_batch * MOM_SPLIT * 3 * (FKMC_MAX_HALF + 1)));
         FKMC_CUDA(ctx, cudaMalloc(&ctx->d_kpm2_arrived, sizeof(int) * (size_t)ctx->max_batch));
@@ -777,10 +834,19 @@ static int launch_moments2d(fkmc_ctx* ctx, mom_args& P, int B) {
     }
     P.part = ctx->d_kpm2_part;
     P.arrived = ctx->d_kpm2_arrived;
-    kpm_moments2d_kernel<HALF, Z, S><<<B * MOM_SPLIT, MOM_WARPS * 32, smem, ctx->stream>>>(P);
-    ctx->launches++;
-    FKMC_CUDA(ctx, cudaGetLastError());
-    return FKMC_OK;
+    if constexpr (KIND == FKMC_CUBIC2D) {
+        // the common case, fully specialised: compile-time schedule, one hopping constant
+        bool uni = true;
+        for (int z = 1; z < Z; ++z) uni = uni && P.slot_val[z] == P.slot_val[0];
+        constexpr int SS = S0 + (HALF == 10 ? 1 : 0);
+        if (uni && S == SS && ctx->kpm2_sched == cubic2d_sched(HALF) && !ctx->kpm_no_sched)
+            return launch_moments2d_s<HALF, Z, SS, cubic2d_sched(HALF), true>(ctx, P, B);
+    }
+    // the honeycomb patch is smaller than the bound used for S0, and the residue constraint can cost one slot
+    if (S <= S0 - 1 && S0 >= 2) return launch_moments2d_s<HALF, Z, (S0 >= 2 ? S0 - 1 : 1), 0ull, false>(ctx, P, B);
+    if (S <= S0) return launch_moments2d_s<HALF, Z, S0, 0ull, false>(ctx, P, B);
+    if (S == S0 + 1) return launch_moments2d_s<HALF, Z, S0 + 1, 0ull, false>(ctx, P, B);
+    return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: patch does not fit the compiled slot counts");
 }
 
 template <int KIND>

@@ -288,6 +288,10 @@ def test_kpm_two_kernel_path_matches_single_kernel_and_oracle(kind, L, U, beta, 
     c.set_option("kpm_v1", 1)
     r1 = c.logz_kpm(fs, U, U / 2, beta, M, 2 * M)
     c.set_option("kpm_v1", 0)
+    c.set_option("kpm_generic_schedule", 1)      # run-time slot schedule instead of the compile-time one (cubic2d)
+    r3 = c.logz_kpm(fs, U, U / 2, beta, M, 2 * M)
+    c.set_option("kpm_generic_schedule", 0)
+    assert np.abs(r3["moments"] - r2["moments"]).max() <= 1e-12
     scale = np.maximum(np.abs(r1["e_min"]), np.abs(r1["e_max"]))
     assert (np.abs(r1["e_min"] - r2["e_min"]) <= 1e-12 * scale).all() and (np.abs(r1["e_max"] - r2["e_max"]) <= 1e-12 * scale).all()
     assert np.abs(r1["moments"] - r2["moments"]).max() <= 1e-12
