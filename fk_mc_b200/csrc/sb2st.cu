@@ -28,6 +28,12 @@ constexpr int SB = 8;     // half bandwidth
 constexpr int WD = 16;    // stored sub-diagonals per column
 constexpr int LAG = 3;    // steps between consecutive sweeps
 
+// Ordering of the band updates against the progress counters.  Writer: band stores (all lanes), __syncwarp, counter store (one
+// lane); reader: counter load, __syncwarp, band loads.  Both sides are plain shared-memory accesses of one SM, which the LSU
+// performs in issue order, so a compiler barrier is all that is needed -- a __threadfence_block() here is a MEMBAR.SC.CTA twice per
+// step, which measured at about half of the step's latency (the step chain is the critical path of the whole kernel).
+__device__ __forceinline__ void sched_fence() { asm volatile("" ::: "memory"); }
+
 // sum over the 8 lanes of a group (m: the group's lane mask)
 __device__ __forceinline__ double gsum8(double x, unsigned m) {
     x += __shfl_xor_sync(m, x, 1);
@@ -95,7 +101,7 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
                 while (prog[jb - 1] < s + LAG) { __nanosleep(FKMC_SB2ST_SLEEP); }
             }
             __syncwarp();
-            __threadfence_block();
+            sched_fence();
             if (act) {
                 if (s == 0) {
                     // ---- step 0: annihilate column j below the sub-diagonal ----
@@ -186,7 +192,7 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
             }
             // publish progress: the writes of this step are visible before the counter moves
             __syncwarp();
-            __threadfence_block();
+            sched_fence();
             if (act && l == 0) prog[j] = done ? (1 << 30) : s + 1;
             ++s;
         }
