@@ -381,6 +381,11 @@ int fkmc_set_option(fkmc_ctx* ctx, const char* name, int value) {
         ctx->kpm_no_sched = value != 0;
         return FKMC_OK;
     }
+    if (std::string(name) == "sy2sb_tiled_min") {  // process-wide: smallest N served by the tiled dense->band kernel (default 256)
+        if (value < 64 || value > 1024) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sy2sb_tiled_min must be in [64, 1024]");
+        fkmc_set_tiled_min(value);
+        return FKMC_OK;
+    }
     if (std::string(name) == "kpm_v1") {
         ctx->kpm_force_v1 = value != 0;
         return FKMC_OK;

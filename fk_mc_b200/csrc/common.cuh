@@ -157,6 +157,7 @@ int fkmc_launch_build_h_tiled(fkmc_ctx* ctx, const int32_t* d_f, int B, double U
 int fkmc_launch_to_tiled(fkmc_ctx* ctx, const double* d_A, int N, int B, double* d_At);
 size_t fkmc_tiled_stride(int N);
 bool fkmc_use_tiled(int N);
+void fkmc_set_tiled_min(int n);  // smallest N served by the tiled dense->band kernel (process-wide; default 256)
 // f -> Hamiltonian -> tridiagonal (d, e) with the context's selected algorithm and matching matrix layout
 int fkmc_build_tridiag(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double* d_d, double* d_e);
 // dense -> tridiagonal with the context's selected algorithm (A is overwritten)

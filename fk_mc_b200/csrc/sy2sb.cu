@@ -42,7 +42,7 @@
 namespace {
 
 constexpr int NB = 8;
-constexpr int NW = 8;        // warps per CTA
+constexpr int NW8 = 8;       // warps per CTA (N > 512); the N <= 512 variant runs 4 warps per CTA and two CTAs per SM
 constexpr int TILE = 1024;   // doubles per tile (no padding)
 constexpr int MAXOWN = 4;    // owned row tiles per warp: N <= 1024 -> nt <= 32 -> 4
 constexpr int QR = 4;        // panel rows per thread during the QR: m <= 1016 -> 4
@@ -280,6 +280,7 @@ __device__ __forceinline__ void tile_symm_t(const double* __restrict__ Tb, const
 // are OWNED by warp a % 8 (their sums stay in its registers for the whole pass); the nt % 8 left-over blocks are FLOATING: their
 // tasks rotate over the warps (at most one per warp and step, always last in the warp's step), and both halves of their result go
 // to shared memory.  That keeps the tile count per warp and step equal to within one.
+template <int NW>
 struct sched {
     int warp, nt, smax, nown, base, rem;
     __device__ __forceinline__ int lim(int s) const { return (s > 0 && 2 * s == nt) ? (nt >> 1) : nt; }
@@ -289,7 +290,7 @@ struct sched {
         if (o < nown) {
             a = warp + NW * o;
         } else if (o == nown) {
-            const int k = (warp - s * rem) & 7;
+            const int k = (warp - s * rem) & (NW - 1);
             if (k >= rem) return -1;
             a = base + k;
         } else {
@@ -338,9 +339,10 @@ __host__ __device__ __forceinline__ size_t scratch_doubles(int N) {
 #define S1_T(var) \
     long long var = 0; \
     if (DBG) var = clock64();
-template <bool DBG>
-__global__ void __launch_bounds__(NW * 32, 1)
-sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restrict__ AB_all, double* __restrict__ scr_all, long long* dbg) {
+template <bool DBG, int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : 2)
+sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restrict__ AB_all, double* __restrict__ scr_all, long long* dbg,
+             unsigned* __restrict__ slot_mask) {
     long long ph_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ps_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, spin_t = 0;
     extern __shared__ __align__(128) double smem[];
     const int tid = threadIdx.x, T = NW * 32, lane = tid & 31, warp = tid >> 5;
@@ -366,7 +368,26 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
     // one scratch slot per SM (a single CTA fits on an SM): the records of the block column in flight stay hot in L2
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    double* Vcm = scr_all + (size_t)smid * scratch_doubles(N);
+    // With two CTAs per SM (NW == 4) each takes one of the SM's two scratch slots: a bit per slot in slot_mask[smid], grabbed
+    // here and released at the end of the kernel.
+    __shared__ int my_slot;
+    if (NW != 8) {
+        if (tid == 0) {
+            int got = -1;
+            while (got < 0) {
+                const unsigned old = atomicOr(slot_mask + smid, 1u);
+                if (!(old & 1u)) got = 0;
+                else {
+                    const unsigned old2 = atomicOr(slot_mask + smid, 2u);
+                    if (!(old2 & 2u)) got = 1;
+                }
+            }
+            my_slot = got;
+        }
+        __syncthreads();
+    }
+    const int slot = (NW != 8) ? my_slot : 0;
+    double* Vcm = scr_all + ((size_t)smid * (NW == 8 ? 1 : 2) + slot) * scratch_doubles(N);
     double* recVp = Vcm + 8 * ld + 32;
     double* recAV = recVp + NT * 256;
     double* recAZ = recAV + 2 * NT * 256;
@@ -592,11 +613,11 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
             for (int o = 0; o < MAXOWN; ++o)
 #pragma unroll
                 for (int x = 0; x < 4; ++x) own[o][x][0] = own[o][x][1] = 0.0;
-            sched sc;
+            sched<NW> sc;
             sc.warp = warp;
             sc.nt = nt;
             sc.smax = nt >> 1;
-            sc.nown = nt >> 3;
+            sc.nown = nt / NW;
             sc.base = sc.nown * NW;
             sc.rem = nt - sc.base;
             // this warp's task list, packed (s | o << 5 | a << 8 | Rmax << 13 | Cmin << 18), task i in lane i % 32 of d[i / 32]
@@ -756,7 +777,7 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
 #pragma unroll
             for (int o = 0; o < MAXOWN; ++o) {
                 const int a = warp + NW * o;
-                if (o < (nt >> 3)) {
+                if (o < nt / NW) {
 #pragma unroll
                     for (int x = 0; x < 4; ++x)
 #pragma unroll
@@ -832,6 +853,13 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
         if (DBG) ph_t[4] += clock64() - ph_t[6], ph_t[6] = 0;
         // (the __syncthreads after the staging of G/M2 at the top of the next iteration orders these writes)
     }
+    if (NW != 8) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAnd(slot_mask + smid, ~(1u << slot));
+        }
+    }
     if (DBG && blockIdx.x == 0) {
         if (tid == 0)
             for (int i = 0; i < 8; ++i) dbg[i] = ph_t[i];
@@ -843,10 +871,15 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
 
 }  // namespace
 
+// warps per CTA: 8 (one CTA per SM) above N = 512, else 4 with two CTAs per SM, so that the panel phases of one matrix run
+// beside the tensor-core pass of another (the QR keeps four panel rows per thread: m <= 4 * 128)
+static int sy2sb_warps(int N) { return N > 512 ? 8 : 4; }
+
 size_t fkmc_sy2sb_smem(int N) {
+    const size_t nw = sy2sb_warps(N);
     const size_t mp = ((N + 31) / 32) * 32, ld = mp + 4;
-    const size_t xsz = std::max<size_t>(8 * ld, (size_t)NW * TILE);
-    return sizeof(double) * ((size_t)NW * TILE + xsz + 8 * (mp + 18) + 3 * 64 + NW * 64) + sizeof(uint64_t) * 2 * NW + sizeof(int) * 32 + 16;
+    const size_t xsz = std::max<size_t>(8 * ld, nw * TILE);
+    return sizeof(double) * (nw * TILE + xsz + 8 * (mp + 18) + 3 * 64 + nw * 64) + sizeof(uint64_t) * 2 * nw + sizeof(int) * 32 + 16;
 }
 size_t fkmc_sy2sb_scratch(int N) { return scratch_doubles(N); }
 
@@ -863,12 +896,15 @@ size_t fkmc_tiled_stride(int N) {
     const size_t nt = (N + 31) / 32;
     return nt * (nt + 1) / 2 * TILE;
 }
-bool fkmc_use_tiled(int N) { return N >= 512 && N % 8 == 0 && N <= 1024; }
+static int g_tiled_min = getenv("FKMC_TILED_MIN") ? atoi(getenv("FKMC_TILED_MIN")) : 256;  // (environment: developer override)
+void fkmc_set_tiled_min(int n) { g_tiled_min = n; }
+bool fkmc_use_tiled(int N) { return N >= g_tiled_min && N % 8 == 0 && N <= 1024; }
 
 // dense -> band on a batch of matrices in the tiled layout (see fkmc_launch_build_h_tiled / fkmc_launch_to_tiled)
 int fkmc_launch_sy2sb_tiled(fkmc_ctx* ctx, double* d_At, int N, int B, double* d_AB) {
     fkmc_prof_scope ps(ctx, "sy2sb");
     if (!fkmc_use_tiled(N)) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sy2sb_tiled: needs 512 <= N <= 1024, N % 8 == 0");
+    const int nw = sy2sb_warps(N), slots = nw == 8 ? 1 : 2;
     const size_t smem = fkmc_sy2sb_smem(N);
     if (smem > ctx->smem_optin) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sy2sb: matrix too large for shared memory");
     // fragment-ordered panel records, one slot per SM
@@ -882,7 +918,7 @@ int fkmc_launch_sy2sb_tiled(fkmc_ctx* ctx, double* d_At, int N, int B, double* d
         cudaFree(d_n);
         ctx->nsmid = (int)h_n;
     }
-    const size_t need = fkmc_sy2sb_scratch(N) * (size_t)ctx->nsmid;
+    const size_t need = fkmc_sy2sb_scratch(N) * (size_t)ctx->nsmid * slots + (size_t)ctx->nsmid;  // + one word per SM: the slot bits
     if (need > ctx->s1_scratch_cap) {
         if (ctx->d_s1_scratch) {
             FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -899,22 +935,31 @@ int fkmc_launch_sy2sb_tiled(fkmc_ctx* ctx, double* d_At, int N, int B, double* d
         long long h[80];
         FKMC_CUDA(ctx, cudaMalloc(&d_dbg, sizeof(h)));
         FKMC_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, sizeof(h), ctx->stream));
-        FKMC_CUDA(ctx, cudaFuncSetAttribute(sy2sb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sy2sb_kernel<true><<<B, NW * 32, smem, ctx->stream>>>(d_At, fkmc_tiled_stride(N), N, d_AB, ctx->d_s1_scratch, d_dbg);
+        if (nw != 8) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "FKMC_S1_TIMING needs N > 512");
+        FKMC_CUDA(ctx, cudaFuncSetAttribute(sy2sb_kernel<true, NW8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sy2sb_kernel<true, NW8><<<B, NW8 * 32, smem, ctx->stream>>>(d_At, fkmc_tiled_stride(N), N, d_AB, ctx->d_s1_scratch, d_dbg, nullptr);
         FKMC_CUDA(ctx, cudaMemcpyAsync(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFree(d_dbg);
         fprintf(stderr, "[s1 timing, CTA 0, cycles] build %lld  qr %lld  T+export %lld  pass %lld (end barrier %lld)  final %lld\n", h[0], h[1], h[2],
                 h[3], h[5], h[4]);
-        for (int w = 0; w < NW; ++w)
+        for (int w = 0; w < NW8; ++w)
             fprintf(stderr, "  warp %d: tasks %lld | tile wait %lld  update %lld  rec issue %lld  symm_t %lld  refill %lld (store-read wait %lld)  adds %lld (spin %lld)\n", w,
                     h[8 + 8 * w + 6], h[8 + 8 * w], h[8 + 8 * w + 1], h[8 + 8 * w + 2], h[8 + 8 * w + 3], h[8 + 8 * w + 4], h[8 + 8 * w + 7],
                     h[8 + 8 * w + 5], h[72 + w]);
         ctx->launches++;
         return FKMC_OK;
     }
-    FKMC_CUDA(ctx, cudaFuncSetAttribute(sy2sb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sy2sb_kernel<false><<<B, NW * 32, smem, ctx->stream>>>(d_At, fkmc_tiled_stride(N), N, d_AB, ctx->d_s1_scratch, nullptr);
+    // the slot bits live behind the scratch slots (zeroed with the scratch; every CTA clears its bit when it ends)
+    unsigned* slot_mask = reinterpret_cast<unsigned*>(ctx->d_s1_scratch + fkmc_sy2sb_scratch(N) * (size_t)ctx->nsmid * slots);
+    if (nw == 8) {
+        FKMC_CUDA(ctx, cudaFuncSetAttribute(sy2sb_kernel<false, NW8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sy2sb_kernel<false, NW8><<<B, NW8 * 32, smem, ctx->stream>>>(d_At, fkmc_tiled_stride(N), N, d_AB, ctx->d_s1_scratch, nullptr, slot_mask);
+    } else {
+        FKMC_CUDA(ctx, cudaFuncSetAttribute(sy2sb_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FKMC_CUDA(ctx, cudaMemsetAsync(slot_mask, 0, sizeof(unsigned) * (size_t)ctx->nsmid, ctx->stream));
+        sy2sb_kernel<false, 4><<<B, 4 * 32, smem, ctx->stream>>>(d_At, fkmc_tiled_stride(N), N, d_AB, ctx->d_s1_scratch, nullptr, slot_mask);
+    }
     ctx->launches++;
     FKMC_CUDA(ctx, cudaGetLastError());
     return FKMC_OK;
