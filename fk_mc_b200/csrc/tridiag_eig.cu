@@ -14,6 +14,10 @@
 
 #include "common.cuh"
 
+#ifndef FKMC_EIG_BISECT
+#define FKMC_EIG_BISECT 6  // bisection steps every lane takes before the Newton phase (measured: 0 -> 14.0 ms, 4 -> 7.9, 6 -> 7.4, 9 -> 7.9, 12 -> 8.5 per 1024 matrices of N = 1024)
+#endif
+
 namespace {
 
 // number of eigenvalues < x.  de[i] = (d_i, e_{i-1}^2), e_{-1} = 0.  Guarded form: an exact zero is nudged off zero, so the
@@ -207,7 +211,7 @@ tridiag_eig_kernel(const double* __restrict__ d_all, const double* __restrict__ 
         int it = 0;
         // (1) a fixed number of bisection steps for every lane (keeps the warp in lockstep on the cheap count-only
         //     recurrence and leaves all but ~0.03 % of the eigenvalues isolated), then more only while not isolated
-        for (; it < 128 && (it < 12 || cc - ca > 1); ++it) {
+        for (; it < 128 && (it < FKMC_EIG_BISECT || cc - ca > 1); ++it) {
             const double mid = 0.5 * (a + c);
             if (mid <= a || mid >= c || c - a <= tolw) break;
             const int cm = sturm_count(de, N, mid);
