@@ -88,3 +88,39 @@ def test_save_all_data_layout(tmp_path):
     # consumer convention (scripts/parse/parse_thermod.py:48-49): (nbins, value, disp, error) = h5["stats"][obs]
     nb, val, disp, err = t["/stats/energy"]
     assert nb >= 4 and abs(val - e.mean()) < 1e-12 and err > 0
+
+
+def test_cpp_data_save_header(tmp_path):
+    """include/fk_mc_b200/data_save.hpp (C++ twin of stats.py + h5out.py): the file it writes is read back with the Python reader
+    and its statistics are compared with the Python implementation on the same series."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe, fn = str(tmp_path / "data_save_test"), str(tmp_path / "cpp.h5")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "data_save_test.cpp"),
+                           "-o", exe])
+    n, beta, vol = 512, 10.0, 64.0
+    txt = subprocess.run([exe, fn, str(n), str(beta), str(vol)], check=True, capture_output=True, text=True).stdout
+    # the same series in Python
+    s, x = 88172645463325252, 0.0
+    e, d2 = np.empty(n), np.empty(n)
+    for i in range(n):
+        s = (s * 6364136223846793005 + 1442695040888963407) % (1 << 64)
+        u = (s >> 11) * (1.0 / 9007199254740992.0) - 0.5
+        x = 0.7 * x + u
+        e[i] = -0.25 + 0.01 * x
+        d2[i] = 0.02 + 0.001 * u
+    t = h5out.H5Reader(fn).tree()
+    assert np.array_equal(t["/mc_data/energies"], e) and np.array_equal(t["/mc_data/d2energies"], d2)
+    assert np.array_equal(t["/mc_data/ipr_history"], np.arange(12).reshape(3, 4) * 0.5)
+    assert t["/parameters/beta"] == beta and t["/parameters/L"] == 8 and t["/parameters/output"] == "output.h5"
+    rep = stats.energy_report(e, d2, beta, vol)
+    for name, rtol in (("energy", 1e-12), ("d2energy", 1e-12), ("cv", 1e-6)):   # cv: a difference of nearly equal means, summed in another order
+        assert np.allclose(t["/stats/" + name], rep[name]["stats"], rtol=rtol, atol=0)
+        assert t["/binning/" + name].shape == (len(rep[name]["binning"]), 5)
+        assert np.allclose(t["/binning/" + name][:, :4], np.array(rep[name]["binning"]), rtol=rtol, atol=0)
+        assert np.allclose(t["/binning/" + name][:, 4], rep[name]["cor_length"], rtol=100 * rtol, atol=1e-9)
+    printed = {ln.split()[0]: [float(v) for v in ln.split()[1:5]] for ln in txt.strip().splitlines()}
+    assert np.allclose(printed["cv"], t["/stats/cv"]) and np.allclose(printed["c_energy"], t["/stats/c_energy"])
