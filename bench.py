@@ -57,7 +57,7 @@ class ClockSampler:
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200", "-i",
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100", "-i",
                                        str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None

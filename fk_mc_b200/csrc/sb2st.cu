@@ -25,7 +25,11 @@ namespace {
 #define FKMC_SB2ST_SLEEP 20
 #endif
 constexpr int SB = 8;     // half bandwidth
-constexpr int WD = 16;    // stored sub-diagonals per column
+#ifndef FKMC_SB2ST_WD
+#define FKMC_SB2ST_WD 19
+#endif
+constexpr int WD = FKMC_SB2ST_WD;    // doubles per stored column: 16 sub-diagonals (band 0..8 + transient fill 9..15) padded to a stride that spreads the three
+                          // access patterns of a step (and the four sweeps of a warp, 24 columns apart) over the banks: 78 wavefronts per step instead of 120
 constexpr int LAG = 3;    // steps between consecutive sweeps
 
 // Ordering of the band updates against the progress counters.  Writer: band stores (all lanes), __syncwarp, counter store (one
