@@ -76,6 +76,9 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
     extern __shared__ double smem[];
     double* Wb = smem;                                         // [N + 16][16]
     volatile int* prog = reinterpret_cast<volatile int*>(Wb + (size_t)(N + 16) * WD);  // [N] steps completed per sweep
+    // per-group broadcast pads (16 doubles: the reflector and the u vector of step (ii)): one store + four 128-bit loads per
+    // lane instead of eight group-masked shuffles each
+    double* bcast = Wb + ((((size_t)(N + 16) * WD + (N + 1) / 2 + 2)) & ~(size_t)1);  // (16-byte aligned)
     const int b = blockIdx.x, tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
     const double* AB = AB_all + (size_t)b * (SB + 1) * N;
 
@@ -87,6 +90,7 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
     __syncthreads();
 
     const int l = lane & 7, q = lane >> 3, gbase = lane & 24;
+    double* bc = bcast + (size_t)(warp * 4 + q) * 16;
     const unsigned gmask = 0xffu << gbase;
     const int nsweeps = N - 2;
     for (int jb = 4 * warp; jb < nsweeps; jb += 4 * nwarps) {
@@ -114,8 +118,15 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
                     if (l < n) Wb[(size_t)j * WD + 1 + l] = (l == 0) ? R.beta : 0.0;
                     vl = R.v;
                     tau = R.tau;
+                    bc[l] = vl;
+                    __syncwarp(gmask);
 #pragma unroll
-                    for (int i = 0; i < SB; ++i) v[i] = __shfl_sync(gmask, vl, gbase + i);
+                    for (int i = 0; i < SB; i += 2) {
+                        const double2 t = *reinterpret_cast<const double2*>(bc + i);
+                        v[i] = t.x;
+                        v[i + 1] = t.y;
+                    }
+                    __syncwarp(gmask);
                 }
                 // One step = three independent block updates with the same reflector (tau = 0 makes all of them the identity):
                 //   (i)   [s >= 1] left-apply H to columns p-7 .. p-1 of the bulge block A(J, .): lane l owns column p-8+l
@@ -170,10 +181,13 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
                 double u = tau * (u0 + u1);                        // u_l = tau (D v)_l
                 const double alpha = -0.5 * tau * gsum8(u * vl, gmask);
                 u = fma(alpha, vl, u);
+                bc[8 + l] = u;
+                __syncwarp(gmask);
 #pragma unroll
-                for (int i = 0; i < SB; ++i) {
-                    const double ui = __shfl_sync(gmask, u, gbase + i);
-                    dcol[i] = dcol[i] - v[i] * u - ui * vl;
+                for (int i = 0; i < SB; i += 2) {
+                    const double2 t = *reinterpret_cast<const double2*>(bc + 8 + i);
+                    dcol[i] = dcol[i] - v[i] * u - t.x * vl;
+                    dcol[i + 1] = dcol[i + 1] - v[i + 1] * u - t.y * vl;
                 }
                 // stores
 #pragma unroll
@@ -186,8 +200,14 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
                     if (l < nn) Wb[(size_t)p * WD + SB + l] = (l == 0) ? R.beta : 0.0;
                     vl = R.v;
                     tau = R.tau;
+                    bc[l] = vl;
+                    __syncwarp(gmask);
 #pragma unroll
-                    for (int i = 0; i < SB; ++i) v[i] = __shfl_sync(gmask, vl, gbase + i);
+                    for (int i = 0; i < SB; i += 2) {
+                        const double2 t = *reinterpret_cast<const double2*>(bc + i);
+                        v[i] = t.x;
+                        v[i + 1] = t.y;
+                    }
                     p = pn;
                     n = nn;
                 } else {
@@ -212,7 +232,7 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
 
 }  // namespace
 
-size_t fkmc_sb2st_smem(int N) { return sizeof(double) * (size_t)(N + 16) * WD + sizeof(int) * (size_t)N + 16; }
+size_t fkmc_sb2st_smem(int N) { return sizeof(double) * ((size_t)(N + 16) * WD + (N + 1) / 2 + 3 + 16 * 4 * 16) + 16; }  // band, counters, broadcast pads (<= 16 warps)
 
 int fkmc_launch_sb2st(fkmc_ctx* ctx, const double* d_AB, int N, int B, double* d_d, double* d_e) {
     fkmc_prof_scope ps(ctx, "sb2st");
