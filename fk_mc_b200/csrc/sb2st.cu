@@ -71,6 +71,39 @@ __device__ __forceinline__ refl make_reflector(double x, int l, int n, unsigned 
     return R;
 }
 
+// The same reflector with the group's x vector exchanged through its shared-memory pad (one store, four 128-bit loads, the norm
+// summed in the lane) instead of three shuffle stages + one broadcast shuffle.  pad: 8 doubles, 16-byte aligned.
+__device__ __forceinline__ refl make_reflector_pad(double x, int l, int n, unsigned m, double* pad) {
+    refl R;
+    pad[l] = x;
+    __syncwarp(m);
+    double xs[SB];
+#pragma unroll
+    for (int i = 0; i < SB; i += 2) {
+        const double2 t = *reinterpret_cast<const double2*>(pad + i);
+        xs[i] = t.x;
+        xs[i + 1] = t.y;
+    }
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+    for (int i = 1; i < SB; ++i) {
+        const double xi = (i < n) ? xs[i] : 0.0;
+        if (i & 1) t1 = fma(xi, xi, t1); else t0 = fma(xi, xi, t0);
+    }
+    const double tail2 = t0 + t1, x0 = xs[0];
+    const bool triv = tail2 <= DBL_MIN;
+    const double s2 = fma(x0, x0, triv ? 1.0 : tail2);
+    const double rs = rsqrt(s2);
+    const double nrm = s2 * rs;
+    const double beta = (x0 >= 0.0) ? -nrm : nrm;
+    const double tau = fma(fabs(x0), rs, 1.0);
+    const double inv = 1.0 / (x0 - beta);
+    R.beta = triv ? x0 : beta;
+    R.tau = triv ? 0.0 : tau;
+    R.v = (l == 0) ? 1.0 : ((l < n && !triv) ? x * inv : 0.0);
+    return R;
+}
+
 __global__ void __launch_bounds__(512, 1)
 sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_all, double* __restrict__ e_all) {
     extern __shared__ double smem[];
@@ -90,7 +123,7 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
     __syncthreads();
 
     const int l = lane & 7, q = lane >> 3, gbase = lane & 24;
-    double* bc = bcast + (size_t)(warp * 4 + q) * 16;
+    double* bc = bcast + (size_t)(warp * 4 + q) * 24;  // [0..7] v, [8..15] u, [16..23] x
     const unsigned gmask = 0xffu << gbase;
     const int nsweeps = N - 2;
     for (int jb = 4 * warp; jb < nsweeps; jb += 4 * nwarps) {
@@ -160,7 +193,7 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
                 for (int c = 0; c < SB; ++c) bel[c] = fma(-z, v[c], bel[c]);
                 const bool more = (n == SB && nn >= 2);
                 // next reflector from the first column of the block below (rows pn.., column p): only this sweep touches it now
-                const refl R = make_reflector(bel[0], l, nn, gmask, gbase);
+                const refl R = make_reflector_pad(bel[0], l, nn, gmask, bc + 16);
                 // (i)
                 double w0 = 0.0, w1 = 0.0;
 #pragma unroll
@@ -232,7 +265,7 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
 
 }  // namespace
 
-size_t fkmc_sb2st_smem(int N) { return sizeof(double) * ((size_t)(N + 16) * WD + (N + 1) / 2 + 3 + 16 * 4 * 16) + 16; }  // band, counters, broadcast pads (<= 16 warps)
+size_t fkmc_sb2st_smem(int N) { return sizeof(double) * ((size_t)(N + 16) * WD + (N + 1) / 2 + 3 + 16 * 4 * 24) + 16; }  // band, counters, broadcast pads (<= 16 warps)
 
 int fkmc_launch_sb2st(fkmc_ctx* ctx, const double* d_AB, int N, int B, double* d_d, double* d_e) {
     fkmc_prof_scope ps(ctx, "sb2st");
