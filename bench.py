@@ -38,7 +38,8 @@ WORKLOADS = {
 }
 SWEEP_LEN = 16      # src/mc_metropolis.cpp:14
 SEED = 32167        # test/fast_update_test.cpp:48, benchmark/fast_update.cpp:152
-CPU_SWEEPS = 8      # sweeps per chain in one CPU sample (about 10 s of work per host thread at c5)
+CPU_SWEEPS_BY_WORKLOAD = {"c5": 8, "c1": 2000, "c2": 48, "c3": 8, "c4t": 6, "c4h": 6}  # sweeps per chain in one CPU sample: about 10 s per host thread
+CPU_SWEEPS = 8
 DMMA_PEAK_TFLOPS = 37.0  # measured on this pool's B200 by tools/probe_dmma.cu (profiles/r01_probe_dmma.txt)
 
 
@@ -91,6 +92,13 @@ class ClockSampler:
         return out
 
 
+def fk_cheb(L, ndim=2, prefactor=2.2):
+    """fk_mc.hxx:60-63: M = even(int(ln N * prefactor)), G = max(2M, 10) (same as fk_mc_b200.cheb_sizes, without importing the package)."""
+    m = int(math.log(float(L ** ndim)) * prefactor)
+    m += m % 2
+    return m, max(2 * m, 10)
+
+
 def kpm_algorithmic_bytes(N, M):
     """streaming formulation, 24 N^2 (M/2 - 1) + 16 N^2 bytes per proposal."""
     return 24.0 * N * N * (M / 2 - 1) + 16.0 * N * N
@@ -117,7 +125,9 @@ def run_reference(args, wl, rank, world):
     line = {"impl": "reference", "metric": "metropolis_proposals_per_sec", "value": value, "unit": "proposals/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "chains": cores, "sweep_len": SWEEP_LEN, "seed": SEED},
+            "config": {"workload": desc, "chains_per_gpu": chains, "sweep_len": SWEEP_LEN, "seed": SEED, "mu_c": U / 2, "mu_f": U / 2,
+                       "moves": "add_remove", "M": (fk_cheb(L)[0] if cheb else None), "G": (fk_cheb(L)[1] if cheb else None),
+                       "cpu_chains_per_step": cores, "cpu_sweeps_per_chain": CPU_SWEEPS},
             "cpu_baseline": {"value": value, "unit": "proposals/s", "cores": cores, "kind": "port",
                              "sample": "%d chains x %d sweeps (16 proposals + 1 measurement each) per step, one chain per host thread" % (cores, CPU_SWEEPS)},
             "e2e": {"value": value, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -137,6 +147,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]
+    global CPU_SWEEPS
+    CPU_SWEEPS = CPU_SWEEPS_BY_WORKLOAD.get(args.workload, 8)
     kind, L, beta, U, cheb, chains, desc = wl
     if args.chains:
         chains = args.chains
