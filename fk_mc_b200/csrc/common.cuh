@@ -90,6 +90,7 @@ struct fkmc_ctx {
     unsigned short* d_kpm2_nb = nullptr;
     double* d_kpm2_part = nullptr;   // [max_batch][2][3][FKMC_MAX_HALF+1] per-CTA partial traces of the moments kernel
     int* d_kpm2_arrived = nullptr;   // [max_batch]
+    int* d_kpm2_order = nullptr;     // [max_batch] launch order of the Lanczos CTAs (longest expected run first)
     double* d_d = nullptr;      // [max_batch][N]
     double* d_e = nullptr;      // [max_batch][N]
     double* d_tau = nullptr;    // [max_batch][N]

@@ -38,6 +38,7 @@ struct lz_args {
     double* ab;   // [B][4]: e_min, e_max written here
     int* flag;
     int* steps;
+    const int* order;  // [B] proposal handled by CTA i: longest expected run first (null: identity)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -222,7 +223,7 @@ template <int KIND>
 __global__ void __launch_bounds__(LZ_T, 4) lanczos2d_kernel(lz_args P) {
     extern __shared__ __align__(16) double sm[];
     const int N = P.N, L = P.L;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = P.order ? P.order[blockIdx.x] : blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NWARP = LZ_T / 32;
     double* vb0 = sm;                                         // [N] v_k, ping
     double* vb1 = vb0 + N;                                    // [N] v_k, pong
@@ -404,6 +405,25 @@ __global__ void __launch_bounds__(LZ_T, 4) lanczos2d_kernel(lz_args P) {
         P.ab[(size_t)b * 4 + 0] = e_min;
         P.ab[(size_t)b * 4 + 1] = e_max;
     }
+}
+
+// Launch order of the Lanczos CTAs: the number of steps a proposal needed in the previous launch predicts what it needs now (a chain's
+// configuration changes by one site per proposal), and the runs differ by up to 2x, so the CTAs go out longest first (counting sort
+// by the previous step count; one CTA).  The first launch sees zeros and keeps the identity order.
+__global__ void __launch_bounds__(1024) lanczos_order_kernel(const int* __restrict__ steps, int B, int* __restrict__ order) {
+    __shared__ int hist[64], start[64];
+    const int tid = threadIdx.x;
+    if (tid < 64) hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < B; i += blockDim.x) atomicAdd(&hist[63 - min(63, max(0, steps[i]) >> 3)], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int k = 0; k < 64; ++k) { start[k] = acc; acc += hist[k]; }
+    }
+    __syncthreads();
+    // the order inside one key is irrelevant (every proposal is computed independently of where its CTA runs)
+    for (int i = tid; i < B; i += blockDim.x) order[atomicAdd(&start[63 - min(63, max(0, steps[i]) >> 3)], 1)] = i;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -881,6 +901,15 @@ int fkmc_launch_kpm2d(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double
     Q.ht = slot_val[0];
     Q.hp = (ctx->kind == FKMC_TRIANGULAR) ? slot_val[4] : 0.0;
     Q.ab = d_ab; Q.flag = ctx->d_flag; Q.steps = ctx->d_kpm_steps;
+    if (!ctx->d_kpm2_order) {
+        FKMC_CUDA(ctx, cudaMalloc(&ctx->d_kpm2_order, sizeof(int) * (size_t)ctx->max_batch));
+        FKMC_CUDA(ctx, cudaMemsetAsync(ctx->d_kpm_steps, 0, sizeof(int) * (size_t)ctx->max_batch, ctx->stream));
+    }
+    if (B >= 2 * ctx->num_sms) {  // below that every CTA starts at once anyway
+        lanczos_order_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_kpm_steps, B, ctx->d_kpm2_order);
+        ctx->launches++;
+        Q.order = ctx->d_kpm2_order;
+    }
     int rc;
     {
         fkmc_prof_scope ps(ctx, "kpm_lanczos");
