@@ -182,6 +182,7 @@ int fkmc_destroy(fkmc_ctx* ctx) {
     cudaFree(ctx->d_flag); cudaFree(ctx->d_moments); cudaFree(ctx->d_ab); cudaFree(ctx->d_aux);
     cudaFree(ctx->d_chebt); cudaFree(ctx->d_lobatto); cudaFree(ctx->d_dtheta);
     cudaFree(ctx->d_kpm2_tabi); cudaFree(ctx->d_kpm2_h1); cudaFree(ctx->d_kpm2_off); cudaFree(ctx->d_kpm2_nb);
+    cudaFree(ctx->d_tile_mask);
     cudaFree(ctx->d_kpm2_part); cudaFree(ctx->d_kpm2_arrived); cudaFree(ctx->d_kpm2_order);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);

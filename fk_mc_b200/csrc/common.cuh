@@ -75,6 +75,7 @@ struct fkmc_ctx {
     double* d_AB = nullptr;     // [max_batch][9][N] band storage of the two-stage reduction
     double* d_s1_scratch = nullptr;  // sy2sb: fragment-ordered panel records, one slot per matrix
     size_t s1_scratch_cap = 0;       // doubles
+    unsigned char* d_tile_mask = nullptr;  // tiled layout: 1 for the tiles of H that can hold a non-zero entry
     int nsmid = 0;                   // %nsmid of the device (scratch slots of sy2sb)
     int tridiag_mode = 2;       // 1: one-stage blocked sytrd, 2: sy2sb + sb2st
     int sb2st_warps = 0;        // 0: automatic

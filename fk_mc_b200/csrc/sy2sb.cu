@@ -36,6 +36,7 @@
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 
@@ -1001,12 +1002,18 @@ int fkmc_launch_to_tiled(fkmc_ctx* ctx, const double* d_A, int N, int B, double*
 // (configuration_t::calc_hamiltonian, src/configuration.cpp:79-91)
 __global__ void __launch_bounds__(256) build_h_tiled_kernel(const int32_t* __restrict__ f, const int* __restrict__ nbr_idx,
                                                             const double* __restrict__ nbr_val, int N, int Z, double U, double mu_c,
-                                                            double* __restrict__ At_all, size_t t_stride) {
+                                                            double* __restrict__ At_all, size_t t_stride, const unsigned char* __restrict__ tile_mask) {
     const int b = blockIdx.y, tile = blockIdx.x;
+    double* dst = At_all + (size_t)b * t_stride + (size_t)tile * TILE;
+    if (!tile_mask[tile]) {
+        // no hopping and no diagonal entry falls into this tile (most tiles of a lattice Hamiltonian): plain 16-byte zero stores
+        double2* d2 = reinterpret_cast<double2*>(dst);
+        for (int e = threadIdx.x; e < TILE / 2; e += blockDim.x) d2[e] = make_double2(0.0, 0.0);
+        return;
+    }
     int R, C;
     tile_decode(tile, R, C);
     const int32_t* fb = f + (size_t)b * N;
-    double* dst = At_all + (size_t)b * t_stride + (size_t)tile * TILE;
     for (int e = threadIdx.x; e < TILE; e += blockDim.x) {
         const int r = e >> 5, c = (e & 31) ^ csw(r);
         const int i = 32 * R + r, j = 32 * C + c;
@@ -1027,10 +1034,25 @@ __global__ void __launch_bounds__(256) build_h_tiled_kernel(const int32_t* __res
 
 int fkmc_launch_build_h_tiled(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double* d_At) {
     fkmc_prof_scope ps(ctx, "build_h");
-    const int nt = (ctx->N + 31) / 32;
-    dim3 grid(nt * (nt + 1) / 2, B);
-    build_h_tiled_kernel<<<grid, 256, 0, ctx->stream>>>(d_f, ctx->d_nbr_idx, ctx->d_nbr_val, ctx->N, ctx->Z, U, mu_c, d_At,
-                                                       fkmc_tiled_stride(ctx->N));
+    const int N = ctx->N, nt = (N + 31) / 32, ntiles = nt * (nt + 1) / 2;
+    if (!ctx->d_tile_mask) {
+        // tiles that can hold a non-zero: the diagonal ones and those a stencil entry of the lower triangle falls into
+        std::vector<unsigned char> mask(ntiles, 0);
+        for (int R = 0; R < nt; ++R) mask[(size_t)R * (R + 1) / 2 + R] = 1;
+        for (int z = 0; z < ctx->Z; ++z)
+            for (int i = 0; i < N; ++i) {
+                const int j = ctx->h_nbr_idx[(size_t)z * N + i];
+                if (j >= N) continue;
+                const int lo = std::max(i, j), up = std::min(i, j);
+                mask[(size_t)(lo >> 5) * ((lo >> 5) + 1) / 2 + (up >> 5)] = 1;
+            }
+        FKMC_CUDA(ctx, cudaMalloc(&ctx->d_tile_mask, ntiles));
+        FKMC_CUDA(ctx, cudaMemcpyAsync(ctx->d_tile_mask, mask.data(), ntiles, cudaMemcpyHostToDevice, ctx->stream));
+        FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    dim3 grid(ntiles, B);
+    build_h_tiled_kernel<<<grid, 256, 0, ctx->stream>>>(d_f, ctx->d_nbr_idx, ctx->d_nbr_val, N, ctx->Z, U, mu_c, d_At, fkmc_tiled_stride(N),
+                                                       ctx->d_tile_mask);
     ctx->launches++;
     FKMC_CUDA(ctx, cudaGetLastError());
     return FKMC_OK;
