@@ -250,6 +250,26 @@ def test_argument_errors(ctx8):
         ctx8.chain_init(4, 1.0, 1.0, mc_add_remove=0.0)  # "No registered moves", mc_metropolis.cpp:35-38
 
 
+@pytest.mark.parametrize("kind,L", [("cubic2d", 20), ("honeycomb", 20), ("cubic2d", 28)])
+def test_calc_ed_partial_tiles(kind, L):
+    """N = 400 / 784: sizes that are not multiples of the 32 x 32 tile, through the 4-warp (N <= 512) and the 8-warp variant of the
+    tiled dense->band kernel; a batch larger than the number of SMs so that scratch slots are reused."""
+    B = 300
+    c = fk.Context(kind, L, max_batch=B)
+    n = c.N
+    rng = np.random.default_rng(5)
+    fs = (rng.random((B, n)) < 0.5).astype(np.int32)
+    r = c.logz_ed(fs, 2.0, 1.0, 5.0)
+    for b in (0, 7, B - 1):
+        ref = o.calc_ed(o.KINDS[kind], L, fs[b], 2.0, 1.0, 5.0)
+        assert np.abs(r["spectrum"][b] - ref["spectrum"]).max() <= TOL * np.abs(ref["spectrum"]).max()
+        assert abs(r["logZ"][b] - ref["logZ"]) <= TOL * abs(ref["logZ"])
+    # every matrix of the batch: trace and Frobenius norm of H from the spectrum
+    tr = r["spectrum"].sum(axis=1)
+    assert np.abs(tr - (2.0 * fs.sum(axis=1) - 1.0 * n)).max() <= 1e-9 * n
+    c.close()
+
+
 # ---------------- calc_chebyshev ----------------
 KPM_CASES = [("cubic2d", 8, 1.0, 1.0), ("cubic2d", 16, 2.0, 10.0), ("cubic3d", 8, 4.0, 5.0), ("triangular", 24, 2.0, 10.0),
              ("honeycomb", 24, 2.0, 10.0), ("cubic2d", 32, 2.0, 20.0), ("cubic1d", 12, 1.5, 3.0), ("honeycomb_ref_lower", 8, 2.0, 4.0)]
