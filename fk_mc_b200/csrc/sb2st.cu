@@ -265,18 +265,20 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
 
 }  // namespace
 
-size_t fkmc_sb2st_smem(int N) { return sizeof(double) * ((size_t)(N + 16) * WD + (N + 1) / 2 + 3 + 16 * 4 * 24) + 16; }  // band, counters, broadcast pads (<= 16 warps)
+// band, counters, broadcast pads (24 doubles per sweep group, four groups per warp)
+static size_t sb2st_smem(int N, int nwarps) { return sizeof(double) * ((size_t)(N + 16) * WD + (N + 1) / 2 + 3 + (size_t)nwarps * 4 * 24) + 16; }
+size_t fkmc_sb2st_smem(int N) { return sb2st_smem(N, 16); }  // upper bound (the warp-count override goes up to 16)
 
 int fkmc_launch_sb2st(fkmc_ctx* ctx, const double* d_AB, int N, int B, double* d_d, double* d_e) {
     fkmc_prof_scope ps(ctx, "sb2st");
-    const size_t smem = fkmc_sb2st_smem(N);
-    if (smem > ctx->smem_optin) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sb2st: matrix too large for shared memory");
     // sweeps in flight <= blocks along the band / lag, four sweeps per warp
     const int nblk = (N + SB - 1) / SB;
     int nwarps = ((nblk + LAG - 1) / LAG + 3) / 4;  // measured: N=1024 flat from 8 to 12 warps, N=256 best at 3 (several CTAs share an SM)
     if (nwarps < 1) nwarps = 1;
     if (nwarps > 12) nwarps = 12;
     if (ctx->sb2st_warps > 0) nwarps = ctx->sb2st_warps;  // tuning override (fkmc_set_option "sb2st_warps")
+    const size_t smem = sb2st_smem(N, nwarps);  // small matrices share an SM: no more shared memory than this launch needs
+    if (smem > ctx->smem_optin) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sb2st: matrix too large for shared memory");
     FKMC_CUDA(ctx, cudaFuncSetAttribute(sb2st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     sb2st_kernel<<<B, nwarps * 32, smem, ctx->stream>>>(d_AB, N, d_d, d_e);
     ctx->launches++;
