@@ -104,6 +104,72 @@ def kpm_algorithmic_bytes(N, M):
     return 24.0 * N * N * (M / 2 - 1) + 16.0 * N * N
 
 
+def make_config(desc, chains, U, cheb, M, G):
+    """The workload description both arms print (identical keys and values, so the driver can match them)."""
+    return {"workload": desc, "chains_per_gpu": chains, "sweep_len": SWEEP_LEN, "seed": SEED, "mu_c": U / 2, "mu_f": U / 2,
+            "moves": "add_remove", "M": M if cheb else None, "G": G if cheb else None,
+            "l2_flush": "256 MiB device memset between timed steps", "parallelism": "chains sharded, %d per GPU" % chains}
+
+
+def _lapack_worker(args):
+    kind_id, L, U, budget_s, seed = args
+    import scipy.linalg as sl
+    from threadpoolctl import threadpool_limits
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as o
+    n = o.lattice_size(kind_id, L)
+    rng = np.random.default_rng(seed)
+    H = o.hopping_dense(kind_id, L) + np.diag(U * (rng.random(n) < 0.5) - U / 2)
+    with threadpool_limits(limits=1):
+        sl.eigvalsh(H, driver="evd", check_finite=False)  # warm-up
+        t0, k = time.perf_counter(), 0
+        while time.perf_counter() - t0 < budget_s:
+            sl.eigvalsh(H, driver="evd", check_finite=False)
+            k += 1
+        return k, time.perf_counter() - t0
+
+
+def lapack_probe(kind, L, beta, U, cheb, cores, budget_s=6.0):
+    """Runs in its own interpreter (no CUDA context, so forking workers is safe): `cores` processes, each solving with one thread."""
+    import multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as o
+    kid = o.KINDS[kind]
+    n = o.lattice_size(kid, L)
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_lapack_worker, [(kid, L, U, budget_s, i) for i in range(cores)])
+    solves_per_s = sum(k / sec for k, sec in res)
+    out = {"kind": "lapack dsyevd (scipy/OpenBLAS), one single-threaded process per core", "cores": cores, "solves_per_sec": solves_per_s,
+           "sample": "%d solves of N=%d in %.1f s" % (sum(k for k, _ in res), n, max(sec for _, sec in res))}
+    if cheb:
+        M, G = fk_cheb(L, 3 if kind == "cubic3d" else (1 if kind == "cubic1d" else 2))
+        f, _ = o.randomize_f(SEED, n, n // 2)
+        t0 = time.perf_counter()
+        reps = 4
+        for _ in range(reps):
+            o.calc_chebyshev(kid, L, f, U, U / 2, beta, M, G, emode=1)
+        t_kpm = (time.perf_counter() - t0) / reps   # one thread; the port runs one chain per thread, so the rate scales with the cores
+        sweep_s = SWEEP_LEN * t_kpm + cores / solves_per_s
+        out["value"] = cores * SWEEP_LEN / sweep_s
+        out["note"] = "16 port KPM evaluations (%.1f ms each) + one dsyevd (%.1f ms) per sweep and core" % (1e3 * t_kpm, 1e3 * cores / solves_per_s)
+    else:
+        out["value"] = solves_per_s
+        out["note"] = "one dsyevd per proposal"
+    out["unit"] = "proposals/s"
+    return out
+
+
+def lapack_baseline(workload, cores):
+    """The stronger CPU reference of BASELINE.md section 3 / SURVEY 8d: LAPACK dsyevd (eigenvalues only) in place of the port's Eigen-style
+    unblocked solver.  Reported beside the port; proposals/s the CPU arm would reach with it."""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "lapack-probe", "--workload", workload, "--cores", str(cores)],
+                             capture_output=True, text=True, timeout=300)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:  # the baseline is context, never a reason to lose the bench line
+        return {"unavailable": repr(e)[:200]}
+
+
 def run_reference(args, wl, rank, world):
     """CPU arm: the oracle restatement of the reference algorithm on all host cores (kind = "port":
     the reference cannot be built in this image).  P independent chains, chain r seeded SEED + r, as mpirun -np P would."""
@@ -112,6 +178,9 @@ def run_reference(args, wl, rank, world):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as o
     kind, L, beta, U, cheb, chains, desc = wl
+    if args.chains:
+        chains = args.chains
+    ndim = 3 if kind == "cubic3d" else (1 if kind == "cubic1d" else 2)
     cores = os.cpu_count() or 1
     p = o.make_params(kind=o.KINDS[kind], L=L, beta=beta, U=U, cheb_moves=cheb, emode=1, seed=SEED, nsweeps=CPU_SWEEPS, sweep_len=SWEEP_LEN,
                       ntherm_sweeps=0, measure_energy=True)
@@ -125,11 +194,10 @@ def run_reference(args, wl, rank, world):
     line = {"impl": "reference", "metric": "metropolis_proposals_per_sec", "value": value, "unit": "proposals/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "chains_per_gpu": chains, "sweep_len": SWEEP_LEN, "seed": SEED, "mu_c": U / 2, "mu_f": U / 2,
-                       "moves": "add_remove", "M": (fk_cheb(L)[0] if cheb else None), "G": (fk_cheb(L)[1] if cheb else None),
-                       "cpu_chains_per_step": cores, "cpu_sweeps_per_chain": CPU_SWEEPS},
+            "config": make_config(desc, chains, U, cheb, *fk_cheb(L, ndim)),
             "cpu_baseline": {"value": value, "unit": "proposals/s", "cores": cores, "kind": "port",
-                             "sample": "%d chains x %d sweeps (16 proposals + 1 measurement each) per step, one chain per host thread" % (cores, CPU_SWEEPS)},
+                             "sample": "%d chains x %d sweeps (16 proposals + 1 measurement each) per step, one chain per host thread" % (cores, CPU_SWEEPS),
+                             "lapack": lapack_baseline(args.workload, cores)},
             "e2e": {"value": value, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -139,7 +207,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "lapack-probe"])
+    ap.add_argument("--cores", type=int, default=0, help="(lapack-probe) worker processes")
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -158,6 +227,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, wl, rank, world)
+        return
+    if args.impl == "lapack-probe":
+        print(json.dumps(lapack_probe(kind, L, beta, U, cheb, args.cores or (os.cpu_count() or 1))), flush=True)
         return
 
     import torch
@@ -342,15 +414,14 @@ def main():
         sec, _ = o.bench_chains(p, cores)
         cpu_baseline = {"value": cores * SWEEP_LEN * CPU_SWEEPS / sec, "unit": "proposals/s", "cores": cores, "kind": "port",
                         "sample": "%d chains x %d sweeps (16 proposals + 1 measurement each), one chain per host thread, %.1f s"
-                                  % (cores, CPU_SWEEPS, sec)}
+                                  % (cores, CPU_SWEEPS, sec),
+                        "lapack": lapack_baseline(args.workload, cores)}
 
     if rank == 0:
         line = {"metric": "metropolis_proposals_per_sec", "value": value, "unit": "proposals/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": desc, "chains_per_gpu": chains, "sweep_len": SWEEP_LEN, "seed": SEED, "mu_c": U / 2, "mu_f": U / 2,
-                           "moves": "add_remove", "M": M if cheb else None, "G": G if cheb else None,
-                           "l2_flush": "256 MiB device memset between timed steps", "parallelism": "chains sharded, %d per GPU" % chains},
+                "config": make_config(desc, chains, U, cheb, M, G),
                 "sweeps_per_sec": value / SWEEP_LEN, "roofline": roofline, "roofline_dense": roofline_dense, "roofline_kpm": roofline_kpm,
                 "dominant_kernel": dominant, "kernels": {**fam, **sub},
                 "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks,

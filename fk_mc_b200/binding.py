@@ -30,7 +30,8 @@ class ChainParams(C.Structure):
                 ("mc_flip", C.c_double), ("mc_add_remove", C.c_double), ("mc_reshuffle", C.c_double),
                 ("cheb_moves", C.c_int32), ("cheb_prefactor", C.c_double), ("seed", C.c_int64), ("chain0", C.c_int32),
                 ("nf_start", C.c_int32), ("sweep_len", C.c_int32), ("ntherm_sweeps", C.c_int32),
-                ("measure_energy", C.c_int32), ("record_trace", C.c_int32), ("max_sweeps", C.c_int32)]
+                ("measure_energy", C.c_int32), ("record_trace", C.c_int32), ("max_sweeps", C.c_int32),
+                ("measure_history", C.c_int32), ("measure_ipr", C.c_int32), ("n_W", C.c_int32), ("W", C.c_double * 8)]
 
 
 def build_library(force=False):
@@ -264,11 +265,15 @@ class Context:
     # ---- chains ----
     def chain_init(self, n_chains, beta, U, mu_c=None, mu_f=None, mc_flip=0.0, mc_add_remove=1.0, mc_reshuffle=0.0,
                    cheb_moves=False, cheb_prefactor=2.2, seed=32167, chain0=0, nf_start=None, sweep_len=16, ntherm_sweeps=1,
-                   measure_energy=True, record_trace=False, max_sweeps=64):
+                   measure_energy=True, record_trace=False, max_sweeps=64, measure_history=False, measure_ipr=False, W=()):
+        W = [float(w) for w in W]
+        if len(W) > 8:
+            raise FkmcError(1, "at most 8 f-f interaction terms")
         p = ChainParams(beta, U, U / 2 if mu_c is None else mu_c, U / 2 if mu_f is None else mu_f, mc_flip, mc_add_remove,
                         mc_reshuffle, int(cheb_moves), cheb_prefactor, seed, chain0,
                         self.N // 2 if nf_start is None else nf_start, sweep_len, ntherm_sweeps, int(measure_energy),
-                        int(record_trace), max_sweeps)
+                        int(record_trace), max_sweeps, int(measure_history), int(measure_ipr), len(W),
+                        (C.c_double * 8)(*(W + [0.0] * (8 - len(W)))))
         self._ck(self.lib.fkmc_chain_init(self.h, int(n_chains), C.byref(p)))
         self.chain_params = p
         self.n_chains = n_chains
@@ -287,6 +292,22 @@ class Context:
                                                 _ptr(ec, C.c_double), _ptr(nf, C.c_int32)))
         m = n.value
         return dict(n_measured=m, energies=e[:m], d2energies=d2[:m], c_energies=ec[:m], nf=nf[:m])
+
+    def chain_get_history(self):
+        """Per-sweep histories: dict(n_measured, spectrum_mean [C,N], spectrum_history / focc_history / ipr_history [n,C,N]);
+        entries whose measure is off are None."""
+        p, Cn, N = self.chain_params, self.n_chains, self.N
+        exact = (not p.cheb_moves) or p.measure_energy or p.measure_ipr
+        sm = np.zeros((Cn, N)) if exact else None
+        sh = np.zeros((p.max_sweeps, Cn, N)) if exact and p.measure_history else None
+        fo = np.zeros((p.max_sweeps, Cn, N), dtype=np.int32) if p.measure_history else None
+        ip = np.zeros((p.max_sweeps, Cn, N)) if p.measure_ipr else None
+        n = C.c_int(0)
+        self._ck(self.lib.fkmc_chain_get_history(self.h, C.byref(n), _ptr(sm, C.c_double), _ptr(sh, C.c_double), _ptr(fo, C.c_int32),
+                                                 _ptr(ip, C.c_double)))
+        m = n.value
+        cut = lambda a: None if a is None else a[:m]  # noqa: E731
+        return dict(n_measured=m, spectrum_mean=sm, spectrum_history=cut(sh), focc_history=cut(fo), ipr_history=cut(ip))
 
     def chain_get_state(self, spectrum=False):
         Cn = self.n_chains

@@ -78,7 +78,7 @@ int fkmc_tridiagonalize(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_d, d
 
 int fkmc_build_tridiag(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double* d_d, double* d_e) {
     const int N = ctx->N;
-    if (ctx->tridiag_mode == 2 && fkmc_use_tiled(N) && fkmc_sy2sb_smem(N) <= ctx->smem_optin && fkmc_sb2st_smem(N) <= ctx->smem_optin) {
+    if (ctx->tridiag_mode == 2 && fkmc_use_tiled(ctx, N) && fkmc_sy2sb_smem(N) <= ctx->smem_optin && fkmc_sb2st_smem(N) <= ctx->smem_optin) {
         // large matrices: tiled lower-triangular layout, bulk-async dense->band, then band->tridiagonal
         int rc = fkmc_launch_build_h_tiled(ctx, d_f, B, U, mu_c, ctx->d_A);
         if (rc) return rc;
@@ -90,9 +90,8 @@ int fkmc_build_tridiag(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, doubl
     return fkmc_tridiagonalize(ctx, ctx->d_A, N, B, d_d, d_e);
 }
 
-namespace {
-
-int check_flag(fkmc_ctx* ctx) {
+// Reads (and clears) the device-side non-convergence flag the kernels set when an iteration cap is hit; synchronises the stream.
+int fkmc_check_flag(fkmc_ctx* ctx) {
     int flag = 0;
     FKMC_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -102,6 +101,10 @@ int check_flag(fkmc_ctx* ctx) {
     }
     return FKMC_OK;
 }
+
+namespace {
+
+int check_flag(fkmc_ctx* ctx) { return fkmc_check_flag(ctx); }
 
 int upload_f(fkmc_ctx* ctx, const int32_t* f, int B) {
     if (!f) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "f is NULL");
@@ -382,9 +385,14 @@ int fkmc_set_option(fkmc_ctx* ctx, const char* name, int value) {
         ctx->kpm_no_sched = value != 0;
         return FKMC_OK;
     }
-    if (std::string(name) == "sy2sb_tiled_min") {  // process-wide: smallest N served by the tiled dense->band kernel (default 256)
+    if (std::string(name) == "sy2sb_tiled_min") {  // smallest N served by the tiled dense->band kernel (default 256)
         if (value < 64 || value > 1024) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sy2sb_tiled_min must be in [64, 1024]");
-        fkmc_set_tiled_min(value);
+        ctx->tiled_min = value;
+        return FKMC_OK;
+    }
+    if (std::string(name) == "lanczos_max_steps") {  // 0: the kernels' own cap (384)
+        if (value < 0) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "lanczos_max_steps must be >= 0");
+        ctx->lanczos_cap = value;
         return FKMC_OK;
     }
     if (std::string(name) == "kpm_v1") {

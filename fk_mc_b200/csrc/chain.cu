@@ -26,6 +26,9 @@ struct chain_dev {
     int32_t *nf_cur, *nf_prop;
     int64_t* naccept;
     double *ec_cur, *d2_cur;
+    double *eff_cur, *eff_prop;  // calc_ff_energy() of the current / proposed configuration
+    const double* W;             // f-f interaction W[0..nW) (1-D lattices only; nW = 0 otherwise)
+    int nW;
     int V, n_chains;
     int n_moves;
     int move_kind[3];
@@ -41,6 +44,21 @@ __device__ void randomize_f_dev(mt19937_dev& g, int V, int nf, int32_t* f) {
         while (f[ind] == 1) ind = g.uniform_int((uint32_t)V);
         f[ind] = 1;
     }
+}
+
+// configuration_t::calc_ff_energy (src/configuration.cpp:59-77), 1-D only: sum_i f_i sum_l W_l (f_{i-l} + [l > 0] f_{i+l}); whole warp
+__device__ double ff_energy_warp(const int32_t* f, int V, const double* W, int nW, int lane) {
+    if (nW == 0) return 0.0;
+    double e = 0.0;
+    for (int i = lane; i < V; i += 32) {
+        if (!f[i]) continue;
+        for (int l = 0; l < nW; ++l) {
+            const int left = (i - l % V + V) % V, right = (i + l) % V;
+            e += W[l] * (double)f[left];
+            if (l > 0) e += W[l] * (double)f[right];
+        }
+    }
+    return warp_sum(e);
 }
 
 __global__ void chain_init_kernel(chain_dev C, int64_t seed, int chain0, int nf_start) {
@@ -64,7 +82,8 @@ __global__ void chain_init_kernel(chain_dev C, int64_t seed, int chain0, int nf_
     __syncwarp();
     int32_t* fp = C.f_prop + (size_t)c * C.V;
     for (int i = lane; i < C.V; i += 32) fp[i] = f[i];
-    if (lane == 0) C.nf_prop[c] = C.nf_cur[c];
+    const double eff = ff_energy_warp(f, C.V, C.W, C.nW, lane);
+    if (lane == 0) { C.nf_prop[c] = C.nf_cur[c]; C.eff_cur[c] = eff; C.eff_prop[c] = eff; }
 }
 
 // attempt(): the RNG part.  src/moves.cpp:5-21,35-49,52-67 and twins in src/moves_chebyshev.cpp
@@ -125,6 +144,11 @@ __global__ void chain_propose_kernel(chain_dev C) {
             C.nf_prop[c] = nf;
         }
     }
+    if (C.nW > 0) {
+        __syncwarp();
+        const double eff = kind == -1 ? C.eff_cur[c] : ff_energy_warp(fp, V, C.W, C.nW, lane);
+        if (lane == 0) C.eff_prop[c] = eff;
+    }
     if (lane == 0) { C.prop_move[c] = kind; C.prop_a[c] = a; C.prop_b[c] = b; }
 }
 
@@ -149,20 +173,22 @@ __global__ void chain_accept_kernel(chain_dev C, const double* __restrict__ logz
         } else {
             const int kind = C.prop_move[c];
             const double lz_old = C.logz_cur[c];
+            const double ff_diff = C.nW > 0 ? C.eff_prop[c] - C.eff_cur[c] : 0.0;  // 0 unless 1-D with W (configuration.cpp:62)
             double w = 0.0;
             if (kind == FKMC_MOVE_ADDREMOVE) {
                 const double ratio = exp(lz_new - lz_old);
                 const int a = C.prop_a[c];
                 const int occupied_after = 1 - C.f_cur[(size_t)c * V + a];
                 w = occupied_after ? ratio * C.exp_beta_mu_f : ratio / C.exp_beta_mu_f;
+                if (C.nW > 0) w *= exp(-C.beta * ff_diff);  // moves.cpp:63-65
             } else if (kind == FKMC_MOVE_FLIP) {
-                w = exp(lz_new - lz_old);
+                w = exp(lz_new - lz_old - C.beta * ff_diff);  // moves_chebyshev.cpp:21-22 (E_ff included uniformly)
             } else if (kind == FKMC_MOVE_RESHUFFLE) {
                 const double log_ratio = lz_new - lz_old;
                 const double dn = (double)C.nf_prop[c] - (double)C.nf_cur[c];
-                if (C.beta * C.mu_f * dn > 2.7182818 - log_ratio) w = 1.0;
-                else if (C.beta * C.mu_f * dn + log_ratio < 0) w = 0.0;
-                else w = exp(log_ratio) * exp(C.beta * (C.mu_f * dn));
+                if (C.beta * C.mu_f * dn - ff_diff > 2.7182818 - log_ratio) w = 1.0;
+                else if (C.beta * C.mu_f * dn - ff_diff + log_ratio < 0) w = 0.0;
+                else w = exp(log_ratio) * exp(C.beta * (C.mu_f * dn - ff_diff));
             }
             mt19937_dev g(C.mt + (size_t)c * FKMC_MT_WORDS);
             const double u = g.canonical();
@@ -176,6 +202,7 @@ __global__ void chain_accept_kernel(chain_dev C, const double* __restrict__ logz
         if (accept) {
             C.logz_cur[c] = lz_new;
             C.nf_cur[c] = C.nf_prop[c];
+            C.eff_cur[c] = C.eff_prop[c];
             if (!init) C.naccept[c] += 1;
             if (ecd2) { C.ec_cur[c] = ecd2[(size_t)c * ecd2_stride + 1]; C.d2_cur[c] = ecd2[(size_t)c * ecd2_stride + 2]; }
             const int s = C.prop_slot[c];
@@ -191,7 +218,7 @@ __global__ void chain_accept_kernel(chain_dev C, const double* __restrict__ logz
     }
 }
 
-// measure_energy::accumulate: E = E_c - mu_f N_f (+ E_ff = 0 for D >= 2), d2E, E_c
+// measure_energy::accumulate: E = E_c - mu_f N_f + E_ff (E_ff = 0 for D >= 2), d2E, E_c
 __global__ void chain_measure_kernel(chain_dev C, const double* __restrict__ ecd2, int stride, double* s_e, double* s_d2,
                                      double* s_ec, int32_t* s_nf, long row) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -201,7 +228,7 @@ __global__ void chain_measure_kernel(chain_dev C, const double* __restrict__ ecd
     const size_t o = (size_t)row * C.n_chains + c;
     s_ec[o] = ec;
     s_d2[o] = d2;
-    s_e[o] = ec - C.mu_f * (double)C.nf_cur[c];
+    s_e[o] = ec - C.mu_f * (double)C.nf_cur[c] + C.eff_cur[c];
     s_nf[o] = C.nf_cur[c];
 }
 
@@ -213,33 +240,49 @@ __global__ void rng_stream_kernel(uint32_t* state, int64_t seed, int mode, int V
         out[i] = mode == 0 ? (double)g.next() : (mode == 1 ? (double)g.uniform_int((uint32_t)V) : g.canonical());
 }
 
+// measure_spectrum (src/measures/spectrum.cpp:13-21: running mean of the sorted spectrum), measure_spectrum_history
+// (src/measures/spectrum_history.cpp:13-19) and measure_focc (src/measures/focc_history.cpp:7-12) for one measured sweep.
+// One CTA per chain.  spec points at slot 0 of the spectra; cur_slot == nullptr means "slot 0" (Chebyshev moves: the measurement solve).
+__global__ void __launch_bounds__(256) chain_history_kernel(chain_dev C, const double* __restrict__ spec, size_t slot_stride, const int32_t* __restrict__ cur_slot,
+                                                          int N, double* __restrict__ spec_mean, long count, double* __restrict__ spec_hist_row,
+                                                          int32_t* __restrict__ focc_row) {
+    const int c = blockIdx.x;
+    const double* sp = spec + (cur_slot ? (size_t)cur_slot[c] * slot_stride : 0) + (size_t)c * N;
+    if (spec_mean) {
+        double* m = spec_mean + (size_t)c * N;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            const double v = sp[i];
+            m[i] = (m[i] * (double)count + v) / (double)(count + 1);  // spectrum.cpp:17-19
+            if (spec_hist_row) spec_hist_row[(size_t)c * N + i] = v;
+        }
+    }
+    if (focc_row) {
+        const int32_t* f = C.f_cur + (size_t)c * C.V;
+        for (int i = threadIdx.x; i < C.V; i += blockDim.x) focc_row[(size_t)c * C.V + i] = f[i];
+    }
+}
+
 template <class T>
 int dev_alloc(fkmc_ctx* ctx, T** p, size_t n) {
     FKMC_CUDA(ctx, cudaMalloc((void**)p, sizeof(T) * (n ? n : 1)));
     return FKMC_OK;
 }
 
-chain_dev make_dev(fkmc_ctx* ctx, int32_t* nf_cur, int32_t* nf_prop, int32_t* prop_slot, double* ec, double* d2) {
+chain_dev make_dev(fkmc_ctx* ctx) {
     fkmc_chain_state& S = ctx->chain;
     chain_dev C{};
     C.mt = S.mt; C.f_cur = S.f_cur; C.f_prop = S.f_prop; C.logz_cur = S.logz_cur;
-    C.cur_slot = S.cur_slot; C.prop_slot = prop_slot; C.prop_move = S.prop_move; C.prop_a = S.prop_a; C.prop_b = S.prop_b;
-    C.nf_cur = nf_cur; C.nf_prop = nf_prop; C.naccept = S.naccept; C.ec_cur = ec; C.d2_cur = d2;
+    C.cur_slot = S.cur_slot; C.prop_slot = S.prop_slot; C.prop_move = S.prop_move; C.prop_a = S.prop_a; C.prop_b = S.prop_b;
+    C.nf_cur = S.nf_cur; C.nf_prop = S.nf_prop; C.naccept = S.naccept; C.ec_cur = S.ec_cur; C.d2_cur = S.d2_cur;
+    C.eff_cur = S.eff_cur; C.eff_prop = S.eff_prop; C.W = S.d_W; C.nW = (ctx->ndim == 1) ? S.p.n_W : 0;
     C.V = ctx->N; C.n_chains = S.n_chains; C.n_moves = S.n_moves;
     for (int i = 0; i < 3; ++i) { C.move_kind[i] = S.move_kind[i]; C.move_cp[i] = S.move_cp[i]; }
     C.beta = S.p.beta; C.mu_f = S.p.mu_f; C.exp_beta_mu_f = std::exp(S.p.beta * S.p.mu_f);  // moves.hpp:49
     return C;
 }
 
-// extra per-chain device arrays not in the public state struct
-struct chain_extra {
-    int32_t *nf_cur = nullptr, *nf_prop = nullptr, *prop_slot = nullptr;
-    double *ec = nullptr, *d2 = nullptr;
-};
-std::map<fkmc_ctx*, chain_extra> g_extra;
-
 // evaluate logZ of f_prop for all chains; returns pointers to (logz, stride) and the E_c/d2E block
-int evaluate_proposals(fkmc_ctx* ctx, const chain_extra& X, const double** lz, int* lz_stride, const double** ecd2, int* ecd2_stride) {
+int evaluate_proposals(fkmc_ctx* ctx, const double** lz, int* lz_stride, const double** ecd2, int* ecd2_stride) {
     fkmc_chain_state& S = ctx->chain;
     const int C = S.n_chains, N = ctx->N;
     if (S.p.cheb_moves) {
@@ -250,7 +293,7 @@ int evaluate_proposals(fkmc_ctx* ctx, const chain_extra& X, const double** lz, i
         int rc = fkmc_build_tridiag(ctx, S.f_prop, C, S.p.U, S.p.mu_c, ctx->d_d, ctx->d_e);
         if (rc) return rc;
         // spectrum of the proposal goes to the chain's non-current slot: spec[0] + slot * (C*N)
-        rc = fkmc_launch_tridiag_eig(ctx, ctx->d_d, ctx->d_e, N, C, S.p.beta, S.spec[0], N, X.prop_slot, (long)C * N, ctx->d_out,
+        rc = fkmc_launch_tridiag_eig(ctx, ctx->d_d, ctx->d_e, N, C, S.p.beta, S.spec[0], N, S.prop_slot, (long)C * N, ctx->d_out,
                                      nullptr, nullptr);
         if (rc) return rc;
         *lz = ctx->d_out; *lz_stride = 8; *ecd2 = ctx->d_out; *ecd2_stride = 8;
@@ -267,12 +310,9 @@ int fkmc_chain_free(fkmc_ctx* ctx) {
     cudaFree(S.spec[0]); cudaFree(S.cur_slot); cudaFree(S.prop_move); cudaFree(S.prop_a); cudaFree(S.prop_b);
     cudaFree(S.naccept); cudaFree(S.s_energy); cudaFree(S.s_d2energy); cudaFree(S.s_cenergy); cudaFree(S.s_nf);
     cudaFree(S.t_move); cudaFree(S.t_a); cudaFree(S.t_b); cudaFree(S.t_acc); cudaFree(S.t_w); cudaFree(S.t_u); cudaFree(S.t_lz);
-    auto it = g_extra.find(ctx);
-    if (it != g_extra.end()) {
-        cudaFree(it->second.nf_cur); cudaFree(it->second.nf_prop); cudaFree(it->second.prop_slot);
-        cudaFree(it->second.ec); cudaFree(it->second.d2);
-        g_extra.erase(it);
-    }
+    cudaFree(S.nf_cur); cudaFree(S.nf_prop); cudaFree(S.prop_slot); cudaFree(S.ec_cur); cudaFree(S.d2_cur);
+    cudaFree(S.eff_cur); cudaFree(S.eff_prop); cudaFree(S.d_W);
+    cudaFree(S.spec_mean); cudaFree(S.spec_hist); cudaFree(S.focc_hist); cudaFree(S.ipr_hist); cudaFree(S.ipr_evals);
     S = fkmc_chain_state();
     return FKMC_OK;
 }
@@ -282,6 +322,7 @@ extern "C" int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_par
     if (n_chains < 1 || n_chains > ctx->max_batch) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "n_chains must be in [1, max_batch]");
     if (p->sweep_len < 1 || p->max_sweeps < 1) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sweep_len and max_sweeps must be >= 1");
     if (p->nf_start < 0 || p->nf_start > ctx->N) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "nf_start out of range");
+    if (p->n_W < 0 || p->n_W > FKMC_MAX_W) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "n_W must be in [0, 8]");
     FKMC_CUDA(ctx, cudaSetDevice(ctx->device));
     fkmc_chain_free(ctx);
     fkmc_chain_state& S = ctx->chain;
@@ -313,13 +354,16 @@ extern "C" int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_par
         int rc = fkmc_prepare_cheb(ctx, S.M, S.G);
         if (rc) return rc;
     }
-    if (!p->cheb_moves || p->measure_energy) {
+    // which measures run (fk_mc.hxx:94-124): energy + spectrum whenever an exact spectrum exists per sweep (exact moves, or
+    // measure_energy / measure_ipr asked for it); spectrum_history and focc_history with measure_history; ipr with measure_ipr
+    const bool exact_measure = !p->cheb_moves || p->measure_energy || p->measure_ipr;
+    if (exact_measure) {
         int rc = fkmc_ensure_dense_ws(ctx);
         if (rc) return rc;
     }
     const size_t C = n_chains, V = ctx->N;
     const size_t rows = p->max_sweeps, steps = (size_t)p->max_sweeps * p->sweep_len;
-    chain_extra X;
+    S.active = true;  // from here on fkmc_chain_free releases whatever has been allocated
     int rc = 0;
     rc |= dev_alloc(ctx, &S.mt, C * FKMC_MT_WORDS);
     rc |= dev_alloc(ctx, &S.f_cur, C * V);
@@ -336,24 +380,40 @@ extern "C" int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_par
     rc |= dev_alloc(ctx, &S.s_d2energy, rows * C);
     rc |= dev_alloc(ctx, &S.s_cenergy, rows * C);
     rc |= dev_alloc(ctx, &S.s_nf, rows * C);
-    rc |= dev_alloc(ctx, &X.nf_cur, C);
-    rc |= dev_alloc(ctx, &X.nf_prop, C);
-    rc |= dev_alloc(ctx, &X.prop_slot, C);
-    rc |= dev_alloc(ctx, &X.ec, C);
-    rc |= dev_alloc(ctx, &X.d2, C);
+    rc |= dev_alloc(ctx, &S.nf_cur, C);
+    rc |= dev_alloc(ctx, &S.nf_prop, C);
+    rc |= dev_alloc(ctx, &S.prop_slot, C);
+    rc |= dev_alloc(ctx, &S.ec_cur, C);
+    rc |= dev_alloc(ctx, &S.d2_cur, C);
+    rc |= dev_alloc(ctx, &S.eff_cur, C);
+    rc |= dev_alloc(ctx, &S.eff_prop, C);
+    rc |= dev_alloc(ctx, &S.d_W, (size_t)FKMC_MAX_W);
+    if (exact_measure) {
+        rc |= dev_alloc(ctx, &S.spec_mean, C * V);
+        if (p->measure_history) rc |= dev_alloc(ctx, &S.spec_hist, rows * C * V);
+    }
+    if (p->measure_history) rc |= dev_alloc(ctx, &S.focc_hist, rows * C * V);
+    if (p->measure_ipr) {
+        rc |= dev_alloc(ctx, &S.ipr_hist, rows * C * V);
+        rc |= dev_alloc(ctx, &S.ipr_evals, C * V);
+    }
     if (p->record_trace) {
         rc |= dev_alloc(ctx, &S.t_move, steps * C); rc |= dev_alloc(ctx, &S.t_a, steps * C); rc |= dev_alloc(ctx, &S.t_b, steps * C);
         rc |= dev_alloc(ctx, &S.t_acc, steps * C); rc |= dev_alloc(ctx, &S.t_w, steps * C); rc |= dev_alloc(ctx, &S.t_u, steps * C);
         rc |= dev_alloc(ctx, &S.t_lz, steps * C);
     }
-    if (rc) return FKMC_ERR_CUDA;
+    if (rc) {
+        fkmc_chain_free(ctx);
+        return FKMC_ERR_CUDA;
+    }
     S.spec[1] = S.spec[0] + C * V;
-    S.active = true;
-    g_extra[ctx] = X;
     S.sweeps_done = 0;
     S.measured = 0;
+    S.spec_count = 0;
+    if (S.spec_mean) FKMC_CUDA(ctx, cudaMemsetAsync(S.spec_mean, 0, sizeof(double) * C * V, ctx->stream));
+    if (p->n_W > 0) FKMC_CUDA(ctx, cudaMemcpyAsync(S.d_W, p->W, sizeof(double) * p->n_W, cudaMemcpyHostToDevice, ctx->stream));
 
-    chain_dev D = make_dev(ctx, X.nf_cur, X.nf_prop, X.prop_slot, X.ec, X.d2);
+    chain_dev D = make_dev(ctx);
     const int blocks = (n_chains * 32 + 127) / 128;
     {
         fkmc_prof_scope ps(ctx, "chain_init");
@@ -364,15 +424,14 @@ extern "C" int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_par
     // evaluate the initial configuration (the reference does it lazily inside the first attempt())
     const double *lz, *ecd2;
     int lzs, es;
-    rc = evaluate_proposals(ctx, X, &lz, &lzs, &ecd2, &es);
+    rc = evaluate_proposals(ctx, &lz, &lzs, &ecd2, &es);
     if (rc) return rc;
     trace_dev TR{};
     TR.step = -1;
     chain_accept_kernel<<<blocks, 128, 0, ctx->stream>>>(D, lz, lzs, ecd2, es, 1, TR);
     ctx->launches++;
     FKMC_CUDA(ctx, cudaGetLastError());
-    FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return FKMC_OK;
+    return fkmc_check_flag(ctx);  // synchronises; FKMC_ERR_NOCONV when a kernel hit its iteration cap
 }
 
 extern "C" int fkmc_chain_run_sweeps(fkmc_ctx* ctx, int n_sweeps) {
@@ -381,10 +440,10 @@ extern "C" int fkmc_chain_run_sweeps(fkmc_ctx* ctx, int n_sweeps) {
     if (!S.active) return fkmc_set_error(ctx, FKMC_ERR_STATE, "fkmc_chain_init has not been called");
     if (S.sweeps_done + n_sweeps > S.p.max_sweeps) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "more sweeps than max_sweeps");
     FKMC_CUDA(ctx, cudaSetDevice(ctx->device));
-    chain_extra& X = g_extra[ctx];
-    chain_dev D = make_dev(ctx, X.nf_cur, X.nf_prop, X.prop_slot, X.ec, X.d2);
+    chain_dev D = make_dev(ctx);
     const int C = S.n_chains, N = ctx->N;
     const int blocks = (C * 32 + 127) / 128;
+    const bool exact_measure = !S.p.cheb_moves || S.p.measure_energy || S.p.measure_ipr;
     for (int sw = 0; sw < n_sweeps; ++sw) {
         for (int m = 0; m < S.p.sweep_len; ++m) {
             {
@@ -394,7 +453,7 @@ extern "C" int fkmc_chain_run_sweeps(fkmc_ctx* ctx, int n_sweeps) {
             }
             const double *lz, *ecd2;
             int lzs, es;
-            int rc = evaluate_proposals(ctx, X, &lz, &lzs, &ecd2, &es);
+            int rc = evaluate_proposals(ctx, &lz, &lzs, &ecd2, &es);
             if (rc) return rc;
             trace_dev TR{};
             TR.step = -1;
@@ -412,7 +471,15 @@ extern "C" int fkmc_chain_run_sweeps(fkmc_ctx* ctx, int n_sweeps) {
         if (S.sweeps_done >= S.p.ntherm_sweeps) {
             const double* ecd2 = nullptr;
             int es = 0;
-            if (S.p.measure_energy && S.p.cheb_moves) {
+            const double* spec = S.spec[0];        // spectrum of the current configurations ...
+            const int32_t* slot = S.cur_slot;      // ... in the chain's current slot (exact moves)
+            if (S.p.measure_ipr) {
+                // measure_ipr::accumulate (ipr.hpp:39-56): calc_ed(true); the energy / spectrum measures that follow hit its cache
+                int rc = fkmc_eigvec_pipeline(ctx, S.f_cur, C, S.p.U, S.p.mu_c, S.p.beta, S.ipr_evals, ctx->d_out, nullptr, nullptr,
+                                              S.ipr_hist + (size_t)S.measured * C * N);
+                if (rc) return rc;
+                if (S.p.cheb_moves) { ecd2 = ctx->d_out; es = 8; spec = S.ipr_evals; slot = nullptr; }
+            } else if (S.p.cheb_moves && S.p.measure_energy) {
                 // Chebyshev moves never fill ed_data_: measure_energy triggers a fresh exact eigensolve
                 int rc = fkmc_build_tridiag(ctx, S.f_cur, C, S.p.U, S.p.mu_c, ctx->d_d, ctx->d_e);
                 if (rc) return rc;
@@ -420,19 +487,29 @@ extern "C" int fkmc_chain_run_sweeps(fkmc_ctx* ctx, int n_sweeps) {
                 if (rc) return rc;
                 ecd2 = ctx->d_out;
                 es = 8;
+                slot = nullptr;
             }
-            if (S.p.measure_energy) {
+            if (exact_measure && S.p.measure_energy) {
                 fkmc_prof_scope ps(ctx, "chain_step");
                 chain_measure_kernel<<<(C + 127) / 128, 128, 0, ctx->stream>>>(D, ecd2, es, S.s_energy, S.s_d2energy, S.s_cenergy, S.s_nf,
                                                                             S.measured);
                 ctx->launches++;
+            }
+            if (exact_measure || S.p.measure_history) {
+                fkmc_prof_scope ps(ctx, "chain_step");
+                chain_history_kernel<<<C, 256, 0, ctx->stream>>>(D, spec, (size_t)C * N, slot, N, exact_measure ? S.spec_mean : nullptr, S.spec_count,
+                                                                  S.spec_hist ? S.spec_hist + (size_t)S.measured * C * N : nullptr,
+                                                                  S.focc_hist ? S.focc_hist + (size_t)S.measured * C * N : nullptr);
+                ctx->launches++;
+                if (exact_measure) S.spec_count++;
             }
             S.measured++;
         }
         S.sweeps_done++;
     }
     FKMC_CUDA(ctx, cudaGetLastError());
-    return FKMC_OK;
+    // one host synchronisation per call: a Lanczos / bisection iteration cap hit anywhere in these sweeps is reported here
+    return fkmc_check_flag(ctx);
 }
 
 static int copy_out(fkmc_ctx* ctx, void* dst, const void* src, size_t bytes) {
@@ -511,6 +588,25 @@ extern "C" int fkmc_chain_ipr(fkmc_ctx* ctx, double* evals, double* ipr) {
     const size_t C = S.n_chains, N = ctx->N;
     if ((rc = fkmc_eigvec_pipeline(ctx, S.f_cur, (int)C, S.p.U, S.p.mu_c, S.p.beta, ctx->d_evals, ctx->d_out, nullptr, ipr, nullptr))) return rc;
     if (evals) FKMC_CUDA(ctx, cudaMemcpyAsync(evals, ctx->d_evals, sizeof(double) * C * N, cudaMemcpyDeviceToHost, ctx->stream));
+    FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FKMC_OK;
+}
+
+extern "C" int fkmc_chain_get_history(fkmc_ctx* ctx, int* n_measured, double* spectrum_mean, double* spectrum_history, int32_t* focc_history,
+                                      double* ipr_history) {
+    if (!ctx) return FKMC_ERR_INVALID;
+    fkmc_chain_state& S = ctx->chain;
+    if (!S.active) return fkmc_set_error(ctx, FKMC_ERR_STATE, "no chains");
+    const size_t C = S.n_chains, N = ctx->N, n = (size_t)S.measured * C * N;
+    if (n_measured) *n_measured = (int)S.measured;
+    if ((spectrum_mean && !S.spec_mean) || (spectrum_history && !S.spec_hist) || (focc_history && !S.focc_hist) || (ipr_history && !S.ipr_hist))
+        return fkmc_set_error(ctx, FKMC_ERR_STATE, "this history is not being measured (measure_history / measure_ipr / exact spectrum)");
+    int rc = 0;
+    rc |= copy_out(ctx, spectrum_mean, S.spec_mean, C * N * 8);
+    rc |= copy_out(ctx, spectrum_history, S.spec_hist, n * 8);
+    rc |= copy_out(ctx, focc_history, S.focc_hist, n * 4);
+    rc |= copy_out(ctx, ipr_history, S.ipr_hist, n * 8);
+    if (rc) return rc;
     FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FKMC_OK;
 }

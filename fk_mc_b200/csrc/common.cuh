@@ -43,6 +43,19 @@ struct fkmc_chain_state {
     int32_t* prop_a = nullptr;
     int32_t* prop_b = nullptr;
     int64_t* naccept = nullptr;
+    int32_t *nf_cur = nullptr, *nf_prop = nullptr;  // [n_chains] occupied sites of the current / proposed configuration
+    int32_t* prop_slot = nullptr;                   // [n_chains] spectrum slot the pending proposal is written to
+    double *ec_cur = nullptr, *d2_cur = nullptr;    // [n_chains] E_c, d2E of the current configuration (exact moves)
+    double *eff_cur = nullptr, *eff_prop = nullptr; // [n_chains] calc_ff_energy() of the current / proposed configuration (1-D, W != {})
+    double* d_W = nullptr;                          // [n_W] f-f interaction
+    // per-sweep histories (measure_spectrum, measure_spectrum_history, measure_focc, measure_ipr)
+    double* spec_mean = nullptr;     // [n_chains][N] running mean of the sorted spectrum
+    double* spec_hist = nullptr;     // [max_sweeps][n_chains][N]
+    int32_t* focc_hist = nullptr;    // [max_sweeps][n_chains][V]
+    double* ipr_hist = nullptr;      // [max_sweeps][n_chains][N]
+    double* ipr_evals = nullptr;     // [n_chains][N] spectrum of the eigenvector solve of the last measured sweep
+    long spec_count = 0;             // measurements folded into spec_mean
+    int* h_flag = nullptr;           // pinned copy of the non-convergence flag
     double *s_energy = nullptr, *s_d2energy = nullptr, *s_cenergy = nullptr;  // [max_sweeps][n_chains]
     int32_t* s_nf = nullptr;
     // trace [max_steps][n_chains]
@@ -79,6 +92,8 @@ struct fkmc_ctx {
     int nsmid = 0;                   // %nsmid of the device (scratch slots of sy2sb)
     int tridiag_mode = 2;       // 1: one-stage blocked sytrd, 2: sy2sb + sb2st
     int sb2st_warps = 0;        // 0: automatic
+    int tiled_min = 256;        // smallest N served by the tiled dense->band kernel ("sy2sb_tiled_min")
+    int lanczos_cap = 0;        // > 0: Lanczos step cap of the KPM kernels ("lanczos_max_steps"; tests force non-convergence with it)
     int kpm_force_generic = 0;  // 1: always use the full-lattice-vector KPM kernel (for cross-checks)
     int kpm_force_v1 = 0;       // 1: single-kernel KPM (kpm.cu) even where the two-kernel 2-D path (kpm2d.cu) applies
     int kpm2_H = 0;             // radius of the cached patch tables of kpm2d.cu
@@ -158,8 +173,7 @@ int fkmc_launch_sy2sb_tiled(fkmc_ctx* ctx, double* d_At, int N, int B, double* d
 int fkmc_launch_build_h_tiled(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double* d_At);
 int fkmc_launch_to_tiled(fkmc_ctx* ctx, const double* d_A, int N, int B, double* d_At);
 size_t fkmc_tiled_stride(int N);
-bool fkmc_use_tiled(int N);
-void fkmc_set_tiled_min(int n);  // smallest N served by the tiled dense->band kernel (process-wide; default 256)
+bool fkmc_use_tiled(const fkmc_ctx* ctx, int N);
 // f -> Hamiltonian -> tridiagonal (d, e) with the context's selected algorithm and matching matrix layout
 int fkmc_build_tridiag(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double* d_d, double* d_e);
 // dense -> tridiagonal with the context's selected algorithm (A is overwritten)
@@ -183,6 +197,8 @@ int fkmc_eigvec_pipeline(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, dou
                          double* h_evecs, double* h_ipr_host, double* d_ipr);
 // chains
 int fkmc_chain_free(fkmc_ctx* ctx);
+// reads and clears the non-convergence flag (synchronises the stream): FKMC_OK or FKMC_ERR_NOCONV
+int fkmc_check_flag(fkmc_ctx* ctx);
 
 #ifdef __CUDACC__
 // ---- device helpers ----

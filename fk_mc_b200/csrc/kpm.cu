@@ -40,6 +40,7 @@ struct kpm_args {
     int L;                  // linear lattice size (patch variant)
     int nwarps_cols;        // warps that run the column recursion
     int vec_doubles;        // size of the shared vector region (>= 2 Nv per column warp and >= the Lanczos need)
+    int kmax;               // Lanczos step cap (KPM_KMAX unless the "lanczos_max_steps" option lowers it)
 };
 
 // number of eigenvalues of the k x k Lanczos tridiagonal below x.  ab[i] = (alpha_i, beta_i^2) with beta_0 = 0
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(KIND ? 256 : 384, KIND ? 2 : 1) kpm_kernel(kpm
 #ifdef FKMC_KPM_TIMING
     long long t_ritz = 0, t_start = clock64(), t_tmp = 0;
 #endif
-    const int kcap = min(KPM_KMAX, N);
+    const int kcap = min(P.kmax, N);
     double e_min = 0.0, e_max = 0.0, gl = DBL_MAX, gh = -DBL_MAX, hscale = 0.0;
     bool converged = false;
     int k = 0;
@@ -581,6 +582,7 @@ int fkmc_launch_kpm(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double m
     }
     P.chebt = ctx->d_chebt; P.lobatto = ctx->d_lobatto; P.dtheta = ctx->d_dtheta;
     P.moments = d_moments; P.ab = d_ab; P.logz = d_logz; P.flag = ctx->d_flag; P.steps = ctx->d_kpm_steps;
+    P.kmax = ctx->lanczos_cap > 0 ? std::min(ctx->lanczos_cap, KPM_KMAX) : KPM_KMAX;
     if (fkmc_kpm2d_applicable(ctx, M)) return fkmc_launch_kpm2d(ctx, d_f, B, U, mu_c, beta, M, G, P.slot_val, d_moments, d_ab, d_logz);
     switch (M / 2) {
 #define FKMC_KPM_CASE(H) case H: return launch_kpm_t<H>(ctx, P, B);

@@ -39,6 +39,7 @@ struct lz_args {
     int* flag;
     int* steps;
     const int* order;  // [B] proposal handled by CTA i: longest expected run first (null: identity)
+    int kmax;          // Lanczos step cap (LZ_KMAX unless the "lanczos_max_steps" option lowers it)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(LZ_T, 4) lanczos2d_kernel(lz_args P) {
         __syncthreads();
     }
 
-    const int kcap = min(LZ_KMAX, N);
+    const int kcap = min(P.kmax, N);
     double e_min = 0.0, e_max = 0.0, gl = DBL_MAX, gh = -DBL_MAX, hscale = 0.0;
     double prev_min = 0.0, prev_max = 0.0;
     bool have_prev = false, converged = false;
@@ -901,6 +902,7 @@ int fkmc_launch_kpm2d(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double
     Q.ht = slot_val[0];
     Q.hp = (ctx->kind == FKMC_TRIANGULAR) ? slot_val[4] : 0.0;
     Q.ab = d_ab; Q.flag = ctx->d_flag; Q.steps = ctx->d_kpm_steps;
+    Q.kmax = ctx->lanczos_cap > 0 ? std::min(ctx->lanczos_cap, LZ_KMAX) : LZ_KMAX;
     if (!ctx->d_kpm2_order) {
         FKMC_CUDA(ctx, cudaMalloc(&ctx->d_kpm2_order, sizeof(int) * (size_t)ctx->max_batch));
         FKMC_CUDA(ctx, cudaMemsetAsync(ctx->d_kpm_steps, 0, sizeof(int) * (size_t)ctx->max_batch, ctx->stream));

@@ -897,14 +897,12 @@ size_t fkmc_tiled_stride(int N) {
     const size_t nt = (N + 31) / 32;
     return nt * (nt + 1) / 2 * TILE;
 }
-static int g_tiled_min = getenv("FKMC_TILED_MIN") ? atoi(getenv("FKMC_TILED_MIN")) : 256;  // (environment: developer override)
-void fkmc_set_tiled_min(int n) { g_tiled_min = n; }
-bool fkmc_use_tiled(int N) { return N >= g_tiled_min && N % 8 == 0 && N <= 1024; }
+bool fkmc_use_tiled(const fkmc_ctx* ctx, int N) { return N >= ctx->tiled_min && N % 8 == 0 && N <= 1024; }
 
 // dense -> band on a batch of matrices in the tiled layout (see fkmc_launch_build_h_tiled / fkmc_launch_to_tiled)
 int fkmc_launch_sy2sb_tiled(fkmc_ctx* ctx, double* d_At, int N, int B, double* d_AB) {
     fkmc_prof_scope ps(ctx, "sy2sb");
-    if (!fkmc_use_tiled(N)) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sy2sb_tiled: needs 512 <= N <= 1024, N % 8 == 0");
+    if (!fkmc_use_tiled(ctx, N)) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sy2sb_tiled: needs 512 <= N <= 1024, N % 8 == 0");
     const int nw = sy2sb_warps(N), slots = nw == 8 ? 1 : 2;
     const size_t smem = fkmc_sy2sb_smem(N);
     if (smem > ctx->smem_optin) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sy2sb: matrix too large for shared memory");
@@ -1060,7 +1058,7 @@ int fkmc_launch_build_h_tiled(fkmc_ctx* ctx, const int32_t* d_f, int B, double U
 
 // column-major entry point (stage-level API and small matrices)
 int fkmc_launch_sy2sb(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_AB) {
-    if (!fkmc_use_tiled(N)) return fkmc_launch_sy2sb_small(ctx, d_A, N, B, d_AB);
+    if (!fkmc_use_tiled(ctx, N)) return fkmc_launch_sy2sb_small(ctx, d_A, N, B, d_AB);
     // convert in place is not possible (layouts overlap): stage through a scratch allocation
     double* d_At = nullptr;
     FKMC_CUDA(ctx, cudaMalloc(&d_At, sizeof(double) * fkmc_tiled_stride(N) * (size_t)B));

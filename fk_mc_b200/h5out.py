@@ -336,17 +336,18 @@ class H5Reader:
 def save_all_data(fname, params, energies, d2energies, c_energies, beta, volume, max_depth=None, histories=None):
     """Reference layout of prog/data_save.hxx (save_all_data -> save_measurements + energy / cv statistics).
 
-    params: dict of run parameters (the alps::params dump); energies, d2energies, c_energies: 1-D series
-    (all chains concatenated, as the reference concatenates the ranks); histories: optional dict of 2-D
+    params: dict of run parameters (the alps::params dump); energies, d2energies, c_energies: 1-D series (one chain, or
+    already pooled) or 2-D [measurement][chain] as fkmc_chain_get_series returns them -- pooled CHAIN-MAJOR like the
+    reference's rank-by-rank gather (stats.pool_chains); histories: optional dict of 2-D
     [index][measurement] arrays for /mc_data (ipr_history, spectrum_history, focc_history).
     Returns the per-observable statistics that were written (dict name -> (binning rows, stats 4-vector))."""
     w = H5Writer()
     w.require_group("/parameters")
     for k, v in sorted(params.items()):
         w["/parameters/" + k] = v
-    e = np.asarray(energies, dtype=np.float64).ravel()
-    d2 = np.asarray(d2energies, dtype=np.float64).ravel()
-    ce = np.asarray(c_energies, dtype=np.float64).ravel()
+    e = stats.pool_chains(energies)
+    d2 = stats.pool_chains(d2energies)
+    ce = stats.pool_chains(c_energies)
     w["/mc_data/energies"] = e
     w["/mc_data/d2energies"] = d2
     w["/mc_data/c_energies"] = ce

@@ -44,13 +44,16 @@ def gather_series(local, total_chains, group=None, device=None):
 
 
 def reduce_moments(local, levels=16, group=None, device=None):
-    """Sum over ranks of per-bin-level accumulators [levels, 3] = (n, sum x, sum x^2) of a pooled series.
+    """Sum over ranks of per-bin-level accumulators [levels, 3] = (n, sum x, sum x^2) of a pooled series
+    (`local`: one chain's 1-D series or [measurement][chain]; a bin never mixes chains only when the per-chain length is a
+    multiple of the bin width -- the same caveat the reference's concatenated ranks have).
 
     The cheap alternative to gather_series when only /stats is wanted: a few KB per observable."""
     import torch
     import torch.distributed as dist
 
-    x = np.asarray(local, dtype=np.float64).reshape(-1)
+    from .stats import pool_chains
+    x = pool_chains(local)  # [measurement][chain] -> chain-major: bins run along Monte Carlo time inside a chain
     acc = np.zeros((levels, 3))
     cur = x
     for lv in range(levels):

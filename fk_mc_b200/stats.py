@@ -12,6 +12,21 @@ import numpy as np
 MAX_BIN_DEPTH = 15  # BINNING_RANGE in include/fk_mc/binning.hpp:18
 
 
+def pool_chains(series):
+    """Series of several chains -> one 1-D series, CHAIN-MAJOR: chain 0's measurements in Monte Carlo time order, then chain 1's, ...
+
+    The library returns per-chain series as [measurement][chain] (fkmc_chain_get_series).  The reference gathers the ranks one
+    after the other (src/measures/energy.cpp:32-47), so its bins run along MC time inside one rank; flattening [measurement][chain]
+    row by row would instead average neighbouring *independent* chains in the shallow bin levels and hide the autocorrelation.
+    A 1-D input is one chain (or an already pooled series) and is returned as is."""
+    a = np.asarray(series, dtype=np.float64)
+    if a.ndim == 1:
+        return a
+    if a.ndim != 2:
+        raise ValueError("series must be 1-D (one chain / already pooled) or 2-D [measurement][chain]")
+    return np.ascontiguousarray(a.T).reshape(-1)
+
+
 def calc_stats(x):
     """(n, mean, unbiased variance, sqrt(variance / n)) -- binning.hpp:89-96."""
     x = np.asarray(x, dtype=np.float64)
@@ -92,9 +107,9 @@ def max_bin_depth(n_samples, min_bins=4):
 
 def energy_report(energies, d2energies, beta, volume, max_depth=None):
     """save_energy (prog/data_save.hxx:158-199): binning of E and d2E, jackknife of the specific heat.  The reference bins the
-    series in reverse order (rbegin..rend); so do we."""
-    e = np.asarray(energies, dtype=np.float64).reshape(-1)[::-1]
-    d2 = np.asarray(d2energies, dtype=np.float64).reshape(-1)[::-1]
+    series in reverse order (rbegin..rend); so do we.  2-D input is [measurement][chain] and is pooled chain-major (pool_chains)."""
+    e = pool_chains(energies)[::-1]
+    d2 = pool_chains(d2energies)[::-1]
     if max_depth is None:
         max_depth = max_bin_depth(e.size)
     out = {}

@@ -299,6 +299,17 @@ private:
     }
 };
 
+// [measurement][chain] (what fkmc_chain_get_series returns) -> one series, CHAIN-MAJOR: chain 0's measurements in Monte Carlo time
+// order, then chain 1's, ... -- the order in which the reference gathers its ranks (src/measures/energy.cpp:32-47), so that bins run
+// along MC time inside a chain instead of averaging neighbouring independent chains.
+inline std::vector<double> pool_chains(const std::vector<double>& series, size_t n_measured, size_t n_chains) {
+    if (series.size() != n_measured * n_chains) throw std::logic_error("pool_chains: series is not [n_measured][n_chains]");
+    std::vector<double> out(series.size());
+    for (size_t m = 0; m < n_measured; ++m)
+        for (size_t c = 0; c < n_chains; ++c) out[c * n_measured + m] = series[m * n_chains + c];
+    return out;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 using param_map = std::map<std::string, h5_writer::scalar>;
 
@@ -308,7 +319,7 @@ struct saved_stats {
 };
 
 // prog/data_save.hxx (save_all_data -> save_measurements + energy / specific heat statistics) for the observables of the
-// weight-evaluation path.  Series = all chains concatenated, as the reference concatenates the ranks; they are binned in
+// weight-evaluation path.  Series = all chains concatenated chain after chain (pool_chains), as the reference concatenates the ranks; they are binned in
 // reverse order (rbegin..rend), like the reference.  histories: optional [index][measurement] tables for /mc_data.
 inline std::map<std::string, saved_stats> save_all_data(const std::string& fname, const param_map& params, const std::vector<double>& energies,
                                                         const std::vector<double>& d2energies, const std::vector<double>& c_energies,

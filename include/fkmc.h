@@ -39,6 +39,8 @@ enum fkmc_lattice_kind {
     FKMC_HONEYCOMB_REF_LOWER = 7  /* literal fill_honeycomb as Eigen's lower-triangle solver sees it */
 };
 
+#define FKMC_MAX_W 8
+
 enum fkmc_move_kind { FKMC_MOVE_FLIP = 0, FKMC_MOVE_ADDREMOVE = 1, FKMC_MOVE_RESHUFFLE = 2 };
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -92,10 +94,12 @@ int fkmc_sb2st_batched(fkmc_ctx* ctx, const double* AB, int N, int B, double* d,
  *          "kpm_generic" = 1 forces the full-lattice-vector KPM kernel (default 0: local-patch kernel when it applies)
  *          "kpm_v1" = 1 forces the single-kernel KPM path (csrc/kpm.cu) where the two-kernel 2-D path (csrc/kpm2d.cu:
  *          strip Lanczos + ring-ordered patch recursion) would apply; for cross-checks
- *          "sy2sb_tiled_min" = n: smallest N served by the tiled dense->band kernel (process-wide, default 256; below it the
+ *          "sy2sb_tiled_min" = n: smallest N served by the tiled dense->band kernel (per context, default 256; below it the
  *          column-major small-matrix kernel runs); for cross-checks
  *          "kpm_generic_schedule" = 1 keeps the moments kernel of csrc/kpm2d.cu on its run-time slot schedule (default 0: the
- *          compile-time schedule where one is known, i.e. cubic2d with a single hopping constant); for cross-checks */
+ *          compile-time schedule where one is known, i.e. cubic2d with a single hopping constant); for cross-checks
+ *          "lanczos_max_steps" = n > 0 lowers the Lanczos step cap of the KPM kernels (default 0: 384); the tests use it to force
+ *          FKMC_ERR_NOCONV */
 int fkmc_set_option(fkmc_ctx* ctx, const char* name, int value);
 /* eigenvalues (ascending) of B symmetric tridiagonals by Sturm bisection */
 int fkmc_tridiag_eigvals_batched(fkmc_ctx* ctx, const double* d, const double* e, int N, int B, double* evals);
@@ -117,11 +121,16 @@ typedef struct fkmc_chain_params {
     int32_t ntherm_sweeps;                       /* sweeps before measuring starts */
     int32_t measure_energy;                      /* energy/spectrum measures (exact calc_ed per measured sweep) */
     int32_t record_trace;                        /* keep per-step (site, weight, u, accepted) for parity tests */
-    int32_t max_sweeps;                          /* capacity of the series / trace buffers */
+    int32_t max_sweeps;                          /* capacity of the series / trace / history buffers */
+    int32_t measure_history;                     /* fk_mc.hxx:185: spectrum_history (when an exact spectrum is measured) and focc_history */
+    int32_t measure_ipr;                         /* fk_mc.hxx:195: measure_ipr -> ipr_history (calc_ed(true) per measured sweep) */
+    int32_t n_W;                                 /* 1-D lattices: f-f interaction W[0..n_W) (config_params::W, configuration.hpp:15-19); */
+    double W[FKMC_MAX_W];                        /* ignored for D >= 2 where calc_ff_energy() == 0 (configuration.cpp:62) */
 } fkmc_chain_params;
 
 int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_params* p);
-/* mc_metropolis::update + measure, n_sweeps times (src/mc_metropolis.cpp:34-61) */
+/* mc_metropolis::update + measure, n_sweeps times (src/mc_metropolis.cpp:34-61).  Synchronises once at the end of the call
+ * and returns FKMC_ERR_NOCONV when any evaluation of these sweeps hit the Lanczos / bisection iteration cap. */
 int fkmc_chain_run_sweeps(fkmc_ctx* ctx, int n_sweeps);
 /* series: [n_measured][n_chains] each (observables_t::energies, d2energies, c_energies, fk_mc.hpp:13-34); any may be NULL */
 int fkmc_chain_get_series(fkmc_ctx* ctx, int* n_measured, double* energies, double* d2energies, double* c_energies,
@@ -131,6 +140,13 @@ int fkmc_chain_get_state(fkmc_ctx* ctx, int32_t* f, double* logZ, int64_t* nacce
 /* trace: [n_steps][n_chains] each; n_steps = sweeps run * sweep_len */
 int fkmc_chain_get_trace(fkmc_ctx* ctx, int* n_steps, int32_t* move, int32_t* site_a, int32_t* site_b, int32_t* accepted,
                          double* weight, double* u, double* logz_new);
+/* per-sweep histories of the measured sweeps (any pointer may be NULL; FKMC_ERR_STATE when that measure is off):
+ *   spectrum_mean    [n_chains][N]              measure_spectrum, src/measures/spectrum.cpp:13-21 (running mean per chain)
+ *   spectrum_history [n_measured][n_chains][N]  measure_spectrum_history, src/measures/spectrum_history.cpp:13-19
+ *   focc_history     [n_measured][n_chains][V]  measure_focc, src/measures/focc_history.cpp:7-12
+ *   ipr_history      [n_measured][n_chains][N]  measure_ipr, include/fk_mc/measures/ipr.hpp:39-56 */
+int fkmc_chain_get_history(fkmc_ctx* ctx, int* n_measured, double* spectrum_mean, double* spectrum_history, int32_t* focc_history,
+                           double* ipr_history);
 /* measure_ipr on the chains' current configurations: evals [n_chains][N] (or NULL), ipr [n_chains][N] */
 int fkmc_chain_ipr(fkmc_ctx* ctx, double* evals, double* ipr);
 /* device pointers to the series (for the end-of-run NCCL gather): energies, d2energies, c_energies as

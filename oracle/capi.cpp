@@ -184,6 +184,20 @@ int orc_mc_run(const mc_params* p, int rank, int* tr_move, int* tr_site_a, int* 
     ORC_CATCH
 }
 
+// per-sweep histories of one chain: spectrum_history [nsweeps][N], focc_history [nsweeps][V] (either may be null)
+int orc_mc_histories(const mc_params* p, int rank, double* spectrum_history, int* focc_history) {
+    ORC_TRY
+    mc_result res;
+    mc_run(*p, rank, res, nullptr);
+    if (spectrum_history)
+        for (size_t m = 0; m < res.spectrum_history.size(); ++m)
+            std::memcpy(spectrum_history + m * res.spectrum_history[m].size(), res.spectrum_history[m].data(), sizeof(double) * res.spectrum_history[m].size());
+    if (focc_history)
+        for (size_t m = 0; m < res.focc_history.size(); ++m)
+            std::memcpy(focc_history + m * res.focc_history[m].size(), res.focc_history[m].data(), sizeof(int) * res.focc_history[m].size());
+    ORC_CATCH
+}
+
 // CPU baseline: nthreads independent chains (rank r seeded SEED+r, src/mc_metropolis.cpp:25), exactly
 // the reference's MPI layout (ranks never communicate while sampling).  Timed with steady_clock
 // around the sampling loop like prog/fk_mc_exec.cpp:149-152.  Returns wall seconds in *seconds.

@@ -58,9 +58,11 @@ struct engine {
     std::unique_ptr<chebyshev_eval> cheb;
     random_generator random;
     config_state config, new_config;
-    std::vector<double> W;  // f-f interaction (1-D only; empty here)
+    std::vector<double> W;  // f-f interaction (1-D only)
 
-    engine(const mc_params& p_, int rank) : p(p_), lat(make_lattice(p_.kind, p_.L, p_.t, p_.tp)), random(p_.seed + rank) {}
+    engine(const mc_params& p_, int rank) : p(p_), lat(make_lattice(p_.kind, p_.L, p_.t, p_.tp)), random(p_.seed + rank) {
+        if (lat.ndim == 1) W.assign(p_.W, p_.W + p_.n_W);  // fk_mc.hxx:40-45: W only reaches the configuration on 1-D lattices
+    }
 
     void ensure_ed(config_state& c, bool evecs = false) {
         if (c.ed_valid && (!evecs || !c.ed.evecs.empty())) return;
@@ -205,7 +207,9 @@ void mc_run(const mc_params& p, int rank, mc_result& res, mc_trace* trace) {
                 // src/measures/spectrum.cpp:13-21
                 for (int i = 0; i < V; ++i) res.spectrum_avg[i] = (res.spectrum_avg[i] * specZ + config.ed.spectrum[i]) / (specZ + 1);
                 specZ++;
+                res.spectrum_history.push_back(config.ed.spectrum);
             }
+            res.focc_history.push_back(config.f);
             res.nf_series.push_back(config.nf());
         }
         measure_count++;

@@ -122,6 +122,8 @@ struct mc_params {
     int nsweeps, sweep_len, ntherm_sweeps;
     int measure_energy;  // register energy/spectrum measures (exact calc_ed per sweep)
     int measure_ipr;
+    int n_W;        // 1-D lattices: f-f interaction W[0..n_W) (config_params::W); calc_ff_energy() is 0 for D >= 2
+    double W[8];
 };
 struct mc_trace {
     std::vector<int> move, site_a, site_b, accepted;
@@ -130,6 +132,8 @@ struct mc_trace {
 struct mc_result {
     std::vector<double> energies, d2energies, c_energies, spectrum_avg;
     std::vector<std::vector<double>> ipr_history;  // [measurement][state]
+    std::vector<std::vector<double>> spectrum_history;  // [measurement][index]   (src/measures/spectrum_history.cpp:13-19)
+    std::vector<std::vector<int>> focc_history;         // [measurement][site]    (src/measures/focc_history.cpp:7-12)
     std::vector<int> f_final, nf_series;
     long naccept = 0;
     double logz_final = 0;

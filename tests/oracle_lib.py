@@ -27,7 +27,7 @@ class McParams(C.Structure):
                 ("mc_add_remove", C.c_double), ("mc_reshuffle", C.c_double), ("cheb_moves", C.c_int),
                 ("cheb_prefactor", C.c_double), ("emode", C.c_int), ("seed", C.c_long), ("nf_start", C.c_int),
                 ("nsweeps", C.c_int), ("sweep_len", C.c_int), ("ntherm_sweeps", C.c_int), ("measure_energy", C.c_int),
-                ("measure_ipr", C.c_int)]
+                ("measure_ipr", C.c_int), ("n_W", C.c_int), ("W", C.c_double * 8)]
 
 
 def build(force=False):
@@ -182,12 +182,13 @@ def measure_ipr(evecs):
 
 def make_params(kind=CUBIC2D, L=8, t=1.0, tp=1.0, beta=1.0, U=1.0, mu_c=None, mu_f=None, mc_flip=0.0, mc_add_remove=1.0,
                 mc_reshuffle=0.0, cheb_moves=False, cheb_prefactor=2.2, emode=0, seed=32167, nf_start=None, nsweeps=8,
-                sweep_len=16, ntherm_sweeps=1, measure_energy=True, measure_ipr=False):
+                sweep_len=16, ntherm_sweeps=1, measure_energy=True, measure_ipr=False, W=()):
     n = lattice_size(kind, L)
+    W = [float(w) for w in W]
     return McParams(kind, L, t, tp, beta, U, U / 2 if mu_c is None else mu_c, U / 2 if mu_f is None else mu_f, mc_flip,
                     mc_add_remove, mc_reshuffle, int(cheb_moves), cheb_prefactor, emode, seed,
                     n // 2 if nf_start is None else nf_start, nsweeps, sweep_len, ntherm_sweeps, int(measure_energy),
-                    int(measure_ipr))
+                    int(measure_ipr), len(W), (C.c_double * 8)(*(W + [0.0] * (8 - len(W)))))
 
 
 def mc_run(p, rank=0, trace=True):
@@ -206,6 +207,14 @@ def mc_run(p, rank=0, trace=True):
                          _p(f_final, C.c_int), C.byref(nacc), C.byref(lzf), _p(ipr, C.c_double)))
     return dict(trace=tr if trace else None, energies=en, d2energies=d2, c_energies=ce, spectrum_avg=sp, f_final=f_final,
                 naccept=nacc.value, logz_final=lzf.value, ipr_history=ipr)
+
+
+def mc_histories(p, rank=0):
+    """spectrum_history [nsweeps, N] and focc_history [nsweeps, V] of one oracle chain."""
+    n = lattice_size(p.kind, p.L)
+    sh, fo = np.zeros((p.nsweeps, n)), np.zeros((p.nsweeps, n), np.int32)
+    _ck(lib().orc_mc_histories(C.byref(p), rank, _p(sh, C.c_double), _p(fo, C.c_int)))
+    return sh, fo
 
 
 def bench_chains(p, nthreads, rank0=0):

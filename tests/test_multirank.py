@@ -48,7 +48,7 @@ def _worker(rank, world, port, total, n_meas, out_dir):
     ref = np.zeros((4, 3))
     for r in range(world):
         rc0, rn = parallel.partition_chains(total, world, r)
-        x = np.array([[1000.0 * m + (rc0 + c) for c in range(rn)] for m in range(n_meas)]).reshape(-1)
+        x = np.array([[1000.0 * m + (rc0 + c) for c in range(rn)] for m in range(n_meas)]).reshape(n_meas, rn).T.reshape(-1)  # chain-major
         for lv in range(4):
             if x.size:
                 ref[lv] += (x.size, x.sum(), (x * x).sum())

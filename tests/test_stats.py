@@ -1,5 +1,7 @@
 """Host statistics (fk_mc_b200/stats.py) against the reference's Mathematica goldens (test/binning_test.cpp:60-63,
 test/jackknife_test.cpp:56-134) and against the oracle restatement."""
+import math
+
 import numpy as np
 import pytest
 
@@ -71,3 +73,28 @@ def test_plaintext_layout(tmp_path):
     table = np.loadtxt(tmp_path / "cv_binning.dat")
     assert table.shape == (len(rep["cv"]["binning"]), 5)
     assert table[0, 0] == 256 and table[1, 0] == 128
+
+
+def test_multi_chain_series_are_pooled_chain_major():
+    """[measurement][chain] series must be binned along Monte Carlo time inside a chain (the reference gathers rank after rank,
+    src/measures/energy.cpp:32-47): with strongly autocorrelated chains the error bar has to GROW with the bin level; a
+    measurement-major flattening averages independent chains first and reports a flat (too small) error."""
+    rng = np.random.default_rng(7)
+    n_meas, n_chains, rho = 512, 64, 0.95
+    x = np.zeros((n_meas, n_chains))
+    x[0] = rng.normal(size=n_chains)
+    for m in range(1, n_meas):
+        x[m] = rho * x[m - 1] + math.sqrt(1 - rho * rho) * rng.normal(size=n_chains)   # AR(1), tau_int ~ 19
+    pooled = stats.pool_chains(x)
+    assert np.array_equal(pooled[:n_meas], x[:, 0]) and np.array_equal(pooled[n_meas:2 * n_meas], x[:, 1])
+    assert np.array_equal(stats.pool_chains(pooled), pooled)
+    with pytest.raises(ValueError):
+        stats.pool_chains(np.zeros((2, 2, 2)))
+    rep = stats.energy_report(x, x * x, 1.0, 1.0, max_depth=8)
+    err = [r[3] for r in rep["energy"]["binning"]]
+    assert err[6] > 3.0 * err[0]                      # autocorrelation visible: (1+rho)/(1-rho) = 39 -> factor ~ 6
+    wrong = [r[3] for r in stats.accumulate_binning(x.reshape(-1)[::-1], 6)]
+    assert wrong[5] < 1.5 * wrong[0]                  # what the measurement-major flattening used to report
+    # true error of the mean of all samples, from the exact AR(1) autocorrelation time
+    true_err = math.sqrt((1 + rho) / (1 - rho) / x.size)
+    assert 0.6 * true_err < err[8] < 1.6 * true_err
