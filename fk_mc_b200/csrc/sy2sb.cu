@@ -40,6 +40,13 @@
 
 #include "common.cuh"
 
+// Developer ablation builds (make VARIANT=ablN EXTRA=-DFKMC_ABL=N; results are WRONG, only the timing is of interest):
+//   1 no partner adds into shared memory   2 no transposed SYMM   3 operand records loaded once per pass   4 no tile stores
+//   5 no tile loads (stale buffers)        6 no owned-row accumulation
+#ifndef FKMC_ABL
+#define FKMC_ABL 0
+#endif
+
 namespace {
 
 constexpr int NB = 8;
@@ -250,7 +257,7 @@ __device__ __forceinline__ void tile_update_symm(double* __restrict__ Tb, double
                 {
                     const int off = ((8 * x + g) << 5) + ((8 * (2 * half + yy) + 2 * t) ^ cs);
                     *reinterpret_cast<double2*>(Tb + off) = make_double2(acc[x][yy][0], acc[x][yy][1]);  // for the transposed reads
-                    st_stream2(gT + off, acc[x][yy][0], acc[x][yy][1], pol);                             // the tile itself, straight from registers
+                    if (FKMC_ABL != 4) st_stream2(gT + off, acc[x][yy][0], acc[x][yy][1], pol);                             // the tile itself, straight from registers
                 }
         }
 #pragma unroll
@@ -665,8 +672,10 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
                 rec8 vRq;
                 if (!diag) vRq = load_rec(recVp, T0 + Rmax, lane, pol_keep);
                 S1_T(q0)
+                if (FKMC_ABL != 5) {
                 mbar_wait(bar, (phb >> slot) & 1);
                 phb ^= 1u << slot;
+                }
                 S1_T(q1)
                 double accR[4][2], accC[2][4][2];
 #pragma unroll
@@ -680,7 +689,7 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
                 }
                 S1_T(q2)
                 // the operand records of the next task travel while this one finishes
-                if (i + 1 < ntasks) {
+                if (i + 1 < ntasks && FKMC_ABL != 3) {
                     const int D1 = task(i + 1), n1R = (D1 >> 13) & 31, n1C = (D1 >> 18) & 31;
                     if (upd) {
                         uvR = load_rec(uV, T0 + n1R, lane, pol_keep);
@@ -691,11 +700,11 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
                     vCp = load_rec(recVp, T0 + n1C, lane, pol_keep);
                 }
                 S1_T(q3)
-                if (!diag) tile_symm_t(Tb, vRq, lane, accC);
+                if (!diag && FKMC_ABL != 2) tile_symm_t(Tb, vRq, lane, accC);
                 S1_T(q4)
                 // refill this buffer with the task after next once the store has read it
                 {
-                    if (i + 2 < ntasks) {
+                    if (i + 2 < ntasks && FKMC_ABL != 5) {
                         const int D2 = task(i + 2);
                         tile_load(Tb, bar, At, T0 + ((D2 >> 13) & 31), T0 + ((D2 >> 18) & 31), lane, pol_stream);
                     }
@@ -721,6 +730,7 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
                     }
                     const int need = sc.before_partner(pblk, s);
                     S1_T(sp0)
+                    if (FKMC_ABL != 1) {
                     while (ld_flag(blkstep + pblk) < need) {
                     }
                     if (DBG) spin_t += clock64() - sp0;
@@ -731,8 +741,20 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
                         for (int h = 0; h < 2; ++h) yp[h * ldy + 8 * x] += accR[x][h];
                     __syncwarp();
                     if (lane == 0) st_flag(blkstep + pblk, need + 1);
+                    } else {
+                        // keep the values alive so that the DMMAs that produced them are not optimised away
+                        double sink = 0.0;
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) sink += accR[x][0] + accR[x][1];
+                        if (sink == 1.2345e300) Y[lane] = sink;
+                    }
                 }
-                if (!fl) {
+                if (!fl && FKMC_ABL == 6) {
+                    double sink = 0.0;
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) sink += ow[x][0] + ow[x][1];
+                    if (sink == 1.2345e300) own[0][0][0] = sink;
+                } else if (!fl) {
 #pragma unroll
                     for (int oo = 0; oo < MAXOWN; ++oo)
                         if (oo == o) {
@@ -741,7 +763,7 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
                         }
                 } else {
                     const int need2 = sc.before_own(a, s);
-                    while (ld_flag(blkstep + a) < need2) {
+                    while (FKMC_ABL != 1 && ld_flag(blkstep + a) < need2) {
                     }
                     double* yo = Y + 32 * (T0 + a) + g + 2 * t * ldy;
 #pragma unroll
