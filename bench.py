@@ -394,14 +394,20 @@ def main():
     # ---- final collective: gather the per-chain series (the only inter-GPU traffic of a run) ----
     gather_ms = None
     if world > 1:
-        se = ctx.chain_get_series()
-        loc = torch.from_numpy(se["energies"]).cuda()
+        # fkmc_gather_series: ncclAllGather straight from the chain engine's device buffers (the library resolves libnccl itself);
+        # torch.distributed only carries the 128-byte communicator id between the processes
+        ids = [fk.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(ids[0], world, rank)
+        ctx.gather_series()  # warm-up (communicator set-up)
         torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
-        allv = parallel.gather_series(loc, world * chains)
-        torch.cuda.synchronize()
+        allv = ctx.gather_series()
         gather_ms = (time.perf_counter() - t0) * 1e3
-        assert allv.shape[1] == world * chains
+        assert allv["energies"].shape == (total_sweeps, world * chains)
+        mine = ctx.chain_get_series()["energies"]
+        assert np.array_equal(allv["energies"][:, rank * chains:(rank + 1) * chains], mine)
 
     # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) ----
     cpu_baseline = None

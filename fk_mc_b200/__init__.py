@@ -7,8 +7,8 @@ used by the tests and the benchmark; the C++ host mirror of the reference API li
 missing, and every compute call fails when no sm_100 GPU is present.
 """
 from .binding import (  # noqa: F401
-    ChainParams, Context, FkmcError, KINDS, LIB_PATH, build_library, cheb_sizes, exported_symbols, load_library,
+    ChainParams, Context, FkmcError, KINDS, LIB_PATH, build_library, cheb_sizes, exported_symbols, load_library, nccl_unique_id,
 )
 
 __all__ = ["ChainParams", "Context", "FkmcError", "KINDS", "LIB_PATH", "build_library", "cheb_sizes", "exported_symbols",
-           "load_library"]
+           "load_library", "nccl_unique_id"]

@@ -69,6 +69,15 @@ def load_library():
     return lib
 
 
+def nccl_unique_id():
+    """128-byte ncclUniqueId (rank 0 calls this and hands the bytes to the other ranks over any host channel)."""
+    buf = (C.c_char * 128)()
+    rc = load_library().fkmc_nccl_unique_id(buf)
+    if rc != 0:
+        raise FkmcError(rc, load_library().fkmc_last_error(None).decode())
+    return bytes(buf.raw)
+
+
 def cheb_sizes(msize, prefactor=2.2):
     """fk_mc.hxx:60-63: M = even(int(ln N * prefactor)), G = max(2M, 10)."""
     m = int(math.log(float(msize)) * prefactor)
@@ -332,6 +341,27 @@ class Context:
         k = n.value
         return dict(n_steps=k, move=move[:k], site_a=a[:k], site_b=b[:k], accepted=acc[:k], weight=w[:k], u=u[:k],
                     logz_new=lz[:k])
+
+    # ---- end-of-run collective (NCCL resolved inside the library; no torch involved) ----
+    def comm_init(self, unique_id, nranks, rank):
+        """Join the NCCL communicator described by the 128-byte id rank 0 obtained from nccl_unique_id() (collective)."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._ck(self.lib.fkmc_comm_init(self.h, buf, int(nranks), int(rank)))
+        self.nranks = nranks
+
+    def gather_series(self):
+        """All-gather of the energy series over every rank's chains: dict(n_measured, energies / d2energies / c_energies
+        [n_measured, nranks * n_chains] in global chain order).  Local series when no communicator was initialised."""
+        nr = getattr(self, "nranks", 1)
+        p, Cn = self.chain_params, self.n_chains
+        e = np.zeros((p.max_sweeps, nr * Cn))
+        d2, ec = np.zeros_like(e), np.zeros_like(e)
+        n, tot = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.fkmc_gather_series(self.h, C.byref(n), C.byref(tot), _ptr(e, C.c_double), _ptr(d2, C.c_double),
+                                             _ptr(ec, C.c_double), None))
+        m = n.value
+        flat = lambda a: a.reshape(-1)[: m * tot.value].reshape(m, tot.value)  # noqa: E731
+        return dict(n_measured=m, energies=flat(e), d2energies=flat(d2), c_energies=flat(ec))
 
     def chain_series_dev(self):
         e, d2, ec, ld = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int(0)

@@ -127,6 +127,12 @@ struct fkmc_ctx {
 
     fkmc_chain_state chain;
 
+    // end-of-run collective (gather.cu)
+    void* nccl_comm = nullptr;  // ncclComm_t
+    int nccl_nranks = 0, nccl_rank = 0;
+    double* d_gather = nullptr;  // gathered + reordered series
+    size_t gather_cap = 0;       // doubles per half
+
     // instrumentation
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool profiling = false;
@@ -197,6 +203,7 @@ int fkmc_eigvec_pipeline(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, dou
                          double* h_evecs, double* h_ipr_host, double* d_ipr);
 // chains
 int fkmc_chain_free(fkmc_ctx* ctx);
+extern "C" int fkmc_comm_destroy(fkmc_ctx* ctx);
 // reads and clears the non-convergence flag (synchronises the stream): FKMC_OK or FKMC_ERR_NOCONV
 int fkmc_check_flag(fkmc_ctx* ctx);
 

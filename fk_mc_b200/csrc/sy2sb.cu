@@ -896,7 +896,10 @@ sy2sb_kernel(double* __restrict__ A_all, size_t a_stride, int N, double* __restr
 
 // warps per CTA: 8 (one CTA per SM) above N = 512, else 4 with two CTAs per SM, so that the panel phases of one matrix run
 // beside the tensor-core pass of another (the QR keeps four panel rows per thread: m <= 4 * 128)
-static int sy2sb_warps(int N) { return N > 512 ? 8 : 4; }
+static int sy2sb_warps(int N) {
+    if (const char* e = getenv("FKMC_S1_WARPS")) return atoi(e) == 4 && N <= 512 ? 4 : 8;  // (environment: developer override)
+    return N > 512 ? 8 : 4;
+}
 
 size_t fkmc_sy2sb_smem(int N) {
     const size_t nw = sy2sb_warps(N);

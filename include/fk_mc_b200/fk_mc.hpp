@@ -13,12 +13,14 @@
 #include <array>
 #include <cmath>
 #include <functional>
+#include <limits>
 #include <map>
 #include <memory>
 #include <numeric>
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <variant>
 #include <vector>
 
 #include "../fkmc.h"
@@ -94,19 +96,19 @@ protected:
 
 /// src/lattice/hypercubic.cpp:116-131
 template <size_t D>
-hypercubic_lattice<D>& fill_nearest_neighbors(hypercubic_lattice<D>& l, double t) {
-    l.build(D == 1 ? FKMC_CUBIC1D : (D == 2 ? FKMC_CUBIC2D : FKMC_CUBIC3D), l.dims()[0], t, 0.0);
+hypercubic_lattice<D>& fill_nearest_neighbors(hypercubic_lattice<D>& l, double t, int device = 0, int max_batch = 1) {
+    l.build(D == 1 ? FKMC_CUBIC1D : (D == 2 ? FKMC_CUBIC2D : FKMC_CUBIC3D), l.dims()[0], t, 0.0, device, max_batch);
     return l;
 }
 /// src/lattice/hypercubic.cpp:137-155
-inline hypercubic_lattice<2>& fill_triangular(hypercubic_lattice<2>& l, double t, double tp) {
-    l.build(FKMC_TRIANGULAR, l.dims()[0], t, tp);
+inline hypercubic_lattice<2>& fill_triangular(hypercubic_lattice<2>& l, double t, double tp, int device = 0, int max_batch = 1) {
+    l.build(FKMC_TRIANGULAR, l.dims()[0], t, tp, device, max_batch);
     return l;
 }
 /// src/lattice/hypercubic.cpp:160-203 (intended symmetric brick wall; literal_lower = what Eigen's solver sees of the literal matrix)
-inline hypercubic_lattice<2>& fill_honeycomb(hypercubic_lattice<2>& l, double t, bool literal_lower = false) {
+inline hypercubic_lattice<2>& fill_honeycomb(hypercubic_lattice<2>& l, double t, bool literal_lower = false, int device = 0, int max_batch = 1) {
     if (l.dims()[0] % 2 != 0) throw std::logic_error("Need even size");
-    l.build(literal_lower ? FKMC_HONEYCOMB_REF_LOWER : FKMC_HONEYCOMB, l.dims()[0], t, 0.0);
+    l.build(literal_lower ? FKMC_HONEYCOMB_REF_LOWER : FKMC_HONEYCOMB, l.dims()[0], t, 0.0, device, max_batch);
     return l;
 }
 
@@ -402,6 +404,61 @@ struct measure_energy {
     std::vector<double>&_energies, &_d2energies, &_c_energies;
 };
 
+/// src/measures/spectrum.cpp:13-21: running mean of the sorted spectrum
+struct measure_spectrum {
+    measure_spectrum(configuration_t& in, std::vector<double>& average_spectrum) : config(in), _average_spectrum(average_spectrum) {}
+    void accumulate(double /*sign*/) {
+        config.calc_ed(false);
+        const auto& spectrum = config.ed_data_.cached_spectrum;
+        if (_average_spectrum.size() != spectrum.size()) _average_spectrum.assign(spectrum.size(), 0.0);
+        for (size_t i = 0; i < spectrum.size(); ++i) _average_spectrum[i] = (_average_spectrum[i] * _Z + spectrum[i]) / (_Z + 1);
+        _Z++;
+    }
+    configuration_t& config;
+    int _Z = 0;
+    std::vector<double>& _average_spectrum;
+};
+
+/// src/measures/spectrum_history.cpp:13-19: history [eigenvalue index][measurement]
+struct measure_spectrum_history {
+    measure_spectrum_history(configuration_t& in, std::vector<std::vector<double>>& spectrum_history) : config(in), spectrum_history_(spectrum_history) {
+        spectrum_history_.resize(config.lattice_.msize());
+    }
+    void accumulate(double /*sign*/) {
+        config.calc_ed(false);
+        for (size_t i = 0; i < spectrum_history_.size(); ++i) spectrum_history_[i].push_back(config.ed_data_.cached_spectrum[i]);
+    }
+    configuration_t& config;
+    std::vector<std::vector<double>>& spectrum_history_;
+};
+
+/// src/measures/focc_history.cpp:7-12: history [site][measurement]
+struct measure_focc {
+    measure_focc(configuration_t& in, std::vector<std::vector<double>>& focc_history) : config(in), focc_history_(focc_history) {
+        focc_history_.resize(config.lattice_.volume());
+    }
+    void accumulate(double /*sign*/) {
+        for (size_t i = 0; i < focc_history_.size(); ++i) focc_history_[i].push_back(config.f_config_[i]);
+    }
+    configuration_t& config;
+    std::vector<std::vector<double>>& focc_history_;
+};
+
+/// include/fk_mc/measures/ipr.hpp:39-56: ||psi_k||_4 / ||psi_k||_2^2 per eigenstate; history [state][measurement].  The eigenvectors stay on
+/// the device (fkmc_ipr_batched); the spectrum cache is refreshed from the same solve.
+struct measure_ipr {
+    measure_ipr(configuration_t& in, std::vector<std::vector<double>>& ipr_vals) : config(in), ipr_vals_(ipr_vals) { ipr_vals_.resize(config.lattice_.msize()); }
+    void accumulate(double /*sign*/) {
+        const size_t N = config.lattice_.msize();
+        std::vector<double> ev(N), ipr(N);
+        fkmc_check(fkmc_ipr_batched(config.lattice_.ctx(), config.f_config_.data(), 1, config.params_.U, config.params_.mu_c, config.params_.beta, ev.data(),
+                                    ipr.data()), config.lattice_.ctx());
+        for (size_t i = 0; i < N; ++i) ipr_vals_[i].push_back(ipr[i]);
+    }
+    configuration_t& config;
+    std::vector<std::vector<double>>& ipr_vals_;
+};
+
 /// Batched product path: n_chains reference ranks on one GPU (fkmc_chain_*).  chain c == the reference's MPI rank chain0 + c.
 struct batched_chains {
     batched_chains(abstract_lattice& lat, int n_chains, const fkmc_chain_params& p) : lat_(lat), n_(n_chains), p_(p) {
@@ -416,6 +473,34 @@ struct batched_chains {
         e.resize(size_t(n_meas) * n_); d2.resize(e.size()); ec.resize(e.size());
         return n_meas;
     }
+    /// per-sweep histories as the C ABI returns them: spectrum_mean [chain][N], the others [measurement][chain][N] (empty when not measured)
+    int histories(std::vector<double>& spectrum_mean, std::vector<double>& spectrum_history, std::vector<int32_t>& focc_history, std::vector<double>& ipr_history) {
+        const size_t N = lat_.msize(), full = size_t(p_.max_sweeps) * n_ * N;
+        const bool exact = !p_.cheb_moves || p_.measure_energy || p_.measure_ipr;
+        spectrum_mean.assign(exact ? size_t(n_) * N : 0, 0.0);
+        spectrum_history.assign(exact && p_.measure_history ? full : 0, 0.0);
+        focc_history.assign(p_.measure_history ? full : 0, 0);
+        ipr_history.assign(p_.measure_ipr ? full : 0, 0.0);
+        int n_meas = 0;
+        fkmc_check(fkmc_chain_get_history(lat_.ctx(), &n_meas, spectrum_mean.empty() ? nullptr : spectrum_mean.data(),
+                                          spectrum_history.empty() ? nullptr : spectrum_history.data(), focc_history.empty() ? nullptr : focc_history.data(),
+                                          ipr_history.empty() ? nullptr : ipr_history.data()), lat_.ctx());
+        const size_t used = size_t(n_meas) * n_ * N;
+        if (!spectrum_history.empty()) spectrum_history.resize(used);
+        if (!focc_history.empty()) focc_history.resize(used);
+        if (!ipr_history.empty()) ipr_history.resize(used);
+        return n_meas;
+    }
+    std::vector<int32_t> f_config() {
+        std::vector<int32_t> f(size_t(n_) * lat_.volume());
+        fkmc_check(fkmc_chain_get_state(lat_.ctx(), f.data(), nullptr, nullptr, nullptr), lat_.ctx());
+        return f;
+    }
+    std::vector<int64_t> naccept() {
+        std::vector<int64_t> a(n_);
+        fkmc_check(fkmc_chain_get_state(lat_.ctx(), nullptr, nullptr, a.data(), nullptr), lat_.ctx());
+        return a;
+    }
     abstract_lattice& lat_;
     int n_;
     fkmc_chain_params p_;
@@ -425,6 +510,53 @@ struct batched_chains {
 
 namespace alps {
 typedef double mc_weight_t;
+
+/// Minimal stand-in for alps::params as fk_mc uses it (define<T>(name, default, description), p[name] readable as its type and
+/// assignable): CLI / ini parsing is out of scope, the table of names, types and defaults is the reference's.
+class params {
+public:
+    typedef std::variant<long, double, bool, std::string, std::vector<double>> value_t;
+    struct ref {
+        value_t* v;
+        std::string name;
+        template <typename T> T as() const {
+            if (!v) throw std::logic_error("parameter '" + name + "' is not defined");
+            if constexpr (std::is_same<T, std::string>::value) return std::get<std::string>(*v);
+            else if constexpr (std::is_same<T, std::vector<double>>::value) return std::get<std::vector<double>>(*v);
+            else {
+                if (auto q = std::get_if<long>(v)) return T(*q);
+                if (auto q = std::get_if<double>(v)) return T(*q);
+                if (auto q = std::get_if<bool>(v)) return T(*q);
+                throw std::logic_error("parameter '" + name + "' is not numeric");
+            }
+        }
+        template <typename T> operator T() const { return as<T>(); }
+        template <typename T> ref& operator=(const T& x) {
+            if constexpr (std::is_same<T, bool>::value) *v = x;
+            else if constexpr (std::is_integral<T>::value) *v = long(x);
+            else if constexpr (std::is_floating_point<T>::value) *v = double(x);
+            else if constexpr (std::is_same<T, std::vector<double>>::value) *v = x;
+            else *v = std::string(x);
+            return *this;
+        }
+    };
+    template <typename T> params& define(const std::string& name, T def, const std::string& descr) {
+        if (!vals_.count(name)) (*this)[name] = def;  // an explicitly set value wins over the default, as with alps::params
+        descr_[name] = descr;
+        return *this;
+    }
+    ref operator[](const std::string& name) { return ref{&vals_[name], name}; }
+    ref operator[](const std::string& name) const {
+        auto it = vals_.find(name);
+        return ref{it == vals_.end() ? nullptr : const_cast<value_t*>(&it->second), name};
+    }
+    bool exists(const std::string& name) const { return vals_.count(name) > 0; }
+    const std::map<std::string, value_t>& values() const { return vals_; }
+
+private:
+    std::map<std::string, value_t> vals_;
+    std::map<std::string, std::string> descr_;
+};
 
 /// Metropolis engine with the reference's registry and accept test (src/mc_metropolis.cpp:34-61, include/fk_mc/mc_metropolis.hpp)
 struct mc_metropolis {
@@ -438,8 +570,22 @@ struct mc_metropolis {
         std::shared_ptr<void> ptr_;
         std::function<void(mc_weight_t)> accumulate_;
     };
+    typedef params parameters_type;
     mc_metropolis(long seed, int rank, long nsweeps, long sweep_len, long ntherm_sweeps)
         : random(seed + rank), rank_(rank), measure_sweeps_(nsweeps), sweep_len_(sweep_len), thermalization_sweeps_(ntherm_sweeps) {}
+    /// src/mc_metropolis.cpp:21-32 (define_parameters must have been called): seed SEED + rank
+    mc_metropolis(parameters_type const& p, int rank)
+        : mc_metropolis(p["SEED"].as<long>(), rank, p["nsweeps"].as<long>(), p["sweep_len"].as<long>(), p["ntherm_sweeps"].as<long>()) {}
+    /// src/mc_metropolis.cpp:11-19
+    static parameters_type& define_parameters(parameters_type& p) {
+        p.define<int>("nsweeps", 1024, "Total number of sweeps (1 sweep = #sweep_len moves + 1 measurement)")
+            .define<int>("sweep_len", 16, "Number of moves between subsequent measurements")
+            .define<int>("ntherm_sweeps", 1, "How many sweeps to do before start measuring")
+            .define<bool>("show_output", true, "Show run progress of mc");
+        p["nprocs"] = 1;
+        return p;
+    }
+    long sweep_count() const { return sweep_count_; }
     template <typename Move_t>
     bool add_move(Move_t&& move, std::string name, double move_prob = 1.0) {
         typedef typename std::remove_reference<Move_t>::type m_type;
@@ -505,3 +651,165 @@ protected:
     mc_weight_t phase_ = 1.0;
 };
 }  // namespace alps
+
+namespace fk {
+typedef alps::params parameters_t;
+
+/// include/fk_mc/fk_mc.hpp:13-34: time series of one chain (index-major histories: [index][measurement])
+struct observables_t {
+    std::vector<double> energies, c_energies, d2energies, nf0, nfpi, spectrum, stiffness;
+    std::vector<std::vector<double>> spectrum_history, ipr_history, cond_history, focc_history;
+    void reserve(int n) { energies.reserve(n); d2energies.reserve(n); c_energies.reserve(n); }
+};
+
+/// include/fk_mc/fk_mc.hpp:36-65, fk_mc.hxx:35-125,177-207.  One object is one Markov chain driven step by step through the
+/// registered moves and measures (batch of one on the GPU); run_batched() runs `n_chains` such chains -- the reference's MPI ranks
+/// rank .. rank + n_chains - 1 -- resident on the GPU (fkmc_chain_*), which is the product path.
+template <typename LatticeType>
+class fk_mc : public alps::mc_metropolis {
+    typedef alps::mc_metropolis base;
+    static_assert(!std::is_same<LatticeType, abstract_lattice>::value, "Can't construct mc for an unspecified lattice");
+
+public:
+    typedef configuration_t config_t;
+    typedef LatticeType lattice_type;
+    parameters_t p;
+    std::shared_ptr<lattice_type> lattice_ptr;
+    std::shared_ptr<configuration_t> config_ptr;
+    observables_t observables;
+
+    lattice_type const& lattice() const { return *lattice_ptr; }
+    configuration_t const& config() const { return *config_ptr; }
+    parameters_t& parameters() { return p; }
+
+    /// fk_mc.hxx:177-207: model and move parameters with the reference's names and defaults (+ those of mc_metropolis); SEED := seed
+    static parameters_t& define_parameters(parameters_t& p) {
+        base::define_parameters(p);
+        p.define<double>("beta", 10.0, "Inverse temperature")
+            .define<double>("U", 1.0, "FK U")
+            .define<double>("mu_c", 0.5, "Chemical potential of c electrons")
+            .define<double>("mu_f", 0.5, "Chemical potential of f electrons");
+        p.define<double>("mc_flip", 0.0, "Make flip moves")
+            .define<double>("mc_add_remove", 1.0, "Make add/remove moves")
+            .define<double>("mc_reshuffle", 0.0, "Make reshuffle moves")
+            .define<bool>("cheb_moves", false, "Allow moves using Chebyshev sampling")
+            .define<double>("cheb_prefactor", 2.2, "Prefactor for number of Chebyshev polynomials = #ln(Volume)")
+            .define<bool>("measure_history", true, "Measure the history")
+            .define<int>("Nf_start", 5, "Starting number of f-electrons")
+            .define<int>("seed", int(std::random_device()()), "Seed for random number generator")
+            .define<bool>("measure_ipr", false, "Measure inverse participation ratio")
+            .define<bool>("measure_eigenfunctions", false, "Measure eigenfunctions")
+            .define<double>("cond_offset", 0.05, "dos offset from the real axis")
+            .define<bool>("measure_stiffness", false, "Measure stiffness/conductivity");
+        p["SEED"] = p["seed"].as<long>();
+        return p;
+    }
+
+    fk_mc(parameters_t const& p_, int rank = 0) : base(p_, rank), p(p_), rank0_(rank) {}
+
+    /// fk_mc.hxx:35-125.  The lattice is taken by reference (it owns a GPU context and is not copyable; the reference copies it).
+    void initialize(lattice_type& l, bool randomize_config = true, std::vector<double> /*wgrid_conductivity*/ = {0.0}) {
+        lattice_ptr = std::shared_ptr<lattice_type>(&l, [](lattice_type*) {});
+        const std::vector<double> W = (l.ndim() == 1 && p.exists("W")) ? p["W"].template as<std::vector<double>>() : std::vector<double>();
+        config_ptr = std::make_shared<configuration_t>(l, p["beta"], p["U"], p["mu_c"], p["mu_f"], W);
+        configuration_t& config = *config_ptr;
+        if (randomize_config) config.randomize_f(this->rng(), p["Nf_start"].template as<long>());
+        config.calc_hamiltonian();
+        const double beta = p["beta"];
+        const bool cheb_move = p["cheb_moves"];
+        if (cheb_move) {
+            int cheb_size = int(std::log(double(l.msize())) * double(p["cheb_prefactor"]));
+            cheb_size += cheb_size % 2;
+            cheb_ptr_.reset(new chebyshev::chebyshev_eval(cheb_size, std::max(cheb_size * 2, 10)));  // owned for the life of the object
+        }
+        const double eps = std::numeric_limits<double>::epsilon();
+        struct entry { const char* key; const char* name; };
+        for (entry m : {entry{"mc_flip", "flip"}, entry{"mc_add_remove", "add_remove"}, entry{"mc_reshuffle", "reshuffle"}}) {
+            const double w = p[m.key];
+            if (!(w > eps)) continue;
+            const std::string nm = m.name;
+            if (nm == "flip") {
+                if (!cheb_move) this->add_move(move_flip(beta, config, this->rng()), nm, w);
+                else this->add_move(chebyshev::move_flip(beta, config, *cheb_ptr_, this->rng()), nm, w);
+            } else if (nm == "add_remove") {
+                if (!cheb_move) this->add_move(move_addremove(beta, config, this->rng()), nm, w);
+                else this->add_move(chebyshev::move_addremove(beta, config, *cheb_ptr_, this->rng()), nm, w);
+            } else {
+                if (!cheb_move) this->add_move(move_randomize(beta, config, this->rng()), nm, w);
+                else this->add_move(chebyshev::move_randomize(beta, config, *cheb_ptr_, this->rng()), nm, w);
+            }
+        }
+        observables.reserve(int(p["nsweeps"].template as<long>()));
+        const bool history = p["measure_history"], ipr = p["measure_ipr"];
+        if (history && ipr) this->add_measure(measure_ipr(config, observables.ipr_history), "ipr");
+        const bool calc_spectrum = !cheb_move || ipr;
+        if (calc_spectrum) {
+            this->add_measure(measure_energy(beta, config, observables.energies, observables.d2energies, observables.c_energies), "energy");
+            this->add_measure(measure_spectrum(config, observables.spectrum), "spectrum");
+            if (history) this->add_measure(measure_spectrum_history(config, observables.spectrum_history), "spectrum_history");
+        }
+        if (history) this->add_measure(measure_focc(config, observables.focc_history), "focc_history");
+    }
+
+    /// The same run for `n_chains` chains at once on the lattice's GPU: chain c is the reference's MPI rank (rank + c) with seed
+    /// SEED + rank + c.  Parameters map field by field onto fkmc_chain_params; which measures run follows initialize().
+    /// Returns per-chain observables (chain-major, i.e. ready to be concatenated like the reference's gathered ranks).
+    std::vector<observables_t> run_batched(lattice_type& l, int n_chains) {
+        fkmc_chain_params cp{};
+        cp.beta = p["beta"]; cp.U = p["U"]; cp.mu_c = p["mu_c"]; cp.mu_f = p["mu_f"];
+        cp.mc_flip = p["mc_flip"]; cp.mc_add_remove = p["mc_add_remove"]; cp.mc_reshuffle = p["mc_reshuffle"];
+        cp.cheb_moves = bool(p["cheb_moves"]); cp.cheb_prefactor = p["cheb_prefactor"];
+        cp.seed = p["SEED"].template as<long>(); cp.chain0 = rank0_;
+        cp.nf_start = int(p["Nf_start"].template as<long>());
+        cp.sweep_len = int(p["sweep_len"].template as<long>());
+        cp.ntherm_sweeps = int(p["ntherm_sweeps"].template as<long>());
+        cp.max_sweeps = int(p["nsweeps"].template as<long>()) + cp.ntherm_sweeps;
+        const bool history = p["measure_history"], ipr = p["measure_ipr"];
+        cp.measure_ipr = history && ipr;
+        cp.measure_energy = !cp.cheb_moves || ipr;
+        cp.measure_history = history;
+        if (l.ndim() == 1 && p.exists("W")) {
+            const std::vector<double> W = p["W"].template as<std::vector<double>>();
+            if (W.size() > FKMC_MAX_W) throw std::logic_error("at most 8 f-f interaction terms");
+            cp.n_W = int(W.size());
+            std::copy(W.begin(), W.end(), cp.W);
+        }
+        batched_chains bc(l, n_chains, cp);
+        bc.run_sweeps(cp.max_sweeps);
+        std::vector<observables_t> out(n_chains);
+        const size_t N = l.msize(), C = n_chains;
+        std::vector<double> e, d2, ec, smean, shist, ihist;
+        std::vector<int32_t> fhist;
+        const int n_meas = cp.measure_energy ? bc.series(e, d2, ec) : 0;
+        const int n_hist = bc.histories(smean, shist, fhist, ihist);
+        for (size_t c = 0; c < C; ++c) {
+            observables_t& o = out[c];
+            for (int m = 0; m < n_meas; ++m) {
+                o.energies.push_back(e[m * C + c]); o.d2energies.push_back(d2[m * C + c]); o.c_energies.push_back(ec[m * C + c]);
+            }
+            if (!smean.empty()) o.spectrum.assign(smean.begin() + c * N, smean.begin() + (c + 1) * N);
+            auto unpack = [&](auto& src, std::vector<std::vector<double>>& dst) {
+                if (src.empty()) return;
+                dst.assign(N, std::vector<double>(n_hist));
+                for (int m = 0; m < n_hist; ++m)
+                    for (size_t i = 0; i < N; ++i) dst[i][m] = double(src[(size_t(m) * C + c) * N + i]);
+            };
+            unpack(shist, o.spectrum_history);
+            unpack(fhist, o.focc_history);
+            unpack(ihist, o.ipr_history);
+        }
+        batched_naccept_ = bc.naccept();
+        batched_f_ = bc.f_config();
+        return out;
+    }
+    const std::vector<int64_t>& batched_naccept() const { return batched_naccept_; }
+    const std::vector<int32_t>& batched_f_config() const { return batched_f_; }
+
+private:
+    std::unique_ptr<chebyshev::chebyshev_eval> cheb_ptr_;
+    int rank0_ = 0;
+    std::vector<int64_t> batched_naccept_;
+    std::vector<int32_t> batched_f_;
+};
+
+}  // namespace fk

@@ -153,6 +153,21 @@ int fkmc_chain_ipr(fkmc_ctx* ctx, double* evals, double* ipr);
  * [max_sweeps][n_chains] doubles */
 int fkmc_chain_series_dev(fkmc_ctx* ctx, void** energies, void** d2energies, void** c_energies, int* ld);
 
+/* ---- end-of-run collective over NCCL (NVLink / NVSwitch), one context per rank ------------------ */
+/* Replaces the root-0 reduce/gather of measure_energy::collect_results (src/measures/energy.cpp:32-47).  libnccl is loaded at run
+ * time (dlopen "libnccl.so.2"; FKMC_NCCL_LIB overrides), so single-GPU use needs no NCCL.
+ * fkmc_nccl_unique_id: rank 0 fills a 128-byte ncclUniqueId which the caller distributes to the other ranks by any host channel.
+ * fkmc_comm_init: every rank joins the communicator (collective call).
+ * fkmc_gather_series: collective.  All ranks run the same number of chains and measured sweeps.  The three energy series are
+ *   all-gathered from the chain engine's device buffers and reordered on the device to [n_measured][nranks * n_chains] in global
+ *   chain order (chain id = the reference's MPI rank).  Host pointers (any may be NULL) receive copies; *out_dev (may be NULL) is
+ *   set to the device buffer holding energies | d2energies | c_energies back to back.  Without a communicator: the local series. */
+int fkmc_nccl_unique_id(void* id128);
+int fkmc_comm_init(fkmc_ctx* ctx, const void* id128, int nranks, int rank);
+int fkmc_comm_destroy(fkmc_ctx* ctx);
+int fkmc_gather_series(fkmc_ctx* ctx, int* n_measured, int* total_chains, double* energies, double* d2energies, double* c_energies,
+                       void** out_dev);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Lanczos steps each of the last B KPM evaluations needed for e_min / e_max (the reference's ARPACK iteration count analogue) */
 int fkmc_kpm_last_steps(fkmc_ctx* ctx, int B, int32_t* steps);

@@ -1,12 +1,20 @@
-// Drives the C++ host mirror (include/fk_mc_b200/fk_mc.hpp) the way prog/fk_mc_exec.cpp + fk_mc.hxx:35-125 drive the
-// reference: lattice -> configuration_t -> randomize_f -> register moves / measures -> run.  Prints the observables so that
-// tests/test_gpu_parity.py can compare them with the CPU oracle.  usage: host_api_test L beta U cheb(0|1) mc_flip nsweeps seed rank
+// Drives the C++ host mirror (include/fk_mc_b200/fk_mc.hpp) the way prog/fk_mc_exec.cpp drives the reference:
+//   parameters_t p; fk_mc<lattice_t>::define_parameters(p); ...; fk_mc<lattice_t> mc(p, rank); mc.initialize(lattice); mc.run();
+// (prog/fk_mc_exec.cpp:43,121-151, include/fk_mc/fk_mc.hxx:35-125,177-207), then the same run as a batch of chains resident on the
+// GPU (fk_mc::run_batched -> fkmc_chain_*).  Prints the observables so that tests/test_gpu_parity.py can compare them with the
+// CPU oracle.  usage: host_api_test L beta U cheb(0|1) mc_flip nsweeps seed rank
 #include <cstdio>
 #include <cstdlib>
 
 #include "fk_mc_b200/fk_mc.hpp"
 
 using namespace fk;
+
+static void print_series(const char* name, const std::vector<double>& v) {
+    printf("%s", name);
+    for (double e : v) printf(" %.17g", e);
+    printf("\n");
+}
 
 int main(int argc, char** argv) {
     if (argc < 9) return 2;
@@ -19,40 +27,62 @@ int main(int argc, char** argv) {
     const int rank = atoi(argv[8]);
     try {
         typedef hypercubic_lattice<2> lattice_t;
+        typedef fk_mc<lattice_t> qmc_t;
         lattice_t lattice(L);
-        fill_nearest_neighbors(lattice, 1.0);
-        alps::mc_metropolis mc(seed, rank, nsweeps, /*sweep_len=*/16, /*ntherm_sweeps=*/1);
-        configuration_t config(lattice, beta, U, U / 2, U / 2);
-        config.randomize_f(mc.rng(), lattice.volume() / 2);  // fk_mc.hxx:46, fk_mc_exec.cpp:124
-        config.calc_hamiltonian();
-        int cheb_size = int(std::log(lattice.msize()) * 2.2);  // fk_mc.hxx:60-63
-        cheb_size += cheb_size % 2;
-        chebyshev::chebyshev_eval cheb(cheb_size, std::max(cheb_size * 2, 10));
-        if (mc_flip > std::numeric_limits<double>::epsilon()) {
-            if (!cheb_move) mc.add_move(move_flip(beta, config, mc.rng()), "flip", mc_flip);
-            else mc.add_move(chebyshev::move_flip(beta, config, cheb, mc.rng()), "flip", mc_flip);
+        fill_nearest_neighbors(lattice, 1.0, /*device=*/0, /*max_batch=*/2);
+        parameters_t p;
+        p["seed"] = seed;                       // command-line values are set before define_parameters, as alps::params does
+        qmc_t::define_parameters(p);
+        if (int(p["sweep_len"]) != 16 || int(p["ntherm_sweeps"]) != 1 || double(p["cheb_prefactor"]) != 2.2 || double(p["mc_add_remove"]) != 1.0) {
+            printf("exception defaults differ from fk_mc.hxx:177-207 / mc_metropolis.cpp:11-19\n");
+            return 1;
         }
-        if (!cheb_move) mc.add_move(move_addremove(beta, config, mc.rng()), "add_remove", 1.0);
-        else mc.add_move(chebyshev::move_addremove(beta, config, cheb, mc.rng()), "add_remove", 1.0);
-        std::vector<double> energies, d2energies, c_energies;
-        mc.add_measure(measure_energy(beta, config, energies, d2energies, c_energies), "energy");
+        p["beta"] = beta; p["U"] = U; p["mu_c"] = U / 2; p["mu_f"] = U / 2;
+        p["mc_flip"] = mc_flip; p["cheb_moves"] = cheb_move; p["nsweeps"] = nsweeps;
+        p["Nf_start"] = int(lattice.volume() / 2);   // fk_mc_exec.cpp:124
+        p["measure_ipr"] = cheb_move;                // Chebyshev moves only measure the energy when an exact spectrum is asked for (fk_mc.hxx:110-118)
+        qmc_t mc(p, rank);
+        mc.initialize(lattice, true);
         mc.run();
         printf("naccept %ld\n", mc.naccept());
-        printf("energies");
-        for (double e : energies) printf(" %.17g", e);
-        printf("\nd2energies");
-        for (double e : d2energies) printf(" %.17g", e);
-        printf("\nf");
-        for (int f : config.f_config_) printf(" %d", f);
+        print_series("energies", mc.observables.energies);
+        print_series("d2energies", mc.observables.d2energies);
+        print_series("spectrum_mean", mc.observables.spectrum);
+        printf("history_shape %zu %zu %zu\n", mc.observables.spectrum_history.size(), mc.observables.spectrum_history.empty() ? 0 : mc.observables.spectrum_history[0].size(),
+               mc.observables.focc_history.size());
+        printf("f");
+        for (int f : mc.config().f_config_) printf(" %d", f);
         printf("\n");
+        // the batched product path: ranks rank, rank + 1 as two chains resident on the GPU
+        qmc_t mcb(p, rank);
+        auto obs = mcb.run_batched(lattice, 2);
+        for (int c = 0; c < 2; ++c) {
+            printf("b%d_naccept %ld\n", c, long(mcb.batched_naccept()[c]));
+            print_series(c ? "b1_energies" : "b0_energies", obs[c].energies);
+            print_series(c ? "b1_spectrum_mean" : "b0_spectrum_mean", obs[c].spectrum);
+            printf("b%d_f", c);
+            for (size_t i = 0; i < lattice.volume(); ++i) printf(" %d", mcb.batched_f_config()[c * lattice.volume() + i]);
+            printf("\n");
+        }
+        printf("b_history_shape %zu %zu %zu\n", obs[0].spectrum_history.size(), obs[0].spectrum_history.empty() ? 0 : obs[0].spectrum_history[0].size(),
+               obs[0].focc_history.size());
         // error behaviour: mismatched parameters throw std::logic_error like configuration.cpp:38
         configuration_t other(lattice, beta + 1, U, U / 2, U / 2);
         bool threw = false;
-        try { other = config; } catch (std::logic_error&) { threw = true; }
+        try { other = mc.config(); } catch (std::logic_error&) { threw = true; }
         printf("mismatch_throws %d\n", int(threw));
         bool threw2 = false;
         try { hypercubic_lattice<2> odd(7); fill_honeycomb(odd, 1.0); } catch (std::logic_error&) { threw2 = true; }
         printf("honeycomb_odd_throws %d\n", int(threw2));
+        bool threw3 = false;   // no registered moves: mc_metropolis.cpp:35-38
+        try {
+            parameters_t q = p;
+            q["mc_flip"] = 0.0; q["mc_add_remove"] = 0.0;
+            qmc_t none(q, 0);
+            none.initialize(lattice, true);
+            none.update();
+        } catch (std::logic_error&) { threw3 = true; }
+        printf("no_moves_throws %d\n", int(threw3));
     } catch (std::exception& e) {
         printf("exception %s\n", e.what());
         return 1;

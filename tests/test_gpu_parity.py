@@ -648,6 +648,8 @@ def test_cpp_host_api_matches_oracle(tmp_path, cheb, flip):
     L, beta, U, nsw, seed, rank = 8, 4.0, 4.0, 3, 32167, 2
     out = subprocess.check_output([exe, str(L), str(beta), str(U), str(cheb), str(flip), str(nsw), str(seed), str(rank)]).decode()
     rows = {ln.split()[0]: ln.split()[1:] for ln in out.strip().splitlines()}
+    assert "exception" not in rows, out
+    # fk_mc<hypercubic_lattice<2>>: define_parameters -> initialize -> run (one chain, batch of one per evaluation) ...
     p = o.make_params(kind=o.CUBIC2D, L=L, beta=beta, U=U, mc_flip=flip, cheb_moves=bool(cheb), seed=seed, nsweeps=nsw, sweep_len=16,
                       ntherm_sweeps=1)
     r = o.mc_run(p, rank=rank)
@@ -655,7 +657,17 @@ def test_cpp_host_api_matches_oracle(tmp_path, cheb, flip):
     assert np.array_equal(np.array(rows["f"], dtype=np.int32), r["f_final"])
     assert np.allclose(np.array(rows["energies"], dtype=float), r["energies"], rtol=1e-10)
     assert np.allclose(np.array(rows["d2energies"], dtype=float), r["d2energies"], rtol=1e-9)
-    assert rows["mismatch_throws"] == ["1"] and rows["honeycomb_odd_throws"] == ["1"]
+    assert np.allclose(np.array(rows["spectrum_mean"], dtype=float), r["spectrum_avg"], rtol=0, atol=1e-10 * np.abs(r["spectrum_avg"]).max())
+    assert rows["history_shape"] == [str(L * L), str(nsw), str(L * L)]      # [index][measurement] like observables_t
+    # ... and fk_mc::run_batched: ranks `rank` and `rank + 1` as two device-resident chains
+    for c in range(2):
+        rb = o.mc_run(p, rank=rank + c)
+        assert int(rows["b%d_naccept" % c][0]) == rb["naccept"]
+        assert np.array_equal(np.array(rows["b%d_f" % c], dtype=np.int32), rb["f_final"])
+        assert np.allclose(np.array(rows["b%d_energies" % c], dtype=float), rb["energies"], rtol=1e-10)
+        assert np.allclose(np.array(rows["b%d_spectrum_mean" % c], dtype=float), rb["spectrum_avg"], rtol=0, atol=1e-10 * np.abs(rb["spectrum_avg"]).max())
+    assert rows["b_history_shape"] == [str(L * L), str(nsw), str(L * L)]
+    assert rows["mismatch_throws"] == ["1"] and rows["honeycomb_odd_throws"] == ["1"] and rows["no_moves_throws"] == ["1"]
 
 
 # ---------------- eigenvector path: calc_ed(true), measure_ipr ----------------
