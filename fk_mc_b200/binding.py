@@ -31,7 +31,8 @@ class ChainParams(C.Structure):
                 ("cheb_moves", C.c_int32), ("cheb_prefactor", C.c_double), ("seed", C.c_int64), ("chain0", C.c_int32),
                 ("nf_start", C.c_int32), ("sweep_len", C.c_int32), ("ntherm_sweeps", C.c_int32),
                 ("measure_energy", C.c_int32), ("record_trace", C.c_int32), ("max_sweeps", C.c_int32),
-                ("measure_history", C.c_int32), ("measure_ipr", C.c_int32), ("n_W", C.c_int32), ("W", C.c_double * 8)]
+                ("measure_history", C.c_int32), ("measure_ipr", C.c_int32), ("n_W", C.c_int32), ("W", C.c_double * 8),
+                ("fast_update", C.c_int32), ("fu_refresh_sweeps", C.c_int32)]
 
 
 def build_library(force=False):
@@ -266,6 +267,19 @@ class Context:
                                                        _ptr(ev, C.c_double)))
         return ev
 
+    def secular_update(self, lam, z, rho):
+        """Eigenvalues of diag(lam) + rho z z^T (batched rank-one secular solver): lam, z [B, N], rho [B] -> [B, N]."""
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        if lam.ndim == 1:
+            lam, z = lam[None], z[None]
+        B, n = lam.shape
+        rho = np.ascontiguousarray(np.broadcast_to(np.asarray(rho, dtype=np.float64), (B,)))
+        out = np.zeros((B, n))
+        self._ck(self.lib.fkmc_secular_update_batched(self.h, _ptr(lam, C.c_double), _ptr(z, C.c_double), _ptr(rho, C.c_double), n, B,
+                                                      _ptr(out, C.c_double)))
+        return out
+
     def rng_stream(self, seed, mode, V, count):
         out = np.zeros(count)
         self._ck(self.lib.fkmc_rng_stream(self.h, C.c_int64(seed), mode, V, count, _ptr(out, C.c_double)))
@@ -274,7 +288,8 @@ class Context:
     # ---- chains ----
     def chain_init(self, n_chains, beta, U, mu_c=None, mu_f=None, mc_flip=0.0, mc_add_remove=1.0, mc_reshuffle=0.0,
                    cheb_moves=False, cheb_prefactor=2.2, seed=32167, chain0=0, nf_start=None, sweep_len=16, ntherm_sweeps=1,
-                   measure_energy=True, record_trace=False, max_sweeps=64, measure_history=False, measure_ipr=False, W=()):
+                   measure_energy=True, record_trace=False, max_sweeps=64, measure_history=False, measure_ipr=False, W=(),
+                   fast_update=False, fu_refresh_sweeps=0):
         W = [float(w) for w in W]
         if len(W) > 8:
             raise FkmcError(1, "at most 8 f-f interaction terms")
@@ -282,7 +297,7 @@ class Context:
                         mc_reshuffle, int(cheb_moves), cheb_prefactor, seed, chain0,
                         self.N // 2 if nf_start is None else nf_start, sweep_len, ntherm_sweeps, int(measure_energy),
                         int(record_trace), max_sweeps, int(measure_history), int(measure_ipr), len(W),
-                        (C.c_double * 8)(*(W + [0.0] * (8 - len(W)))))
+                        (C.c_double * 8)(*(W + [0.0] * (8 - len(W)))), int(fast_update), int(fu_refresh_sweeps))
         self._ck(self.lib.fkmc_chain_init(self.h, int(n_chains), C.byref(p)))
         self.chain_params = p
         self.n_chains = n_chains

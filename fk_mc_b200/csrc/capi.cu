@@ -97,7 +97,8 @@ int fkmc_check_flag(fkmc_ctx* ctx) {
     FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (flag) {
         FKMC_CUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
-        return fkmc_set_error(ctx, FKMC_ERR_NOCONV, flag & 1 ? "bisection iteration cap hit" : "Lanczos step cap hit before e_min/e_max stagnated");
+        return fkmc_set_error(ctx, FKMC_ERR_NOCONV, flag & 4 ? "fast update: tracked spectrum failed its consistency check (trace invariant / refresh); rerun with fast_update = 0"
+                                                          : (flag & 1 ? "bisection / secular iteration cap hit" : "Lanczos step cap hit before e_min/e_max stagnated"));
     }
     return FKMC_OK;
 }
@@ -423,6 +424,27 @@ int fkmc_tridiag_eigvals_batched(fkmc_ctx* ctx, const double* d, const double* e
         rc = check_flag(ctx);
     }
     cudaFree(dd); cudaFree(de); cudaFree(dv); cudaFree(dout);
+    return rc;
+}
+
+int fkmc_secular_update_batched(fkmc_ctx* ctx, const double* lam, const double* z, const double* rho, int N, int B, double* lam_new) {
+    if (!ctx || !lam || !z || !rho || !lam_new || N < 1 || B < 1) return FKMC_ERR_INVALID;
+    FKMC_CUDA(ctx, cudaSetDevice(ctx->device));
+    double *dl = nullptr, *dz = nullptr, *dr = nullptr, *dout = nullptr;
+    const size_t n = N, b = B;
+    FKMC_CUDA(ctx, cudaMalloc(&dl, sizeof(double) * b * n));
+    FKMC_CUDA(ctx, cudaMalloc(&dz, sizeof(double) * b * n));
+    FKMC_CUDA(ctx, cudaMalloc(&dr, sizeof(double) * b));
+    FKMC_CUDA(ctx, cudaMalloc(&dout, sizeof(double) * b * n));
+    FKMC_CUDA(ctx, cudaMemcpyAsync(dl, lam, sizeof(double) * b * n, cudaMemcpyHostToDevice, ctx->stream));
+    FKMC_CUDA(ctx, cudaMemcpyAsync(dz, z, sizeof(double) * b * n, cudaMemcpyHostToDevice, ctx->stream));
+    FKMC_CUDA(ctx, cudaMemcpyAsync(dr, rho, sizeof(double) * b, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = fkmc_launch_secular_only(ctx, N, B, dl, dz, dr, dout);
+    if (!rc) {
+        FKMC_CUDA(ctx, cudaMemcpyAsync(lam_new, dout, sizeof(double) * b * n, cudaMemcpyDeviceToHost, ctx->stream));
+        rc = check_flag(ctx);
+    }
+    cudaFree(dl); cudaFree(dz); cudaFree(dr); cudaFree(dout);
     return rc;
 }
 

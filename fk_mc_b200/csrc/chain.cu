@@ -25,6 +25,7 @@ struct chain_dev {
     int32_t *prop_move, *prop_a, *prop_b;
     int32_t *nf_cur, *nf_prop;
     int64_t* naccept;
+    int32_t* acc_flag;  // [n_chains] accept decision of the last step (fast update), may be null
     double *ec_cur, *d2_cur;
     double *eff_cur, *eff_prop;  // calc_ff_energy() of the current / proposed configuration
     const double* W;             // f-f interaction W[0..nW) (1-D lattices only; nW = 0 otherwise)
@@ -211,6 +212,7 @@ __global__ void chain_accept_kernel(chain_dev C, const double* __restrict__ logz
         }
     }
     accept = __shfl_sync(0xffffffffu, accept, 0);
+    if (lane == 0 && C.acc_flag) C.acc_flag[c] = init ? 0 : accept;
     if (accept) {
         const int32_t* fp = C.f_prop + (size_t)c * V;
         int32_t* f = C.f_cur + (size_t)c * V;
@@ -274,6 +276,7 @@ chain_dev make_dev(fkmc_ctx* ctx) {
     C.mt = S.mt; C.f_cur = S.f_cur; C.f_prop = S.f_prop; C.logz_cur = S.logz_cur;
     C.cur_slot = S.cur_slot; C.prop_slot = S.prop_slot; C.prop_move = S.prop_move; C.prop_a = S.prop_a; C.prop_b = S.prop_b;
     C.nf_cur = S.nf_cur; C.nf_prop = S.nf_prop; C.naccept = S.naccept; C.ec_cur = S.ec_cur; C.d2_cur = S.d2_cur;
+    C.acc_flag = S.fu_acc;
     C.eff_cur = S.eff_cur; C.eff_prop = S.eff_prop; C.W = S.d_W; C.nW = (ctx->ndim == 1) ? S.p.n_W : 0;
     C.V = ctx->N; C.n_chains = S.n_chains; C.n_moves = S.n_moves;
     for (int i = 0; i < 3; ++i) { C.move_kind[i] = S.move_kind[i]; C.move_cp[i] = S.move_cp[i]; }
@@ -282,13 +285,18 @@ chain_dev make_dev(fkmc_ctx* ctx) {
 }
 
 // evaluate logZ of f_prop for all chains; returns pointers to (logz, stride) and the E_c/d2E block
-int evaluate_proposals(fkmc_ctx* ctx, const double** lz, int* lz_stride, const double** ecd2, int* ecd2_stride) {
+int evaluate_proposals(fkmc_ctx* ctx, const double** lz, int* lz_stride, const double** ecd2, int* ecd2_stride, bool full_solve = false) {
     fkmc_chain_state& S = ctx->chain;
     const int C = S.n_chains, N = ctx->N;
     if (S.p.cheb_moves) {
         int rc = fkmc_launch_kpm(ctx, S.f_prop, C, S.p.U, S.p.mu_c, S.p.beta, S.M, S.G, ctx->d_moments, ctx->d_ab, S.logz_prop);
         if (rc) return rc;
         *lz = S.logz_prop; *lz_stride = 1; *ecd2 = nullptr; *ecd2_stride = 0;
+    } else if (S.fu_vt && !full_solve) {
+        // rank-one secular updates of the tracked eigen-decomposition (secular.cu)
+        int rc = fkmc_fu_evaluate(ctx);
+        if (rc) return rc;
+        *lz = ctx->d_out; *lz_stride = 8; *ecd2 = ctx->d_out; *ecd2_stride = 8;
     } else {
         int rc = fkmc_build_tridiag(ctx, S.f_prop, C, S.p.U, S.p.mu_c, ctx->d_d, ctx->d_e);
         if (rc) return rc;
@@ -312,6 +320,7 @@ int fkmc_chain_free(fkmc_ctx* ctx) {
     cudaFree(S.t_move); cudaFree(S.t_a); cudaFree(S.t_b); cudaFree(S.t_acc); cudaFree(S.t_w); cudaFree(S.t_u); cudaFree(S.t_lz);
     cudaFree(S.nf_cur); cudaFree(S.nf_prop); cudaFree(S.prop_slot); cudaFree(S.ec_cur); cudaFree(S.d2_cur);
     cudaFree(S.eff_cur); cudaFree(S.eff_prop); cudaFree(S.d_W);
+    if (S.fu_vt) fkmc_fu_free(ctx);
     cudaFree(S.spec_mean); cudaFree(S.spec_hist); cudaFree(S.focc_hist); cudaFree(S.ipr_hist); cudaFree(S.ipr_evals);
     S = fkmc_chain_state();
     return FKMC_OK;
@@ -323,6 +332,8 @@ extern "C" int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_par
     if (p->sweep_len < 1 || p->max_sweeps < 1) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sweep_len and max_sweeps must be >= 1");
     if (p->nf_start < 0 || p->nf_start > ctx->N) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "nf_start out of range");
     if (p->n_W < 0 || p->n_W > FKMC_MAX_W) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "n_W must be in [0, 8]");
+    if (p->fast_update && (p->cheb_moves || p->mc_reshuffle > std::numeric_limits<double>::epsilon() || ctx->N > 1024 || ctx->N < 2))
+        return fkmc_set_error(ctx, FKMC_ERR_INVALID, "fast_update needs exact moves, mc_reshuffle = 0 and 2 <= N <= 1024");
     FKMC_CUDA(ctx, cudaSetDevice(ctx->device));
     fkmc_chain_free(ctx);
     fkmc_chain_state& S = ctx->chain;
@@ -406,6 +417,11 @@ extern "C" int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_par
         fkmc_chain_free(ctx);
         return FKMC_ERR_CUDA;
     }
+    if (p->fast_update && (rc = fkmc_fu_alloc(ctx))) {
+        const std::string msg = ctx->err;
+        fkmc_chain_free(ctx);
+        return fkmc_set_error(ctx, rc, msg);
+    }
     S.spec[1] = S.spec[0] + C * V;
     S.sweeps_done = 0;
     S.measured = 0;
@@ -424,13 +440,14 @@ extern "C" int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_par
     // evaluate the initial configuration (the reference does it lazily inside the first attempt())
     const double *lz, *ecd2;
     int lzs, es;
-    rc = evaluate_proposals(ctx, &lz, &lzs, &ecd2, &es);
+    rc = evaluate_proposals(ctx, &lz, &lzs, &ecd2, &es, /*full_solve=*/true);
     if (rc) return rc;
     trace_dev TR{};
     TR.step = -1;
     chain_accept_kernel<<<blocks, 128, 0, ctx->stream>>>(D, lz, lzs, ecd2, es, 1, TR);
     ctx->launches++;
     FKMC_CUDA(ctx, cudaGetLastError());
+    if (S.fu_vt && (rc = fkmc_fu_refresh(ctx, /*check=*/0))) return rc;  // eigenvectors of the initial configurations
     return fkmc_check_flag(ctx);  // synchronises; FKMC_ERR_NOCONV when a kernel hit its iteration cap
 }
 
@@ -465,6 +482,14 @@ extern "C" int fkmc_chain_run_sweeps(fkmc_ctx* ctx, int n_sweeps) {
                 fkmc_prof_scope ps(ctx, "chain_step");
                 chain_accept_kernel<<<blocks, 128, 0, ctx->stream>>>(D, lz, lzs, ecd2, es, 0, TR);
                 ctx->launches++;
+            }
+            if (S.fu_vt && (rc = fkmc_fu_commit(ctx))) return rc;  // accepted chains: V <- V Q
+        }
+        if (S.fu_vt) {
+            const int every = S.p.fu_refresh_sweeps > 0 ? S.p.fu_refresh_sweeps : 64;
+            if ((S.sweeps_done + 1) % every == 0) {
+                int rc = fkmc_fu_refresh(ctx, /*check=*/1);
+                if (rc) return rc;
             }
         }
         // measure(): src/mc_metropolis.cpp:54-61

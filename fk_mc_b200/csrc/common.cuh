@@ -55,7 +55,16 @@ struct fkmc_chain_state {
     double* ipr_hist = nullptr;      // [max_sweeps][n_chains][N]
     double* ipr_evals = nullptr;     // [n_chains][N] spectrum of the eigenvector solve of the last measured sweep
     long spec_count = 0;             // measurements folded into spec_mean
-    int* h_flag = nullptr;           // pinned copy of the non-convergence flag
+    // fast update of the dense moves (secular.cu): eigenvectors of the current configurations and per-stage root data
+    double* fu_vt = nullptr;         // [2][n_chains][N][N] site-major eigenvectors, double-buffered
+    int32_t* fu_vslot = nullptr;     // [n_chains]
+    double *fu_poles = nullptr, *fu_mu = nullptr, *fu_zhat = nullptr, *fu_inrm = nullptr;  // [2][n_chains][N]
+    int32_t* fu_org = nullptr;       // [2][n_chains][N]
+    int32_t* fu_nstage = nullptr;    // [n_chains]
+    double* fu_rho = nullptr;        // [2][n_chains]
+    int32_t* fu_acc = nullptr;       // [n_chains] accept flag of the last step
+    double* fu_fresh = nullptr;      // [n_chains][N] spectrum of the last refresh
+    double* fu_maxdev = nullptr;     // [n_chains] relative deviation tracked vs fresh spectrum at the last refresh
     double *s_energy = nullptr, *s_d2energy = nullptr, *s_cenergy = nullptr;  // [max_sweeps][n_chains]
     int32_t* s_nf = nullptr;
     // trace [max_steps][n_chains]
@@ -201,6 +210,15 @@ int fkmc_launch_kpm2d(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double
 // eigenvector path (measurement sweeps): evals/out on the device, eigenvectors and IPR to the host (or IPR to d_ipr)
 int fkmc_eigvec_pipeline(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, double* d_evals, double* d_out,
                          double* h_evecs, double* h_ipr_host, double* d_ipr);
+// eigenvector path with device outputs only: evals [B][N], out [B][8], vt [B][N][N] site-major (vt[b][i][k] = component i of eigenvector k)
+int fkmc_eigvec_pipeline_dev(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, double* d_evals, double* d_out, double* d_vt);
+// fast update of the dense moves (secular.cu)
+int fkmc_fu_alloc(fkmc_ctx* ctx);
+void fkmc_fu_free(fkmc_ctx* ctx);
+int fkmc_fu_refresh(fkmc_ctx* ctx, int check);
+int fkmc_fu_evaluate(fkmc_ctx* ctx);
+int fkmc_fu_commit(fkmc_ctx* ctx);
+int fkmc_launch_secular_only(fkmc_ctx* ctx, int N, int B, const double* d_lam, const double* d_z, const double* d_rho, double* d_out);
 // chains
 int fkmc_chain_free(fkmc_ctx* ctx);
 extern "C" int fkmc_comm_destroy(fkmc_ctx* ctx);

@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(128) stein_kernel(stein_args P) {
 // sytrd (v_i in column i below the diagonal, leading 1 explicit at row i+1), tau[i] their scalars.
 __global__ void __launch_bounds__(BT_THREADS, 1)
 backtransform_kernel(const double* __restrict__ A_all, const double* __restrict__ tau_all, const double* __restrict__ zt_all, int N,
-                     double* __restrict__ evecs_all /*[B][N][N] col-major or null*/, double* __restrict__ ipr_all /*[B][N] or null*/) {
+                     double* __restrict__ evecs_all /*[B][N][N] col-major or null*/, double* __restrict__ ipr_all /*[B][N] or null*/,
+                     double* __restrict__ vt_all /*[B][N][N] site-major (vt[i][k]) or null*/) {
     extern __shared__ double zb[];  // [N][17] (padded rows)
     __shared__ double wpart[BT_THREADS / 32][BT_COLS];
     __shared__ double wfull[BT_COLS];
@@ -208,6 +209,13 @@ backtransform_kernel(const double* __restrict__ A_all, const double* __restrict_
             if (cc < ncol) ev[(size_t)(c0 + cc) * N + i] = zb[i * LDZ + cc];
         }
     }
+    if (vt_all) {
+        double* vt = vt_all + (size_t)b * N * N;
+        for (int idx = tid; idx < N * BT_COLS; idx += BT_THREADS) {
+            const int i = idx / BT_COLS, cc = idx % BT_COLS;
+            if (cc < ncol) vt[(size_t)i * N + c0 + cc] = zb[i * LDZ + cc];
+        }
+    }
     if (ipr_all) {
         // ipr_k = ||psi||_4 / ||psi||_2^2  (include/fk_mc/measures/ipr.hpp:47-53)
         double s2 = 0.0, s4 = 0.0;
@@ -233,8 +241,8 @@ backtransform_kernel(const double* __restrict__ A_all, const double* __restrict_
 
 // Eigen-decomposition of the Hamiltonians of B configurations (device f).  Outputs on the device: evals [B][N],
 // optionally evecs [B][N][N] (column-major) and ipr [B][N]; logZ etc. in d_out [B][8].  Processes the batch in chunks.
-int fkmc_eigvec_pipeline(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, double* d_evals, double* d_out,
-                         double* h_evecs, double* h_ipr_host, double* d_ipr) {
+static int eigvec_pipeline_impl(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, double* d_evals, double* d_out,
+                                double* h_evecs, double* h_ipr_host, double* d_ipr, double* d_vt) {
     const int N = ctx->N;
     const size_t NN = (size_t)N * N;
     if (sizeof(double) * (size_t)N * (BT_COLS + 1) + 4096 > ctx->smem_optin)
@@ -270,7 +278,7 @@ int fkmc_eigvec_pipeline(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, dou
         {
             fkmc_prof_scope ps(ctx, "backtransform");
             dim3 grid((N + BT_COLS - 1) / BT_COLS, nb);
-            backtransform_kernel<<<grid, BT_THREADS, smem, ctx->stream>>>(ctx->d_A, ctx->d_tau, d_zt, N, d_ev, iprp);
+            backtransform_kernel<<<grid, BT_THREADS, smem, ctx->stream>>>(ctx->d_A, ctx->d_tau, d_zt, N, d_ev, iprp, d_vt ? d_vt + (size_t)b0 * NN : nullptr);
             ctx->launches++;
         }
         if (cudaGetLastError() != cudaSuccess) { rc = fkmc_set_error(ctx, FKMC_ERR_CUDA, "eigenvector kernels failed to launch"); break; }
@@ -280,4 +288,15 @@ int fkmc_eigvec_pipeline(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, dou
     }
     cudaFree(d_zt); cudaFree(d_scr); cudaFree(d_ev); cudaFree(d_ip);
     return rc;
+}
+
+int fkmc_eigvec_pipeline(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, double* d_evals, double* d_out,
+                         double* h_evecs, double* h_ipr_host, double* d_ipr) {
+    return eigvec_pipeline_impl(ctx, d_f, B, U, mu_c, beta, d_evals, d_out, h_evecs, h_ipr_host, d_ipr, nullptr);
+}
+
+int fkmc_eigvec_pipeline_dev(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, double* d_evals, double* d_out, double* d_vt) {
+    int rc = fkmc_ensure_dense_ws(ctx);
+    if (rc) return rc;
+    return eigvec_pipeline_impl(ctx, d_f, B, U, mu_c, beta, d_evals, d_out, nullptr, nullptr, nullptr, d_vt);
 }

@@ -103,6 +103,9 @@ int fkmc_sb2st_batched(fkmc_ctx* ctx, const double* AB, int N, int B, double* d,
 int fkmc_set_option(fkmc_ctx* ctx, const char* name, int value);
 /* eigenvalues (ascending) of B symmetric tridiagonals by Sturm bisection */
 int fkmc_tridiag_eigvals_batched(fkmc_ctx* ctx, const double* d, const double* e, int N, int B, double* evals);
+/* eigenvalues (ascending) of diag(lam) + rho z z^T for B problems: lam [B][N] ascending, z [B][N], rho [B] -> lam_new [B][N].
+ * The rank-one secular solver behind chain parameter fast_update (csrc/secular.cu; the step benchmark/fast_update.cpp times). */
+int fkmc_secular_update_batched(fkmc_ctx* ctx, const double* lam, const double* z, const double* rho, int N, int B, double* lam_new);
 /* device std::mt19937 + libstdc++ distributions: mode 0 raw words, 1 uniform_int(0,V-1), 2 uniform_real(0,1) */
 int fkmc_rng_stream(fkmc_ctx* ctx, int64_t seed, int mode, int V, int count, double* out);
 
@@ -126,6 +129,13 @@ typedef struct fkmc_chain_params {
     int32_t measure_ipr;                         /* fk_mc.hxx:195: measure_ipr -> ipr_history (calc_ed(true) per measured sweep) */
     int32_t n_W;                                 /* 1-D lattices: f-f interaction W[0..n_W) (config_params::W, configuration.hpp:15-19); */
     double W[FKMC_MAX_W];                        /* ignored for D >= 2 where calc_ff_energy() == 0 (configuration.cpp:62) */
+    int32_t fast_update;                         /* exact moves only: 1 = re-weight add_remove / flip proposals through rank-one secular
+                                                    updates of the tracked eigen-decomposition (O(N^2) per proposal, an N^3 eigenvector
+                                                    update only on accept; benchmark/fast_update.cpp) instead of a fresh
+                                                    eigensolve per proposal.  Same spectra (1e-13) and accept sequence.  Needs N <= 1024,
+                                                    mc_reshuffle == 0 and 2 N^2 doubles of device memory per chain. */
+    int32_t fu_refresh_sweeps;                   /* fast_update: full re-diagonalisation + consistency check every this many sweeps
+                                                    (0: default 64) */
 } fkmc_chain_params;
 
 int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_params* p);

@@ -570,6 +570,94 @@ def test_binned_observables_within_jackknife_error():
     c.close()
 
 
+# ---------------- fast update of the dense moves: rank-one secular solver + tracked eigenvectors ----------------
+@pytest.mark.parametrize("n", [2, 7, 64, 100, 256, 576, 1024])
+def test_secular_update_stage(ctx8, n):
+    """eig(diag(lam) + rho z z^T) against LAPACK: random problems of both signs, tiny and exactly zero components, exactly
+    degenerate and nearly degenerate poles, rho = 0."""
+    rng = np.random.default_rng(n)
+    B = 8
+    lam = np.sort(rng.normal(size=(B, n)) * 2, axis=1)
+    z = rng.normal(size=(B, n))
+    z /= np.linalg.norm(z, axis=1, keepdims=True)
+    rho = np.array([2.0, -2.0, 0.37, -8.0, 1.0, -1.0, 0.0, 4.0])
+    if n > 4:
+        z[2, ::3] = 0.0                        # exact zeros: those poles stay eigenvalues
+        z[3, 1::2] *= 1e-12                    # tiny components
+        lam[4, n // 2:n // 2 + 3] = lam[4, n // 2]   # exactly degenerate poles
+        lam[5, 1:] = np.sort(lam[5, 0] + np.cumsum(np.abs(rng.normal(size=n - 1)) * 1e-9))  # a cluster with gaps ~1e-9
+        z[2] /= np.linalg.norm(z[2]); z[3] /= np.linalg.norm(z[3])
+    got = ctx8.secular_update(lam, z, rho)
+    for b in range(B):
+        ref = sl.eigvalsh(np.diag(lam[b]) + rho[b] * np.outer(z[b], z[b]))
+        scale = max(1.0, np.abs(ref).max())
+        assert np.abs(got[b] - ref).max() <= 1e-13 * scale * max(1, n // 64), (n, b)
+        assert (np.diff(got[b]) >= 0).all()
+
+
+FAST_CASES = [("cubic2d", 8, 1.0, 1.0, 0.0), ("cubic2d", 8, 4.0, 4.0, 0.5), ("cubic2d", 8, 4.0, 4.0, 1.0), ("cubic2d", 16, 2.0, 10.0, 0.3),
+              ("cubic3d", 4, 4.0, 5.0, 0.5), ("triangular", 6, 2.0, 10.0, 0.0), ("honeycomb", 6, 2.0, 10.0, 0.3), ("cubic1d", 16, 2.0, 3.0, 0.5)]
+
+
+@pytest.mark.parametrize("kind,L,U,beta,flip", FAST_CASES)
+def test_fast_update_chain_matches_oracle(kind, L, U, beta, flip):
+    """The secular fast-update path must give the oracle's (i.e. the full eigensolve's) weights, accept/reject sequence, energies and
+    final spectrum; refresh every 2 sweeps exercises the re-diagonalisation and its consistency check."""
+    nch, nsw, sl_ = 4, 5, 16
+    c = fk.Context(kind, L, max_batch=nch)
+    add = 0.0 if flip == 1.0 else 1.0
+    c.chain_init(nch, beta, U, mc_flip=flip, mc_add_remove=add, seed=32167, sweep_len=sl_, ntherm_sweeps=1, measure_energy=True,
+                 record_trace=True, max_sweeps=nsw + 1, fast_update=True, fu_refresh_sweeps=2)
+    c.chain_run_sweeps(nsw + 1)
+    tr, se, st = c.chain_get_trace(), c.chain_get_series(), c.chain_get_state(spectrum=True)
+    for ch in range(nch):
+        p = o.make_params(kind=o.KINDS[kind], L=L, beta=beta, U=U, mc_flip=flip, mc_add_remove=add, seed=32167, nsweeps=nsw, sweep_len=sl_,
+                          ntherm_sweeps=1)
+        r = o.mc_run(p, rank=ch)
+        t = r["trace"]
+        wtol = max(1e-9, TOL * float(np.abs(t["logz_new"]).max()))
+        assert np.array_equal(t["u"], tr["u"][:, ch]) and np.array_equal(t["site_a"], tr["site_a"][:, ch])
+        assert (np.abs(t["weight"] - tr["weight"][:, ch]) <= wtol * np.maximum(1.0, np.abs(t["weight"]))).all()
+        assert np.array_equal(t["accepted"], tr["accepted"][:, ch])
+        assert np.array_equal(r["f_final"], st["f"][ch]) and r["naccept"] == st["naccept"][ch]
+        assert np.abs(r["energies"] - se["energies"][:, ch]).max() <= 1e-9 * max(1.0, np.abs(r["energies"]).max())
+        assert np.abs(r["d2energies"] - se["d2energies"][:, ch]).max() <= 1e-9 * max(1.0, np.abs(r["d2energies"]).max())
+        ref = o.calc_ed(o.KINDS[kind], L, r["f_final"], U, U / 2, beta)["spectrum"]
+        assert np.abs(st["spectrum"][ch] - ref).max() <= TOL * np.abs(ref).max()
+    c.close()
+
+
+def test_fast_update_equals_full_solve_at_baseline_size():
+    """c2 shape (cubic2d L=16, beta=10, U=2): 64 chains x 12 sweeps without any refresh -- the tracked spectra stay within 1e-11 of a
+    fresh eigensolve of the final configurations, and the accept sequence equals the full-solve path's."""
+    nch, nsw, L, U, beta = 64, 12, 16, 2.0, 10.0
+    res = []
+    for fast in (False, True):
+        c = fk.Context("cubic2d", L, max_batch=nch)
+        c.chain_init(nch, beta, U, mc_flip=0.2, seed=4242, sweep_len=16, ntherm_sweeps=0, record_trace=True, max_sweeps=nsw, fast_update=fast,
+                     fu_refresh_sweeps=1000)
+        c.chain_run_sweeps(nsw)
+        res.append((c.chain_get_trace(), c.chain_get_state(spectrum=True), c.chain_get_series()))
+        if fast:
+            fresh = c.logz_ed(res[-1][1]["f"], U, U / 2, beta)["spectrum"]
+            assert np.abs(res[-1][1]["spectrum"] - fresh).max() <= 1e-11 * np.abs(fresh).max()
+        c.close()
+    (tf, sf, ef), (tq, sq, eq) = res
+    assert np.array_equal(tf["accepted"], tq["accepted"]) and np.array_equal(sf["f"], sq["f"])
+    assert np.abs(tf["weight"] - tq["weight"]).max() <= 1e-8 * max(1.0, np.abs(tf["weight"]).max())
+    assert np.abs(ef["energies"] - eq["energies"]).max() <= 1e-9 * np.abs(ef["energies"]).max()
+    assert tq["accepted"].mean() > 0.02  # some moves were accepted, i.e. the eigenvector update ran
+
+
+def test_fast_update_rejects_unsupported_setups():
+    c = fk.Context("cubic2d", 8, max_batch=2)
+    with pytest.raises(fk.FkmcError):
+        c.chain_init(2, 1.0, 1.0, cheb_moves=True, fast_update=True)
+    with pytest.raises(fk.FkmcError):
+        c.chain_init(2, 1.0, 1.0, mc_reshuffle=0.1, fast_update=True)
+    c.close()
+
+
 def test_chain_golden_trace(golden):
     for t in golden["mc_trace"]["traces"]:
         c = fk.Context("cubic2d", 8, max_batch=2)
