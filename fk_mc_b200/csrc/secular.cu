@@ -50,29 +50,50 @@ struct fu_args {
     int* flag;
 };
 
-__device__ __forceinline__ double block_sum_t(double v, double* red) { return block_sum(v, red); }
+// Block reductions written WITHOUT lane-0 predicates: nvcc 12.9 (sm_100a, -O3) folds `buf + 8 (tid >> 5)` into `buf + (tid >> 2)` under a
+// `(tid & 31) == 0` predicate and then reuses that address for unpredicated per-warp accesses of the same inlined function, which land a few
+// bytes off (compute-sanitizer: misaligned shared access).  After a butterfly reduction every lane holds the result, so all lanes store it.
+__device__ __forceinline__ double block_sum_t(double v, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    red[warp] = v;
+    __syncthreads();
+    double s = lane < nw ? red[lane] : 0.0;
+    s = warp_sum(s);
+    __syncthreads();
+    return s;
+}
+__device__ __forceinline__ double block_max_t(double v, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    red[warp] = v;
+    __syncthreads();
+    double s = lane < nw ? red[lane] : -DBL_MAX;
+    s = warp_max(s);
+    __syncthreads();
+    return s;
+}
 
 // inclusive max-scan over the block (n <= blockDim.x values, one per thread; identity -inf for the rest)
-__device__ double block_max_scan(double v, double* buf) {
+__device__ __forceinline__ double block_max_scan(double v, double* buf) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const double u = __shfl_up_sync(0xffffffffu, v, o);
         if (lane >= o) v = fmax(v, u);
     }
-    if (lane == 31) buf[warp] = v;
+    const double vlast = __shfl_sync(0xffffffffu, v, 31);
+    buf[warp] = vlast;  // every lane stores the same value (see block_sum_t)
     __syncthreads();
-    if (warp == 0) {
-        double w = lane < nw ? buf[lane] : -DBL_MAX;
+    // every warp scans the per-warp totals itself (nw <= 32)
+    double w = lane < nw ? buf[lane] : -DBL_MAX;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double u = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= o) w = fmax(w, u);
-        }
-        buf[32 + lane] = w;
+    for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w = fmax(w, u);
     }
-    __syncthreads();
-    if (warp > 0) v = fmax(v, buf[32 + warp - 1]);
+    const double prev = __shfl_sync(0xffffffffu, w, (warp + 31) & 31);  // inclusive total of the warps before this one
+    if (warp > 0) v = fmax(v, prev);
     __syncthreads();
     return v;
 }
@@ -80,7 +101,7 @@ __device__ double block_max_scan(double v, double* buf) {
 // One rank-one stage on the poles d[0..N) (ascending, strictly separated, in shared memory) with weights z2[0..N) (> 0) and
 // strength rho: thread j < N returns root j (ascending order) as (origin, mu).  sumz2 = sum z2.  Shared arrays cd / cz hold the
 // canonical problem (rho > 0): for rho < 0 the poles are negated and reversed.
-__device__ void secular_stage(int N, int j, const double* d, const double* z2, double rho, double sumz2, double* cd, double* cz, int& org_out,
+__device__ __forceinline__ void secular_stage(int N, int j, const double* d, const double* z2, double rho, double sumz2, double* cd, double* cz, int& org_out,
                               double& mu_out, bool& ok) {
     const int tid = threadIdx.x;
     const bool rev = rho < 0.0;
@@ -135,6 +156,7 @@ __device__ void secular_stage(int N, int j, const double* d, const double* z2, d
             if (fv == 0.0) break;
             // rounding level of f: when |f| is below it the root is resolved
             const double ferr = 8.0 * DBL_EPSILON * (1.0 + fabs(psi) + fabs(phi));
+            if (fabs(fv) <= ferr) break;   // m is the root to rounding: keep it
             double eta;
             if (last) {
                 // one-sided: interpolate psi by s / (dj - x) + p through value and slope -> x+ = dj + s / (1 + p) ... as a correction
@@ -164,7 +186,7 @@ __device__ void secular_stage(int N, int j, const double* d, const double* z2, d
             }
             double mn = m + eta;
             if (!(mn > lo && mn < hi)) mn = 0.5 * (lo + hi);       // safeguard: bisection
-            if (fabs(fv) <= ferr || mn == m || hi - lo <= 2.0 * DBL_EPSILON * fmax(fabs(lo), fabs(hi))) done = true;
+            if (mn == m || hi - lo <= 2.0 * DBL_EPSILON * fmax(fabs(lo), fabs(hi))) done = true;
             if (fabs(mn - m) <= 4.0 * DBL_EPSILON * fabs(mn)) done = true;
             m = mn;
             if (it == FU_MAXIT - 1 && !done) ok = false;
@@ -213,20 +235,7 @@ __global__ void __launch_bounds__(1024) fu_eval_kernel(fu_args P) {
     // scale of the spectrum (separation floor)
     double scale = 0.0;
     if (tid < N) scale = fabs(lam[tid]);
-    scale = fmax(scale, 1.0);
-    {
-        double v = warp_max(scale);
-        if ((tid & 31) == 0) red[tid >> 5] = v;
-        __syncthreads();
-        if (tid < 32) {
-            double w = tid < ((blockDim.x + 31) >> 5) ? red[tid] : 0.0;
-            w = warp_max(w);
-            if (tid == 0) red[64] = w;
-        }
-        __syncthreads();
-        scale = red[64];
-        __syncthreads();
-    }
+    scale = block_max_t(fmax(scale, 1.0), red);
     const double gmin = 4.0 * DBL_EPSILON * scale;
     double cur = (tid < N) ? lam[tid] : 0.0;   // this thread's pole of the running stage
     bool all_ok = true;
@@ -360,17 +369,7 @@ __global__ void __launch_bounds__(1024) secular_only_kernel(int N, const double*
     const double* lam = lam_all + (size_t)b * N;
     const double rho = rho_all[b];
     double scale = (tid < N) ? fmax(fabs(lam[tid]), 1.0) : 1.0;
-    scale = warp_max(scale);
-    if ((tid & 31) == 0) red[tid >> 5] = scale;
-    __syncthreads();
-    if (tid == 0) {
-        double w = 1.0;
-        for (int i = 0; i < ((int)blockDim.x + 31) / 32; ++i) w = fmax(w, red[i]);
-        red[64] = w;
-    }
-    __syncthreads();
-    scale = red[64];
-    __syncthreads();
+    scale = block_max_t(scale, red);
     const double gmin = 4.0 * DBL_EPSILON * scale;
     double v = (tid < N) ? lam[tid] - (double)tid * gmin : -DBL_MAX;
     v = block_max_scan(v, red);
