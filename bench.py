@@ -211,6 +211,8 @@ def main():
     ap.add_argument("--cores", type=int, default=0, help="(lapack-probe) worker processes")
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
+    ap.add_argument("--fast-update", action="store_true",
+                    help="dense-move workloads: rank-one secular re-weighting with tracked eigenvectors (chain parameter fast_update)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -254,8 +256,9 @@ def main():
     M, G = fk.cheb_sizes(N, 2.2)
     total_sweeps = args.warmup + args.steps
     chain0, _ = parallel.partition_chains(world * chains, world, rank)
+    fast = bool(args.fast_update and not cheb)
     ctx.chain_init(chains, beta, U, cheb_moves=cheb, seed=SEED, chain0=chain0, sweep_len=SWEEP_LEN, ntherm_sweeps=0,
-                   measure_energy=True, max_sweeps=total_sweeps)
+                   measure_energy=True, max_sweeps=total_sweeps, fast_update=fast)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     with torch.cuda.stream(stream):
@@ -267,6 +270,7 @@ def main():
         ctx.profile_reset()
         sampler = ClockSampler(local_rank) if rank == 0 else None
         launches0 = ctx.launch_count()
+        nacc0 = int(ctx.chain_get_state()["naccept"].sum())
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         torch.cuda.synchronize()
@@ -280,6 +284,7 @@ def main():
         ms_total = ev0.elapsed_time(ev1)
         clocks = sampler.stop() if sampler else None
         launches = ctx.launch_count() - launches0 + args.steps  # + the flush kernels
+        accepted = int(ctx.chain_get_state()["naccept"].sum()) - nacc0
         ctx.profile_enable(False)
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     lt = torch.tensor([launches], dtype=torch.float64, device="cuda")
@@ -292,7 +297,8 @@ def main():
 
     # per-kernel-family device time inside the timed region (events recorded on the launching stream)
     fam = {}
-    for name in ("kpm", "sytrd", "sy2sb", "sb2st", "tridiag_eig", "build_h", "chain_step"):
+    for name in ("kpm", "sytrd", "sy2sb", "sb2st", "tridiag_eig", "build_h", "chain_step", "fu_eval", "fu_prepare", "fu_gemm", "fu_refresh", "stein",
+                 "backtransform"):
         tot, n = ctx.profile_get(name)
         if n:
             fam[name] = {"ms_per_launch": tot / n, "launches": n, "share": tot / ms_total}
@@ -330,8 +336,16 @@ def main():
         rl_dense = {"kernel": dense_name + "_kernel", "bound": "tensor", "achieved": a2, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                     "frac": a2 / DMMA_PEAK_TFLOPS, "traffic": tr_d, "peak_source": "measured FP64 DMMA (tools/probe_dmma.cu)",
                     "note": "4/3 N^3 flop per matrix, all of it issued as DMMA.8x8x4 in the dense->band stage"}
+    rl_fast = None
+    if "fu_gemm" in fam:
+        # eigenvector update of the accepted moves: 2 N^3 flop each, all DMMA (csrc/secular.cu: fu_gemm_kernel)
+        tot_ms = fam["fu_gemm"]["ms_per_launch"] * fam["fu_gemm"]["launches"]
+        a3 = 2.0 * N ** 3 * accepted / (tot_ms * 1e-3) * 1e-12
+        rl_fast = {"kernel": "fu_gemm_kernel", "bound": "tensor", "achieved": a3, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                   "frac": a3 / DMMA_PEAK_TFLOPS, "traffic": None, "peak_source": "measured FP64 DMMA (tools/probe_dmma.cu)",
+                   "note": "V <- V Q on accepted moves only: 2 N^3 flop x %d accepted of %d proposals in the timed region" % (accepted, chains * SWEEP_LEN * args.steps)}
     dominant = max(fam, key=lambda k: fam[k]["share"])
-    roofline = rl_kpm if dominant == "kpm" else (rl_dense if rl_dense is not None else rl_kpm)
+    roofline = rl_kpm if dominant == "kpm" else (rl_fast if (fast and rl_fast is not None) else (rl_dense if rl_dense is not None else rl_kpm))
     roofline_dense = rl_dense
     roofline_kpm = rl_kpm
 
@@ -427,7 +441,8 @@ def main():
         line = {"metric": "metropolis_proposals_per_sec", "value": value, "unit": "proposals/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": make_config(desc, chains, U, cheb, M, G),
+                "config": dict(make_config(desc, chains, U, cheb, M, G), **({"fast_update": True} if fast else {})),
+                "accept_rate": accepted / float(chains * SWEEP_LEN * args.steps),
                 "sweeps_per_sec": value / SWEEP_LEN, "roofline": roofline, "roofline_dense": roofline_dense, "roofline_kpm": roofline_kpm,
                 "dominant_kernel": dominant, "kernels": {**fam, **sub},
                 "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks,

@@ -57,6 +57,7 @@ struct fkmc_chain_state {
     long spec_count = 0;             // measurements folded into spec_mean
     // fast update of the dense moves (secular.cu): eigenvectors of the current configurations and per-stage root data
     double* fu_vt = nullptr;         // [2][n_chains][N][N] site-major eigenvectors, double-buffered
+    double* fu_q = nullptr;          // [n_chains][N][N] right factor Q of the pending eigenvector update
     int32_t* fu_vslot = nullptr;     // [n_chains]
     double *fu_poles = nullptr, *fu_mu = nullptr, *fu_zhat = nullptr, *fu_inrm = nullptr;  // [2][n_chains][N]
     int32_t* fu_org = nullptr;       // [2][n_chains][N]

@@ -74,6 +74,16 @@ __device__ __forceinline__ double block_max_t(double v, double* red) {
     return s;
 }
 
+// 1 / x to full double precision without the special-case handling of the IEEE division sequence: MUFU.RCP64H seed (2^-23) and two
+// Newton steps.  |x| is a distance between a trial root and a pole: never zero, never denormal in practice (floors above).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+
 // inclusive max-scan over the block (n <= blockDim.x values, one per thread; identity -inf for the rest)
 __device__ __forceinline__ double block_max_scan(double v, double* buf) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = (blockDim.x + 31) >> 5;
@@ -123,7 +133,7 @@ __device__ __forceinline__ void secular_stage(int N, int j, const double* d, con
         if (!last) {
             const double xm = 0.5 * gap;
             double fm = 0.0;
-            for (int k = 0; k < N; ++k) fm += cz[k] / ((cd[k] - dl) - xm);
+            for (int k = 0; k < N; ++k) fm = fma(cz[k], fast_rcp((cd[k] - dl) - xm), fm);
             fm = fma(R, fm, 1.0);
             if (fm < 0.0) o = jc + 1;  // root in the upper half
         }
@@ -141,7 +151,7 @@ __device__ __forceinline__ void secular_stage(int N, int j, const double* d, con
             // psi: poles <= jc, phi: poles > jc; values and derivatives
             double psi = 0.0, dpsi = 0.0, phi = 0.0, dphi = 0.0;
             for (int k = 0; k < N; ++k) {   // one uniform loop for the whole warp (shared-memory broadcasts); the split point is per thread
-                const double r = 1.0 / ((cd[k] - dorg) - m);
+                const double r = fast_rcp((cd[k] - dorg) - m);
                 const double t = cz[k] * r, t2 = t * r;
                 const bool low = k <= jc;
                 psi += low ? t : 0.0;
@@ -200,7 +210,7 @@ __device__ __forceinline__ void secular_stage(int N, int j, const double* d, con
 // sites -> proposal spectrum.  One CTA per chain, one thread per root (N <= 1024).
 // shared: d[N] z2[N] cd[N] cz[N] lamn[N] zs[N] (signed z) zh[N] red[72]
 __global__ void __launch_bounds__(1024) fu_eval_kernel(fu_args P) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     const int N = P.N, c = blockIdx.x, tid = threadIdx.x;
     double* d = sm;
     double* z2 = d + N;
@@ -359,7 +369,7 @@ __global__ void __launch_bounds__(1024) fu_eval_kernel(fu_args P) {
 // stage-level entry (tests): roots of diag(lam) + rho z z^T for a batch; one CTA per problem
 __global__ void __launch_bounds__(1024) secular_only_kernel(int N, const double* __restrict__ lam_all, const double* __restrict__ z_all, const double* __restrict__ rho_all,
                                                           double* __restrict__ out_all, int* flag) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     const int b = blockIdx.x, tid = threadIdx.x;
     double* d = sm;
     double* z2 = d + N;
@@ -392,7 +402,7 @@ __global__ void __launch_bounds__(1024) secular_only_kernel(int N, const double*
 
 // accepted chains: zhat / column norms of the last stage (stage 0 of a flip already has them)
 __global__ void __launch_bounds__(1024) fu_prepare_kernel(fu_args P, const int32_t* __restrict__ accepted) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     const int N = P.N, c = blockIdx.x, tid = threadIdx.x;
     if (!accepted[c]) return;
     const int nst = P.nstage[c];
@@ -437,6 +447,10 @@ __global__ void __launch_bounds__(1024) fu_prepare_kernel(fu_args P, const int32
 }
 
 // ---- V <- V Q for accepted chains: C[i][j] = sum_k A[i][k] Q[k][j],  Q[k][j] = zhat_k inrm_j / ((p_k - p_{o_j}) - mu_j) ----
+// DMMA without the volatile qualifier (a pure function of its operands): ptxas may interleave it with the divisions that build Q
+__device__ __forceinline__ void dmma_nv(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 constexpr int GM = 128, GN = 64, GK = 32;
 constexpr int SA = GK + 4;   // row stride of the A chunk (== 4 mod 16: conflict-free fragment reads)
 constexpr int SB = GN + 4;   // row stride of the Q chunk
@@ -444,6 +458,7 @@ constexpr int SB = GN + 4;   // row stride of the Q chunk
 struct gemm_args {
     int N, n_chains, stage;
     double* vt;                // [2][C][N][N]
+    double* q;                 // [C][N][N] right factor of the accepted chains, row-major Q[k][j]
     const int32_t* vslot;
     const int32_t* accepted;
     const int32_t* nstage;
@@ -451,13 +466,40 @@ struct gemm_args {
     const int32_t* org;
 };
 
+// Q[k][j] = zhat_k inrm_j / ((p_k - p_{o_j}) - mu_j) of one stage, written once per accepted chain (N^2 divisions), so that the
+// N^3 product below is a plain GEMM whose inner loop carries no FP64 divisions competing with the DMMAs for the FP64 pipe.
+// grid (ceil(N / 32), C): one CTA fills 32 rows.
+__global__ void __launch_bounds__(256) fu_qgen_kernel(gemm_args P) {
+    const int c = blockIdx.y;
+    if (!P.accepted[c] || P.stage >= P.nstage[c]) return;
+    const int N = P.N, tid = threadIdx.x;
+    const size_t base = ((size_t)P.stage * P.n_chains + c) * N;
+    __shared__ double pk[32], zk[32];
+    const int k0 = blockIdx.x * 32;
+    if (tid < 32 && k0 + tid < N) {
+        pk[tid] = P.poles[base + k0 + tid];
+        zk[tid] = P.zhat[base + k0 + tid];
+    }
+    __syncthreads();
+    double* Q = P.q + (size_t)c * N * N;
+    for (int j = tid; j < N; j += 256) {
+        const double pj = P.poles[base + P.org[base + j]], mj = P.mu[base + j], nj = P.inrm[base + j];
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r)
+            if (k0 + r < N) Q[(size_t)(k0 + r) * N + j] = zk[r] * nj / ((pk[r] - pj) - mj);
+    }
+}
+
+// C = A Q for accepted chains: A = eigenvectors (site-major, [i][k]) in the source slot, C -> the other slot.
+// CTA tile 128 x 64, 8 warps of 32 x 32 (16 DMMA accumulators each), K in chunks of 32 staged through shared memory with register
+// prefetch of the next chunk; two CTAs per SM.
 __global__ void __launch_bounds__(256, 2) fu_gemm_kernel(gemm_args P) {
     const int c = blockIdx.y;
     if (!P.accepted[c] || P.stage >= P.nstage[c]) return;
     const int N = P.N, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int ntn = (N + GN - 1) / GN;
     const int i0 = (blockIdx.x / ntn) * GM, j0 = (blockIdx.x % ntn) * GN;
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     double* As = sm;                 // [2][GM][SA]
     double* Bs = As + 2 * GM * SA;   // [2][GK][SB]
     // stage 0 reads slot s and writes slot 1 - s; stage 1 (second half of a flip) goes back
@@ -465,19 +507,8 @@ __global__ void __launch_bounds__(256, 2) fu_gemm_kernel(gemm_args P) {
     const int src = P.stage == 0 ? s0 : 1 - s0, dst = 1 - src;
     const size_t NN = (size_t)N * N;
     const double* A = P.vt + ((size_t)src * P.n_chains + c) * NN;
+    const double* Bq = P.q + (size_t)c * NN;
     double* Cm = P.vt + ((size_t)dst * P.n_chains + c) * NN;
-    const size_t base = ((size_t)P.stage * P.n_chains + c) * N;
-    const double* pol = P.poles + base;
-    const double* zh = P.zhat + base;
-    // this thread generates column jq of the Q chunk, rows kq + 4 r
-    const int jq = tid & (GN - 1), kq = tid >> 6;
-    const int jg = j0 + jq;
-    double pj = 0.0, mj = 0.0, nj = 0.0;
-    if (jg < N) {
-        pj = pol[P.org[base + jg]];
-        mj = P.mu[base + jg];
-        nj = P.inrm[base + jg];
-    }
     const int wm = warp >> 1, wn = warp & 1;  // warp tile: rows 32 wm .. +31, cols 32 wn .. +31
     double acc[4][4][2];
 #pragma unroll
@@ -486,48 +517,40 @@ __global__ void __launch_bounds__(256, 2) fu_gemm_kernel(gemm_args P) {
         for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
     const int nchunk = (N + GK - 1) / GK;
     // A chunk: 128 rows x 32 doubles; thread loads row (tid >> 1), 16 doubles starting at 16 (tid & 1)
+    // B chunk: 32 rows x 64 doubles; thread loads row (tid >> 3), 8 doubles starting at 8 (tid & 7)
     const int ar = tid >> 1, ac = (tid & 1) * 16;
+    const int br = tid >> 3, bc = (tid & 7) * 8;
     const bool vec_ok = (N % 2 == 0);
-    double areg[16];
-    auto load_a = [&](int ch) {
-        const int gi = i0 + ar, k0 = ch * GK + ac;
-#pragma unroll
-        for (int u = 0; u < 16; u += 2) {
-            double x = 0.0, y = 0.0;
-            if (gi < N) {
-                if (vec_ok && k0 + u + 1 < N) {
-                    const double2 v = *reinterpret_cast<const double2*>(A + (size_t)gi * N + k0 + u);
-                    x = v.x; y = v.y;
-                } else {
-                    if (k0 + u < N) x = A[(size_t)gi * N + k0 + u];
-                    if (k0 + u + 1 < N) y = A[(size_t)gi * N + k0 + u + 1];
-                }
-            }
-            areg[u] = x; areg[u + 1] = y;
+    // 16-byte asynchronous copies global -> shared (LDGSTS), zero-filled past the matrix edge; odd N takes a synchronous scalar path
+    auto copy2 = [&](double* dstp, const double* M, int row, int col) {
+        if (vec_ok) {
+            const int nb = (row < N && col < N) ? 16 : 0;   // N even and col even: a pair is either inside or outside
+            const double* srcp = nb ? M + (size_t)row * N + col : M;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dstp)), "l"(srcp), "r"(nb) : "memory");
+        } else {
+            dstp[0] = (row < N && col < N) ? M[(size_t)row * N + col] : 0.0;
+            dstp[1] = (row < N && col + 1 < N) ? M[(size_t)row * N + col + 1] : 0.0;
         }
     };
-    auto store_a = [&](int buf) {
-        double* dstp = As + (size_t)buf * GM * SA + ar * SA + ac;
+    auto issue = [&](int ch, int buf) {
+        double* ap = As + (size_t)buf * GM * SA + ar * SA + ac;
 #pragma unroll
-        for (int u = 0; u < 16; u += 2) *reinterpret_cast<double2*>(dstp + u) = make_double2(areg[u], areg[u + 1]);
-    };
-    auto gen_b = [&](int ch, int buf) {
-        double* bp = Bs + (size_t)buf * GK * SB;
+        for (int u = 0; u < 16; u += 2) copy2(ap + u, A, i0 + ar, ch * GK + ac + u);
+        double* bp = Bs + (size_t)buf * GK * SB + br * SB + bc;
 #pragma unroll
-        for (int r = 0; r < GK / 4; ++r) {
-            const int kl = kq + 4 * r, kg = ch * GK + kl;
-            double q = 0.0;
-            if (kg < N && jg < N) q = zh[kg] * nj / ((pol[kg] - pj) - mj);
-            bp[kl * SB + jq] = q;
-        }
+        for (int u = 0; u < 8; u += 2) copy2(bp + u, Bq, ch * GK + br, j0 + bc + u);
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    load_a(0);
-    store_a(0);
-    gen_b(0, 0);
-    __syncthreads();
+    issue(0, 0);
     for (int ch = 0; ch < nchunk; ++ch) {
         const int buf = ch & 1;
-        if (ch + 1 < nchunk) load_a(ch + 1);           // global loads in flight during the DMMAs
+        if (ch + 1 < nchunk) {
+            issue(ch + 1, buf ^ 1);   // the other buffer was released by the barrier that ended the previous iteration
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
         const double* ap = As + (size_t)buf * GM * SA + (32 * wm) * SA;
         const double* bp = Bs + (size_t)buf * GK * SB + 32 * wn;
 #pragma unroll
@@ -540,11 +563,7 @@ __global__ void __launch_bounds__(256, 2) fu_gemm_kernel(gemm_args P) {
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
-        }
-        if (ch + 1 < nchunk) {
-            store_a(buf ^ 1);
-            gen_b(ch + 1, buf ^ 1);
+                for (int b = 0; b < 4; ++b) dmma_nv(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
         }
         __syncthreads();
     }
@@ -604,6 +623,7 @@ int fkmc_fu_alloc(fkmc_ctx* ctx) {
     auto al = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes) == cudaSuccess ? 0 : 1; };
     int rc = 0;
     rc |= al((void**)&S.fu_vt, sizeof(double) * 2 * C * N * N);
+    rc |= al((void**)&S.fu_q, sizeof(double) * C * N * N);
     rc |= al((void**)&S.fu_vslot, sizeof(int32_t) * C);
     rc |= al((void**)&S.fu_poles, sizeof(double) * 2 * C * N);
     rc |= al((void**)&S.fu_org, sizeof(int32_t) * 2 * C * N);
@@ -615,7 +635,7 @@ int fkmc_fu_alloc(fkmc_ctx* ctx) {
     rc |= al((void**)&S.fu_acc, sizeof(int32_t) * C);
     rc |= al((void**)&S.fu_fresh, sizeof(double) * C * N);
     rc |= al((void**)&S.fu_maxdev, sizeof(double) * C);
-    if (rc) return fkmc_set_error(ctx, FKMC_ERR_CUDA, "fast_update: out of device memory (2 N^2 doubles per chain)");
+    if (rc) return fkmc_set_error(ctx, FKMC_ERR_CUDA, "fast_update: out of device memory (3 N^2 doubles per chain)");
     FKMC_CUDA(ctx, cudaMemsetAsync(S.fu_vslot, 0, sizeof(int32_t) * C, ctx->stream));
     FKMC_CUDA(ctx, cudaMemsetAsync(S.fu_acc, 0, sizeof(int32_t) * C, ctx->stream));
     FKMC_CUDA(ctx, cudaMemsetAsync(S.fu_nstage, 0, sizeof(int32_t) * C, ctx->stream));
@@ -624,7 +644,7 @@ int fkmc_fu_alloc(fkmc_ctx* ctx) {
 
 void fkmc_fu_free(fkmc_ctx* ctx) {
     fkmc_chain_state& S = ctx->chain;
-    cudaFree(S.fu_vt); cudaFree(S.fu_vslot); cudaFree(S.fu_poles); cudaFree(S.fu_org); cudaFree(S.fu_mu); cudaFree(S.fu_zhat);
+    cudaFree(S.fu_vt); cudaFree(S.fu_q); cudaFree(S.fu_vslot); cudaFree(S.fu_poles); cudaFree(S.fu_org); cudaFree(S.fu_mu); cudaFree(S.fu_zhat);
     cudaFree(S.fu_inrm); cudaFree(S.fu_nstage); cudaFree(S.fu_rho); cudaFree(S.fu_acc); cudaFree(S.fu_fresh); cudaFree(S.fu_maxdev);
 }
 
@@ -678,7 +698,7 @@ int fkmc_fu_commit(fkmc_ctx* ctx) {
         ctx->launches++;
     }
     gemm_args G{};
-    G.N = N; G.n_chains = C; G.vt = S.fu_vt; G.vslot = S.fu_vslot; G.accepted = S.fu_acc; G.nstage = S.fu_nstage;
+    G.N = N; G.n_chains = C; G.vt = S.fu_vt; G.q = S.fu_q; G.vslot = S.fu_vslot; G.accepted = S.fu_acc; G.nstage = S.fu_nstage;
     G.poles = S.fu_poles; G.mu = S.fu_mu; G.zhat = S.fu_zhat; G.inrm = S.fu_inrm; G.org = S.fu_org;
     const size_t smem = sizeof(double) * (2 * GM * SA + 2 * GK * SB);
     FKMC_CUDA(ctx, cudaFuncSetAttribute(fu_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -688,8 +708,9 @@ int fkmc_fu_commit(fkmc_ctx* ctx) {
         fkmc_prof_scope ps(ctx, "fu_gemm");
         for (int st = 0; st < nstages; ++st) {
             G.stage = st;
+            fu_qgen_kernel<<<dim3((N + 31) / 32, C), 256, 0, ctx->stream>>>(G);
             fu_gemm_kernel<<<dim3(tiles, C), 256, smem, ctx->stream>>>(G);
-            ctx->launches++;
+            ctx->launches += 2;
         }
     }
     fu_commit_kernel<<<(C + 127) / 128, 128, 0, ctx->stream>>>(C, S.fu_acc, S.fu_nstage, S.fu_vslot);

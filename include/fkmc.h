@@ -133,7 +133,7 @@ typedef struct fkmc_chain_params {
                                                     updates of the tracked eigen-decomposition (O(N^2) per proposal, an N^3 eigenvector
                                                     update only on accept; benchmark/fast_update.cpp) instead of a fresh
                                                     eigensolve per proposal.  Same spectra (1e-13) and accept sequence.  Needs N <= 1024,
-                                                    mc_reshuffle == 0 and 2 N^2 doubles of device memory per chain. */
+                                                    mc_reshuffle == 0 and 3 N^2 doubles of device memory per chain. */
     int32_t fu_refresh_sweeps;                   /* fast_update: full re-diagonalisation + consistency check every this many sweeps
                                                     (0: default 64) */
 } fkmc_chain_params;
