@@ -37,6 +37,24 @@ constexpr int LAG = 3;    // steps between consecutive sweeps
 // performs in issue order, so a compiler barrier is all that is needed -- a __threadfence_block() here is a MEMBAR.SC.CTA twice per
 // step, which measured at about half of the step's latency (the step chain is the critical path of the whole kernel).
 __device__ __forceinline__ void sched_fence() { asm volatile("" ::: "memory"); }
+// progress counters with release / acquire semantics at CTA scope (PTX memory model: the band stores of a step happen-before the
+// band loads of the sweep that waits on its counter).  FKMC_SB2ST_RELAXED restores the plain volatile accesses.
+__device__ __forceinline__ int prog_load(const int* p) {
+    int v;
+#ifdef FKMC_SB2ST_RELAXED
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+#else
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+#endif
+    return v;
+}
+__device__ __forceinline__ void prog_store(int* p, int v) {
+#ifdef FKMC_SB2ST_RELAXED
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+#else
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+#endif
+}
 
 // sum over the 8 lanes of a group (m: the group's lane mask)
 __device__ __forceinline__ double gsum8(double x, unsigned m) {
@@ -108,7 +126,7 @@ __global__ void __launch_bounds__(512, 1)
 sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_all, double* __restrict__ e_all) {
     extern __shared__ double smem[];
     double* Wb = smem;                                         // [N + 16][16]
-    volatile int* prog = reinterpret_cast<volatile int*>(Wb + (size_t)(N + 16) * WD);  // [N] steps completed per sweep
+    int* prog = reinterpret_cast<int*>(Wb + (size_t)(N + 16) * WD);  // [N] steps completed per sweep
     // per-group broadcast pads (16 doubles: the reflector and the u vector of step (ii)): one store + four 128-bit loads per
     // lane instead of eight group-masked shuffles each
     double* bcast = Wb + ((((size_t)(N + 16) * WD + (N + 1) / 2 + 2)) & ~(size_t)1);  // (16-byte aligned)
@@ -139,7 +157,7 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
             const bool act = !done && s >= 0;
             // only the first sweep of the warp depends on another warp: sweep jb-1 must have finished step s+2
             if (q == 0 && act && jb > 0) {
-                while (prog[jb - 1] < s + LAG) { __nanosleep(FKMC_SB2ST_SLEEP); }
+                while (prog_load(prog + jb - 1) < s + LAG) { __nanosleep(FKMC_SB2ST_SLEEP); }
             }
             __syncwarp();
             sched_fence();
@@ -250,7 +268,7 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
             // publish progress: the writes of this step are visible before the counter moves
             __syncwarp();
             sched_fence();
-            if (act && l == 0) prog[j] = done ? (1 << 30) : s + 1;
+            if (act && l == 0) prog_store(prog + j, done ? (1 << 30) : s + 1);
             ++s;
         }
     }

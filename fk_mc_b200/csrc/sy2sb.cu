@@ -124,15 +124,23 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Per-block progress counters in shared memory.  Writer: Y adds (all lanes), __syncwarp, counter store (lane 0); reader: counter load,
-// then Y adds.  Both sides are plain shared-memory accesses of one SM, which the LSU performs in issue order, so volatile accesses with
-// compiler barriers are enough -- a release/acquire pair would also wait for the global operand loads that are in flight on purpose.
+// then Y adds.  Release / acquire at CTA scope gives the happens-before edge the PTX memory model asks for; FKMC_S1_RELAXED builds the
+// former volatile accesses (plain shared-memory accesses of one SM are performed in issue order by the LSU) for timing comparisons.
 __device__ __forceinline__ int ld_flag(const int* p) {
     int v;
+#ifdef FKMC_S1_RELAXED
     asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+#else
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+#endif
     return v;
 }
 __device__ __forceinline__ void st_flag(int* p, int v) {
+#ifdef FKMC_S1_RELAXED
     asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+#else
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+#endif
 }
 __device__ __forceinline__ void st_stream2(double* p, double a, double b, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(a), "d"(b), "l"(pol) : "memory");
