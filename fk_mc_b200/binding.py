@@ -196,6 +196,16 @@ class Context:
                                            _ptr(ev, C.c_double), _ptr(ip, C.c_double)))
         return dict(spectrum=ev, ipr=ip)
 
+    def stiffness(self, f, U, mu_c, beta, offset=0.05, wgrid=(0.0,)):
+        """measure_stiffness::accumulate on the GPU: returns (stiffness [B], conductivity [B, n_w])."""
+        f = self._f(f)
+        B = f.shape[0]
+        wg = np.ascontiguousarray(wgrid, dtype=np.float64)
+        st, cd = np.zeros(B), np.zeros((B, max(len(wg), 1)))
+        self._ck(self.lib.fkmc_stiffness_batched(self.h, _ptr(f, C.c_int32), B, C.c_double(U), C.c_double(mu_c), C.c_double(beta),
+                                                 C.c_double(offset), len(wg), _ptr(wg, C.c_double), _ptr(st, C.c_double), _ptr(cd, C.c_double)))
+        return st, cd[:, :len(wg)]
+
     def chain_ipr(self):
         ev, ip = np.zeros((self.n_chains, self.N)), np.zeros((self.n_chains, self.N))
         self._ck(self.lib.fkmc_chain_ipr(self.h, _ptr(ev, C.c_double), _ptr(ip, C.c_double)))

@@ -398,6 +398,10 @@ int fkmc_set_option(fkmc_ctx* ctx, const char* name, int value) {
         ctx->lanczos_cap = value;
         return FKMC_OK;
     }
+    if (std::string(name) == "eigvec_v1") {
+        ctx->eigvec_v1 = value != 0;
+        return FKMC_OK;
+    }
     if (std::string(name) == "kpm_v1") {
         ctx->kpm_force_v1 = value != 0;
         return FKMC_OK;

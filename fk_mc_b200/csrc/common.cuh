@@ -104,6 +104,7 @@ struct fkmc_ctx {
     int sb2st_warps = 0;        // 0: automatic
     int tiled_min = 256;        // smallest N served by the tiled dense->band kernel ("sy2sb_tiled_min")
     int lanczos_cap = 0;        // > 0: Lanczos step cap of the KPM kernels ("lanczos_max_steps"; tests force non-convergence with it)
+    int eigvec_v1 = 0;          // 1: per-reflector back-transformation kernel instead of the blocked DMMA one (cross-checks)
     int kpm_force_generic = 0;  // 1: always use the full-lattice-vector KPM kernel (for cross-checks)
     int kpm_force_v1 = 0;       // 1: single-kernel KPM (kpm.cu) even where the two-kernel 2-D path (kpm2d.cu) applies
     int kpm2_H = 0;             // radius of the cached patch tables of kpm2d.cu

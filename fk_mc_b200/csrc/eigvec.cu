@@ -237,12 +237,208 @@ backtransform_kernel(const double* __restrict__ A_all, const double* __restrict_
     }
 }
 
+
+// ---- blocked back-transformation on the FP64 tensor cores ----------------------------------------------------------------------
+// The reflectors of the one-stage tridiagonalisation are grouped 32 at a time into compact-WY block reflectors,
+// H_{i0} ... H_{i0+31} = I - V T V^T  (T upper triangular, LAPACK dlarft "forward, columnwise"), and applied from the last group to
+// the first:  Z <- Z - V (T (V^T Z)).  Both products are DMMA GEMMs; a CTA keeps 16 eigenvector columns in shared memory for the
+// whole kernel and streams V from L2.  Three block barriers per GROUP instead of two per REFLECTOR.
+constexpr int BG = 32;          // reflectors per group
+constexpr int ZLD = 20;         // row stride of the Z block in shared memory (== 4 mod 16: conflict-free B-operand reads)
+
+// T factors: grid (ngroups, B), 256 threads.  V[r][q] = A[(i0+q) N + r] for r > i0+q (leading 1 stored explicitly), 0 above.
+__global__ void __launch_bounds__(256) larft_kernel(const double* __restrict__ A_all, const double* __restrict__ tau_all, int N, int ngroups,
+                                                    double* __restrict__ T_all) {
+    __shared__ double Vs[32][33];
+    __shared__ double G[32][33];
+    const int grp = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int i0 = grp * BG;
+    const double* A = A_all + (size_t)b * N * N;
+    const double* tau = tau_all + (size_t)b * N;
+    // this thread's 4 (a, c) pairs of the Gram matrix: a = w + 8 u, c = lane
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int r0 = i0 + 1; r0 < N; r0 += 32) {
+        // tile Vs[rr][q], rr = row r0 + rr: warp w loads columns q = w, w+8, w+16, w+24 (coalesced along r)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = w + 8 * u, r = r0 + lane, col = i0 + q;
+            Vs[lane][q] = (r < N && col < N - 1 && r > col) ? A[(size_t)col * N + r] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int a = w + 8 * u;
+            double sacc = acc[u];
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) sacc = fma(Vs[rr][a], Vs[rr][lane], sacc);
+            acc[u] = sacc;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) G[w + 8 * u][lane] = acc[u];
+    __syncthreads();
+    if (w == 0) {
+        // lane i owns row i of T:  T[i][j] = -tau_j sum_{l=i}^{j-1} T[i][l] G[l][j]  (i < j),  T[j][j] = tau_j
+        double tr[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int col = i0 + j;
+            const double tj = (col < N - 1) ? tau[col] : 0.0;
+            double sacc = 0.0;
+#pragma unroll
+            for (int l = 0; l < 32; ++l)
+                if (l < j) sacc = (l >= lane) ? fma(tr[l], G[l][j], sacc) : sacc;
+            tr[j] = (j == lane) ? tj : ((j > lane) ? -tj * sacc : 0.0);
+        }
+        double* T = T_all + ((size_t)b * ngroups + grp) * BG * BG;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) T[lane * BG + j] = tr[j];
+    }
+}
+
+// Z = H_0 ... H_{n-2} Z_T for 16 eigenvector columns per CTA, then the outputs of the per-reflector kernel above.
+__global__ void __launch_bounds__(256, 1)
+backtransform_wy_kernel(const double* __restrict__ A_all, const double* __restrict__ T_all, const double* __restrict__ zt_all, int N, int ngroups,
+                        double* __restrict__ evecs_all, double* __restrict__ ipr_all, double* __restrict__ vt_all) {
+    extern __shared__ __align__(16) double zsm[];
+    const int Np = (N + 7) & ~7;                 // rows padded to the DMMA row block
+    double* Z = zsm;                             // [Np][ZLD]
+    double* Wp = Z + (size_t)Np * ZLD;           // [8 warps][32][16] partial V^T Z
+    double* W2 = Wp + 8 * 512;                   // [32][17] T (V^T Z)
+    double* Ts = W2 + 32 * 17;                   // [32][33]
+    const int b = blockIdx.y, c0 = blockIdx.x * 16, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const double* A = A_all + (size_t)b * N * N;
+    const double* zt = zt_all + (size_t)b * N * N;
+    const int ncol = min(16, N - c0);
+    for (int idx = tid; idx < Np * 16; idx += 256) {
+        const int i = idx >> 4, cc = idx & 15;
+        Z[i * ZLD + cc] = (i < N && cc < ncol) ? zt[(size_t)i * N + c0 + cc] : 0.0;
+    }
+    __syncthreads();
+    for (int grp = ngroups - 1; grp >= 0; --grp) {
+        const int i0 = grp * BG;
+        const int rlo = (i0 + 1) & ~3;           // first k4 step that can hold a non-zero of V (rows > i0)
+        // ---- (1) partial W = V^T Z over this warp's k4 steps: 4 (q blocks) x 2 (column blocks) accumulators ----
+        double acc[4][2][2];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int n = 0; n < 2; ++n) acc[a][n][0] = acc[a][n][1] = 0.0;
+        for (int r0 = rlo + 4 * warp; r0 < N; r0 += 32) {
+            const int r = r0 + t;
+            double af[4], bf[2];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int col = i0 + 8 * a + g;   // A operand: V^T[q = 8a + g][r]
+                af[a] = (r < N && col < N - 1 && r > col) ? __ldg(A + (size_t)col * N + r) : 0.0;
+            }
+#pragma unroll
+            for (int n = 0; n < 2; ++n) bf[n] = (r < Np) ? Z[r * ZLD + 8 * n + g] : 0.0;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int n = 0; n < 2; ++n) dmma884(acc[a][n][0], acc[a][n][1], af[a], bf[n]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+                Wp[warp * 512 + (8 * a + g) * 16 + 8 * n + 2 * t] = acc[a][n][0];
+                Wp[warp * 512 + (8 * a + g) * 16 + 8 * n + 2 * t + 1] = acc[a][n][1];
+            }
+        // T of this group
+        const double* T = T_all + ((size_t)b * ngroups + grp) * BG * BG;
+        for (int idx = tid; idx < BG * BG; idx += 256) Ts[(idx >> 5) * 33 + (idx & 31)] = T[idx];
+        __syncthreads();
+        // ---- (2) W = sum of the partials (fixed order); W2 = T W ----
+        {
+            const int q = tid >> 4, cc = tid & 15;   // 256 threads: rows q and q + 16
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double s = 0.0;
+#pragma unroll
+                for (int ww = 0; ww < 8; ++ww) s += Wp[ww * 512 + (q + 16 * h) * 16 + cc];
+                W2[(q + 16 * h) * 17 + cc] = s;   // W for now
+            }
+        }
+        __syncthreads();
+        double w2a = 0.0, w2b = 0.0;
+        {
+            const int q = tid >> 4, cc = tid & 15;
+            for (int l = q; l < BG; ++l) w2a = fma(Ts[q * 33 + l], W2[l * 17 + cc], w2a);           // T upper triangular
+            for (int l = q + 16; l < BG; ++l) w2b = fma(Ts[(q + 16) * 33 + l], W2[l * 17 + cc], w2b);
+        }
+        __syncthreads();
+        {
+            const int q = tid >> 4, cc = tid & 15;
+            W2[q * 17 + cc] = w2a;
+            W2[(q + 16) * 17 + cc] = w2b;
+        }
+        __syncthreads();
+        // ---- (3) Z -= V W2 over this warp's 8-row blocks ----
+        for (int rb = ((i0 + 1) & ~7) + 8 * warp; rb < N; rb += 64) {
+            const int r = rb + g;
+            double c[2][2];
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+                const double2 v = *reinterpret_cast<const double2*>(Z + r * ZLD + 8 * n + 2 * t);
+                c[n][0] = v.x;
+                c[n][1] = v.y;
+            }
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const int col = i0 + 4 * kk + t;     // A operand: -V[r][q = 4 kk + t]
+                const double av = (r < N && col < N - 1 && r > col) ? -__ldg(A + (size_t)col * N + r) : 0.0;
+#pragma unroll
+                for (int n = 0; n < 2; ++n) dmma884(c[n][0], c[n][1], av, W2[(4 * kk + t) * 17 + 8 * n + g]);
+            }
+#pragma unroll
+            for (int n = 0; n < 2; ++n) *reinterpret_cast<double2*>(Z + r * ZLD + 8 * n + 2 * t) = make_double2(c[n][0], c[n][1]);
+        }
+        __syncthreads();
+    }
+    if (evecs_all) {
+        double* ev = evecs_all + (size_t)b * N * N;
+        for (int idx = tid; idx < N * 16; idx += 256) {
+            const int cc = idx / N, i = idx % N;
+            if (cc < ncol) ev[(size_t)(c0 + cc) * N + i] = Z[i * ZLD + cc];
+        }
+    }
+    if (vt_all) {
+        double* vt = vt_all + (size_t)b * N * N;
+        for (int idx = tid; idx < N * 16; idx += 256) {
+            const int i = idx >> 4, cc = idx & 15;
+            if (cc < ncol) vt[(size_t)i * N + c0 + cc] = Z[i * ZLD + cc];
+        }
+    }
+    if (ipr_all) {
+        // ipr_k = ||psi||_4 / ||psi||_2^2  (include/fk_mc/measures/ipr.hpp:47-53): thread (cc, rl) sums rows rl, rl + 16, ...
+        const int cc = tid & 15, rl = tid >> 4;
+        double s2 = 0.0, s4 = 0.0;
+        for (int r = rl; r < N; r += 16) {
+            const double x = Z[r * ZLD + cc], x2 = x * x;
+            s2 += x2;
+            s4 = fma(x2, x2, s4);
+        }
+        __syncthreads();
+        Wp[tid] = s2;
+        Wp[256 + tid] = s4;
+        __syncthreads();
+        if (tid < ncol) {
+            double a2 = 0.0, a4 = 0.0;
+            for (int rr = 0; rr < 16; ++rr) { a2 += Wp[rr * 16 + tid]; a4 += Wp[256 + rr * 16 + tid]; }
+            ipr_all[(size_t)b * N + c0 + tid] = sqrt(sqrt(a4)) / a2;
+        }
+    }
+}
+
 }  // namespace
 
 // Eigen-decomposition of the Hamiltonians of B configurations (device f).  Outputs on the device: evals [B][N],
 // optionally evecs [B][N][N] (column-major) and ipr [B][N]; logZ etc. in d_out [B][8].  Processes the batch in chunks.
 static int eigvec_pipeline_impl(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, double* d_evals, double* d_out,
-                                double* h_evecs, double* h_ipr_host, double* d_ipr, double* d_vt) {
+                                double* h_evecs, double* h_ipr_host, double* d_ipr, double* d_vt, double* d_evecs_dev = nullptr) {
     const int N = ctx->N;
     const size_t NN = (size_t)N * N;
     if (sizeof(double) * (size_t)N * (BT_COLS + 1) + 4096 > ctx->smem_optin)
@@ -250,14 +446,23 @@ static int eigvec_pipeline_impl(fkmc_ctx* ctx, const int32_t* d_f, int B, double
     // chunk so that scratch (6 N^2 doubles per matrix) stays below ~6 GB
     int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, (size_t)(6.0e9 / (6.0 * NN * 8.0))));
     chunk = std::min(chunk, ctx->max_batch);
-    double *d_zt = nullptr, *d_scr = nullptr, *d_ev = nullptr, *d_ip = nullptr;
+    double *d_zt = nullptr, *d_scr = nullptr, *d_ev_host = nullptr, *d_ip = nullptr;
     FKMC_CUDA(ctx, cudaMalloc(&d_zt, sizeof(double) * NN * chunk));
     FKMC_CUDA(ctx, cudaMalloc(&d_scr, sizeof(double) * 5 * NN * chunk));
-    if (h_evecs) FKMC_CUDA(ctx, cudaMalloc(&d_ev, sizeof(double) * NN * chunk));
+    if (h_evecs) FKMC_CUDA(ctx, cudaMalloc(&d_ev_host, sizeof(double) * NN * chunk));
     if (!d_ipr && h_ipr_host) FKMC_CUDA(ctx, cudaMalloc(&d_ip, sizeof(double) * (size_t)N * chunk));
     int rc = FKMC_OK;
     const size_t smem = sizeof(double) * (size_t)N * (BT_COLS + 1);
     cudaFuncSetAttribute(backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // blocked (compact-WY, DMMA) back-transformation when its shared-memory footprint fits; "eigvec_v1" = 1 keeps the per-reflector kernel
+    const int ngroups = (N - 1 + BG - 1) / BG;
+    const size_t smem_wy = sizeof(double) * ((size_t)((N + 7) & ~7) * ZLD + 8 * 512 + 32 * 17 + 32 * 33);
+    const bool use_wy = !ctx->eigvec_v1 && N >= 8 && smem_wy <= ctx->smem_optin;
+    double* d_T = nullptr;
+    if (use_wy) {
+        FKMC_CUDA(ctx, cudaMalloc(&d_T, sizeof(double) * (size_t)chunk * ngroups * BG * BG));
+        cudaFuncSetAttribute(backtransform_wy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wy);
+    }
     for (int b0 = 0; b0 < B && !rc; b0 += chunk) {
         const int nb = std::min(chunk, B - b0);
         const int32_t* f = d_f + (size_t)b0 * N;
@@ -278,15 +483,23 @@ static int eigvec_pipeline_impl(fkmc_ctx* ctx, const int32_t* d_f, int B, double
         {
             fkmc_prof_scope ps(ctx, "backtransform");
             dim3 grid((N + BT_COLS - 1) / BT_COLS, nb);
-            backtransform_kernel<<<grid, BT_THREADS, smem, ctx->stream>>>(ctx->d_A, ctx->d_tau, d_zt, N, d_ev, iprp, d_vt ? d_vt + (size_t)b0 * NN : nullptr);
-            ctx->launches++;
+            double* vtp = d_vt ? d_vt + (size_t)b0 * NN : nullptr;
+            double* d_ev = d_evecs_dev ? d_evecs_dev + (size_t)b0 * NN : d_ev_host;
+            if (use_wy) {
+                larft_kernel<<<dim3(ngroups, nb), 256, 0, ctx->stream>>>(ctx->d_A, ctx->d_tau, N, ngroups, d_T);
+                backtransform_wy_kernel<<<grid, 256, smem_wy, ctx->stream>>>(ctx->d_A, d_T, d_zt, N, ngroups, d_ev, iprp, vtp);
+                ctx->launches += 2;
+            } else {
+                backtransform_kernel<<<grid, BT_THREADS, smem, ctx->stream>>>(ctx->d_A, ctx->d_tau, d_zt, N, d_ev, iprp, vtp);
+                ctx->launches++;
+            }
         }
         if (cudaGetLastError() != cudaSuccess) { rc = fkmc_set_error(ctx, FKMC_ERR_CUDA, "eigenvector kernels failed to launch"); break; }
-        if (h_evecs) cudaMemcpyAsync(h_evecs + (size_t)b0 * NN, d_ev, sizeof(double) * NN * nb, cudaMemcpyDeviceToHost, ctx->stream);
+        if (h_evecs) cudaMemcpyAsync(h_evecs + (size_t)b0 * NN, d_ev_host, sizeof(double) * NN * nb, cudaMemcpyDeviceToHost, ctx->stream);
         if (h_ipr_host && !d_ipr) cudaMemcpyAsync(h_ipr_host + (size_t)b0 * N, d_ip, sizeof(double) * (size_t)N * nb, cudaMemcpyDeviceToHost, ctx->stream);
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = fkmc_set_error(ctx, FKMC_ERR_CUDA, cudaGetErrorString(cudaGetLastError())); break; }
     }
-    cudaFree(d_zt); cudaFree(d_scr); cudaFree(d_ev); cudaFree(d_ip);
+    cudaFree(d_zt); cudaFree(d_scr); cudaFree(d_ev_host); cudaFree(d_ip); cudaFree(d_T);
     return rc;
 }
 
@@ -299,4 +512,12 @@ int fkmc_eigvec_pipeline_dev(fkmc_ctx* ctx, const int32_t* d_f, int B, double U,
     int rc = fkmc_ensure_dense_ws(ctx);
     if (rc) return rc;
     return eigvec_pipeline_impl(ctx, d_f, B, U, mu_c, beta, d_evals, d_out, nullptr, nullptr, nullptr, d_vt);
+}
+
+// both eigenvector layouts on the device: evecs [B][N][N] eigenvector-major (evecs[b][k][i]) and vt [B][N][N] site-major (vt[b][i][k])
+int fkmc_eigvec_pipeline_dev2(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, double* d_evals, double* d_out, double* d_evecs,
+                              double* d_vt) {
+    int rc = fkmc_ensure_dense_ws(ctx);
+    if (rc) return rc;
+    return eigvec_pipeline_impl(ctx, d_f, B, U, mu_c, beta, d_evals, d_out, nullptr, nullptr, nullptr, d_vt, d_evecs);
 }

@@ -1,8 +1,8 @@
-"""Measurement-sweep observables built on the GPU eigen-decomposition (fkmc_eigh_batched).
+"""Measurement-sweep observables built on the GPU eigen-decomposition.
 
-measure_stiffness::accumulate (include/fk_mc/measures/stiffness.hpp:69-187) for hypercubic lattices with t = 1: the spectrum,
-Fermi factors and eigenvectors come from the GPU; the two N x N x N contractions (V^T T V, V^T J V) and the O(N^2) Kubo sum run
-here with numpy -- this is a measurement-only path (the reference does not even register the measure at HEAD, fk_mc.hxx:101-105).
+measure_stiffness::accumulate (include/fk_mc/measures/stiffness.hpp:69-187) for hypercubic lattices: `stiffness` runs entirely on the
+GPU (fkmc_stiffness_batched: eigenvectors, V^T Jm V as a DMMA GEMM, Kubo sums); `stiffness_host_contraction` keeps the numpy version of
+the contractions as a cross-check (t = 1).  The reference does not register the measure at HEAD (fk_mc.hxx:101-105).
 """
 import numpy as np
 
@@ -16,7 +16,12 @@ def _shift_index(L, ndim):
 
 
 def stiffness(ctx, f, U, mu_c, beta, ndim=2, offset=0.05, wgrid=(0.0,)):
-    """Returns (stiffness [B], conductivity [B, n_w]) for configurations f [B, V]."""
+    """Returns (stiffness [B], conductivity [B, n_w]) for configurations f [B, V]: everything on the GPU (fkmc_stiffness_batched)."""
+    return ctx.stiffness(f, U, mu_c, beta, offset=offset, wgrid=wgrid)
+
+
+def stiffness_host_contraction(ctx, f, U, mu_c, beta, ndim=2, offset=0.05, wgrid=(0.0,)):
+    """Cross-check of fkmc_stiffness_batched: GPU eigen-decomposition, the contractions and Kubo sums in numpy."""
     r = ctx.eigh(f, U, mu_c, beta)
     B = r["spectrum"].shape[0]
     n, L = ctx.N, ctx.L

@@ -70,6 +70,12 @@ int fkmc_eigh_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, double m
  * every eigenstate; ipr: [B][N] (ipr_k <-> evals[k]).  The eigenvectors stay on the device. */
 int fkmc_ipr_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, double mu_c, double beta, double* evals, double* ipr);
 
+/* measure_stiffness::accumulate, include/fk_mc/measures/stiffness.hpp:129-187 (cubic2d / cubic3d, current along the first
+ * coordinate): calc_ed(true), mJ = V^T Jm V as a DMMA GEMM, Kubo sums on the device.  stiffness: [B]; cond: [B][n_w] optical
+ * conductivity on wgrid[n_w] with Lorentzian broadening `offset` (cond_offset, fk_mc.hxx:197); n_w may be 0. */
+int fkmc_stiffness_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, double mu_c, double beta, double offset, int n_w,
+                           const double* wgrid, double* stiffness, double* cond);
+
 /* chebyshev_eval(max_moment, grid) + calc_chebyshev, include/fk_mc/chebyshev.hpp:21-54,
  * src/configuration.cpp:94-205.  moments: [B][M] (chebyshev_cache::moments), ab: [B][4] =
  * {e_min, e_max, a, b}, logZ: [B].  M must be even. */
@@ -98,6 +104,7 @@ int fkmc_sb2st_batched(fkmc_ctx* ctx, const double* AB, int N, int B, double* d,
  *          column-major small-matrix kernel runs); for cross-checks
  *          "kpm_generic_schedule" = 1 keeps the moments kernel of csrc/kpm2d.cu on its run-time slot schedule (default 0: the
  *          compile-time schedule where one is known, i.e. cubic2d with a single hopping constant); for cross-checks
+ *          "eigvec_v1" = 1 back-transforms the eigenvectors reflector by reflector (default 0: compact-WY groups of 32 on DMMA)
  *          "lanczos_max_steps" = n > 0 lowers the Lanczos step cap of the KPM kernels (default 0: 384); the tests use it to force
  *          FKMC_ERR_NOCONV */
 int fkmc_set_option(fkmc_ctx* ctx, const char* name, int value);

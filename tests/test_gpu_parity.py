@@ -829,3 +829,32 @@ def test_stiffness_reference_goldens(U, f, golden):
     assert st[0] == pytest.approx(ref, abs=1e-8)
     assert cond[0, 0] == pytest.approx(cref[0], rel=1e-6, abs=1e-9)
     c.close()
+
+
+@pytest.mark.parametrize("kind,L,ndim", [("cubic2d", 8, 2), ("cubic3d", 4, 3), ("cubic2d", 16, 2)])
+def test_stiffness_gpu_contraction_matches_host(kind, L, ndim):
+    """fkmc_stiffness_batched (V^T Jm V on DMMA, Kubo sums on the device) against the numpy contraction of the same GPU eigenvectors and
+    against the oracle, ten frequencies (more than one accumulation pass), a batch of three configurations."""
+    from fk_mc_b200 import measures
+    U, beta = 2.0, 5.0
+    c = fk.Context(kind, L, max_batch=3)
+    n = c.N
+    fs = np.stack([o.randomize_f(7 + i, n, n // 2)[0] for i in range(3)])
+    wg = np.linspace(-3.0, 3.0, 10)
+    st, cd = c.stiffness(fs, U, U / 2, beta, offset=0.05, wgrid=wg)
+    sh, ch = measures.stiffness_host_contraction(c, fs, U, U / 2, beta, ndim=ndim, offset=0.05, wgrid=wg)
+    assert np.abs(st - sh).max() <= 1e-9 * max(1.0, np.abs(sh).max())
+    assert np.abs(cd - ch).max() <= 1e-8 * max(1.0, np.abs(ch).max())
+    if ndim == 2:
+        for b in range(3):
+            ref, cref = o.stiffness(o.KINDS[kind], L, fs[b], U, U / 2, beta, offset=0.05, wgrid=wg)
+            assert st[b] == pytest.approx(ref, abs=1e-8)
+            assert np.abs(cd[b] - cref).max() <= 1e-6 * max(1.0, np.abs(cref).max())
+    c.close()
+
+
+def test_stiffness_rejects_other_lattices():
+    c = fk.Context("triangular", 6)
+    with pytest.raises(fk.FkmcError):
+        c.stiffness(np.zeros(36, np.int32), 1.0, 0.5, 1.0)
+    c.close()
