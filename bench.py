@@ -41,6 +41,7 @@ SEED = 32167        # test/fast_update_test.cpp:48, benchmark/fast_update.cpp:15
 CPU_SWEEPS_BY_WORKLOAD = {"c5": 8, "c1": 2000, "c2": 48, "c3": 8, "c4t": 6, "c4h": 6}  # sweeps per chain in one CPU sample: about 10 s per host thread
 CPU_SWEEPS = 8
 DMMA_PEAK_TFLOPS = 37.0  # measured on this pool's B200 by tools/probe_dmma.cu (profiles/r01_probe_dmma.txt)
+DFMA_PEAK_TFLOPS = 36.8  # same probe, plain FP64 FMA
 
 
 def measured_peaks():
@@ -213,6 +214,8 @@ def main():
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: the workload's)")
     ap.add_argument("--fast-update", action="store_true",
                     help="dense-move workloads: rank-one secular re-weighting with tracked eigenvectors (chain parameter fast_update)")
+    ap.add_argument("--measure-ipr", action="store_true",
+                    help="measurement path (c): every sweep also measures the IPR of all eigenstates (calc_ed(true) per chain, ipr.hpp:39-56)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -258,7 +261,8 @@ def main():
     chain0, _ = parallel.partition_chains(world * chains, world, rank)
     fast = bool(args.fast_update and not cheb)
     ctx.chain_init(chains, beta, U, cheb_moves=cheb, seed=SEED, chain0=chain0, sweep_len=SWEEP_LEN, ntherm_sweeps=0,
-                   measure_energy=True, max_sweeps=total_sweeps, fast_update=fast)
+                   measure_energy=True, max_sweeps=total_sweeps, fast_update=fast, measure_ipr=args.measure_ipr,
+                   measure_history=False)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     with torch.cuda.stream(stream):
@@ -308,6 +312,11 @@ def main():
         if n:
             sub[name] = {"ms_per_launch": tot / n, "launches": n, "share": tot / ms_total, "part_of": "kpm"}
     peaks, peak_src = measured_peaks()
+    traffic_file = None
+    for cand in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        if os.path.exists(os.path.join(ROOT, "profiles", cand)):
+            traffic_file = cand
+            break
     # roofline of the dominant kernel (largest share of the timed region); both candidates are always reported
     rl_kpm = rl_dense = None
     if "kpm" in fam:
@@ -315,27 +324,56 @@ def main():
         achieved = bytes_launch / (fam["kpm"]["ms_per_launch"] * 1e-3) * 1e-9
         tr_k = None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["kpm"]
+            tr = json.load(open(os.path.join(ROOT, "profiles", traffic_file)))["kpm"]
             tr_k = tr["bytes_per_launch"] * chains / tr["units_per_launch"]
         except Exception:
             pass
-        rl_kpm = {"kernel": "lanczos2d_kernel + kpm_moments2d_kernel" if sub else "kpm_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                  "frac": achieved / peaks["hbm_gbs"], "traffic": tr_k, "peak_source": peak_src,
-                  "note": "algorithmic bytes of the streaming formulation (SURVEY 8d); the kernel keeps the recursion in shared memory, "
-                          "so DRAM traffic is far below it and frac exceeds 1"}
+        # What binds the fused kernels is the FP64 pipe, not HBM: flops the algorithm needs WITH locality (T_m e_j lives on the sites within m hops
+        # of j: 2m^2+2m+1 in 2-D, (2z+3) flop per element update, two patch dot products per column) plus the Lanczos steps actually taken
+        zc = {"cubic2d": 4, "triangular": 6, "honeycomb": 3, "cubic3d": 6, "cubic1d": 2}[kind]
+        half = M // 2
+        if kind in ("cubic2d", "triangular", "honeycomb"):
+            sup = lambda m: min(N, 2 * m * m + 2 * m + 1) if kind != "triangular" else min(N, 3 * m * m + 3 * m + 1)  # noqa: E731
+        else:
+            sup = lambda m: N  # noqa: E731  (3-D / 1-D run the full-lattice-vector kernel)
+        f_mom = N * (sum(sup(m) * (2 * zc + 3) for m in range(2, half + 1)) + 4 * sup(half))
+        try:
+            lz_steps = float(np.mean(ctx.kpm_last_steps(chains)))
+        except Exception:
+            lz_steps = 135.0
+        f_lz = 2 * lz_steps * N * (2 * zc + 7) / 2  # one Lanczos run delivers both e_min and e_max
+        a_fp = (f_mom + f_lz) * chains / (fam["kpm"]["ms_per_launch"] * 1e-3) * 1e-12
+        rl_kpm = {"kernel": "lanczos2d_kernel + kpm_moments2d_kernel" if sub else "kpm_kernel", "bound": "fp64", "achieved": a_fp, "peak": DFMA_PEAK_TFLOPS,
+                  "unit": "TFLOP/s", "frac": a_fp / DFMA_PEAK_TFLOPS, "traffic": tr_k, "peak_source": "measured FP64 DFMA (tools/probe_dmma.cu)",
+                  "flop_per_proposal": {"moments": f_mom, "lanczos": f_lz, "lanczos_steps": lz_steps},
+                  "hbm_contract": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                                   "peak_source": peak_src,
+                                   "note": "algorithmic bytes of the STREAMING formulation (SURVEY 8d: 24 N^2 (M/2-1) + 16 N^2 per proposal); the kernels keep "
+                                           "the recursion in shared memory and touch ~8 KB of DRAM per proposal, so this ratio exceeds 1 and bounds nothing"},
+                  "note": "the fused KPM kernels are bound by the FP64 pipe and shared-memory wavefronts (ncu: profiles/r01_ncu_summary_kpm_moments_v2.txt), "
+                          "so the roofline is flops-with-locality against the measured DFMA peak"}
     dense_name = "sy2sb" if "sy2sb" in fam else ("sytrd" if "sytrd" in fam else None)
     if dense_name:
         fl = 4.0 / 3.0 * N ** 3 * chains
         a2 = fl / (fam[dense_name]["ms_per_launch"] * 1e-3) * 1e-12
         tr_d = None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))[dense_name]
+            tr = json.load(open(os.path.join(ROOT, "profiles", traffic_file)))[dense_name]
             tr_d = tr["bytes_per_launch"] * chains / tr["units_per_launch"]
         except Exception:
             pass
         rl_dense = {"kernel": dense_name + "_kernel", "bound": "tensor", "achieved": a2, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                     "frac": a2 / DMMA_PEAK_TFLOPS, "traffic": tr_d, "peak_source": "measured FP64 DMMA (tools/probe_dmma.cu)",
                     "note": "4/3 N^3 flop per matrix, all of it issued as DMMA.8x8x4 in the dense->band stage"}
+    rl_meas = None
+    if args.measure_ipr and "sytrd" in fam:
+        # one-stage tridiagonalisation that keeps its reflectors for the back-transformation: the SYMV streams the trailing matrix once per
+        # column (8 N^3 / 6 bytes) and the rank-64 updates once per panel of 32 columns (read + write)
+        by = 8.0 * N ** 3 / 6.0 * (1.0 + 2.0 / 32.0) * chains
+        a4 = by / (fam["sytrd"]["ms_per_launch"] * 1e-3) * 1e-9
+        rl_meas = {"kernel": "sytrd_lower_kernel", "bound": "hbm", "achieved": a4, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a4 / peaks["hbm_gbs"],
+                   "traffic": None, "peak_source": peak_src,
+                   "note": "measurement path (c): eigenvectors need the reflectors of the one-stage reduction, whose SYMV half is memory bound"}
     rl_fast = None
     if "fu_gemm" in fam:
         # eigenvector update of the accepted moves: 2 N^3 flop each, all DMMA (csrc/secular.cu: fu_gemm_kernel)
@@ -346,6 +384,8 @@ def main():
                    "note": "V <- V Q on accepted moves only: 2 N^3 flop x %d accepted of %d proposals in the timed region" % (accepted, chains * SWEEP_LEN * args.steps)}
     dominant = max(fam, key=lambda k: fam[k]["share"])
     roofline = rl_kpm if dominant == "kpm" else (rl_fast if (fast and rl_fast is not None) else (rl_dense if rl_dense is not None else rl_kpm))
+    if dominant in ("sytrd", "backtransform", "stein") and rl_meas is not None:
+        roofline = rl_meas
     roofline_dense = rl_dense
     roofline_kpm = rl_kpm
 
@@ -382,7 +422,11 @@ def main():
                 acc = np.abs(w) > rng.random(chains)
                 f_host[rows[~acc], sites[~acc]] ^= 1          # reject: undo
                 lz_cur = np.where(acc, lz_new, lz_cur)
-            if cheb:                                          # measurement sweep: exact spectrum -> energy
+            if args.measure_ipr:                              # measurement sweep with eigenvectors: spectrum + IPR of every eigenstate
+                h2d += f_host.nbytes
+                r = ctx.ipr(f_host, U, U / 2, beta)
+                d2h += r["spectrum"].nbytes + r["ipr"].nbytes
+            elif cheb:                                        # measurement sweep: exact spectrum -> energy
                 h2d += f_host.nbytes
                 r = ctx.logz_ed(f_host, U, U / 2, beta)
                 d2h += r["spectrum"].nbytes + r["logZ"].nbytes
@@ -441,9 +485,11 @@ def main():
         line = {"metric": "metropolis_proposals_per_sec", "value": value, "unit": "proposals/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": dict(make_config(desc, chains, U, cheb, M, G), **({"fast_update": True} if fast else {})),
+                "config": dict(make_config(desc, chains, U, cheb, M, G), **({"fast_update": True} if fast else {}),
+                               **({"measure_ipr": True} if args.measure_ipr else {})),
                 "accept_rate": accepted / float(chains * SWEEP_LEN * args.steps),
                 "sweeps_per_sec": value / SWEEP_LEN, "roofline": roofline, "roofline_dense": roofline_dense, "roofline_kpm": roofline_kpm,
+                "roofline_fast_update": rl_fast, "roofline_measurement": rl_meas, "traffic_source": traffic_file,
                 "dominant_kernel": dominant, "kernels": {**fam, **sub},
                 "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks,
                 "final_gather_ms": gather_ms}

@@ -388,6 +388,12 @@ class Context:
         flat = lambda a: a.reshape(-1)[: m * tot.value].reshape(m, tot.value)  # noqa: E731
         return dict(n_measured=m, energies=flat(e), d2energies=flat(d2), c_energies=flat(ec))
 
+    def kpm_last_steps(self, B):
+        """Lanczos steps each of the last B KPM evaluations needed (the ARPACK iteration-count analogue)."""
+        st = np.zeros(B, dtype=np.int32)
+        self._ck(self.lib.fkmc_kpm_last_steps(self.h, int(B), _ptr(st, C.c_int32)))
+        return st
+
     def chain_series_dev(self):
         e, d2, ec, ld = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int(0)
         self._ck(self.lib.fkmc_chain_series_dev(self.h, C.byref(e), C.byref(d2), C.byref(ec), C.byref(ld)))

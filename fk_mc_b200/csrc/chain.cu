@@ -498,7 +498,11 @@ extern "C" int fkmc_chain_run_sweeps(fkmc_ctx* ctx, int n_sweeps) {
             int es = 0;
             const double* spec = S.spec[0];        // spectrum of the current configurations ...
             const int32_t* slot = S.cur_slot;      // ... in the chain's current slot (exact moves)
-            if (S.p.measure_ipr) {
+            if (S.p.measure_ipr && S.fu_vt) {
+                // fast update: the eigenvectors of the current configurations are tracked, the IPR is a reduction over them
+                int rc = fkmc_fu_ipr(ctx, S.ipr_hist + (size_t)S.measured * C * N);
+                if (rc) return rc;
+            } else if (S.p.measure_ipr) {
                 // measure_ipr::accumulate (ipr.hpp:39-56): calc_ed(true); the energy / spectrum measures that follow hit its cache
                 int rc = fkmc_eigvec_pipeline(ctx, S.f_cur, C, S.p.U, S.p.mu_c, S.p.beta, S.ipr_evals, ctx->d_out, nullptr, nullptr,
                                               S.ipr_hist + (size_t)S.measured * C * N);

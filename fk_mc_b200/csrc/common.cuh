@@ -220,6 +220,7 @@ void fkmc_fu_free(fkmc_ctx* ctx);
 int fkmc_fu_refresh(fkmc_ctx* ctx, int check);
 int fkmc_fu_evaluate(fkmc_ctx* ctx);
 int fkmc_fu_commit(fkmc_ctx* ctx);
+int fkmc_fu_ipr(fkmc_ctx* ctx, double* d_ipr);
 int fkmc_launch_secular_only(fkmc_ctx* ctx, int N, int B, const double* d_lam, const double* d_z, const double* d_rho, double* d_out);
 // chains
 int fkmc_chain_free(fkmc_ctx* ctx);

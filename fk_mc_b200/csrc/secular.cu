@@ -501,6 +501,20 @@ __global__ void fu_commit_kernel(int n_chains, const int32_t* __restrict__ accep
     if (accepted[c] && nstage[c] == 1) vslot[c] ^= 1;  // one GEMM moved the eigenvectors to the other slot; a flip's two GEMMs come back
 }
 
+// measure_ipr (include/fk_mc/measures/ipr.hpp:39-56) from the tracked eigenvectors: ipr_k = ||psi_k||_4 / ||psi_k||_2^2.  thread = state k
+__global__ void __launch_bounds__(256) fu_ipr_kernel(int N, int n_chains, const double* __restrict__ vt_all, const int32_t* __restrict__ vslot, double* __restrict__ ipr) {
+    const int c = blockIdx.y, k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= N) return;
+    const double* vt = vt_all + ((size_t)vslot[c] * n_chains + c) * (size_t)N * N;
+    double s2 = 0.0, s4 = 0.0;
+    for (int i = 0; i < N; ++i) {
+        const double x = vt[(size_t)i * N + k], x2 = x * x;
+        s2 += x2;
+        s4 = fma(x2, x2, s4);
+    }
+    ipr[(size_t)c * N + k] = sqrt(sqrt(s4)) / s2;
+}
+
 // refresh: scatter the freshly computed spectra into the chains' current slots and compare with the tracked ones
 __global__ void __launch_bounds__(256) fu_refresh_kernel(int N, int n_chains, const double* __restrict__ fresh, double* __restrict__ spec, const int32_t* __restrict__ cur_slot,
                                                         int32_t* __restrict__ vslot, double tol, int check, int* flag, double* __restrict__ maxdev) {
@@ -636,6 +650,17 @@ int fkmc_launch_secular_only(fkmc_ctx* ctx, int N, int B, const double* d_lam, c
     if (N > 1024) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "secular update: N > 1024");
     const int T = ((N + 31) / 32) * 32;
     secular_only_kernel<<<B, T, sizeof(double) * (4 * (size_t)N + 80), ctx->stream>>>(N, d_lam, d_z, d_rho, d_out, ctx->d_flag);
+    ctx->launches++;
+    FKMC_CUDA(ctx, cudaGetLastError());
+    return FKMC_OK;
+}
+
+// IPR of the chains' current eigenstates from the tracked eigenvectors (no eigensolve): d_ipr [n_chains][N]
+int fkmc_fu_ipr(fkmc_ctx* ctx, double* d_ipr) {
+    fkmc_chain_state& S = ctx->chain;
+    const int N = ctx->N, C = S.n_chains;
+    fkmc_prof_scope ps(ctx, "fu_ipr");
+    fu_ipr_kernel<<<dim3((N + 255) / 256, C), 256, 0, ctx->stream>>>(N, C, S.fu_vt, S.fu_vslot, d_ipr);
     ctx->launches++;
     FKMC_CUDA(ctx, cudaGetLastError());
     return FKMC_OK;

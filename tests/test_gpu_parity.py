@@ -649,6 +649,27 @@ def test_fast_update_equals_full_solve_at_baseline_size():
     assert tq["accepted"].mean() > 0.02  # some moves were accepted, i.e. the eigenvector update ran
 
 
+def test_fast_update_ipr_history_from_tracked_eigenvectors():
+    """With fast_update the per-sweep IPR comes from the tracked eigenvectors (no eigensolve): same values as the oracle's calc_ed(true)."""
+    nch, nsw, L, U, beta = 3, 4, 8, 4.0, 4.0
+    c = fk.Context("cubic2d", L, max_batch=nch)
+    c.chain_init(nch, beta, U, mc_flip=0.3, seed=32167, sweep_len=16, ntherm_sweeps=1, max_sweeps=nsw + 1, measure_history=True, measure_ipr=True,
+                 fast_update=True, fu_refresh_sweeps=1000)
+    c.chain_run_sweeps(nsw + 1)
+    h = c.chain_get_history()
+    for ch in range(nch):
+        p = o.make_params(kind=o.CUBIC2D, L=L, beta=beta, U=U, mc_flip=0.3, seed=32167, nsweeps=nsw, sweep_len=16, ntherm_sweeps=1, measure_ipr=True)
+        r = o.mc_run(p, rank=ch, trace=False)
+        sh, _ = o.mc_histories(p, rank=ch)
+        assert np.abs(h["spectrum_history"][:, ch] - sh).max() <= TOL * np.abs(sh).max()
+        for m in range(nsw):
+            gaps = np.minimum(np.diff(sh[m], prepend=-np.inf), np.diff(sh[m], append=np.inf))
+            iso = gaps > 1e-6 * np.abs(sh).max()
+            assert iso.sum() > 32
+            assert np.abs(h["ipr_history"][m, ch][iso] - r["ipr_history"][m][iso]).max() <= 1e-7
+    c.close()
+
+
 def test_fast_update_rejects_unsupported_setups():
     c = fk.Context("cubic2d", 8, max_batch=2)
     with pytest.raises(fk.FkmcError):
