@@ -369,7 +369,8 @@ def main():
     if args.measure_ipr and "sytrd" in fam:
         # one-stage tridiagonalisation that keeps its reflectors for the back-transformation: the SYMV streams the trailing matrix once per
         # column (8 N^3 / 6 bytes) and the rank-64 updates once per panel of 32 columns (read + write)
-        by = 8.0 * N ** 3 / 6.0 * (1.0 + 2.0 / 32.0) * chains
+        per_launch = chains * args.steps / float(fam["sytrd"]["launches"])   # the eigenvector pipeline works through the batch in chunks
+        by = 8.0 * N ** 3 / 6.0 * (1.0 + 2.0 / 32.0) * per_launch
         a4 = by / (fam["sytrd"]["ms_per_launch"] * 1e-3) * 1e-9
         rl_meas = {"kernel": "sytrd_lower_kernel", "bound": "hbm", "achieved": a4, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a4 / peaks["hbm_gbs"],
                    "traffic": None, "peak_source": peak_src,

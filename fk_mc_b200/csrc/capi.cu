@@ -181,6 +181,7 @@ int fkmc_destroy(fkmc_ctx* ctx) {
     fkmc_profile_resolve(ctx);
     fkmc_comm_destroy(ctx);
     cudaFree(ctx->d_gather);
+    cudaFree(ctx->d_ev_scratch);
     fkmc_chain_free(ctx);
     cudaFree(ctx->d_AB); cudaFree(ctx->d_kpm_steps); cudaFree(ctx->d_s1_scratch);
     cudaFree(ctx->d_nbr_idx); cudaFree(ctx->d_nbr_val); cudaFree(ctx->d_A); cudaFree(ctx->d_W); cudaFree(ctx->d_d);

@@ -129,6 +129,8 @@ struct fkmc_ctx {
     double* d_ab = nullptr;       // [max_batch][4]
     int* d_kpm_steps = nullptr;   // [max_batch] Lanczos steps of the last KPM launch (diagnostics)
     double* d_aux = nullptr;      // [max_batch][2][N] cached_exp / cached_fermi staging
+    double* d_ev_scratch = nullptr;  // eigenvector path: tridiagonal eigenvectors | inverse-iteration factors | T factors (grown on demand)
+    size_t ev_scratch_cap = 0;       // doubles
 
     // Chebyshev tables for the (M, G) last used
     int cheb_M = 0, cheb_G = 0;

@@ -443,12 +443,29 @@ static int eigvec_pipeline_impl(fkmc_ctx* ctx, const int32_t* d_f, int B, double
     const size_t NN = (size_t)N * N;
     if (sizeof(double) * (size_t)N * (BT_COLS + 1) + 4096 > ctx->smem_optin)
         return fkmc_set_error(ctx, FKMC_ERR_INVALID, "eigenvectors: N too large for the back-transformation kernel");
-    // chunk so that scratch (6 N^2 doubles per matrix) stays below ~6 GB
-    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, (size_t)(6.0e9 / (6.0 * NN * 8.0))));
+    // chunk of the batch: scratch is 6 N^2 doubles per matrix (+ N^2 for a host copy of the eigenvectors); use up to half of the free device
+    // memory, and whole waves of CTAs (the tridiagonalisation runs one CTA per matrix)
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = (size_t)12e9;
+    const double per_matrix = (6.0 + (h_evecs ? 1.0 : 0.0)) * NN * 8.0 + 32.0 * N * 8.0;
+    int chunk = (int)std::max<double>(1.0, std::min<double>((double)B, 0.5 * ((double)free_b + 8.0 * (double)ctx->ev_scratch_cap) / per_matrix));
     chunk = std::min(chunk, ctx->max_batch);
-    double *d_zt = nullptr, *d_scr = nullptr, *d_ev_host = nullptr, *d_ip = nullptr;
-    FKMC_CUDA(ctx, cudaMalloc(&d_zt, sizeof(double) * NN * chunk));
-    FKMC_CUDA(ctx, cudaMalloc(&d_scr, sizeof(double) * 5 * NN * chunk));
+    if (chunk < B && chunk > ctx->num_sms) chunk -= chunk % ctx->num_sms;
+    // the big scratch (inverse-iteration factors, tridiagonal eigenvectors, T factors) is cached in the context: allocating and freeing
+    // tens of GB per call costs more than the kernels
+    const int ngroups_a = (N - 1 + BG - 1) / BG;
+    const size_t need = (size_t)chunk * (6 * NN + (size_t)ngroups_a * BG * BG);
+    if (need > ctx->ev_scratch_cap) {
+        if (ctx->d_ev_scratch) {
+            FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_ev_scratch);
+            ctx->d_ev_scratch = nullptr;
+            ctx->ev_scratch_cap = 0;
+        }
+        FKMC_CUDA(ctx, cudaMalloc(&ctx->d_ev_scratch, sizeof(double) * need));
+        ctx->ev_scratch_cap = need;
+    }
+    double *d_zt = ctx->d_ev_scratch, *d_scr = d_zt + NN * chunk, *d_ev_host = nullptr, *d_ip = nullptr;
     if (h_evecs) FKMC_CUDA(ctx, cudaMalloc(&d_ev_host, sizeof(double) * NN * chunk));
     if (!d_ipr && h_ipr_host) FKMC_CUDA(ctx, cudaMalloc(&d_ip, sizeof(double) * (size_t)N * chunk));
     int rc = FKMC_OK;
@@ -458,9 +475,8 @@ static int eigvec_pipeline_impl(fkmc_ctx* ctx, const int32_t* d_f, int B, double
     const int ngroups = (N - 1 + BG - 1) / BG;
     const size_t smem_wy = sizeof(double) * ((size_t)((N + 7) & ~7) * ZLD + 8 * 512 + 32 * 17 + 32 * 33);
     const bool use_wy = !ctx->eigvec_v1 && N >= 8 && smem_wy <= ctx->smem_optin;
-    double* d_T = nullptr;
+    double* d_T = d_scr + 5 * NN * chunk;
     if (use_wy) {
-        FKMC_CUDA(ctx, cudaMalloc(&d_T, sizeof(double) * (size_t)chunk * ngroups * BG * BG));
         cudaFuncSetAttribute(backtransform_wy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wy);
     }
     for (int b0 = 0; b0 < B && !rc; b0 += chunk) {
@@ -499,7 +515,7 @@ static int eigvec_pipeline_impl(fkmc_ctx* ctx, const int32_t* d_f, int B, double
         if (h_ipr_host && !d_ipr) cudaMemcpyAsync(h_ipr_host + (size_t)b0 * N, d_ip, sizeof(double) * (size_t)N * nb, cudaMemcpyDeviceToHost, ctx->stream);
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = fkmc_set_error(ctx, FKMC_ERR_CUDA, cudaGetErrorString(cudaGetLastError())); break; }
     }
-    cudaFree(d_zt); cudaFree(d_scr); cudaFree(d_ev_host); cudaFree(d_ip); cudaFree(d_T);
+    cudaFree(d_ev_host); cudaFree(d_ip);
     return rc;
 }
 

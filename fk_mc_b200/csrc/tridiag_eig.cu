@@ -10,6 +10,7 @@
 // Sturm count in product form p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (no division; one
 // dependent FMA per row) with periodic power-of-two rescaling; (d_i, e_{i-1}^2) pairs are
 // broadcast from shared memory.
+#include <algorithm>
 #include <cfloat>
 
 #include "common.cuh"
@@ -258,9 +259,9 @@ tridiag_eig_kernel(const double* __restrict__ d_all, const double* __restrict__ 
         lam = 0.5 * (a + c) * sc;
         ev[k] = lam;
     }
-    // ---- fused free energy / Fermi caches / energy measure (T >= N assumed for the reduction) ----
+    // ---- fused free energy / Fermi caches / energy measure ----
     __shared__ double e0s;
-    if (tid == 0) e0s = lam;  // thread 0 holds the smallest eigenvalue
+    if (tid == 0) e0s = ev[0];  // the smallest eigenvalue (thread 0 wrote it itself: k = 0 is its first eigenvalue)
     __syncthreads();
     const double e0 = e0s;
     double lz = 0.0, ec = 0.0, d2 = 0.0;
@@ -269,9 +270,9 @@ tridiag_eig_kernel(const double* __restrict__ d_all, const double* __restrict__ 
         const double logw0 = beta * e0;
         const double w = exp(-beta * (x - e0));
         const double ex = exp(beta * x);
-        lz = log(exp(logw0) + w) - logw0;
-        ec = x / (1.0 + ex);
-        d2 = x * x / (1.0 + 0.5 * (ex + 1.0 / ex));
+        lz += log(exp(logw0) + w) - logw0;
+        ec += x / (1.0 + ex);
+        d2 += x * x / (1.0 + 0.5 * (ex + 1.0 / ex));
         if (exp_all) exp_all[(size_t)b * N + k] = ex;
 #ifndef FKMC_TRIDIAG_DEBUG
         if (fermi_all) fermi_all[(size_t)b * N + k] = 1.0 / (1.0 + ex);
@@ -321,8 +322,8 @@ int fkmc_launch_tridiag_eig(fkmc_ctx* ctx, const double* d_d, const double* d_e,
                             long evals_stride, const int32_t* d_slot, long slot_stride, double* d_out, double* d_exp,
                             double* d_fermi) {
     fkmc_prof_scope ps(ctx, "tridiag_eig");
-    if (N > 1024) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "tridiag_eig: N > 1024 not supported yet");
-    const int T = ((N + 31) / 32) * 32;
+    if (N > 8192) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "tridiag_eig: N > 8192 not supported");
+    const int T = std::min(1024, ((N + 31) / 32) * 32);  // one eigenvalue per thread up to N = 1024, several beyond
     const size_t smem = sizeof(double2) * N + sizeof(double) * 96 + sizeof(int) * T + 16;
     tridiag_eig_kernel<<<B, T, smem, ctx->stream>>>(d_d, d_e, N, beta, d_evals, evals_stride, d_slot, slot_stride, d_out, d_exp,
                                                     d_fermi, ctx->d_flag);

@@ -879,3 +879,35 @@ def test_stiffness_rejects_other_lattices():
     with pytest.raises(fk.FkmcError):
         c.stiffness(np.zeros(36, np.int32), 1.0, 0.5, 1.0)
     c.close()
+
+
+@pytest.mark.parametrize("kind,L", [("honeycomb", 34), ("cubic2d", 36)])
+def test_sizes_above_1024(kind, L):
+    """N > 1024 (e.g. the N ~ 1152 honeycomb extension of BASELINE config 4): the one-stage blocked tridiagonalisation + bisection with
+    several eigenvalues per thread; spectra, logZ, a two-chain run and the eigenvector path against the oracle."""
+    U, beta = 2.0, 10.0
+    c = fk.Context(kind, L, max_batch=2)
+    n = c.N
+    assert n > 1024
+    fs = np.stack([o.randomize_f(32167 + i, n, n // 2)[0] for i in range(2)])
+    r = c.logz_ed(fs, U, U / 2, beta, want_caches=True)
+    for b in range(2):
+        ref = o.calc_ed(o.KINDS[kind], L, fs[b], U, U / 2, beta)
+        assert np.abs(r["spectrum"][b] - ref["spectrum"]).max() <= TOL * np.abs(ref["spectrum"]).max()
+        assert abs(r["logZ"][b] - ref["logZ"]) <= TOL * abs(ref["logZ"])
+        assert np.abs(r["cached_fermi"][b] - ref["cached_fermi"]).max() <= 1e-9
+    k = c.logz_kpm(fs, U, U / 2, beta, *fk.cheb_sizes(n))
+    kref = o.calc_chebyshev(o.KINDS[kind], L, fs[0], U, U / 2, beta, *fk.cheb_sizes(n))
+    assert abs(k["logZ"][0] - kref["logZ"]) <= TOL * abs(kref["logZ"])
+    ri = c.ipr(fs[:1], U, U / 2, beta)
+    assert np.abs(ri["spectrum"][0] - r["spectrum"][0]).max() <= TOL * np.abs(r["spectrum"]).max()
+    assert (ri["ipr"][0] > 0).all() and (ri["ipr"][0] <= 1.0 + 1e-12).all()
+    c.chain_init(2, beta, U, seed=32167, sweep_len=4, ntherm_sweeps=0, record_trace=True, max_sweeps=1)
+    c.chain_run_sweeps(1)
+    tr = c.chain_get_trace()
+    for ch in range(2):
+        p = o.make_params(kind=o.KINDS[kind], L=L, beta=beta, U=U, seed=32167, nsweeps=1, sweep_len=4, ntherm_sweeps=0)
+        t = o.mc_run(p, rank=ch)["trace"]
+        assert np.array_equal(t["accepted"], tr["accepted"][:, ch]) and np.array_equal(t["site_a"], tr["site_a"][:, ch])
+        assert np.abs(t["weight"] - tr["weight"][:, ch]).max() <= max(1e-9, TOL * np.abs(t["logz_new"]).max()) * max(1.0, np.abs(t["weight"]).max())
+    c.close()
