@@ -371,6 +371,16 @@ int fkmc_sb2st_batched(fkmc_ctx* ctx, const double* AB, int N, int B, double* d,
 
 int fkmc_set_option(fkmc_ctx* ctx, const char* name, int value) {
     if (!ctx || !name) return FKMC_ERR_INVALID;
+    // options change which kernels a Metropolis step launches: a captured step graph is stale
+    if (ctx->chain.step_graph) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaGraphExecDestroy(ctx->chain.step_graph);
+        ctx->chain.step_graph = nullptr;
+    }
+    if (std::string(name) == "cuda_graph") {
+        ctx->use_graphs = value != 0;
+        return FKMC_OK;
+    }
     if (std::string(name) == "tridiag") {
         if (value != 1 && value != 2) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "tridiag must be 1 or 2");
         ctx->tridiag_mode = value;

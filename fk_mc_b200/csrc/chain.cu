@@ -321,6 +321,7 @@ int fkmc_chain_free(fkmc_ctx* ctx) {
     cudaFree(S.nf_cur); cudaFree(S.nf_prop); cudaFree(S.prop_slot); cudaFree(S.ec_cur); cudaFree(S.d2_cur);
     cudaFree(S.eff_cur); cudaFree(S.eff_prop); cudaFree(S.d_W);
     if (S.fu_vt) fkmc_fu_free(ctx);
+    if (S.step_graph) cudaGraphExecDestroy(S.step_graph);
     cudaFree(S.spec_mean); cudaFree(S.spec_hist); cudaFree(S.focc_hist); cudaFree(S.ipr_hist); cudaFree(S.ipr_evals);
     S = fkmc_chain_state();
     return FKMC_OK;
@@ -461,29 +462,62 @@ extern "C" int fkmc_chain_run_sweeps(fkmc_ctx* ctx, int n_sweeps) {
     const int C = S.n_chains, N = ctx->N;
     const int blocks = (C * 32 + 127) / 128;
     const bool exact_measure = !S.p.cheb_moves || S.p.measure_energy || S.p.measure_ipr;
+    // one Metropolis step: propose -> weight evaluation -> accept test (-> eigenvector update of the accepted chains)
+    auto step_body = [&](const trace_dev& TR) -> int {
+        {
+            fkmc_prof_scope ps(ctx, "chain_step");
+            chain_propose_kernel<<<blocks, 128, 0, ctx->stream>>>(D);
+            ctx->launches++;
+        }
+        const double *lz, *ecd2;
+        int lzs, es;
+        int rc = evaluate_proposals(ctx, &lz, &lzs, &ecd2, &es);
+        if (rc) return rc;
+        {
+            fkmc_prof_scope ps(ctx, "chain_step");
+            chain_accept_kernel<<<blocks, 128, 0, ctx->stream>>>(D, lz, lzs, ecd2, es, 0, TR);
+            ctx->launches++;
+        }
+        if (S.fu_vt && (rc = fkmc_fu_commit(ctx))) return rc;  // accepted chains: V <- V Q
+        return FKMC_OK;
+    };
+    // The step's launch arguments do not change from step to step (unless a trace row index is recorded), so it is captured once as a
+    // CUDA graph and replayed; event profiling needs the individual launches.
+    const bool use_graph = ctx->use_graphs && !ctx->profiling && !S.p.record_trace && !S.step_graph_failed && !getenv("FKMC_S1_TIMING");
     for (int sw = 0; sw < n_sweeps; ++sw) {
         for (int m = 0; m < S.p.sweep_len; ++m) {
-            {
-                fkmc_prof_scope ps(ctx, "chain_step");
-                chain_propose_kernel<<<blocks, 128, 0, ctx->stream>>>(D);
-                ctx->launches++;
-            }
-            const double *lz, *ecd2;
-            int lzs, es;
-            int rc = evaluate_proposals(ctx, &lz, &lzs, &ecd2, &es);
-            if (rc) return rc;
             trace_dev TR{};
             TR.step = -1;
             if (S.p.record_trace) {
                 TR.move = S.t_move; TR.a = S.t_a; TR.b = S.t_b; TR.acc = S.t_acc; TR.w = S.t_w; TR.u = S.t_u; TR.lz = S.t_lz;
                 TR.step = S.sweeps_done * S.p.sweep_len + m;
             }
-            {
-                fkmc_prof_scope ps(ctx, "chain_step");
-                chain_accept_kernel<<<blocks, 128, 0, ctx->stream>>>(D, lz, lzs, ecd2, es, 0, TR);
-                ctx->launches++;
+            if (use_graph && !S.step_graph && !S.step_graph_failed) {
+                const int64_t l0 = ctx->launches;
+                cudaGraph_t g = nullptr;
+                bool ok = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                if (ok) {
+                    const int rc = step_body(TR);
+                    const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+                    ok = rc == FKMC_OK && e == cudaSuccess && g != nullptr;
+                    if (ok) ok = cudaGraphInstantiate(&S.step_graph, g, 0) == cudaSuccess;
+                    if (g) cudaGraphDestroy(g);
+                }
+                S.step_graph_nodes = (int)(ctx->launches - l0);
+                ctx->launches = l0;
+                if (!ok) {
+                    cudaGetLastError();
+                    S.step_graph = nullptr;
+                    S.step_graph_failed = true;   // run eagerly from now on
+                }
             }
-            if (S.fu_vt && (rc = fkmc_fu_commit(ctx))) return rc;  // accepted chains: V <- V Q
+            if (use_graph && S.step_graph) {
+                FKMC_CUDA(ctx, cudaGraphLaunch(S.step_graph, ctx->stream));
+                ctx->launches += S.step_graph_nodes;
+            } else {
+                const int rc = step_body(TR);
+                if (rc) return rc;
+            }
         }
         if (S.fu_vt) {
             const int every = S.p.fu_refresh_sweeps > 0 ? S.p.fu_refresh_sweeps : 64;

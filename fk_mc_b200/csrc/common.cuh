@@ -31,6 +31,10 @@ struct fkmc_chain_state {
     int move_kind[3] = {0, 0, 0};
     double move_cp[3] = {0, 0, 0};  // cumulative probabilities (std::discrete_distribution)
     long sweeps_done = 0, measured = 0;
+    // one Metropolis step (propose -> evaluate -> accept [-> eigenvector update]) captured as a CUDA graph and replayed sweep_len times per sweep
+    cudaGraphExec_t step_graph = nullptr;
+    int step_graph_nodes = 0;
+    bool step_graph_failed = false;
     // device buffers
     uint32_t* mt = nullptr;     // [n_chains][625] state + index
     int32_t* f_cur = nullptr;   // [n_chains][V]
@@ -104,6 +108,7 @@ struct fkmc_ctx {
     int sb2st_warps = 0;        // 0: automatic
     int tiled_min = 256;        // smallest N served by the tiled dense->band kernel ("sy2sb_tiled_min")
     int lanczos_cap = 0;        // > 0: Lanczos step cap of the KPM kernels ("lanczos_max_steps"; tests force non-convergence with it)
+    int use_graphs = 1;         // 0: launch every kernel of a Metropolis step individually ("cuda_graph" option)
     int eigvec_v1 = 0;          // 1: per-reflector back-transformation kernel instead of the blocked DMMA one (cross-checks)
     int kpm_force_generic = 0;  // 1: always use the full-lattice-vector KPM kernel (for cross-checks)
     int kpm_force_v1 = 0;       // 1: single-kernel KPM (kpm.cu) even where the two-kernel 2-D path (kpm2d.cu) applies

@@ -104,6 +104,8 @@ int fkmc_sb2st_batched(fkmc_ctx* ctx, const double* AB, int N, int B, double* d,
  *          column-major small-matrix kernel runs); for cross-checks
  *          "kpm_generic_schedule" = 1 keeps the moments kernel of csrc/kpm2d.cu on its run-time slot schedule (default 0: the
  *          compile-time schedule where one is known, i.e. cubic2d with a single hopping constant); for cross-checks
+ *          "cuda_graph" = 0 launches the kernels of every Metropolis step one by one (default 1: fkmc_chain_run_sweeps captures a
+ *          step once and replays the graph; event profiling and trace recording also run without the graph)
  *          "eigvec_v1" = 1 back-transforms the eigenvectors reflector by reflector (default 0: compact-WY groups of 32 on DMMA)
  *          "lanczos_max_steps" = n > 0 lowers the Lanczos step cap of the KPM kernels (default 0: 384); the tests use it to force
  *          FKMC_ERR_NOCONV */

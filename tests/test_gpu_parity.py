@@ -911,3 +911,26 @@ def test_sizes_above_1024(kind, L):
         assert np.array_equal(t["accepted"], tr["accepted"][:, ch]) and np.array_equal(t["site_a"], tr["site_a"][:, ch])
         assert np.abs(t["weight"] - tr["weight"][:, ch]).max() <= max(1e-9, TOL * np.abs(t["logz_new"]).max()) * max(1.0, np.abs(t["weight"]).max())
     c.close()
+
+
+@pytest.mark.parametrize("kind,L,cheb,fast,flip", [("cubic2d", 8, True, False, 0.0), ("cubic2d", 16, False, False, 0.3), ("cubic2d", 16, False, True, 0.3),
+                                                   ("cubic3d", 4, True, False, 0.0), ("cubic2d", 32, True, False, 0.0)])
+def test_step_graph_equals_eager_launches(kind, L, cheb, fast, flip):
+    """fkmc_chain_run_sweeps replays one captured CUDA graph per Metropolis step (no trace, no profiling); the chains, series and the
+    launch count must be exactly those of the kernel-by-kernel path."""
+    nch, nsw, U, beta = 6, 3, 2.0, 5.0
+    out = []
+    for graph in (1, 0):
+        c = fk.Context(kind, L, max_batch=nch)
+        c.set_option("cuda_graph", graph)
+        c.chain_init(nch, beta, U, mc_flip=flip, cheb_moves=cheb, seed=11, sweep_len=16, ntherm_sweeps=0, max_sweeps=nsw, fast_update=fast,
+                     fu_refresh_sweeps=2)
+        l0 = c.launch_count()
+        c.chain_run_sweeps(1)
+        c.chain_run_sweeps(nsw - 1)
+        out.append((c.chain_get_state(), c.chain_get_series(), c.launch_count() - l0))
+        c.close()
+    (sg, eg, lg), (se, ee, le) = out
+    assert np.array_equal(sg["f"], se["f"]) and np.array_equal(sg["naccept"], se["naccept"]) and np.array_equal(sg["logZ"], se["logZ"])
+    assert np.array_equal(eg["energies"], ee["energies"]) and np.array_equal(eg["d2energies"], ee["d2energies"])
+    assert lg == le and lg > 0
