@@ -343,6 +343,17 @@ class Context:
         cut = lambda a: None if a is None else a[:m]  # noqa: E731
         return dict(n_measured=m, spectrum_mean=sm, spectrum_history=cut(sh), focc_history=cut(fo), ipr_history=cut(ip))
 
+    def chain_get_fsector(self):
+        """dict(n_measured, nf0, nfpi [n_measured, n_chains]): n_f(q=0) and |n_f(q=pi)| per measured sweep (fsusc0pi.hpp:36-46)."""
+        p, Cn = self.chain_params, self.n_chains
+        n0 = np.zeros((p.max_sweeps, Cn), dtype=np.int32)
+        npi = np.zeros((p.max_sweeps, Cn), dtype=np.int32)
+        n = C.c_int(0)
+        has0 = bool(p.measure_energy) or not p.cheb_moves
+        self._ck(self.lib.fkmc_chain_get_fsector(self.h, C.byref(n), _ptr(n0, C.c_int32) if has0 else None, _ptr(npi, C.c_int32)))
+        m = n.value
+        return dict(n_measured=m, nf0=n0[:m] if has0 else None, nfpi=npi[:m])
+
     def chain_get_state(self, spectrum=False):
         Cn = self.n_chains
         f = np.zeros((Cn, self.N), dtype=np.int32)

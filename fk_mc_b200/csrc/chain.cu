@@ -234,6 +234,23 @@ __global__ void chain_measure_kernel(chain_dev C, const double* __restrict__ ecd
     s_nf[o] = C.nf_cur[c];
 }
 
+// measure_nf0pi::accumulate (include/fk_mc/measures/fsusc0pi.hpp:36-46): n_f(q=0) = sum f (the nf series) and
+// |n_f(q=pi)| = |sum_i (-1)^(sum_d pos_d) f_i| (hypercubic_lattice::FFT_pi, src/lattice/hypercubic.cpp:17-28,78-83).  One warp per chain.
+__global__ void chain_nfpi_kernel(chain_dev C, int L, int ndim, int32_t* __restrict__ s_nfpi, long row) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= C.n_chains) return;
+    const int32_t* f = C.f_cur + (size_t)c * C.V;
+    int acc = 0;
+    for (int i = lane; i < C.V; i += 32) {
+        int idx = i, par = 0;
+        for (int d = 0; d < ndim; ++d) { par += idx % L; idx /= L; }
+        acc += (par & 1) ? -f[i] : f[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_nfpi[(size_t)row * C.n_chains + c] = acc < 0 ? -acc : acc;
+}
+
 __global__ void rng_stream_kernel(uint32_t* state, int64_t seed, int mode, int V, int count, double* out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     mt19937_dev g(state);
@@ -316,7 +333,7 @@ int fkmc_chain_free(fkmc_ctx* ctx) {
     if (!S.active) return FKMC_OK;
     cudaFree(S.mt); cudaFree(S.f_cur); cudaFree(S.f_prop); cudaFree(S.logz_cur); cudaFree(S.logz_prop);
     cudaFree(S.spec[0]); cudaFree(S.cur_slot); cudaFree(S.prop_move); cudaFree(S.prop_a); cudaFree(S.prop_b);
-    cudaFree(S.naccept); cudaFree(S.s_energy); cudaFree(S.s_d2energy); cudaFree(S.s_cenergy); cudaFree(S.s_nf);
+    cudaFree(S.naccept); cudaFree(S.s_energy); cudaFree(S.s_d2energy); cudaFree(S.s_cenergy); cudaFree(S.s_nf); cudaFree(S.s_nfpi);
     cudaFree(S.t_move); cudaFree(S.t_a); cudaFree(S.t_b); cudaFree(S.t_acc); cudaFree(S.t_w); cudaFree(S.t_u); cudaFree(S.t_lz);
     cudaFree(S.nf_cur); cudaFree(S.nf_prop); cudaFree(S.prop_slot); cudaFree(S.ec_cur); cudaFree(S.d2_cur);
     cudaFree(S.eff_cur); cudaFree(S.eff_prop); cudaFree(S.d_W);
@@ -392,6 +409,7 @@ extern "C" int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_par
     rc |= dev_alloc(ctx, &S.s_d2energy, rows * C);
     rc |= dev_alloc(ctx, &S.s_cenergy, rows * C);
     rc |= dev_alloc(ctx, &S.s_nf, rows * C);
+    rc |= dev_alloc(ctx, &S.s_nfpi, rows * C);
     rc |= dev_alloc(ctx, &S.nf_cur, C);
     rc |= dev_alloc(ctx, &S.nf_prop, C);
     rc |= dev_alloc(ctx, &S.prop_slot, C);
@@ -558,6 +576,11 @@ extern "C" int fkmc_chain_run_sweeps(fkmc_ctx* ctx, int n_sweeps) {
                                                                             S.measured);
                 ctx->launches++;
             }
+            {
+                fkmc_prof_scope ps(ctx, "chain_step");
+                chain_nfpi_kernel<<<blocks, 128, 0, ctx->stream>>>(D, ctx->L, ctx->ndim, S.s_nfpi, S.measured);
+                ctx->launches++;
+            }
             if (exact_measure || S.p.measure_history) {
                 fkmc_prof_scope ps(ctx, "chain_step");
                 chain_history_kernel<<<C, 256, 0, ctx->stream>>>(D, spec, (size_t)C * N, slot, N, exact_measure ? S.spec_mean : nullptr, S.spec_count,
@@ -595,6 +618,21 @@ extern "C" int fkmc_chain_get_series(fkmc_ctx* ctx, int* n_measured, double* ene
         rc |= copy_out(ctx, c_energies, S.s_cenergy, n * 8);
         rc |= copy_out(ctx, nf, S.s_nf, n * 4);
     }
+    if (rc) return rc;
+    FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FKMC_OK;
+}
+
+extern "C" int fkmc_chain_get_fsector(fkmc_ctx* ctx, int* n_measured, int32_t* nf0, int32_t* nfpi) {
+    if (!ctx) return FKMC_ERR_INVALID;
+    fkmc_chain_state& S = ctx->chain;
+    if (!S.active) return fkmc_set_error(ctx, FKMC_ERR_STATE, "no chains");
+    const size_t n = (size_t)S.measured * S.n_chains;
+    if (n_measured) *n_measured = (int)S.measured;
+    int rc = 0;
+    if (S.p.measure_energy || !S.p.cheb_moves) rc |= copy_out(ctx, nf0, S.s_nf, n * 4);
+    else if (nf0) return fkmc_set_error(ctx, FKMC_ERR_STATE, "nf0 is recorded with the energy measure");
+    rc |= copy_out(ctx, nfpi, S.s_nfpi, n * 4);
     if (rc) return rc;
     FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FKMC_OK;

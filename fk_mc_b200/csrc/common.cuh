@@ -72,6 +72,7 @@ struct fkmc_chain_state {
     double* fu_maxdev = nullptr;     // [n_chains] relative deviation tracked vs fresh spectrum at the last refresh
     double *s_energy = nullptr, *s_d2energy = nullptr, *s_cenergy = nullptr;  // [max_sweeps][n_chains]
     int32_t* s_nf = nullptr;
+    int32_t* s_nfpi = nullptr;  // [max_sweeps][n_chains] |n_f(q = pi)| = |sum_i (-1)^(x+y+..) f_i|
     // trace [max_steps][n_chains]
     int32_t *t_move = nullptr, *t_a = nullptr, *t_b = nullptr, *t_acc = nullptr;
     double *t_w = nullptr, *t_u = nullptr, *t_lz = nullptr;

@@ -123,6 +123,30 @@ def energy_report(energies, d2energies, beta, volume, max_depth=None):
     return out
 
 
+def fstats_report(nf0, nfpi, max_depth=None):
+    """save_fstats (prog/data_save.hxx:200-236): binning of n_f(q=0), n_f(q=pi), jackknife of the f-susceptibilities <n^2> - <n>^2 and of the
+    Binder cumulants 1 - <n^4> / (3 <n^2>^2) at the bin level picked for fsusc_0.  Input: 1-D series or [measurement][chain] (pooled chain-major);
+    reversed like the reference (rbegin..rend) for the binning rows."""
+    n0, npi = pool_chains(nf0), pool_chains(nfpi)
+    if max_depth is None:
+        max_depth = max_bin_depth(n0.size)
+    out = {}
+    for name, x in (("nf_0", n0), ("nf_pi", npi)):
+        rows = accumulate_binning(x[::-1], max_depth)
+        b = estimate_bin(rows)
+        out[name] = dict(binning=rows, cor_length=calc_cor_length(rows), bin=b, stats=rows[b])
+    disp = lambda x, x2: x2 - x * x  # noqa: E731
+    for name, x in (("fsusc_0", n0), ("fsusc_pi", npi)):
+        rows = accumulate_jackknife(disp, [x, x * x], max_depth)   # the reference passes these series un-reversed
+        b = estimate_bin(rows)
+        out[name] = dict(binning=rows, cor_length=calc_cor_length(rows), bin=b, stats=rows[b])
+    nf_bin = out["fsusc_0"]["bin"]
+    binder = lambda x2, x4: 1.0 - x4 / 3.0 / x2 / x2  # noqa: E731
+    out["binder_0"] = dict(bin=nf_bin, stats=jack(binder, [n0 ** 2, n0 ** 4], nf_bin))
+    out["binder_pi"] = dict(bin=nf_bin, stats=jack(binder, [npi ** 2, npi ** 4], nf_bin))
+    return out
+
+
 # ---- plaintext twin of the reference output (prog/data_save.hxx:9-30, prog/data_save.hpp:124-156, README.md:42-43) ----
 def savetxt(fname, rows):
     """gftools-style plaintext: scientific notation, space separated, one row per line (README example:

@@ -154,6 +154,9 @@ int fkmc_chain_run_sweeps(fkmc_ctx* ctx, int n_sweeps);
 /* series: [n_measured][n_chains] each (observables_t::energies, d2energies, c_energies, fk_mc.hpp:13-34); any may be NULL */
 int fkmc_chain_get_series(fkmc_ctx* ctx, int* n_measured, double* energies, double* d2energies, double* c_energies,
                           int32_t* nf);
+/* f-sector series of the measured sweeps, [n_measured][n_chains] each (measure_nf0pi, include/fk_mc/measures/fsusc0pi.hpp:36-46:
+ * observables_t::nf0 = sum_i f_i and nfpi = |sum_i (-1)^(x+y+..) f_i|); either may be NULL */
+int fkmc_chain_get_fsector(fkmc_ctx* ctx, int* n_measured, int32_t* nf0, int32_t* nfpi);
 /* state: f [n_chains][V], logZ [n_chains], naccept [n_chains] */
 int fkmc_chain_get_state(fkmc_ctx* ctx, int32_t* f, double* logZ, int64_t* naccept, double* spectrum);
 /* trace: [n_steps][n_chains] each; n_steps = sweeps run * sweep_len */

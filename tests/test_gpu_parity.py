@@ -527,6 +527,29 @@ def test_chain_histories_match_oracle(cheb):
     c.close()
 
 
+def test_fsector_series():
+    """nf0 / nfpi series (measure_nf0pi): recomputed from the focc history with the reference's staggered phase (-1)^(x+y)."""
+    nch, nsw, L = 3, 4, 8
+    c = fk.Context("cubic2d", L, max_batch=nch)
+    c.chain_init(nch, 4.0, 4.0, mc_flip=0.3, seed=5, sweep_len=16, ntherm_sweeps=1, max_sweeps=nsw + 1, measure_history=True)
+    c.chain_run_sweeps(nsw + 1)
+    fs, h = c.chain_get_fsector(), c.chain_get_history()
+    idx = np.arange(L * L)
+    phase = np.where(((idx // L) + (idx % L)) % 2 == 0, 1, -1)
+    assert fs["n_measured"] == nsw
+    assert np.array_equal(fs["nf0"], h["focc_history"].sum(axis=2))
+    assert np.array_equal(fs["nfpi"], np.abs((h["focc_history"] * phase).sum(axis=2)))
+    assert np.array_equal(fs["nf0"], c.chain_get_series()["nf"])
+    c.close()
+    c3 = fk.Context("cubic3d", 4, max_batch=2)
+    c3.chain_init(2, 2.0, 2.0, seed=5, sweep_len=16, ntherm_sweeps=0, max_sweeps=2, measure_history=True)
+    c3.chain_run_sweeps(2)
+    i3 = np.arange(64)
+    ph3 = np.where(((i3 // 16) + (i3 // 4) % 4 + i3 % 4) % 2 == 0, 1, -1)
+    assert np.array_equal(c3.chain_get_fsector()["nfpi"], np.abs((c3.chain_get_history()["focc_history"] * ph3).sum(axis=2)))
+    c3.close()
+
+
 def test_histories_off_is_a_state_error():
     c = fk.Context("cubic2d", 8, max_batch=1)
     c.chain_init(1, 1.0, 1.0, max_sweeps=2)

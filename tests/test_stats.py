@@ -98,3 +98,21 @@ def test_multi_chain_series_are_pooled_chain_major():
     # true error of the mean of all samples, from the exact AR(1) autocorrelation time
     true_err = math.sqrt((1 + rho) / (1 - rho) / x.size)
     assert 0.6 * true_err < err[8] < 1.6 * true_err
+
+
+def test_fstats_report():
+    """f-sector statistics (prog/data_save.hxx:200-236) against direct formulas at bin level 0 and against the oracle's jackknife."""
+    rng = np.random.default_rng(3)
+    nf0 = rng.integers(20, 44, size=(64, 4)).astype(float)
+    nfpi = np.abs(rng.integers(-10, 10, size=(64, 4))).astype(float)
+    rep = stats.fstats_report(nf0, nfpi, max_depth=3)
+    x = stats.pool_chains(nf0)
+    assert rep["nf_0"]["binning"][0][1] == pytest.approx(x.mean(), rel=1e-14)
+    n = x.size
+    # jackknife of x2 - x^2 at depth 0: the bias-corrected value is the unbiased variance * (n - 1) / n ... check against the oracle instead
+    ref = o.jackknife(np.stack([x, x * x, np.zeros_like(x)]), 0)   # oracle functor: e2 - de2 - e^2 with de2 = 0  ->  <x^2> - <x>^2
+    got = rep["fsusc_0"]["binning"][0]
+    assert got[1] == pytest.approx(ref[1], rel=1e-12) and got[3] == pytest.approx(ref[3], rel=1e-10)
+    b = rep["binder_pi"]["stats"]
+    y = stats.pool_chains(nfpi)
+    assert b[1] == pytest.approx(1.0 - (y ** 4).mean() / 3.0 / (y ** 2).mean() ** 2, abs=5 * b[3] + 1e-12)
