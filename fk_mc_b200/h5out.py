@@ -333,13 +333,15 @@ class H5Reader:
         return out
 
 
-def save_all_data(fname, params, energies, d2energies, c_energies, beta, volume, max_depth=None, histories=None):
+def save_all_data(fname, params, energies, d2energies, c_energies, beta, volume, max_depth=None, histories=None, nf0=None, nfpi=None):
     """Reference layout of prog/data_save.hxx (save_all_data -> save_measurements + energy / cv statistics).
 
     params: dict of run parameters (the alps::params dump); energies, d2energies, c_energies: 1-D series (one chain, or
     already pooled) or 2-D [measurement][chain] as fkmc_chain_get_series returns them -- pooled CHAIN-MAJOR like the
     reference's rank-by-rank gather (stats.pool_chains); histories: optional dict of 2-D
     [index][measurement] arrays for /mc_data (ipr_history, spectrum_history, focc_history).
+    nf0 / nfpi: optional f-sector series (fkmc_chain_get_fsector) -> /mc_data/{nf0,nfpi} and the save_fstats statistics
+    (nf_0, nf_pi, fsusc_0, fsusc_pi, binder_0, binder_pi; prog/data_save.hxx:200-236).
     Returns the per-observable statistics that were written (dict name -> (binning rows, stats 4-vector))."""
     w = H5Writer()
     w.require_group("/parameters")
@@ -370,5 +372,15 @@ def save_all_data(fname, params, energies, d2energies, c_energies, beta, volume,
     put("d2energy", rep["d2energy"]["binning"])
     put("c_energy", stats.accumulate_binning(ce[::-1], max_depth))  # the reference bins the reversed series
     put("cv", rep["cv"]["binning"])
+    if nf0 is not None and nfpi is not None:
+        w["/mc_data/nf0"] = stats.pool_chains(nf0)
+        w["/mc_data/nfpi"] = stats.pool_chains(nfpi)
+        frep = stats.fstats_report(nf0, nfpi, max_depth)
+        for name in ("nf_0", "nf_pi", "fsusc_0", "fsusc_pi"):
+            put(name, frep[name]["binning"])
+        for name in ("binder_0", "binder_pi"):   # save_bin_data: /stats only
+            st = np.array(frep[name]["stats"], dtype=np.float64)
+            w["/stats/" + name] = st
+            out[name] = (None, st)
     w.save(fname)
     return out

@@ -90,6 +90,25 @@ def test_save_all_data_layout(tmp_path):
     assert nb >= 4 and abs(val - e.mean()) < 1e-12 and err > 0
 
 
+def test_save_all_data_multi_chain_and_fsector(tmp_path):
+    """[measurement][chain] series are written chain after chain (the reference's gathered ranks) and the f-sector statistics of
+    save_fstats (prog/data_save.hxx:200-236) land under /stats and /binning."""
+    rng = np.random.default_rng(2)
+    n_meas, n_chains = 64, 8
+    e = rng.standard_normal((n_meas, n_chains))
+    nf0 = rng.integers(20, 44, size=(n_meas, n_chains))
+    nfpi = np.abs(rng.integers(-9, 9, size=(n_meas, n_chains)))
+    fn = str(tmp_path / "o.h5")
+    h5out.save_all_data(fn, dict(beta=1.0), e, e * e, e, 1.0, 64, nf0=nf0, nfpi=nfpi)
+    t = h5out.H5Reader(fn).tree()
+    assert np.array_equal(t["/mc_data/energies"][:n_meas], e[:, 0]) and np.array_equal(t["/mc_data/energies"][n_meas:2 * n_meas], e[:, 1])
+    assert np.array_equal(t["/mc_data/nf0"][:n_meas], nf0[:, 0])
+    frep = stats.fstats_report(nf0, nfpi, stats.max_bin_depth(e.size))
+    for name in ("nf_0", "nf_pi", "fsusc_0", "fsusc_pi", "binder_0", "binder_pi"):
+        assert np.allclose(t["/stats/" + name], frep[name]["stats"]), name
+    assert t["/binning/fsusc_pi"].shape[1] == 5 and "/binning/binder_0" not in t
+
+
 def test_cpp_data_save_header(tmp_path):
     """include/fk_mc_b200/data_save.hpp (C++ twin of stats.py + h5out.py): the file it writes is read back with the Python reader
     and its statistics are compared with the Python implementation on the same series."""
