@@ -32,7 +32,7 @@ class ChainParams(C.Structure):
                 ("nf_start", C.c_int32), ("sweep_len", C.c_int32), ("ntherm_sweeps", C.c_int32),
                 ("measure_energy", C.c_int32), ("record_trace", C.c_int32), ("max_sweeps", C.c_int32),
                 ("measure_history", C.c_int32), ("measure_ipr", C.c_int32), ("n_W", C.c_int32), ("W", C.c_double * 8),
-                ("fast_update", C.c_int32), ("fu_refresh_sweeps", C.c_int32)]
+                ("measure_eigenfunctions", C.c_int32), ("fast_update", C.c_int32), ("fu_refresh_sweeps", C.c_int32)]
 
 
 def build_library(force=False):
@@ -299,7 +299,7 @@ class Context:
     def chain_init(self, n_chains, beta, U, mu_c=None, mu_f=None, mc_flip=0.0, mc_add_remove=1.0, mc_reshuffle=0.0,
                    cheb_moves=False, cheb_prefactor=2.2, seed=32167, chain0=0, nf_start=None, sweep_len=16, ntherm_sweeps=1,
                    measure_energy=True, record_trace=False, max_sweeps=64, measure_history=False, measure_ipr=False, W=(),
-                   fast_update=False, fu_refresh_sweeps=0):
+                   fast_update=False, fu_refresh_sweeps=0, measure_eigenfunctions=False):
         W = [float(w) for w in W]
         if len(W) > 8:
             raise FkmcError(1, "at most 8 f-f interaction terms")
@@ -307,7 +307,8 @@ class Context:
                         mc_reshuffle, int(cheb_moves), cheb_prefactor, seed, chain0,
                         self.N // 2 if nf_start is None else nf_start, sweep_len, ntherm_sweeps, int(measure_energy),
                         int(record_trace), max_sweeps, int(measure_history), int(measure_ipr), len(W),
-                        (C.c_double * 8)(*(W + [0.0] * (8 - len(W)))), int(fast_update), int(fu_refresh_sweeps))
+                        (C.c_double * 8)(*(W + [0.0] * (8 - len(W)))), int(measure_eigenfunctions), int(fast_update),
+                        int(fu_refresh_sweeps))
         self._ck(self.lib.fkmc_chain_init(self.h, int(n_chains), C.byref(p)))
         self.chain_params = p
         self.n_chains = n_chains
@@ -331,7 +332,7 @@ class Context:
         """Per-sweep histories: dict(n_measured, spectrum_mean [C,N], spectrum_history / focc_history / ipr_history [n,C,N]);
         entries whose measure is off are None."""
         p, Cn, N = self.chain_params, self.n_chains, self.N
-        exact = (not p.cheb_moves) or p.measure_energy or p.measure_ipr
+        exact = (not p.cheb_moves) or p.measure_energy or p.measure_ipr or p.measure_eigenfunctions
         sm = np.zeros((Cn, N)) if exact else None
         sh = np.zeros((p.max_sweeps, Cn, N)) if exact and p.measure_history else None
         fo = np.zeros((p.max_sweeps, Cn, N), dtype=np.int32) if p.measure_history else None
@@ -342,6 +343,14 @@ class Context:
         m = n.value
         cut = lambda a: None if a is None else a[:m]  # noqa: E731
         return dict(n_measured=m, spectrum_mean=sm, spectrum_history=cut(sh), focc_history=cut(fo), ipr_history=cut(ip))
+
+    def chain_get_eigenfunctions(self):
+        """eigenfunctions_history: [n_measured, n_chains, N, N] with [..., i, k] = component i of eigenvector k."""
+        p, Cn, N = self.chain_params, self.n_chains, self.N
+        ev = np.zeros((p.max_sweeps, Cn, N, N))
+        n = C.c_int(0)
+        self._ck(self.lib.fkmc_chain_get_eigenfunctions(self.h, C.byref(n), _ptr(ev, C.c_double)))
+        return np.transpose(ev[:n.value], (0, 1, 3, 2))   # stored eigenvector-major (column-major matrix)
 
     def chain_get_fsector(self):
         """dict(n_measured, nf0, nfpi [n_measured, n_chains]): n_f(q=0) and |n_f(q=pi)| per measured sweep (fsusc0pi.hpp:36-46)."""

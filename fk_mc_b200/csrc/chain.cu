@@ -339,7 +339,7 @@ int fkmc_chain_free(fkmc_ctx* ctx) {
     cudaFree(S.eff_cur); cudaFree(S.eff_prop); cudaFree(S.d_W);
     if (S.fu_vt) fkmc_fu_free(ctx);
     if (S.step_graph) cudaGraphExecDestroy(S.step_graph);
-    cudaFree(S.spec_mean); cudaFree(S.spec_hist); cudaFree(S.focc_hist); cudaFree(S.ipr_hist); cudaFree(S.ipr_evals);
+    cudaFree(S.spec_mean); cudaFree(S.spec_hist); cudaFree(S.focc_hist); cudaFree(S.ipr_hist); cudaFree(S.ipr_evals); cudaFree(S.eig_hist);
     S = fkmc_chain_state();
     return FKMC_OK;
 }
@@ -385,7 +385,7 @@ extern "C" int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_par
     }
     // which measures run (fk_mc.hxx:94-124): energy + spectrum whenever an exact spectrum exists per sweep (exact moves, or
     // measure_energy / measure_ipr asked for it); spectrum_history and focc_history with measure_history; ipr with measure_ipr
-    const bool exact_measure = !p->cheb_moves || p->measure_energy || p->measure_ipr;
+    const bool exact_measure = !p->cheb_moves || p->measure_energy || p->measure_ipr || p->measure_eigenfunctions;
     if (exact_measure) {
         int rc = fkmc_ensure_dense_ws(ctx);
         if (rc) return rc;
@@ -423,10 +423,9 @@ extern "C" int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_par
         if (p->measure_history) rc |= dev_alloc(ctx, &S.spec_hist, rows * C * V);
     }
     if (p->measure_history) rc |= dev_alloc(ctx, &S.focc_hist, rows * C * V);
-    if (p->measure_ipr) {
-        rc |= dev_alloc(ctx, &S.ipr_hist, rows * C * V);
-        rc |= dev_alloc(ctx, &S.ipr_evals, C * V);
-    }
+    if (p->measure_ipr) rc |= dev_alloc(ctx, &S.ipr_hist, rows * C * V);
+    if (p->measure_ipr || p->measure_eigenfunctions) rc |= dev_alloc(ctx, &S.ipr_evals, C * V);
+    if (p->measure_eigenfunctions) rc |= dev_alloc(ctx, &S.eig_hist, rows * C * V * V);
     if (p->record_trace) {
         rc |= dev_alloc(ctx, &S.t_move, steps * C); rc |= dev_alloc(ctx, &S.t_a, steps * C); rc |= dev_alloc(ctx, &S.t_b, steps * C);
         rc |= dev_alloc(ctx, &S.t_acc, steps * C); rc |= dev_alloc(ctx, &S.t_w, steps * C); rc |= dev_alloc(ctx, &S.t_u, steps * C);
@@ -550,7 +549,14 @@ extern "C" int fkmc_chain_run_sweeps(fkmc_ctx* ctx, int n_sweeps) {
             int es = 0;
             const double* spec = S.spec[0];        // spectrum of the current configurations ...
             const int32_t* slot = S.cur_slot;      // ... in the chain's current slot (exact moves)
-            if (S.p.measure_ipr && S.fu_vt) {
+            if (S.p.measure_eigenfunctions) {
+                // measure_eigenfunctions (+ measure_ipr): one calc_ed(true) serves both; the spectrum / energy measures hit its cache
+                int rc = fkmc_eigvec_pipeline_dev2(ctx, S.f_cur, C, S.p.U, S.p.mu_c, S.p.beta, S.ipr_evals, ctx->d_out,
+                                                   S.eig_hist + (size_t)S.measured * C * N * N, nullptr,
+                                                   S.p.measure_ipr ? S.ipr_hist + (size_t)S.measured * C * N : nullptr);
+                if (rc) return rc;
+                if (S.p.cheb_moves) { ecd2 = ctx->d_out; es = 8; spec = S.ipr_evals; slot = nullptr; }
+            } else if (S.p.measure_ipr && S.fu_vt) {
                 // fast update: the eigenvectors of the current configurations are tracked, the IPR is a reduction over them
                 int rc = fkmc_fu_ipr(ctx, S.ipr_hist + (size_t)S.measured * C * N);
                 if (rc) return rc;
@@ -707,6 +713,19 @@ extern "C" int fkmc_chain_get_history(fkmc_ctx* ctx, int* n_measured, double* sp
     rc |= copy_out(ctx, spectrum_history, S.spec_hist, n * 8);
     rc |= copy_out(ctx, focc_history, S.focc_hist, n * 4);
     rc |= copy_out(ctx, ipr_history, S.ipr_hist, n * 8);
+    if (rc) return rc;
+    FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FKMC_OK;
+}
+
+extern "C" int fkmc_chain_get_eigenfunctions(fkmc_ctx* ctx, int* n_measured, double* evecs) {
+    if (!ctx) return FKMC_ERR_INVALID;
+    fkmc_chain_state& S = ctx->chain;
+    if (!S.active) return fkmc_set_error(ctx, FKMC_ERR_STATE, "no chains");
+    if (!S.eig_hist) return fkmc_set_error(ctx, FKMC_ERR_STATE, "measure_eigenfunctions is off");
+    if (n_measured) *n_measured = (int)S.measured;
+    const size_t N = ctx->N;
+    int rc = copy_out(ctx, evecs, S.eig_hist, (size_t)S.measured * S.n_chains * N * N * 8);
     if (rc) return rc;
     FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FKMC_OK;

@@ -57,6 +57,7 @@ struct fkmc_chain_state {
     double* spec_hist = nullptr;     // [max_sweeps][n_chains][N]
     int32_t* focc_hist = nullptr;    // [max_sweeps][n_chains][V]
     double* ipr_hist = nullptr;      // [max_sweeps][n_chains][N]
+    double* eig_hist = nullptr;      // [max_sweeps][n_chains][N][N] eigenvector-major (== column-major matrix)
     double* ipr_evals = nullptr;     // [n_chains][N] spectrum of the eigenvector solve of the last measured sweep
     long spec_count = 0;             // measurements folded into spec_mean
     // fast update of the dense moves (secular.cu): eigenvectors of the current configurations and per-stage root data
@@ -221,6 +222,8 @@ int fkmc_launch_kpm2d(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double
 int fkmc_eigvec_pipeline(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, double* d_evals, double* d_out,
                          double* h_evecs, double* h_ipr_host, double* d_ipr);
 // eigenvector path with device outputs only: evals [B][N], out [B][8], vt [B][N][N] site-major (vt[b][i][k] = component i of eigenvector k)
+int fkmc_eigvec_pipeline_dev2(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, double* d_evals, double* d_out, double* d_evecs,
+                              double* d_vt, double* d_ipr);
 int fkmc_eigvec_pipeline_dev(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, double* d_evals, double* d_out, double* d_vt);
 // fast update of the dense moves (secular.cu)
 int fkmc_fu_alloc(fkmc_ctx* ctx);

@@ -532,8 +532,8 @@ int fkmc_eigvec_pipeline_dev(fkmc_ctx* ctx, const int32_t* d_f, int B, double U,
 
 // both eigenvector layouts on the device: evecs [B][N][N] eigenvector-major (evecs[b][k][i]) and vt [B][N][N] site-major (vt[b][i][k])
 int fkmc_eigvec_pipeline_dev2(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, double* d_evals, double* d_out, double* d_evecs,
-                              double* d_vt) {
+                              double* d_vt, double* d_ipr) {
     int rc = fkmc_ensure_dense_ws(ctx);
     if (rc) return rc;
-    return eigvec_pipeline_impl(ctx, d_f, B, U, mu_c, beta, d_evals, d_out, nullptr, nullptr, nullptr, d_vt, d_evecs);
+    return eigvec_pipeline_impl(ctx, d_f, B, U, mu_c, beta, d_evals, d_out, nullptr, nullptr, d_ipr, d_vt, d_evecs);
 }

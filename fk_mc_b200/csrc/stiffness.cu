@@ -96,9 +96,6 @@ __global__ void __launch_bounds__(1024) kubo_kernel(const double* __restrict__ m
 
 }  // namespace
 
-int fkmc_eigvec_pipeline_dev2(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, double* d_evals, double* d_out, double* d_evecs,
-                              double* d_vt);
-
 extern "C" int fkmc_stiffness_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, double mu_c, double beta, double offset, int n_w,
                                       const double* wgrid, double* stiffness, double* cond) {
     if (!ctx || !f || !stiffness || n_w < 0 || (n_w > 0 && (!wgrid || !cond))) return FKMC_ERR_INVALID;
@@ -138,7 +135,7 @@ extern "C" int fkmc_stiffness_batched(fkmc_ctx* ctx, const int32_t* f, int B, do
     for (int b0 = 0; b0 < B && !rc; b0 += chunk) {
         const int nb = std::min(chunk, B - b0);
         FKMC_ST(cudaMemcpyAsync(d_f, f + (size_t)b0 * N, sizeof(int32_t) * (size_t)N * nb, cudaMemcpyHostToDevice, ctx->stream));
-        if ((rc = fkmc_eigvec_pipeline_dev2(ctx, d_f, nb, U, mu_c, beta, d_evals, ctx->d_out, d_ev, d_vt))) break;
+        if ((rc = fkmc_eigvec_pipeline_dev2(ctx, d_f, nb, U, mu_c, beta, d_evals, ctx->d_out, d_ev, d_vt, nullptr))) break;
         {
             fkmc_prof_scope ps(ctx, "stiffness_jv");
             jv_kernel<<<dim3((N + 255) / 256, nb), 256, 0, ctx->stream>>>(d_vt, N, stride_x, L, ctx->t, d_jv, d_td);

@@ -476,7 +476,7 @@ struct batched_chains {
     /// per-sweep histories as the C ABI returns them: spectrum_mean [chain][N], the others [measurement][chain][N] (empty when not measured)
     int histories(std::vector<double>& spectrum_mean, std::vector<double>& spectrum_history, std::vector<int32_t>& focc_history, std::vector<double>& ipr_history) {
         const size_t N = lat_.msize(), full = size_t(p_.max_sweeps) * n_ * N;
-        const bool exact = !p_.cheb_moves || p_.measure_energy || p_.measure_ipr;
+        const bool exact = !p_.cheb_moves || p_.measure_energy || p_.measure_ipr || p_.measure_eigenfunctions;
         spectrum_mean.assign(exact ? size_t(n_) * N : 0, 0.0);
         spectrum_history.assign(exact && p_.measure_history ? full : 0, 0.0);
         focc_history.assign(p_.measure_history ? full : 0, 0);

@@ -138,6 +138,8 @@ typedef struct fkmc_chain_params {
     int32_t measure_ipr;                         /* fk_mc.hxx:195: measure_ipr -> ipr_history (calc_ed(true) per measured sweep) */
     int32_t n_W;                                 /* 1-D lattices: f-f interaction W[0..n_W) (config_params::W, configuration.hpp:15-19); */
     double W[FKMC_MAX_W];                        /* ignored for D >= 2 where calc_ff_energy() == 0 (configuration.cpp:62) */
+    int32_t measure_eigenfunctions;              /* fk_mc.hxx:196: eigenfunctions_history, N x N eigenvector matrix per chain and measured sweep
+                                                    (max_sweeps * n_chains * N^2 doubles of device memory) */
     int32_t fast_update;                         /* exact moves only: 1 = re-weight add_remove / flip proposals through rank-one secular
                                                     updates of the tracked eigen-decomposition (O(N^2) per proposal, an N^3 eigenvector
                                                     update only on accept; benchmark/fast_update.cpp) instead of a fresh
@@ -169,6 +171,9 @@ int fkmc_chain_get_trace(fkmc_ctx* ctx, int* n_steps, int32_t* move, int32_t* si
  *   ipr_history      [n_measured][n_chains][N]  measure_ipr, include/fk_mc/measures/ipr.hpp:39-56 */
 int fkmc_chain_get_history(fkmc_ctx* ctx, int* n_measured, double* spectrum_mean, double* spectrum_history, int32_t* focc_history,
                            double* ipr_history);
+/* measure_eigenfunctions (src/measures/eigenfunctions.cpp:12-18): evecs [n_measured][n_chains][N][N], each matrix column-major like
+ * ed_cache::cached_evecs (column k <-> eigenvalue k of the spectrum history); needs chain parameter measure_eigenfunctions */
+int fkmc_chain_get_eigenfunctions(fkmc_ctx* ctx, int* n_measured, double* evecs);
 /* measure_ipr on the chains' current configurations: evals [n_chains][N] (or NULL), ipr [n_chains][N] */
 int fkmc_chain_ipr(fkmc_ctx* ctx, double* evals, double* ipr);
 /* device pointers to the series (for the end-of-run NCCL gather): energies, d2energies, c_energies as

@@ -527,6 +527,28 @@ def test_chain_histories_match_oracle(cheb):
     c.close()
 
 
+@pytest.mark.parametrize("cheb", [False, True])
+def test_eigenfunctions_history(cheb):
+    """measure_eigenfunctions (src/measures/eigenfunctions.cpp:12-18): the N x N eigenvector matrix of every chain at every measured sweep
+    diagonalises the Hamiltonian of that sweep's configuration (focc_history) with the eigenvalues of spectrum_history."""
+    nch, nsw, L, U, beta = 2, 3, 8, 4.0, 4.0
+    c = fk.Context("cubic2d", L, max_batch=nch)
+    c.chain_init(nch, beta, U, cheb_moves=cheb, seed=9, sweep_len=16, ntherm_sweeps=0, max_sweeps=nsw, measure_history=True,
+                 measure_eigenfunctions=True, measure_ipr=True)
+    c.chain_run_sweeps(nsw)
+    V, h = c.chain_get_eigenfunctions(), c.chain_get_history()
+    assert V.shape == (nsw, nch, L * L, L * L)
+    H0 = o.hopping_dense(o.CUBIC2D, L)
+    for m in range(nsw):
+        for ch in range(nch):
+            H = H0 + np.diag(U * h["focc_history"][m, ch] - U / 2)
+            ev, W = h["spectrum_history"][m, ch], V[m, ch]
+            assert np.abs(H @ W - W * ev).max() <= 1e-10 * np.abs(ev).max()
+            assert np.abs(W.T @ W - np.eye(L * L)).max() <= 1e-9
+            assert np.allclose(h["ipr_history"][m, ch], (np.sum(W ** 4, axis=0) ** 0.25) / np.sum(W ** 2, axis=0), rtol=1e-10)
+    c.close()
+
+
 def test_fsector_series():
     """nf0 / nfpi series (measure_nf0pi): recomputed from the focc history with the reference's staggered phase (-1)^(x+y)."""
     nch, nsw, L = 3, 4, 8
