@@ -459,6 +459,17 @@ struct measure_ipr {
     std::vector<std::vector<double>>& ipr_vals_;
 };
 
+/// src/measures/eigenfunctions.cpp:12-18: the full eigenvector matrix (column-major N x N, column k <-> eigenvalue k) per measurement
+struct measure_eigenfunctions {
+    measure_eigenfunctions(configuration_t& in, std::vector<std::vector<double>>& eigenfunctions) : config(in), eigenfunctions_(eigenfunctions) {}
+    void accumulate(double /*sign*/) {
+        config.calc_ed(true);
+        eigenfunctions_.push_back(config.ed_data_.cached_evecs);
+    }
+    configuration_t& config;
+    std::vector<std::vector<double>>& eigenfunctions_;
+};
+
 /// Batched product path: n_chains reference ranks on one GPU (fkmc_chain_*).  chain c == the reference's MPI rank chain0 + c.
 struct batched_chains {
     batched_chains(abstract_lattice& lat, int n_chains, const fkmc_chain_params& p) : lat_(lat), n_(n_chains), p_(p) {
@@ -659,6 +670,7 @@ typedef alps::params parameters_t;
 struct observables_t {
     std::vector<double> energies, c_energies, d2energies, nf0, nfpi, spectrum, stiffness;
     std::vector<std::vector<double>> spectrum_history, ipr_history, cond_history, focc_history;
+    std::vector<std::vector<double>> eigenfunctions_history;  // [measurement] -> column-major N x N (the reference: std::vector<dense_m>)
     void reserve(int n) { energies.reserve(n); d2energies.reserve(n); c_energies.reserve(n); }
 };
 
@@ -742,6 +754,7 @@ public:
         observables.reserve(int(p["nsweeps"].template as<long>()));
         const bool history = p["measure_history"], ipr = p["measure_ipr"];
         if (history && ipr) this->add_measure(measure_ipr(config, observables.ipr_history), "ipr");
+        if (bool(p["measure_eigenfunctions"])) this->add_measure(measure_eigenfunctions(config, observables.eigenfunctions_history), "eigenfunctions");
         const bool calc_spectrum = !cheb_move || ipr;
         if (calc_spectrum) {
             this->add_measure(measure_energy(beta, config, observables.energies, observables.d2energies, observables.c_energies), "energy");
@@ -768,6 +781,7 @@ public:
         cp.measure_ipr = history && ipr;
         cp.measure_energy = !cp.cheb_moves || ipr;
         cp.measure_history = history;
+        cp.measure_eigenfunctions = bool(p["measure_eigenfunctions"]);
         if (l.ndim() == 1 && p.exists("W")) {
             const std::vector<double> W = p["W"].template as<std::vector<double>>();
             if (W.size() > FKMC_MAX_W) throw std::logic_error("at most 8 f-f interaction terms");
@@ -797,6 +811,14 @@ public:
             unpack(shist, o.spectrum_history);
             unpack(fhist, o.focc_history);
             unpack(ihist, o.ipr_history);
+        }
+        if (cp.measure_eigenfunctions) {
+            std::vector<double> ev(size_t(cp.max_sweeps) * C * N * N);
+            int n_ev = 0;
+            fkmc_check(fkmc_chain_get_eigenfunctions(l.ctx(), &n_ev, ev.data()), l.ctx());
+            for (size_t c = 0; c < C; ++c)
+                for (int m = 0; m < n_ev; ++m)
+                    out[c].eigenfunctions_history.emplace_back(ev.begin() + (size_t(m) * C + c) * N * N, ev.begin() + (size_t(m) * C + c + 1) * N * N);
         }
         batched_naccept_ = bc.naccept();
         batched_f_ = bc.f_config();
