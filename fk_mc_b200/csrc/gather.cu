@@ -23,7 +23,6 @@ struct nccl_api {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
-    std::string err;
 };
 
 nccl_api* load_nccl() {
@@ -35,20 +34,13 @@ nccl_api* load_nccl() {
             api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
             if (api.handle) break;
         }
-        if (!api.handle) {
-            api.err = std::string("cannot load libnccl: ") + dlerror();
-            return false;
-        }
+        if (!api.handle) return false;
         api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
         api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
         api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
         api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
         api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
-        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.GetErrorString) {
-            api.err = "libnccl lacks a required symbol";
-            return false;
-        }
-        return true;
+        return api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString;
     }();
     return ok ? &api : nullptr;
 }

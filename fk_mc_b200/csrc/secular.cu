@@ -562,7 +562,11 @@ int fkmc_fu_alloc(fkmc_ctx* ctx) {
     rc |= al((void**)&S.fu_acc, sizeof(int32_t) * C);
     rc |= al((void**)&S.fu_fresh, sizeof(double) * C * N);
     rc |= al((void**)&S.fu_maxdev, sizeof(double) * C);
-    if (rc) return fkmc_set_error(ctx, FKMC_ERR_CUDA, "fast_update: out of device memory (3 N^2 doubles per chain)");
+    if (rc) {
+        cudaGetLastError();
+        fkmc_fu_free(ctx);   // whatever was allocated before the failure
+        return fkmc_set_error(ctx, FKMC_ERR_CUDA, "fast_update: out of device memory (3 N^2 doubles per chain)");
+    }
     FKMC_CUDA(ctx, cudaMemsetAsync(S.fu_vslot, 0, sizeof(int32_t) * C, ctx->stream));
     FKMC_CUDA(ctx, cudaMemsetAsync(S.fu_acc, 0, sizeof(int32_t) * C, ctx->stream));
     FKMC_CUDA(ctx, cudaMemsetAsync(S.fu_nstage, 0, sizeof(int32_t) * C, ctx->stream));
@@ -573,6 +577,8 @@ void fkmc_fu_free(fkmc_ctx* ctx) {
     fkmc_chain_state& S = ctx->chain;
     cudaFree(S.fu_vt); cudaFree(S.fu_q); cudaFree(S.fu_vslot); cudaFree(S.fu_poles); cudaFree(S.fu_org); cudaFree(S.fu_mu); cudaFree(S.fu_zhat);
     cudaFree(S.fu_inrm); cudaFree(S.fu_nstage); cudaFree(S.fu_rho); cudaFree(S.fu_acc); cudaFree(S.fu_fresh); cudaFree(S.fu_maxdev);
+    S.fu_vt = S.fu_q = S.fu_poles = S.fu_mu = S.fu_zhat = S.fu_inrm = S.fu_rho = S.fu_fresh = S.fu_maxdev = nullptr;
+    S.fu_vslot = S.fu_org = S.fu_nstage = S.fu_acc = nullptr;
 }
 
 static fu_args make_fu_args(fkmc_ctx* ctx) {
