@@ -333,7 +333,8 @@ class H5Reader:
         return out
 
 
-def save_all_data(fname, params, energies, d2energies, c_energies, beta, volume, max_depth=None, histories=None, nf0=None, nfpi=None):
+def save_all_data(fname, params, energies, d2energies, c_energies, beta, volume, max_depth=None, histories=None, nf0=None, nfpi=None,
+                  spectrum_history=None, ipr_history=None, dos_wgrid=None, dos_offset=0.05):
     """Reference layout of prog/data_save.hxx (save_all_data -> save_measurements + energy / cv statistics).
 
     params: dict of run parameters (the alps::params dump); energies, d2energies, c_energies: 1-D series (one chain, or
@@ -342,6 +343,9 @@ def save_all_data(fname, params, energies, d2energies, c_energies, beta, volume,
     [index][measurement] arrays for /mc_data (ipr_history, spectrum_history, focc_history).
     nf0 / nfpi: optional f-sector series (fkmc_chain_get_fsector) -> /mc_data/{nf0,nfpi} and the save_fstats statistics
     (nf_0, nf_pi, fsusc_0, fsusc_pi, binder_0, binder_pi; prog/data_save.hxx:200-236).
+    spectrum_history / ipr_history ([measurement][chain][N] as fkmc_chain_get_history returns them) with dos_wgrid: the DOS and IPR
+    post-processing of save_glocal / save_ipr (prog/data_save.hxx:265-345,487-532): dos0, dos_err, nc, ipr0, ipr_err; the histories
+    themselves go to /mc_data/{spectrum_history,ipr_history} as [index][measurement] (prog/data_save.hxx:105-137).
     Returns the per-observable statistics that were written (dict name -> (binning rows, stats 4-vector))."""
     w = H5Writer()
     w.require_group("/parameters")
@@ -382,5 +386,19 @@ def save_all_data(fname, params, energies, d2energies, c_energies, beta, volume,
             st = np.array(frep[name]["stats"], dtype=np.float64)
             w["/stats/" + name] = st
             out[name] = (None, st)
+    if spectrum_history is not None:
+        w["/mc_data/spectrum_history"] = np.ascontiguousarray(stats._history_rows(spectrum_history).T)   # [index][measurement]
+        if dos_wgrid is not None:
+            drep = stats.dos_report(spectrum_history, dos_wgrid, dos_offset, beta, max_depth)
+            put("dos0", drep["dos0"]["binning"])
+            w["/stats/dos_err"] = drep["dos_err"]
+            if "nc" in drep:
+                w["/stats/nc"] = np.array(drep["nc"], dtype=np.float64)
+    if ipr_history is not None:
+        w["/mc_data/ipr_history"] = np.ascontiguousarray(stats._history_rows(ipr_history).T)
+        if spectrum_history is not None and dos_wgrid is not None:
+            irep = stats.ipr_report(spectrum_history, ipr_history, dos_wgrid, dos_offset, max_depth)
+            put("ipr0", irep["ipr0"]["binning"])
+            w["/stats/ipr_err"] = irep["ipr_err"]
     w.save(fname)
     return out

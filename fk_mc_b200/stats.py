@@ -147,6 +147,72 @@ def fstats_report(nf0, nfpi, max_depth=None):
     return out
 
 
+def _history_rows(hist):
+    """Per-measurement rows [n_meas_total, N] from a history: [measurement][N] (one chain) or [measurement][chain][N] (pooled chain-major,
+    like the reference's gathered ranks)."""
+    a = np.asarray(hist, dtype=np.float64)
+    if a.ndim == 3:
+        a = np.transpose(a, (1, 0, 2)).reshape(-1, a.shape[2])
+    if a.ndim != 2:
+        raise ValueError("history must be [measurement][N] or [measurement][chain][N]")
+    return a
+
+
+def dos_report(spectrum_history, wgrid, offset, beta, max_depth=None):
+    """save_glocal (prog/data_save.hxx:265-345): local density of states dos(w) = -Im sum_k 1 / (w - eps_k + i offset) / (pi N) of every measured
+    spectrum; binning of dos(0) -> `dos0`; `dos_err` = rows [w, mean, stderr] at the bin level picked for dos0; nc = integral of dos(w) f(w)
+    over the grid (trapezoid) with its error.  spectrum_history: [measurement][N] or [measurement][chain][N]."""
+    sp = _history_rows(spectrum_history)
+    n_meas, vol = sp.shape
+    wgrid = np.asarray(wgrid, dtype=np.float64)
+
+    def dos_at(w):
+        return (offset / ((w - sp) ** 2 + offset * offset)).sum(axis=1) / (math.pi * vol)   # == -Im(sum 1/(w - eps + i offset)) / (pi N)
+
+    if max_depth is None:
+        max_depth = max_bin_depth(n_meas)
+    rows0 = accumulate_binning(dos_at(0.0)[::-1], max_depth)
+    b = estimate_bin(rows0)
+    table = np.zeros((len(wgrid), 3))
+    for i, w in enumerate(wgrid):
+        st = bin_stats(dos_at(w)[::-1], b)
+        table[i] = (w, st[1], st[3])
+    out = dict(dos0=dict(binning=rows0, cor_length=calc_cor_length(rows0), bin=b, stats=rows0[b]), dos_err=table)
+    if len(wgrid) > 1:
+        with np.errstate(over="ignore"):
+            fermi = 1.0 / (1.0 + np.exp(beta * wgrid))
+        trapz = getattr(np, "trapezoid", None) or np.trapz
+        nc = float(trapz(table[:, 1] * fermi, wgrid))
+        nc_err = float(math.sqrt(trapz((table[:, 2] * fermi) ** 2, wgrid)))
+        out["nc"] = (float("nan"), nc, float("nan"), nc_err)   # save_bin_data row: only mean and error are set by the reference
+    return out
+
+
+def ipr_report(spectrum_history, ipr_history, wgrid, offset, max_depth=None):
+    """save_ipr (prog/data_save.hxx:487-532): Lorentzian-weighted inverse participation ratio
+    ipr(w) = sum_k L(w - eps_k) ipr_k^4 / sum_k L(w - eps_k)  (the measure stores the L4 NORM, hence the 4th power); binning of ipr(0) -> `ipr0`;
+    `ipr_err` = rows [w, mean, stderr] at the bin level picked for ipr0."""
+    sp, ip = _history_rows(spectrum_history), _history_rows(ipr_history)
+    if sp.shape != ip.shape:
+        raise ValueError("spectrum_history and ipr_history differ in shape")
+    wgrid = np.asarray(wgrid, dtype=np.float64)
+    ip4 = ip ** 4
+
+    def ipr_at(w):
+        lor = offset / ((w - sp) ** 2 + offset * offset)
+        return (lor * ip4).sum(axis=1) / lor.sum(axis=1)
+
+    if max_depth is None:
+        max_depth = max_bin_depth(sp.shape[0])
+    rows0 = accumulate_binning(ipr_at(0.0)[::-1], max_depth)
+    b = estimate_bin(rows0)
+    table = np.zeros((len(wgrid), 3))
+    for i, w in enumerate(wgrid):
+        st = bin_stats(ipr_at(w)[::-1], b)
+        table[i] = (w, st[1], st[3])
+    return dict(ipr0=dict(binning=rows0, cor_length=calc_cor_length(rows0), bin=b, stats=rows0[b]), ipr_err=table)
+
+
 # ---- plaintext twin of the reference output (prog/data_save.hxx:9-30, prog/data_save.hpp:124-156, README.md:42-43) ----
 def savetxt(fname, rows):
     """gftools-style plaintext: scientific notation, space separated, one row per line (README example:

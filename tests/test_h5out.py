@@ -107,6 +107,17 @@ def test_save_all_data_multi_chain_and_fsector(tmp_path):
     for name in ("nf_0", "nf_pi", "fsusc_0", "fsusc_pi", "binder_0", "binder_pi"):
         assert np.allclose(t["/stats/" + name], frep[name]["stats"]), name
     assert t["/binning/fsusc_pi"].shape[1] == 5 and "/binning/binder_0" not in t
+    # DOS / IPR post-processing from the histories
+    vol = 16
+    sp = np.sort(rng.normal(size=(n_meas, n_chains, vol)), axis=2)
+    ip = rng.uniform(0.2, 1.0, size=(n_meas, n_chains, vol))
+    wg = np.linspace(-1, 1, 5)
+    h5out.save_all_data(fn, dict(beta=1.0), e, e * e, e, 1.0, vol, spectrum_history=sp, ipr_history=ip, dos_wgrid=wg, dos_offset=0.05)
+    t = h5out.H5Reader(fn).tree()
+    assert t["/mc_data/spectrum_history"].shape == (vol, n_meas * n_chains) and np.array_equal(t["/mc_data/spectrum_history"][:, :n_meas], sp[:, 0].T)
+    drep = stats.dos_report(sp, wg, 0.05, 1.0, stats.max_bin_depth(e.size))
+    assert np.allclose(t["/stats/dos0"], drep["dos0"]["stats"]) and np.allclose(t["/stats/dos_err"], drep["dos_err"])
+    assert t["/stats/ipr_err"].shape == (5, 3) and t["/stats/ipr0"].shape == (4,) and np.isfinite(t["/stats/nc"][1])
 
 
 def test_cpp_data_save_header(tmp_path):

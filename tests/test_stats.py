@@ -116,3 +116,31 @@ def test_fstats_report():
     b = rep["binder_pi"]["stats"]
     y = stats.pool_chains(nfpi)
     assert b[1] == pytest.approx(1.0 - (y ** 4).mean() / 3.0 / (y ** 2).mean() ** 2, abs=5 * b[3] + 1e-12)
+
+
+def test_dos_and_ipr_reports():
+    """save_glocal / save_ipr post-processing (prog/data_save.hxx:265-345,487-532) against the defining formulas in complex arithmetic."""
+    rng = np.random.default_rng(11)
+    n_meas, n_chains, vol, off, beta = 32, 3, 16, 0.05, 4.0
+    sp = np.sort(rng.normal(size=(n_meas, n_chains, vol)), axis=2)
+    ip = rng.uniform(0.2, 1.0, size=(n_meas, n_chains, vol))
+    wg = np.linspace(-2.0, 2.0, 9)
+    rep = stats.dos_report(sp, wg, off, beta, max_depth=3)
+    rows = np.transpose(sp, (1, 0, 2)).reshape(-1, vol)                       # chain after chain
+    d0 = np.array([-(1.0 / (0.0 - r + 1j * off)).sum().imag / math.pi / vol for r in rows])
+    assert rep["dos0"]["binning"][0][1] == pytest.approx(d0.mean(), rel=1e-12)
+    assert rep["dos0"]["binning"][0][3] == pytest.approx(stats.calc_stats(d0)[3], rel=1e-12)
+    b = rep["dos0"]["bin"]
+    dw = np.array([-(1.0 / (wg[5] - r + 1j * off)).sum().imag / math.pi / vol for r in rows])
+    st = stats.bin_stats(dw[::-1], b)
+    assert rep["dos_err"][5] == pytest.approx((wg[5], st[1], st[3]), rel=1e-12)
+    assert rep["dos_err"][:, 1].min() > 0 and rep["nc"][1] > 0 and rep["nc"][3] > 0
+    ir = stats.ipr_report(sp, ip, wg, off, max_depth=3)
+    rows_i = np.transpose(ip, (1, 0, 2)).reshape(-1, vol)
+    g = [(1.0 / (0.0 - r + 1j * off)) for r in rows]
+    i0 = np.array([(gi * ri ** 4).sum().imag / gi.sum().imag for gi, ri in zip(g, rows_i)])     # ipr_moment_f's nom / denom
+    assert ir["ipr0"]["binning"][0][1] == pytest.approx(i0.mean(), rel=1e-12)
+    assert ir["ipr_err"].shape == (9, 3) and (ir["ipr_err"][:, 1] > 0).all()
+    # single-chain input [measurement][N] is accepted as is
+    one = stats.dos_report(sp[:, 0], wg, off, beta, max_depth=2)
+    assert one["dos0"]["binning"][0][0] == n_meas
