@@ -60,3 +60,53 @@ def test_null_context_is_rejected():
 
 def test_cheb_sizes_host_logic():
     assert fk.cheb_sizes(64) == (10, 20) and fk.cheb_sizes(1024) == (16, 32) and fk.cheb_sizes(576, 2.5) == (16, 32)
+
+
+def test_cpp_host_mirror_compiles_and_links(tmp_path):
+    """include/fk_mc_b200/fk_mc.hpp (alps::params, fk::fk_mc<Lattice>, moves, measures) builds with plain g++ against the C ABI; on a machine
+    without a GPU the driver program stops at lattice creation with the library's "no CPU fallback" error (no compute without a device)."""
+    import subprocess
+    exe = str(tmp_path / "host_api_test")
+    libdir = os.path.join(ROOT, "fk_mc_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "host_api_test.cpp"), "-o", exe, "-L" + libdir, "-lfkmc_b200", "-Wl,-rpath," + libdir])
+    if not HAVE_GPU:
+        r = subprocess.run([exe, "8", "4", "4", "0", "0.5", "2", "32167", "0"], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU fallback" in r.stdout
+
+
+def test_parameter_table_of_the_cpp_mirror(tmp_path):
+    """fk_mc<L>::define_parameters carries the reference's names and defaults (include/fk_mc/fk_mc.hxx:177-207, src/mc_metropolis.cpp:11-19):
+    checked on the host, no GPU involved."""
+    import subprocess
+    src = tmp_path / "params.cpp"
+    src.write_text('''
+#include <cstdio>
+#include "fk_mc_b200/fk_mc.hpp"
+int main() {
+    fk::parameters_t p;
+    p["seed"] = 42;                                   // a value set before define_parameters wins over the default
+    fk::fk_mc<fk::hypercubic_lattice<2>>::define_parameters(p);
+    printf("%ld %ld %ld %d\\n", long(p["nsweeps"]), long(p["sweep_len"]), long(p["ntherm_sweeps"]), int(bool(p["show_output"])));
+    printf("%g %g %g %g\\n", double(p["beta"]), double(p["U"]), double(p["mu_c"]), double(p["mu_f"]));
+    printf("%g %g %g %d %g\\n", double(p["mc_flip"]), double(p["mc_add_remove"]), double(p["mc_reshuffle"]), int(bool(p["cheb_moves"])), double(p["cheb_prefactor"]));
+    printf("%d %ld %d %d %g %d\\n", int(bool(p["measure_history"])), long(p["Nf_start"]), int(bool(p["measure_ipr"])), int(bool(p["measure_eigenfunctions"])),
+           double(p["cond_offset"]), int(bool(p["measure_stiffness"])));
+    printf("%ld %ld %ld\\n", long(p["seed"]), long(p["SEED"]), long(p["nprocs"]));
+    bool threw = false;
+    try { const fk::parameters_t& q = p; (void)double(q["no_such_parameter"]); } catch (std::logic_error&) { threw = true; }
+    printf("%d\\n", int(threw));
+    return 0;
+}
+''')
+    exe = str(tmp_path / "params")
+    libdir = os.path.join(ROOT, "fk_mc_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), str(src), "-o", exe, "-L" + libdir, "-lfkmc_b200",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([exe]).decode().split("\n")
+    assert out[0] == "1024 16 1 1"
+    assert out[1] == "10 1 0.5 0.5"
+    assert out[2] == "0 1 0 0 2.2"
+    assert out[3] == "1 5 0 0 0.05 0"
+    assert out[4] == "42 42 1"
+    assert out[5] == "1"
