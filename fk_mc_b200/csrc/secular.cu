@@ -131,12 +131,26 @@ __device__ __forceinline__ void secular_stage(int N, int j, const double* d, con
         const double gap = last ? R * sumz2 : cd[jc + 1] - dl;  // root in (dl, dl + gap)
         // which end is nearer: sign of f at the midpoint (poles measured from dl)
         int o = jc;
+        double m0 = NAN;   // initial guess (in x - dl) from the midpoint pass
         if (!last) {
             const double xm = 0.5 * gap;
             double fm = 0.0;
             for (int k = 0; k < N; ++k) fm = fma(cz[k], fast_rcp((cd[k] - dl) - xm), fm);
             fm = fma(R, fm, 1.0);
             if (fm < 0.0) o = jc + 1;  // root in the upper half
+            // dlaed4-style start: the two neighbouring poles exactly, the rest frozen at its midpoint value c:
+            //   c - zl / x + zu / (gap - x) = 0   <=>   c x^2 - (c gap + zl + zu) x + zl gap = 0,  x in (0, gap)
+            const double zl = R * cz[jc], zu = R * cz[jc + 1];
+            const double c = fm - 2.0 * (zu - zl) / gap;
+            const double b = -(c * gap + zl + zu), q = zl * gap;
+            if (c == 0.0) {
+                m0 = -q / b;
+            } else {
+                const double sq = sqrt(fmax(fma(b, b, -4.0 * c * q), 0.0));
+                const double t = (b > 0.0) ? -(b + sq) : (sq - b);
+                const double x1 = 0.5 * t / c, x2 = (t != 0.0) ? 2.0 * q / t : 0.0;
+                m0 = (x1 > 0.0 && x1 < gap) ? x1 : x2;
+            }
         }
         const double dorg = cd[o];
         // bracket in mu = x - dorg
@@ -145,7 +159,8 @@ __device__ __forceinline__ void secular_stage(int N, int j, const double* d, con
         else { lo = -0.5 * gap; hi = 0.0; }
         const double dj = cd[jc] - dorg;                       // lower pole in the shifted variable (0 or -gap)
         const double du = last ? 0.0 : cd[jc + 1] - dorg;      // upper pole (unused for the last root)
-        double m = (o == jc) ? (last ? fmin(0.5 * gap, R * cz[jc]) : 0.25 * gap) : -0.25 * gap;  // start inside the bracket
+        double m = (o == jc) ? m0 : m0 - gap;
+        if (!(m > lo && m < hi)) m = (o == jc) ? (last ? fmin(0.5 * gap, R * cz[jc]) : 0.25 * gap) : -0.25 * gap;  // fall-back start inside the bracket
         if (!(m > lo && m < hi)) m = 0.5 * (lo + hi);
         bool done = false;
         for (int it = 0; it < FU_MAXIT && !done; ++it) {
@@ -196,8 +211,12 @@ __device__ __forceinline__ void secular_stage(int N, int j, const double* d, con
                 }
             }
             double mn = m + eta;
-            if (!(mn > lo && mn < hi)) mn = 0.5 * (lo + hi);       // safeguard: bisection
+            const bool interp = (mn > lo && mn < hi);
+            if (!interp) mn = 0.5 * (lo + hi);                     // safeguard: bisection
             if (mn == m || hi - lo <= 2.0 * DBL_EPSILON * fmax(fabs(lo), fabs(hi))) done = true;
+            // the interpolation converges quadratically: a correction below 1e-9 |mu| leaves an error at rounding level, so it is applied
+            // without a confirming pass
+            if (interp && fabs(mn - m) <= 1e-9 * fabs(mn)) done = true;
             if (fabs(mn - m) <= 4.0 * DBL_EPSILON * fabs(mn)) done = true;
             m = mn;
             if (it == FU_MAXIT - 1 && !done) ok = false;

@@ -782,6 +782,8 @@ public:
         cp.measure_energy = !cp.cheb_moves || ipr;
         cp.measure_history = history;
         cp.measure_eigenfunctions = bool(p["measure_eigenfunctions"]);
+        // not a reference parameter: rank-one secular re-weighting of the dense moves (fkmc.h: fast_update), same results
+        if (p.exists("fast_update")) cp.fast_update = bool(p["fast_update"]) && !cp.cheb_moves && !(cp.mc_reshuffle > 0.0);
         if (l.ndim() == 1 && p.exists("W")) {
             const std::vector<double> W = p["W"].template as<std::vector<double>>();
             if (W.size() > FKMC_MAX_W) throw std::logic_error("at most 8 f-f interaction terms");
