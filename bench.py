@@ -218,6 +218,7 @@ def main():
                     help="measurement path (c): every sweep also measures the IPR of all eigenstates (calc_ed(true) per chain, ipr.hpp:39-56)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short dense-move lines (c2 / c3, full solve and fast update) appended to the default run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]
@@ -482,6 +483,26 @@ def main():
                                   % (cores, CPU_SWEEPS, sec),
                         "lapack": lapack_baseline(args.workload, cores)}
 
+    # ---- the dense-move configurations of BASELINE.json next to the headline (rank 0, N = 1, default workload only): each is this script
+    #      run on that workload for a few sweeps, so that the driver's JSON carries measured numbers for them as well ----
+    extra = None
+    if rank == 0 and world == 1 and args.workload == "c5" and not args.no_extra and not args.measure_ipr:
+        extra = {}
+        for wl_name, fastflag in (("c2", False), ("c2", True), ("c3", False), ("c3", True)):
+            cmd = [sys.executable, os.path.abspath(__file__), "--workload", wl_name, "--no-cpu-baseline", "--no-e2e", "--no-extra", "--steps", "3", "--warmup", "3"]
+            if fastflag:
+                cmd.append("--fast-update")
+            key = wl_name + ("_fast_update" if fastflag else "_full_solve")
+            try:
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+                d = json.loads(r.stdout.strip().splitlines()[-1])
+                extra[key] = {"workload": d["config"]["workload"], "chains_per_gpu": d["config"]["chains_per_gpu"], "value": d["value"], "unit": d["unit"],
+                              "ms_per_step": d["ms_per_step"], "accept_rate": d.get("accept_rate"), "dominant_kernel": d["dominant_kernel"],
+                              "roofline": {k: d["roofline"].get(k) for k in ("kernel", "bound", "achieved", "peak", "unit", "frac")},
+                              "kernels": {k: {"ms_per_launch": v["ms_per_launch"], "share": v["share"]} for k, v in d["kernels"].items()}}
+            except Exception as e:  # never lose the headline line over an extra
+                extra[key] = {"unavailable": repr(e)[:200]}
+
     if rank == 0:
         line = {"metric": "metropolis_proposals_per_sec", "value": value, "unit": "proposals/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -493,7 +514,7 @@ def main():
                 "roofline_fast_update": rl_fast, "roofline_measurement": rl_meas, "traffic_source": traffic_file,
                 "dominant_kernel": dominant, "kernels": {**fam, **sub},
                 "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks,
-                "final_gather_ms": gather_ms}
+                "final_gather_ms": gather_ms, "dense_move_workloads": extra}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

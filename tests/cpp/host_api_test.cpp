@@ -53,7 +53,9 @@ int main(int argc, char** argv) {
         printf("f");
         for (int f : mc.config().f_config_) printf(" %d", f);
         printf("\n");
-        // the batched product path: ranks rank, rank + 1 as two chains resident on the GPU
+        // the batched product path: ranks rank, rank + 1 as two chains resident on the GPU (dense moves re-weighted by rank-one secular
+        // updates: same results as one eigensolve per proposal)
+        p["fast_update"] = !cheb_move;
         qmc_t mcb(p, rank);
         auto obs = mcb.run_batched(lattice, 2);
         for (int c = 0; c < 2; ++c) {
