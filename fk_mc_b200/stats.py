@@ -213,6 +213,102 @@ def ipr_report(spectrum_history, ipr_history, wgrid, offset, max_depth=None):
     return dict(ipr0=dict(binning=rows0, cor_length=calc_cor_length(rows0), bin=b, stats=rows0[b]), ipr_err=table)
 
 
+def fcorrel_report(focc_history, dims, max_depth=None):
+    """save_fcorrel (prog/data_save.hxx:347-420): f-electron density correlations along the lattice axes,
+        C(l) = jackknife over bins of  sum_i sum_d dev_i (dev_{i - l e_d} + dev_{i + l e_d}) / (2 D V),   dev_i = <f_i>_bin - nf_mean_i
+    with nf_mean_i the binned mean of site i at the bin level picked from site 0's series; the bin level for all l is then the one picked for
+    C(0).  Rows of `fcorrel`: [l, C(l), error, C(l) / C(0), error of the ratio], l = 0 .. L/2; `fcorrel_q` = forward DFT of the symmetrised C(r).
+    focc_history: [measurement][V] or [measurement][chain][V]."""
+    fo = _history_rows(focc_history)            # [n_total][V]
+    n_tot, vol = fo.shape
+    dims = tuple(int(d) for d in dims)
+    if int(np.prod(dims)) != vol:
+        raise ValueError("fcorrel_report: dims do not match the history")
+    if max_depth is None:
+        max_depth = max_bin_depth(n_tot)
+    series = [fo[::-1, i] for i in range(vol)]  # reversed like the reference (rbegin..rend)
+    nf_bin = estimate_bin(accumulate_binning(series[0], max_depth))
+    nf_mean = np.array([bin_stats(x, nf_bin)[1] for x in series])
+
+    def fcorrel_f(l):
+        def F(*means):
+            dev = (np.asarray(means) - nf_mean).reshape(dims)
+            out = 0.0
+            for d in range(len(dims)):
+                out += (dev * (np.roll(dev, l, axis=d) + np.roll(dev, -l, axis=d))).sum()
+            return out / vol / (2.0 * len(dims))
+        return F
+
+    c0_rows = accumulate_jackknife(fcorrel_f(0), series, max_depth)
+    nf_bin = estimate_bin(c0_rows)
+    c0_mean, c0_err = c0_rows[nf_bin][1], c0_rows[nf_bin][3]
+    half = dims[0] // 2
+    table = np.zeros((half + 1, 5))
+    cr = np.zeros(dims[0])
+    per_l = {}
+    for l in range(half + 1):
+        st = jack(fcorrel_f(l), series, nf_bin)
+        per_l["fcorrel_%d" % l] = st
+        with np.errstate(divide="ignore", invalid="ignore"):
+            table[l] = (l, st[1], st[3], st[1] / c0_mean,
+                        math.sqrt((st[3] / c0_mean) ** 2 + (st[1] / (c0_mean * c0_mean) * c0_err) ** 2) if c0_mean != 0 else float("nan"))
+        cr[l] = st[1]
+        if l > 0:
+            cr[dims[0] - l] = st[1]
+    return dict(fcorrel=table, fcorrel_q=np.fft.fft(cr), bin=nf_bin, per_l=per_l)
+
+
+def _wstring(w):
+    """The reference's dataset suffix: std::to_string(float(Re w)) and (Im w) with trailing zeros erased, joined by '_' (data_save.hxx:566-571)."""
+    def one(x):
+        return ("%f" % np.float32(x)).rstrip("0")
+    return one(w.real) + "_" + one(w.imag)
+
+
+def gwr_report(eigenfunctions_history, spectrum_history, wgrid, imag_offset, dims, save_only_dos=False):
+    """save_gwr (prog/data_save.hxx:535-709), 2-D lattices: the measurement-averaged Green's function
+        G(w; r1, r2) = < V (w + i xi - eps)^-1 V^T >
+    from the eigenfunction and spectrum histories; per frequency the average and the typical (geometric-mean) local density of states
+    (`tdos` row: Re w, Im w, dos_geom, 0, dos, 0, dos_geom / dos, 0), the full matrix `gr_full`, its translation average G(w; r1 - r2)
+    `gr` [L0][L1] and the lattice Fourier transform `gk` (forward DFT, as FFTW_FORWARD).
+    eigenfunctions_history: [measurement][N][N] or [measurement][chain][N][N] with [..., i, k] = component i of eigenvector k;
+    spectrum_history: [measurement][N] or [measurement][chain][N].  Returns dict(tdos_gwr [n_w, 8], per_w {wstring: {...}})."""
+    ev = np.asarray(eigenfunctions_history, dtype=np.float64)
+    if ev.ndim == 4:
+        ev = np.transpose(ev, (1, 0, 2, 3)).reshape(-1, ev.shape[2], ev.shape[3])
+    sp = _history_rows(spectrum_history)
+    n_meas, vol = sp.shape
+    if ev.shape != (n_meas, vol, vol) or int(np.prod(dims)) != vol or len(dims) != 2:
+        raise ValueError("gwr_report: histories / dims mismatch (2-D lattices only)")
+    L0, L1 = int(dims[0]), int(dims[1])
+    idx = np.arange(vol)
+    p0, p1 = idx // L1, idx % L1                                    # index_to_pos: last coordinate fastest
+    d0 = (L0 + p0[None, :] - p0[:, None]) % L0                      # r_j - r_i
+    d1 = (L1 + p1[None, :] - p1[:, None]) % L1
+    tdos = np.zeros((len(wgrid), 8))
+    per_w = {}
+    for wi, w0 in enumerate(wgrid):
+        w = complex(w0) + 1j * imag_offset
+        g_re, g_im = np.zeros((vol, vol)), np.zeros((vol, vol))
+        for m in range(n_meas):
+            wme = w.real - sp[m]
+            den = 1.0 / (wme * wme + w.imag * w.imag)
+            g_im += (ev[m] * (-w.imag * den)) @ ev[m].T / n_meas
+            g_re += (ev[m] * (wme * den)) @ ev[m].T / n_meas
+        ldos = np.diag(g_im) / (-math.pi)
+        dos_val = ldos.sum() / vol
+        dos_geom = math.exp(np.log(ldos).sum() / vol)
+        tdos[wi] = (w.real, w.imag, dos_geom, 0.0, dos_val, 0.0, dos_geom / dos_val, 0.0)
+        if save_only_dos:
+            continue
+        gr_re, gr_im = np.zeros((L0, L1)), np.zeros((L0, L1))
+        np.add.at(gr_re, (d0, d1), g_re / vol)
+        np.add.at(gr_im, (d0, d1), g_im / vol)
+        gk = np.fft.fft2(gr_re + 1j * gr_im)
+        per_w[_wstring(w)] = dict(tdos=tdos[wi].copy(), gr_full_re=g_re, gr_full_im=g_im, gr_re=gr_re, gr_im=gr_im, gk_re=gk.real, gk_im=gk.imag)
+    return dict(tdos_gwr=tdos, per_w=per_w)
+
+
 # ---- plaintext twin of the reference output (prog/data_save.hxx:9-30, prog/data_save.hpp:124-156, README.md:42-43) ----
 def savetxt(fname, rows):
     """gftools-style plaintext: scientific notation, space separated, one row per line (README example:

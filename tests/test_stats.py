@@ -144,3 +144,70 @@ def test_dos_and_ipr_reports():
     # single-chain input [measurement][N] is accepted as is
     one = stats.dos_report(sp[:, 0], wg, off, beta, max_depth=2)
     assert one["dos0"]["binning"][0][0] == n_meas
+
+
+def test_gwr_report_against_direct_inverse():
+    """save_gwr (prog/data_save.hxx:535-709): G(w) from eigenvectors equals (w + i xi - H)^-1 averaged over the configurations; the translation
+    average and its DFT follow the reference's index conventions; dataset names use the reference's trimmed std::to_string(float)."""
+    L, U, xi = 4, 2.0, 0.05
+    n = L * L
+    H0 = o.hopping_dense(o.CUBIC2D, L)
+    rng = np.random.default_rng(5)
+    fs = (rng.random((3, n)) < 0.5).astype(float)
+    evs, sps = [], []
+    for f in fs:
+        ev, V = np.linalg.eigh(H0 + np.diag(U * f - U / 2))
+        evs.append(V)
+        sps.append(ev)
+    rep = stats.gwr_report(np.array(evs), np.array(sps), [0.0, 0.5], xi, (L, L))
+    assert set(rep["per_w"]) == {"0._0.05", "0.5_0.05"}
+    for w0, key in ((0.0, "0._0.05"), (0.5, "0.5_0.05")):
+        G = np.mean([np.linalg.inv((w0 + 1j * xi) * np.eye(n) - (H0 + np.diag(U * f - U / 2))) for f in fs], axis=0)
+        r = rep["per_w"][key]
+        assert np.abs(r["gr_full_re"] - G.real).max() < 1e-10 and np.abs(r["gr_full_im"] - G.imag).max() < 1e-10
+        ldos = -np.diag(G.imag) / math.pi
+        assert r["tdos"][4] == pytest.approx(ldos.mean(), rel=1e-10) and r["tdos"][2] == pytest.approx(math.exp(np.log(ldos).mean()), rel=1e-10)
+        assert r["tdos"][6] <= 1.0 + 1e-12                       # typical <= average (AM-GM)
+        # G(r1 - r2): element (dy, dx) averages G(i, j) over all i with r_j = r_i + (dy, dx)
+        acc = 0.0
+        for i in range(n):
+            y, x = divmod(i, L)
+            acc += G[i, ((y + 1) % L) * L + (x + 2) % L]
+        assert r["gr_re"][1, 2] + 1j * r["gr_im"][1, 2] == pytest.approx(acc / n, rel=1e-10)
+        gk = np.fft.fft2(r["gr_re"] + 1j * r["gr_im"])
+        assert np.allclose(r["gk_re"], gk.real) and np.allclose(r["gk_im"], gk.imag)
+        assert r["gk_re"][0, 0] + 1j * r["gk_im"][0, 0] == pytest.approx(G.sum() / n, rel=1e-10)   # k = 0 component
+    only = stats.gwr_report(np.array(evs)[:, None], np.array(sps)[:, None], [0.0], xi, (L, L), save_only_dos=True)   # [measurement][chain] input
+    assert only["per_w"] == {} and only["tdos_gwr"][0, 4] == pytest.approx(rep["tdos_gwr"][0, 4], rel=1e-12)
+
+
+def test_fcorrel_report():
+    """save_fcorrel (prog/data_save.hxx:347-420) against a loop transcription of its formula on a small lattice."""
+    rng = np.random.default_rng(8)
+    L, n_meas = 4, 32
+    V = L * L
+    # checkerboard-biased occupations so that the correlator has structure
+    idx = np.arange(V)
+    stag = ((idx // L + idx % L) % 2 == 0)
+    fo = (rng.random((n_meas, V)) < np.where(stag, 0.8, 0.2)).astype(np.int32)
+    rep = stats.fcorrel_report(fo, (L, L), max_depth=2)
+    b = rep["bin"]
+    series = [fo[::-1, i].astype(float) for i in range(V)]
+    nfb = stats.estimate_bin(stats.accumulate_binning(series[0], 2))
+    nf_mean = np.array([stats.bin_stats(x, nfb)[1] for x in series])
+
+    def f_loops(means, l):
+        out = 0.0
+        for i in range(V):
+            y, x = divmod(i, L)
+            for (yl, xl), (yr, xr) in ((((y - l) % L, x), ((y + l) % L, x)), ((y, (x - l) % L), (y, (x + l) % L))):
+                out += (means[i] - nf_mean[i]) * (means[yl * L + xl] - nf_mean[yl * L + xl])
+                out += (means[i] - nf_mean[i]) * (means[yr * L + xr] - nf_mean[yr * L + xr])
+        return out / V / 4.0
+
+    for l in (0, 1, 2):
+        ref = stats.jack(lambda *m: f_loops(m, l), series, b)
+        assert rep["fcorrel"][l, 1] == pytest.approx(ref[1], rel=1e-10, abs=1e-14) and rep["fcorrel"][l, 2] == pytest.approx(ref[3], rel=1e-10, abs=1e-14)
+    assert rep["fcorrel"].shape == (3, 5) and rep["fcorrel"][0, 3] == pytest.approx(1.0)
+    assert rep["fcorrel"][1, 1] * rep["fcorrel"][0, 1] < 0          # nearest neighbours anticorrelated in a checkerboard-biased ensemble
+    assert rep["fcorrel_q"].shape == (L,) and abs(rep["fcorrel_q"][L // 2].real) > abs(rep["fcorrel_q"][0].real)   # weight at q = pi
