@@ -32,7 +32,8 @@ class ChainParams(C.Structure):
                 ("nf_start", C.c_int32), ("sweep_len", C.c_int32), ("ntherm_sweeps", C.c_int32),
                 ("measure_energy", C.c_int32), ("record_trace", C.c_int32), ("max_sweeps", C.c_int32),
                 ("measure_history", C.c_int32), ("measure_ipr", C.c_int32), ("n_W", C.c_int32), ("W", C.c_double * 8),
-                ("measure_eigenfunctions", C.c_int32), ("fast_update", C.c_int32), ("fu_refresh_sweeps", C.c_int32)]
+                ("measure_eigenfunctions", C.c_int32), ("measure_stiffness", C.c_int32), ("n_cond_w", C.c_int32), ("cond_offset", C.c_double),
+                ("cond_wgrid", C.c_double * 32), ("fast_update", C.c_int32), ("fu_refresh_sweeps", C.c_int32)]
 
 
 def build_library(force=False):
@@ -299,7 +300,10 @@ class Context:
     def chain_init(self, n_chains, beta, U, mu_c=None, mu_f=None, mc_flip=0.0, mc_add_remove=1.0, mc_reshuffle=0.0,
                    cheb_moves=False, cheb_prefactor=2.2, seed=32167, chain0=0, nf_start=None, sweep_len=16, ntherm_sweeps=1,
                    measure_energy=True, record_trace=False, max_sweeps=64, measure_history=False, measure_ipr=False, W=(),
-                   fast_update=False, fu_refresh_sweeps=0, measure_eigenfunctions=False):
+                   fast_update=False, fu_refresh_sweeps=0, measure_eigenfunctions=False, measure_stiffness=False, cond_wgrid=(), cond_offset=0.05):
+        cw = [float(w) for w in cond_wgrid]
+        if len(cw) > 32:
+            raise FkmcError(1, "at most 32 conductivity frequencies")
         W = [float(w) for w in W]
         if len(W) > 8:
             raise FkmcError(1, "at most 8 f-f interaction terms")
@@ -307,8 +311,8 @@ class Context:
                         mc_reshuffle, int(cheb_moves), cheb_prefactor, seed, chain0,
                         self.N // 2 if nf_start is None else nf_start, sweep_len, ntherm_sweeps, int(measure_energy),
                         int(record_trace), max_sweeps, int(measure_history), int(measure_ipr), len(W),
-                        (C.c_double * 8)(*(W + [0.0] * (8 - len(W)))), int(measure_eigenfunctions), int(fast_update),
-                        int(fu_refresh_sweeps))
+                        (C.c_double * 8)(*(W + [0.0] * (8 - len(W)))), int(measure_eigenfunctions), int(measure_stiffness), len(cw),
+                        float(cond_offset), (C.c_double * 32)(*(cw + [0.0] * (32 - len(cw)))), int(fast_update), int(fu_refresh_sweeps))
         self._ck(self.lib.fkmc_chain_init(self.h, int(n_chains), C.byref(p)))
         self.chain_params = p
         self.n_chains = n_chains
@@ -351,6 +355,17 @@ class Context:
         n = C.c_int(0)
         self._ck(self.lib.fkmc_chain_get_eigenfunctions(self.h, C.byref(n), _ptr(ev, C.c_double)))
         return np.transpose(ev[:n.value], (0, 1, 3, 2))   # stored eigenvector-major (column-major matrix)
+
+    def chain_get_stiffness(self):
+        """dict(n_measured, stiffness [n_measured, n_chains], cond [n_measured, n_chains, n_cond_w])."""
+        p, Cn = self.chain_params, self.n_chains
+        nw = p.n_cond_w
+        st = np.zeros((p.max_sweeps, Cn))
+        cd = np.zeros((p.max_sweeps, Cn, max(nw, 1)))
+        n = C.c_int(0)
+        self._ck(self.lib.fkmc_chain_get_stiffness(self.h, C.byref(n), _ptr(st, C.c_double), _ptr(cd, C.c_double) if nw else None))
+        m = n.value
+        return dict(n_measured=m, stiffness=st[:m], cond=cd.reshape(-1)[: m * Cn * nw].reshape(m, Cn, nw))
 
     def chain_get_fsector(self):
         """dict(n_measured, nf0, nfpi [n_measured, n_chains]): n_f(q=0) and |n_f(q=pi)| per measured sweep (fsusc0pi.hpp:36-46)."""

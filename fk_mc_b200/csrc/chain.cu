@@ -339,7 +339,7 @@ int fkmc_chain_free(fkmc_ctx* ctx) {
     cudaFree(S.eff_cur); cudaFree(S.eff_prop); cudaFree(S.d_W);
     if (S.fu_vt) fkmc_fu_free(ctx);
     if (S.step_graph) cudaGraphExecDestroy(S.step_graph);
-    cudaFree(S.spec_mean); cudaFree(S.spec_hist); cudaFree(S.focc_hist); cudaFree(S.ipr_hist); cudaFree(S.ipr_evals); cudaFree(S.eig_hist);
+    cudaFree(S.spec_mean); cudaFree(S.spec_hist); cudaFree(S.focc_hist); cudaFree(S.ipr_hist); cudaFree(S.ipr_evals); cudaFree(S.eig_hist); cudaFree(S.s_stiff); cudaFree(S.cond_hist); cudaFree(S.d_cond_w);
     S = fkmc_chain_state();
     return FKMC_OK;
 }
@@ -350,6 +350,8 @@ extern "C" int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_par
     if (p->sweep_len < 1 || p->max_sweeps < 1) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sweep_len and max_sweeps must be >= 1");
     if (p->nf_start < 0 || p->nf_start > ctx->N) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "nf_start out of range");
     if (p->n_W < 0 || p->n_W > FKMC_MAX_W) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "n_W must be in [0, 8]");
+    if (p->measure_stiffness && (p->n_cond_w < 0 || p->n_cond_w > FKMC_MAX_COND_W || (ctx->kind != FKMC_CUBIC2D && ctx->kind != FKMC_CUBIC3D)))
+        return fkmc_set_error(ctx, FKMC_ERR_INVALID, "measure_stiffness needs a cubic2d / cubic3d lattice and n_cond_w in [0, 32]");
     if (p->fast_update && (p->cheb_moves || p->mc_reshuffle > std::numeric_limits<double>::epsilon() || ctx->N > 1024 || ctx->N < 2))
         return fkmc_set_error(ctx, FKMC_ERR_INVALID, "fast_update needs exact moves, mc_reshuffle = 0 and 2 <= N <= 1024");
     FKMC_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -386,7 +388,7 @@ extern "C" int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_par
     // which measures run (fk_mc.hxx:94-124): energy + spectrum whenever an exact spectrum exists per sweep (exact moves, or
     // measure_energy / measure_ipr asked for it); spectrum_history and focc_history with measure_history; ipr with measure_ipr
     const bool exact_measure = !p->cheb_moves || p->measure_energy || p->measure_ipr || p->measure_eigenfunctions;
-    if (exact_measure) {
+    if (exact_measure || p->measure_stiffness) {
         int rc = fkmc_ensure_dense_ws(ctx);
         if (rc) return rc;
     }
@@ -426,6 +428,11 @@ extern "C" int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_par
     if (p->measure_ipr) rc |= dev_alloc(ctx, &S.ipr_hist, rows * C * V);
     if (p->measure_ipr || p->measure_eigenfunctions) rc |= dev_alloc(ctx, &S.ipr_evals, C * V);
     if (p->measure_eigenfunctions) rc |= dev_alloc(ctx, &S.eig_hist, rows * C * V * V);
+    if (p->measure_stiffness) {
+        rc |= dev_alloc(ctx, &S.s_stiff, rows * C);
+        rc |= dev_alloc(ctx, &S.cond_hist, rows * C * (size_t)std::max(p->n_cond_w, 1));
+        rc |= dev_alloc(ctx, &S.d_cond_w, (size_t)FKMC_MAX_COND_W);
+    }
     if (p->record_trace) {
         rc |= dev_alloc(ctx, &S.t_move, steps * C); rc |= dev_alloc(ctx, &S.t_a, steps * C); rc |= dev_alloc(ctx, &S.t_b, steps * C);
         rc |= dev_alloc(ctx, &S.t_acc, steps * C); rc |= dev_alloc(ctx, &S.t_w, steps * C); rc |= dev_alloc(ctx, &S.t_u, steps * C);
@@ -445,6 +452,8 @@ extern "C" int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_par
     S.measured = 0;
     S.spec_count = 0;
     if (S.spec_mean) FKMC_CUDA(ctx, cudaMemsetAsync(S.spec_mean, 0, sizeof(double) * C * V, ctx->stream));
+    if (p->measure_stiffness && p->n_cond_w > 0)
+        FKMC_CUDA(ctx, cudaMemcpyAsync(S.d_cond_w, p->cond_wgrid, sizeof(double) * p->n_cond_w, cudaMemcpyHostToDevice, ctx->stream));
     if (p->n_W > 0) FKMC_CUDA(ctx, cudaMemcpyAsync(S.d_W, p->W, sizeof(double) * p->n_W, cudaMemcpyHostToDevice, ctx->stream));
 
     chain_dev D = make_dev(ctx);
@@ -581,6 +590,12 @@ extern "C" int fkmc_chain_run_sweeps(fkmc_ctx* ctx, int n_sweeps) {
                 chain_measure_kernel<<<(C + 127) / 128, 128, 0, ctx->stream>>>(D, ecd2, es, S.s_energy, S.s_d2energy, S.s_cenergy, S.s_nf,
                                                                             S.measured);
                 ctx->launches++;
+            }
+            if (S.p.measure_stiffness) {
+                // measure_stiffness::accumulate (stiffness.hpp:129-187): its own calc_ed(true) + V^T Jm V on DMMA + Kubo sums
+                int rc = fkmc_stiffness_dev(ctx, S.f_cur, C, S.p.U, S.p.mu_c, S.p.beta, S.p.cond_offset, S.p.n_cond_w, S.d_cond_w,
+                                            S.s_stiff + (size_t)S.measured * C, S.cond_hist + (size_t)S.measured * C * std::max(S.p.n_cond_w, 1));
+                if (rc) return rc;
             }
             {
                 fkmc_prof_scope ps(ctx, "chain_step");
@@ -726,6 +741,20 @@ extern "C" int fkmc_chain_get_eigenfunctions(fkmc_ctx* ctx, int* n_measured, dou
     if (n_measured) *n_measured = (int)S.measured;
     const size_t N = ctx->N;
     int rc = copy_out(ctx, evecs, S.eig_hist, (size_t)S.measured * S.n_chains * N * N * 8);
+    if (rc) return rc;
+    FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FKMC_OK;
+}
+
+extern "C" int fkmc_chain_get_stiffness(fkmc_ctx* ctx, int* n_measured, double* stiffness, double* cond) {
+    if (!ctx) return FKMC_ERR_INVALID;
+    fkmc_chain_state& S = ctx->chain;
+    if (!S.active) return fkmc_set_error(ctx, FKMC_ERR_STATE, "no chains");
+    if (!S.s_stiff) return fkmc_set_error(ctx, FKMC_ERR_STATE, "measure_stiffness is off");
+    if (n_measured) *n_measured = (int)S.measured;
+    const size_t n = (size_t)S.measured * S.n_chains;
+    int rc = copy_out(ctx, stiffness, S.s_stiff, n * 8);
+    if (S.p.n_cond_w > 0) rc |= copy_out(ctx, cond, S.cond_hist, n * S.p.n_cond_w * 8);
     if (rc) return rc;
     FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FKMC_OK;

@@ -57,6 +57,9 @@ struct fkmc_chain_state {
     double* spec_hist = nullptr;     // [max_sweeps][n_chains][N]
     int32_t* focc_hist = nullptr;    // [max_sweeps][n_chains][V]
     double* ipr_hist = nullptr;      // [max_sweeps][n_chains][N]
+    double* s_stiff = nullptr;       // [max_sweeps][n_chains] stiffness series
+    double* cond_hist = nullptr;     // [max_sweeps][n_chains][n_cond_w] optical conductivity
+    double* d_cond_w = nullptr;      // [n_cond_w] frequency grid
     double* eig_hist = nullptr;      // [max_sweeps][n_chains][N][N] eigenvector-major (== column-major matrix)
     double* ipr_evals = nullptr;     // [n_chains][N] spectrum of the eigenvector solve of the last measured sweep
     long spec_count = 0;             // measurements folded into spec_mean
@@ -233,6 +236,9 @@ int fkmc_fu_evaluate(fkmc_ctx* ctx);
 int fkmc_fu_commit(fkmc_ctx* ctx);
 int fkmc_fu_ipr(fkmc_ctx* ctx, double* d_ipr);
 int fkmc_launch_secular_only(fkmc_ctx* ctx, int N, int B, const double* d_lam, const double* d_z, const double* d_rho, double* d_out);
+// measure_stiffness on device configurations (stiffness.cu): d_st [B], d_cd [B][n_w]
+int fkmc_stiffness_dev(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, double offset, int n_w, const double* d_w,
+                       double* d_st, double* d_cd);
 // chains
 int fkmc_chain_free(fkmc_ctx* ctx);
 extern "C" int fkmc_comm_destroy(fkmc_ctx* ctx);

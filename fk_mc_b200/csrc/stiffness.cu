@@ -96,24 +96,18 @@ __global__ void __launch_bounds__(1024) kubo_kernel(const double* __restrict__ m
 
 }  // namespace
 
-extern "C" int fkmc_stiffness_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, double mu_c, double beta, double offset, int n_w,
-                                      const double* wgrid, double* stiffness, double* cond) {
-    if (!ctx || !f || !stiffness || n_w < 0 || (n_w > 0 && (!wgrid || !cond))) return FKMC_ERR_INVALID;
+// Device-side core: configurations d_f [B][N] (device) -> d_st [B], d_cd [B][n_w] (device).  d_w: the frequency grid on the device.
+int fkmc_stiffness_dev(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, double offset, int n_w, const double* d_w,
+                       double* d_st, double* d_cd) {
     if (ctx->kind != FKMC_CUBIC2D && ctx->kind != FKMC_CUBIC3D)
         return fkmc_set_error(ctx, FKMC_ERR_INVALID, "stiffness: hypercubic lattices with D >= 2 only (stiffness.hpp:147)");
-    if (B < 1 || B > ctx->max_batch) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "B must be in [1, max_batch]");
-    FKMC_CUDA(ctx, cudaSetDevice(ctx->device));
     const int N = ctx->N, L = ctx->L;
     const size_t NN = (size_t)N * N;
     const int stride_x = N / L;  // L^(D-1): the first coordinate is the slowest
-    // chunk: 4 N^2 doubles per matrix here + the pipeline's own scratch
-    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, (size_t)(4.0e9 / (4.0 * NN * 8.0))));
-    double *d_ev = nullptr, *d_vt = nullptr, *d_jv = nullptr, *d_mj = nullptr, *d_td = nullptr, *d_evals = nullptr, *d_w = nullptr, *d_st = nullptr, *d_cd = nullptr;
-    int32_t* d_f = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(d_ev); cudaFree(d_vt); cudaFree(d_jv); cudaFree(d_mj); cudaFree(d_td); cudaFree(d_evals); cudaFree(d_w); cudaFree(d_st); cudaFree(d_cd);
-        cudaFree(d_f);
-    };
+    // chunk: 4 N^2 doubles per matrix here (+ the eigenvector pipeline's own scratch)
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, (size_t)(4.0e9 / (4.0 * NN * 8.0))));
+    double *d_ev = nullptr, *d_vt = nullptr, *d_jv = nullptr, *d_mj = nullptr, *d_td = nullptr, *d_evals = nullptr;
+    auto cleanup = [&]() { cudaFree(d_ev); cudaFree(d_vt); cudaFree(d_jv); cudaFree(d_mj); cudaFree(d_td); cudaFree(d_evals); };
 #define FKMC_ST(call)                                                                                       \
     do {                                                                                                    \
         cudaError_t e__ = (call);                                                                           \
@@ -125,17 +119,11 @@ extern "C" int fkmc_stiffness_batched(fkmc_ctx* ctx, const int32_t* f, int B, do
     FKMC_ST(cudaMalloc(&d_mj, sizeof(double) * NN * chunk));
     FKMC_ST(cudaMalloc(&d_td, sizeof(double) * (size_t)N * chunk));
     FKMC_ST(cudaMalloc(&d_evals, sizeof(double) * (size_t)N * chunk));
-    FKMC_ST(cudaMalloc(&d_w, sizeof(double) * std::max(n_w, 1)));
-    FKMC_ST(cudaMalloc(&d_st, sizeof(double) * chunk));
-    FKMC_ST(cudaMalloc(&d_cd, sizeof(double) * (size_t)chunk * std::max(n_w, 1)));
-    FKMC_ST(cudaMalloc(&d_f, sizeof(int32_t) * (size_t)N * chunk));
-    if (n_w) FKMC_ST(cudaMemcpyAsync(d_w, wgrid, sizeof(double) * n_w, cudaMemcpyHostToDevice, ctx->stream));
     FKMC_ST(cudaFuncSetAttribute(gemm_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fkgemm::smem_bytes()));
     int rc = FKMC_OK;
     for (int b0 = 0; b0 < B && !rc; b0 += chunk) {
         const int nb = std::min(chunk, B - b0);
-        FKMC_ST(cudaMemcpyAsync(d_f, f + (size_t)b0 * N, sizeof(int32_t) * (size_t)N * nb, cudaMemcpyHostToDevice, ctx->stream));
-        if ((rc = fkmc_eigvec_pipeline_dev2(ctx, d_f, nb, U, mu_c, beta, d_evals, ctx->d_out, d_ev, d_vt, nullptr))) break;
+        if ((rc = fkmc_eigvec_pipeline_dev2(ctx, d_f + (size_t)b0 * N, nb, U, mu_c, beta, d_evals, ctx->d_out, d_ev, d_vt, nullptr))) break;
         {
             fkmc_prof_scope ps(ctx, "stiffness_jv");
             jv_kernel<<<dim3((N + 255) / 256, nb), 256, 0, ctx->stream>>>(d_vt, N, stride_x, L, ctx->t, d_jv, d_td);
@@ -149,15 +137,39 @@ extern "C" int fkmc_stiffness_batched(fkmc_ctx* ctx, const int32_t* f, int B, do
         {
             fkmc_prof_scope ps(ctx, "stiffness_kubo");
             const int T = std::min(1024, ((N + 31) / 32) * 32);
-            kubo_kernel<<<nb, T, sizeof(double) * (2 * (size_t)N + 40), ctx->stream>>>(d_mj, d_evals, d_td, N, beta, offset, n_w, d_w, d_st, d_cd);
+            kubo_kernel<<<nb, T, sizeof(double) * (2 * (size_t)N + 40), ctx->stream>>>(d_mj, d_evals, d_td, N, beta, offset, n_w, d_w, d_st + b0,
+                                                                                       d_cd + (size_t)b0 * n_w);
             ctx->launches++;
         }
         FKMC_ST(cudaGetLastError());
-        FKMC_ST(cudaMemcpyAsync(stiffness + b0, d_st, sizeof(double) * nb, cudaMemcpyDeviceToHost, ctx->stream));
-        if (n_w) FKMC_ST(cudaMemcpyAsync(cond + (size_t)b0 * n_w, d_cd, sizeof(double) * (size_t)nb * n_w, cudaMemcpyDeviceToHost, ctx->stream));
-        FKMC_ST(cudaStreamSynchronize(ctx->stream));
+        FKMC_ST(cudaStreamSynchronize(ctx->stream));   // the scratch of this chunk is reused by the next one
     }
 #undef FKMC_ST
+    cleanup();
+    return rc;
+}
+
+extern "C" int fkmc_stiffness_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, double mu_c, double beta, double offset, int n_w,
+                                      const double* wgrid, double* stiffness, double* cond) {
+    if (!ctx || !f || !stiffness || n_w < 0 || (n_w > 0 && (!wgrid || !cond))) return FKMC_ERR_INVALID;
+    if (B < 1 || B > ctx->max_batch) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "B must be in [1, max_batch]");
+    FKMC_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int N = ctx->N;
+    double *d_w = nullptr, *d_st = nullptr, *d_cd = nullptr;
+    auto cleanup = [&]() { cudaFree(d_w); cudaFree(d_st); cudaFree(d_cd); };
+    if (cudaMalloc(&d_w, sizeof(double) * std::max(n_w, 1)) != cudaSuccess || cudaMalloc(&d_st, sizeof(double) * B) != cudaSuccess ||
+        cudaMalloc(&d_cd, sizeof(double) * (size_t)B * std::max(n_w, 1)) != cudaSuccess) {
+        cleanup();
+        return fkmc_set_error(ctx, FKMC_ERR_CUDA, "stiffness: out of device memory");
+    }
+    cudaMemcpyAsync(ctx->d_f, f, sizeof(int32_t) * (size_t)B * N, cudaMemcpyHostToDevice, ctx->stream);
+    if (n_w) cudaMemcpyAsync(d_w, wgrid, sizeof(double) * n_w, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = fkmc_stiffness_dev(ctx, ctx->d_f, B, U, mu_c, beta, offset, n_w, d_w, d_st, d_cd);
+    if (!rc) {
+        cudaMemcpyAsync(stiffness, d_st, sizeof(double) * B, cudaMemcpyDeviceToHost, ctx->stream);
+        if (n_w) cudaMemcpyAsync(cond, d_cd, sizeof(double) * (size_t)B * n_w, cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fkmc_set_error(ctx, FKMC_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
+    }
     cleanup();
     if (rc) return rc;
     return fkmc_check_flag(ctx);

@@ -720,7 +720,8 @@ public:
     fk_mc(parameters_t const& p_, int rank = 0) : base(p_, rank), p(p_), rank0_(rank) {}
 
     /// fk_mc.hxx:35-125.  The lattice is taken by reference (it owns a GPU context and is not copyable; the reference copies it).
-    void initialize(lattice_type& l, bool randomize_config = true, std::vector<double> /*wgrid_conductivity*/ = {0.0}) {
+    void initialize(lattice_type& l, bool randomize_config = true, std::vector<double> wgrid_conductivity = {0.0}) {
+        wgrid_cond_ = std::move(wgrid_conductivity);  // used by run_batched when measure_stiffness is set (fk_mc.hxx:101-105 keeps it commented out)
         lattice_ptr = std::shared_ptr<lattice_type>(&l, [](lattice_type*) {});
         const std::vector<double> W = (l.ndim() == 1 && p.exists("W")) ? p["W"].template as<std::vector<double>>() : std::vector<double>();
         config_ptr = std::make_shared<configuration_t>(l, p["beta"], p["U"], p["mu_c"], p["mu_f"], W);
@@ -782,6 +783,13 @@ public:
         cp.measure_energy = !cp.cheb_moves || ipr;
         cp.measure_history = history;
         cp.measure_eigenfunctions = bool(p["measure_eigenfunctions"]);
+        if (bool(p["measure_stiffness"]) && l.ndim() >= 2) {
+            if (wgrid_cond_.size() > FKMC_MAX_COND_W) throw std::logic_error("at most 32 conductivity frequencies");
+            cp.measure_stiffness = 1;
+            cp.n_cond_w = int(wgrid_cond_.size());
+            cp.cond_offset = p["cond_offset"];
+            std::copy(wgrid_cond_.begin(), wgrid_cond_.end(), cp.cond_wgrid);
+        }
         // not a reference parameter: rank-one secular re-weighting of the dense moves (fkmc.h: fast_update), same results
         if (p.exists("fast_update")) cp.fast_update = bool(p["fast_update"]) && !cp.cheb_moves && !(cp.mc_reshuffle > 0.0);
         if (l.ndim() == 1 && p.exists("W")) {
@@ -822,6 +830,19 @@ public:
                 for (int m = 0; m < n_ev; ++m)
                     out[c].eigenfunctions_history.emplace_back(ev.begin() + (size_t(m) * C + c) * N * N, ev.begin() + (size_t(m) * C + c + 1) * N * N);
         }
+        if (cp.measure_stiffness) {
+            const size_t nw = size_t(cp.n_cond_w);
+            std::vector<double> st(size_t(cp.max_sweeps) * C), cd(size_t(cp.max_sweeps) * C * std::max<size_t>(nw, 1));
+            int n_st = 0;
+            fkmc_check(fkmc_chain_get_stiffness(l.ctx(), &n_st, st.data(), cd.data()), l.ctx());
+            for (size_t c = 0; c < C; ++c) {
+                out[c].cond_history.assign(nw, std::vector<double>(n_st));  // frequency-major like stiffness.hpp:86
+                for (int m = 0; m < n_st; ++m) {
+                    out[c].stiffness.push_back(st[m * C + c]);
+                    for (size_t w = 0; w < nw; ++w) out[c].cond_history[w][m] = cd[(size_t(m) * C + c) * nw + w];
+                }
+            }
+        }
         batched_naccept_ = bc.naccept();
         batched_f_ = bc.f_config();
         return out;
@@ -832,6 +853,7 @@ public:
 private:
     std::unique_ptr<chebyshev::chebyshev_eval> cheb_ptr_;
     int rank0_ = 0;
+    std::vector<double> wgrid_cond_{0.0};
     std::vector<int64_t> batched_naccept_;
     std::vector<int32_t> batched_f_;
 };

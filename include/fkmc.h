@@ -40,6 +40,7 @@ enum fkmc_lattice_kind {
 };
 
 #define FKMC_MAX_W 8
+#define FKMC_MAX_COND_W 32
 
 enum fkmc_move_kind { FKMC_MOVE_FLIP = 0, FKMC_MOVE_ADDREMOVE = 1, FKMC_MOVE_RESHUFFLE = 2 };
 
@@ -140,6 +141,11 @@ typedef struct fkmc_chain_params {
     double W[FKMC_MAX_W];                        /* ignored for D >= 2 where calc_ff_energy() == 0 (configuration.cpp:62) */
     int32_t measure_eigenfunctions;              /* fk_mc.hxx:196: eigenfunctions_history, N x N eigenvector matrix per chain and measured sweep
                                                     (max_sweeps * n_chains * N^2 doubles of device memory) */
+    int32_t measure_stiffness;                   /* fk_mc.hxx:198 (registration commented out at HEAD, fk_mc.hxx:101-105): measure_stiffness per measured
+                                                    sweep -> stiffness series and cond_history on cond_wgrid; cubic2d / cubic3d only */
+    int32_t n_cond_w;                            /* number of conductivity frequencies (<= FKMC_MAX_COND_W; the exec's wgrid_conductivity) */
+    double cond_offset;                          /* Lorentzian broadening (fk_mc.hxx:197, default 0.05) */
+    double cond_wgrid[FKMC_MAX_COND_W];
     int32_t fast_update;                         /* exact moves only: 1 = re-weight add_remove / flip proposals through rank-one secular
                                                     updates of the tracked eigen-decomposition (O(N^2) per proposal, an N^3 eigenvector
                                                     update only on accept; benchmark/fast_update.cpp) instead of a fresh
@@ -174,6 +180,9 @@ int fkmc_chain_get_history(fkmc_ctx* ctx, int* n_measured, double* spectrum_mean
 /* measure_eigenfunctions (src/measures/eigenfunctions.cpp:12-18): evecs [n_measured][n_chains][N][N], each matrix column-major like
  * ed_cache::cached_evecs (column k <-> eigenvalue k of the spectrum history); needs chain parameter measure_eigenfunctions */
 int fkmc_chain_get_eigenfunctions(fkmc_ctx* ctx, int* n_measured, double* evecs);
+/* measure_stiffness series (include/fk_mc/measures/stiffness.hpp:129-187): stiffness [n_measured][n_chains] (observables_t::stiffness) and
+ * cond [n_measured][n_chains][n_cond_w] (observables_t::cond_history, frequency-major there); needs chain parameter measure_stiffness */
+int fkmc_chain_get_stiffness(fkmc_ctx* ctx, int* n_measured, double* stiffness, double* cond);
 /* measure_ipr on the chains' current configurations: evals [n_chains][N] (or NULL), ipr [n_chains][N] */
 int fkmc_chain_ipr(fkmc_ctx* ctx, double* evals, double* ipr);
 /* device pointers to the series (for the end-of-run NCCL gather): energies, d2energies, c_energies as

@@ -56,8 +56,12 @@ int main(int argc, char** argv) {
         // the batched product path: ranks rank, rank + 1 as two chains resident on the GPU (dense moves re-weighted by rank-one secular
         // updates: same results as one eigensolve per proposal)
         p["fast_update"] = !cheb_move;
+        p["measure_stiffness"] = true;
         qmc_t mcb(p, rank);
+        mcb.initialize(lattice, true, {0.0, 0.5});
         auto obs = mcb.run_batched(lattice, 2);
+        printf("b_stiffness_shape %zu %zu %zu\n", obs[0].stiffness.size(), obs[0].cond_history.size(), obs[0].cond_history.empty() ? 0 : obs[0].cond_history[0].size());
+        print_series("b0_stiffness", obs[0].stiffness);
         for (int c = 0; c < 2; ++c) {
             printf("b%d_naccept %ld\n", c, long(mcb.batched_naccept()[c]));
             print_series(c ? "b1_energies" : "b0_energies", obs[c].energies);

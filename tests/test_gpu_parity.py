@@ -821,6 +821,7 @@ def test_cpp_host_api_matches_oracle(tmp_path, cheb, flip):
         assert np.allclose(np.array(rows["b%d_energies" % c], dtype=float), rb["energies"], rtol=1e-10)
         assert np.allclose(np.array(rows["b%d_spectrum_mean" % c], dtype=float), rb["spectrum_avg"], rtol=0, atol=1e-10 * np.abs(rb["spectrum_avg"]).max())
     assert rows["b_history_shape"] == [str(L * L), str(nsw), str(L * L)]
+    assert rows["b_stiffness_shape"] == [str(nsw), "2", str(nsw)] and len(rows["b0_stiffness"]) == nsw
     assert rows["mismatch_throws"] == ["1"] and rows["honeycomb_odd_throws"] == ["1"] and rows["no_moves_throws"] == ["1"]
 
 
@@ -916,6 +917,33 @@ def test_stiffness_gpu_contraction_matches_host(kind, L, ndim):
             ref, cref = o.stiffness(o.KINDS[kind], L, fs[b], U, U / 2, beta, offset=0.05, wgrid=wg)
             assert st[b] == pytest.approx(ref, abs=1e-8)
             assert np.abs(cd[b] - cref).max() <= 1e-6 * max(1.0, np.abs(cref).max())
+    c.close()
+
+
+@pytest.mark.parametrize("cheb", [False, True])
+def test_chain_measure_stiffness_series(cheb):
+    """Chain parameter measure_stiffness (fk_mc.hxx:101-105, stiffness.hpp:129-187): the stiffness / conductivity of every measured
+    sweep's configuration (from focc_history) equals the oracle's measure on that configuration."""
+    L, U, beta, n_chains, nsw = 6, 2.0, 4.0, 3, 4
+    wg = [0.0, 0.5, 1.0]
+    c = fk.Context("cubic2d", L, max_batch=n_chains)
+    c.chain_init(n_chains, beta, U, U / 2, U / 2, seed=77, sweep_len=5, max_sweeps=nsw, cheb_moves=cheb, measure_history=True,
+                 measure_stiffness=True, cond_wgrid=wg, cond_offset=0.07)
+    c.chain_run_sweeps(nsw)
+    r = c.chain_get_stiffness()
+    h = c.chain_get_history()
+    nm = r["n_measured"]
+    assert nm == h["n_measured"] >= 3 and r["stiffness"].shape == (nm, n_chains) and r["cond"].shape == (nm, n_chains, 3)
+    for m in range(nm):
+        for k in range(n_chains):
+            f = h["focc_history"][m, k].astype(np.int32)
+            ref, cref = o.stiffness(o.CUBIC2D, L, f, U, U / 2, beta, offset=0.07, wgrid=np.array(wg))
+            assert r["stiffness"][m, k] == pytest.approx(ref, abs=1e-8)
+            assert np.abs(r["cond"][m, k] - cref).max() <= 1e-6 * max(1.0, np.abs(cref).max())
+    c.close()
+    c = fk.Context("triangular", 6)
+    with pytest.raises(fk.FkmcError):
+        c.chain_init(1, beta, U, U / 2, U / 2, measure_stiffness=True)
     c.close()
 
 
