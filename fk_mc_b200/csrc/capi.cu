@@ -60,6 +60,7 @@ int fkmc_ensure_dense_ws(fkmc_ctx* ctx) {
     rc |= dalloc(ctx, &ctx->d_A, B * N * N);
     rc |= dalloc(ctx, &ctx->d_W, B * N * FKMC_SYTRD_NB);
     rc |= dalloc(ctx, &ctx->d_AB, B * N * 9);
+    if (ctx->band_bw > 0) rc |= dalloc(ctx, &ctx->d_band, B * fkmc_band_stride((int)N));
     rc |= dalloc(ctx, &ctx->d_d, B * N);
     rc |= dalloc(ctx, &ctx->d_e, B * N);
     rc |= dalloc(ctx, &ctx->d_tau, B * N);
@@ -78,6 +79,12 @@ int fkmc_tridiagonalize(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_d, d
 
 int fkmc_build_tridiag(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double* d_d, double* d_e) {
     const int N = ctx->N;
+    if (ctx->tridiag_mode == 2 && fkmc_use_band(ctx) && ctx->d_band && fkmc_sb2st_smem(N) <= ctx->smem_optin) {
+        // two-dimensional lattices: folded ordering = band matrix; band -> band (DMMA block bulge chasing) -> tridiagonal
+        int rc = fkmc_launch_band_reduce(ctx, d_f, B, U, mu_c, ctx->d_band, ctx->d_AB);
+        if (rc) return rc;
+        return fkmc_launch_sb2st(ctx, ctx->d_AB, N, B, d_d, d_e);
+    }
     if (ctx->tridiag_mode == 2 && fkmc_use_tiled(ctx, N) && fkmc_sy2sb_smem(N) <= ctx->smem_optin && fkmc_sb2st_smem(N) <= ctx->smem_optin) {
         // large matrices: tiled lower-triangular layout, bulk-async dense->band, then band->tridiagonal
         int rc = fkmc_launch_build_h_tiled(ctx, d_f, B, U, mu_c, ctx->d_A);
@@ -167,6 +174,7 @@ int fkmc_create(fkmc_ctx** out, int device, int lattice_kind, int L, double t, d
     cudaMemcpy(ctx->d_nbr_idx, ctx->h_nbr_idx.data(), sizeof(int) * Z * N, cudaMemcpyHostToDevice);
     cudaMemcpy(ctx->d_nbr_val, ctx->h_nbr_val.data(), sizeof(double) * Z * N, cudaMemcpyHostToDevice);
     cudaMemset(ctx->d_flag, 0, sizeof(int));
+    if (fkmc_band_setup(ctx)) return fail("band setup");
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
     if (cudaGetLastError() != cudaSuccess) return fail("context setup");
@@ -182,6 +190,7 @@ int fkmc_destroy(fkmc_ctx* ctx) {
     fkmc_comm_destroy(ctx);
     cudaFree(ctx->d_gather);
     cudaFree(ctx->d_ev_scratch);
+    cudaFree(ctx->d_band0); cudaFree(ctx->d_band_perm); cudaFree(ctx->d_band);
     fkmc_chain_free(ctx);
     cudaFree(ctx->d_AB); cudaFree(ctx->d_kpm_steps); cudaFree(ctx->d_s1_scratch);
     cudaFree(ctx->d_nbr_idx); cudaFree(ctx->d_nbr_val); cudaFree(ctx->d_A); cudaFree(ctx->d_W); cudaFree(ctx->d_d);
@@ -397,6 +406,15 @@ int fkmc_set_option(fkmc_ctx* ctx, const char* name, int value) {
     }
     if (std::string(name) == "kpm_generic_schedule") {
         ctx->kpm_no_sched = value != 0;
+        return FKMC_OK;
+    }
+    if (std::string(name) == "band_path") {  // 1 (default): eigenvalue-only solves of banded lattice matrices start from the band (sb2sb.cu)
+        ctx->band_path = value != 0;
+        return FKMC_OK;
+    }
+    if (std::string(name) == "band_min") {  // smallest N served by the band path (default 256)
+        if (value < 16) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "band_min must be >= 16");
+        ctx->band_min = value;
         return FKMC_OK;
     }
     if (std::string(name) == "sy2sb_tiled_min") {  // smallest N served by the tiled dense->band kernel (default 256)

@@ -104,6 +104,11 @@ struct fkmc_ctx {
     // workspaces sized for max_batch
     double* d_A = nullptr;      // [max_batch][N][N] dense Hamiltonians (column-major, lower triangle live)
     double* d_W = nullptr;      // [max_batch][N][NB] panel workspace
+    // band path (sb2sb.cu): folded site ordering with half-bandwidth band_bw <= 64 (0: not available), static hopping tiles, work band
+    int band_bw = 0, band_path = 1, band_min = 256;
+    double* d_band0 = nullptr;
+    int* d_band_perm = nullptr;
+    double* d_band = nullptr;   // [max_batch][fkmc_band_stride(N)]
     double* d_AB = nullptr;     // [max_batch][9][N] band storage of the two-stage reduction
     double* d_s1_scratch = nullptr;  // sy2sb: fragment-ordered panel records, one slot per matrix
     size_t s1_scratch_cap = 0;       // doubles
@@ -194,6 +199,11 @@ int fkmc_launch_build_h(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, doub
 int fkmc_launch_sytrd(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_d, double* d_e, double* d_tau, double* d_W);
 // two-stage tridiagonalisation
 int fkmc_launch_sy2sb(fkmc_ctx* ctx, double* d_A, int N, int B, double* d_AB);
+// band path: lattice matrix in a folded ordering (half-bandwidth <= 64) -> half-bandwidth 8 (sb2sb.cu)
+size_t fkmc_band_stride(int N);
+int fkmc_band_setup(fkmc_ctx* ctx);
+bool fkmc_use_band(const fkmc_ctx* ctx);
+int fkmc_launch_band_reduce(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double* d_band, double* d_AB);
 int fkmc_launch_sb2st(fkmc_ctx* ctx, const double* d_AB, int N, int B, double* d_d, double* d_e);
 size_t fkmc_sy2sb_smem(int N);
 size_t fkmc_sy2sb_scratch(int N);

@@ -954,6 +954,74 @@ def test_stiffness_rejects_other_lattices():
     c.close()
 
 
+# ---------------- band path: folded lattice ordering, band -> band (sb2sb.cu) -> tridiagonal ----------------
+@pytest.mark.parametrize("kind,L,U", [("cubic2d", 16, 2.0), ("cubic2d", 24, 0.5), ("cubic2d", 26, 4.0), ("cubic2d", 32, 1.0), ("triangular", 24, 2.0),
+                                      ("triangular", 31, 2.0), ("honeycomb", 24, 2.0), ("honeycomb", 32, 1.0)])
+def test_band_path_spectra(kind, L, U):
+    """calc_ed(false) through the band path (sites reordered so that the lattice matrix has half-bandwidth <= 64, block bulge chasing on
+    DMMA down to half-bandwidth 8) against the oracle and against the dense reduction of the same configurations; N = 676 is not a
+    multiple of the tile, triangular L = 31 has the maximal bandwidth (2L + 1 = 63), ordered / empty / full configurations included."""
+    beta = 7.0
+    c = fk.Context(kind, L, max_batch=5)
+    n = c.N
+    fs = np.stack([o.randomize_f(11 + i, n, n // 2)[0] for i in range(2)] + [np.zeros(n, np.int32), np.ones(n, np.int32),
+                                                                              (np.arange(n) % 2).astype(np.int32)])
+    c.profile_enable(True)
+    c.profile_reset()
+    rb = c.logz_ed(fs, U, U / 2, beta, want_caches=True)
+    assert c.profile_get("sb2sb")[1] >= 1 and c.profile_get("sy2sb")[1] == 0      # the band kernels did run
+    c.set_option("band_path", 0)
+    c.profile_reset()
+    rd = c.logz_ed(fs, U, U / 2, beta)
+    assert c.profile_get("sb2sb")[1] == 0
+    c.profile_enable(False)
+    for b in range(len(fs)):
+        ref = o.calc_ed(o.KINDS[kind], L, fs[b], U, U / 2, beta)
+        scale = np.abs(ref["spectrum"]).max()
+        assert np.abs(rb["spectrum"][b] - ref["spectrum"]).max() <= TOL * scale
+        assert np.abs(rb["spectrum"][b] - rd["spectrum"][b]).max() <= 1e-12 * scale
+        assert abs(rb["logZ"][b] - ref["logZ"]) <= TOL * abs(ref["logZ"])
+        assert np.abs(rb["cached_fermi"][b] - ref["cached_fermi"]).max() <= 1e-9
+    c.close()
+
+
+def test_band_path_selection():
+    """The band path needs half-bandwidth <= 64 after folding and N >= band_min: cubic3d (2 L^2 = 128), triangular L = 32 (65) and small
+    lattices stay on the dense reduction; the option band_min moves the threshold."""
+    for kind, L, expect in [("cubic3d", 8, False), ("triangular", 32, False), ("cubic2d", 12, False), ("cubic2d", 16, True), ("cubic1d", 300, True)]:
+        c = fk.Context(kind, L, max_batch=1)
+        f = o.randomize_f(3, c.N, c.N // 2)[0]
+        c.profile_enable(True)
+        r = c.logz_ed(f, 1.0, 0.5, 2.0)
+        assert (c.profile_get("sb2sb")[1] > 0) == expect, (kind, L)
+        ref = o.calc_ed(o.KINDS[kind], L, f, 1.0, 0.5, 2.0)
+        assert np.abs(r["spectrum"][0] - ref["spectrum"]).max() <= TOL * np.abs(ref["spectrum"]).max()
+        if kind == "cubic2d" and L == 12:
+            c.set_option("band_min", 64)
+            c.profile_reset()
+            r = c.logz_ed(f, 1.0, 0.5, 2.0)
+            assert c.profile_get("sb2sb")[1] > 0
+            assert np.abs(r["spectrum"][0] - ref["spectrum"]).max() <= TOL * np.abs(ref["spectrum"]).max()
+        c.close()
+
+
+def test_band_path_chain_equals_dense_chain():
+    """Dense moves at N = 256 with the band path on and off: identical accept / reject sequences and final configurations."""
+    L, U, beta, n_chains = 16, 3.0, 4.0, 6
+    out = []
+    for bp in (1, 0):
+        c = fk.Context("cubic2d", L, max_batch=n_chains)
+        c.set_option("band_path", bp)
+        c.chain_init(n_chains, beta, U, U / 2, U / 2, mc_flip=0.5, mc_add_remove=0.5, seed=5, sweep_len=4, max_sweeps=5)
+        c.chain_run_sweeps(5)
+        st = c.chain_get_state()
+        se = c.chain_get_series()
+        out.append((st, se))
+        c.close()
+    assert np.array_equal(out[0][0]["f"], out[1][0]["f"]) and np.array_equal(out[0][0]["naccept"], out[1][0]["naccept"])
+    assert np.allclose(out[0][1]["energies"], out[1][1]["energies"], rtol=1e-11, atol=1e-11)
+
+
 @pytest.mark.parametrize("kind,L", [("honeycomb", 34), ("cubic2d", 36)])
 def test_sizes_above_1024(kind, L):
     """N > 1024 (e.g. the N ~ 1152 honeycomb extension of BASELINE config 4): the one-stage blocked tridiagonalisation + bisection with
