@@ -216,6 +216,7 @@ def main():
                     help="dense-move workloads: rank-one secular re-weighting with tracked eigenvectors (chain parameter fast_update)")
     ap.add_argument("--measure-ipr", action="store_true",
                     help="measurement path (c): every sweep also measures the IPR of all eigenstates (calc_ed(true) per chain, ipr.hpp:39-56)")
+    ap.add_argument("--dense-path", action="store_true", help="full solves through the dense N^3 reduction (sy2sb) instead of the band path (sb2sb)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the short dense-move lines (c2 / c3, full solve and fast update) appended to the default run")
@@ -255,6 +256,8 @@ def main():
 
     stream = torch.cuda.Stream()
     ctx = fk.Context(kind, L, max_batch=chains, device=local_rank)
+    if args.dense_path:
+        ctx.set_option("band_path", 0)
     ctx.set_stream(stream.cuda_stream)
     N = ctx.N
     M, G = fk.cheb_sizes(N, 2.2)
@@ -302,7 +305,7 @@ def main():
 
     # per-kernel-family device time inside the timed region (events recorded on the launching stream)
     fam = {}
-    for name in ("kpm", "sytrd", "sy2sb", "sb2st", "tridiag_eig", "build_h", "chain_step", "fu_eval", "fu_prepare", "fu_gemm", "fu_refresh", "stein",
+    for name in ("kpm", "sytrd", "sy2sb", "sb2sb", "band_build", "sb2st", "tridiag_eig", "build_h", "chain_step", "fu_eval", "fu_prepare", "fu_gemm", "fu_refresh", "stein",
                  "backtransform"):
         tot, n = ctx.profile_get(name)
         if n:
@@ -366,6 +369,31 @@ def main():
         rl_dense = {"kernel": dense_name + "_kernel", "bound": "tensor", "achieved": a2, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                     "frac": a2 / DMMA_PEAK_TFLOPS, "traffic": tr_d, "peak_source": "measured FP64 DMMA (tools/probe_dmma.cu)",
                     "note": "4/3 N^3 flop per matrix, all of it issued as DMMA.8x8x4 in the dense->band stage"}
+    rl_band = None
+    if "sb2sb" in fam:
+        # band path (csrc/sb2sb.cu): the folded lattice matrix (half-bandwidth <= 64) to half-bandwidth 8 by block bulge chasing.  Useful flops of
+        # one step (64 x 8 reflector block applied to a 64 x 56 block from the left, a 64 x 64 block from the right and a symmetric 64 x 64 block
+        # from both sides, lower half): 4*64*8*56 + 4*64*8*64 + 2*64*64*8 + 2*64*65*8; the first step of a sweep has no left block
+        nsteps = first = 0
+        for j in range((N + 7) // 8):
+            if 8 * j + 8 >= N:
+                break
+            k = (N - 8 * j - 8 + 63) // 64
+            nsteps += k
+            first += 1
+        fl = (nsteps * (4 * 64 * 8 * 64 + 2 * 64 * 64 * 8 + 2 * 64 * 65 * 8) + (nsteps - first) * 4 * 64 * 8 * 56) * float(chains)
+        a5 = fl / (fam["sb2sb"]["ms_per_launch"] * 1e-3) * 1e-12
+        tr_b = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", traffic_file)))["sb2sb"]
+            tr_b = tr["bytes_per_launch"] * chains / tr["units_per_launch"]
+        except Exception:
+            pass
+        rl_band = {"kernel": "sb2sb_kernel", "bound": "tensor", "achieved": a5, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": a5 / DMMA_PEAK_TFLOPS,
+                   "traffic": tr_b, "peak_source": "measured FP64 DMMA (tools/probe_dmma.cu)", "steps_per_matrix": nsteps,
+                   "dense_equivalent_tflops": 4.0 / 3.0 * N ** 3 * chains / (fam["sb2sb"]["ms_per_launch"] * 1e-3) * 1e-12,
+                   "note": "band -> band reduction of the folded lattice matrix: %.3g flop per matrix instead of the 4/3 N^3 = %.3g of the dense reduction; "
+                           "all of it DMMA.8x8x4; dense_equivalent_tflops = 4/3 N^3 over the same time" % (fl / chains, 4.0 / 3.0 * N ** 3)}
     rl_meas = None
     if args.measure_ipr and "sytrd" in fam:
         # one-stage tridiagonalisation that keeps its reflectors for the back-transformation: the SYMV streams the trailing matrix once per
@@ -388,6 +416,8 @@ def main():
     roofline = rl_kpm if dominant == "kpm" else (rl_fast if (fast and rl_fast is not None) else (rl_dense if rl_dense is not None else rl_kpm))
     if dominant in ("sytrd", "backtransform", "stein") and rl_meas is not None:
         roofline = rl_meas
+    if rl_band is not None and (dominant == "sb2sb" or (not fast and dominant not in ("kpm",) and rl_dense is None)):
+        roofline = rl_band
     roofline_dense = rl_dense
     roofline_kpm = rl_kpm
 
@@ -507,11 +537,11 @@ def main():
         line = {"metric": "metropolis_proposals_per_sec", "value": value, "unit": "proposals/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": dict(make_config(desc, chains, U, cheb, M, G), **({"fast_update": True} if fast else {}),
+                "config": dict(make_config(desc, chains, U, cheb, M, G), **({"fast_update": True} if fast else {}), **({"dense_path": True} if args.dense_path else {}),
                                **({"measure_ipr": True} if args.measure_ipr else {})),
                 "accept_rate": accepted / float(chains * SWEEP_LEN * args.steps),
                 "sweeps_per_sec": value / SWEEP_LEN, "roofline": roofline, "roofline_dense": roofline_dense, "roofline_kpm": roofline_kpm,
-                "roofline_fast_update": rl_fast, "roofline_measurement": rl_meas, "traffic_source": traffic_file,
+                "roofline_fast_update": rl_fast, "roofline_measurement": rl_meas, "roofline_band": rl_band, "traffic_source": traffic_file,
                 "dominant_kernel": dominant, "kernels": {**fam, **sub},
                 "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks,
                 "final_gather_ms": gather_ms, "dense_move_workloads": extra}

@@ -26,24 +26,19 @@ namespace {
 
 constexpr int VS = 12;                 // row stride (doubles) of the 64 x 8 operand arrays in shared memory
 constexpr int NT = 16;                 // tile diagonals stored per block row
-#ifndef FKMC_SBR_ISOLATE
-#define FKMC_SBR_ISOLATE 0
-#endif
 // FP64 arbitration (tools/ubench/contend.cu): a warp issuing scalar DFMA next to DMMA-streaming warps of the same sub-partition waits 73
-// cycles per instruction with one such neighbour and starves with two; warps of other sub-partitions do not matter.  With FKMC_SBR_ISOLATE
-// the CTA has twelve warps: warp 0 factors panels alone on its sub-partition (warps 4 and 8 only take part in the sweep barriers), the
-// eight compute warps are 1,2,3,5,6,7,9,10 (warp 11 idles), one CTA per SM: the factorisation drops from 13.2k to 6.4k cycles per step,
-// but one CTA per SM has nothing to run under it (35.7 ms per 1024 matrices at N = 1024 against 31.9 ms for two nine-warp CTAs per SM,
-// the default).
-#if FKMC_SBR_ISOLATE
-constexpr int SBR_THREADS = 384;
-constexpr int SBR_CTAS = 1;
-constexpr int SBR_SYNC = 288;          // threads on the panel / compute named barriers
-#else
-constexpr int SBR_THREADS = 288;       // eight compute warps + the panel warp
-constexpr int SBR_CTAS = 2;
-constexpr int SBR_SYNC = 288;
+// cycles per instruction with one such neighbour and starves with two; warps of other sub-partitions do not matter.  The panel
+// factorisation is a serial chain of scalar FP64 work, so it gets a sub-partition without tensor work: the CTA has eleven warps, those
+// whose hardware slot (%warpid) is a multiple of four hold the panel warp (the other one or two idle), the eight compute warps are
+// taken from the rest.  Two CTAs per SM: both panel warps share sub-partition 0, the 16 compute warps the other three.
+// (Measured at N = 1024, 1024 matrices: panel warp next to compute warps 31.9 ms, 13.2k cycles per factorisation; isolated 6.4k.)
+#ifndef FKMC_SBR_WARPS
+#define FKMC_SBR_WARPS 10
 #endif
+constexpr int SBR_WARPS = FKMC_SBR_WARPS;
+constexpr int SBR_THREADS = SBR_WARPS * 32;
+constexpr int SBR_CTAS = 2;
+constexpr int SBR_SYNC = 288;          // threads on the panel / compute named barriers (panel warp + eight compute warps)
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -74,6 +69,7 @@ struct sbr_smem {
     double XY[64 * VS];     // X = S V T (rows read back by the owning warp only), later overwritten by Y
     double W[64 * VS];      // W[col][refl] = (T^T V^T B)^T
     double Zp[8][64];       // per-warp partials of (V^T X)^T
+    double pad[368];   // the panel warp's reduction scratch
 };
 static_assert(sizeof(sbr_smem) <= 115712, "two CTAs per SM");
 
@@ -91,27 +87,35 @@ __device__ __forceinline__ double rcp_seed(double x) {
     return y;
 }
 
-// Sums eight per-lane partials over the warp: reduce-scatter butterfly (4 + 2 + 1 exchanges), two plain stages, then one broadcast per
-// value: 17 double shuffles instead of 40.
-__device__ __forceinline__ void warp_sum8(double (&v)[8], int lane) {
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-    double t[4], u[2];
+// Warp-wide sums of eight per-lane partials plus the broadcast of one lane's eight values, through shared memory (shuffles and shared
+// memory use the same queue, which the compute warps keep busy: fewer, wider operations win).  The 32 x 8 partials are transposed through
+// the pad (row stride 10 doubles, each group of eight rows shifted by a further 8: 128-bit stores and 64-bit column loads conflict free), lane l adds
+// the eight partials of column l % 8 held by its group of eight lanes, two shuffle stages add the four groups, the totals and the
+// source lane's row go back through the pad.  pad: 368 doubles owned by the warp, 16-byte aligned.
+__device__ __forceinline__ void warp_sum8_bcast(double (&v)[8], double (&h)[8], int src, int lane, double* pad) {
+    double* row = pad + lane * 10 + (lane >> 3) * 8;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const double send = b4 ? v[j] : v[j + 4], keep = b4 ? v[j + 4] : v[j];
-        t[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    for (int k = 0; k < 8; k += 2) *reinterpret_cast<double2*>(row + k) = make_double2(v[k], v[k + 1]);
+    double* hrow = pad + 352;
+    if (lane == src) {
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) *reinterpret_cast<double2*>(hrow + k) = make_double2(h[k], h[k + 1]);
     }
+    __syncwarp();
+    const int gb = lane & 24;
+    const double* col = pad + gb * 10 + (gb >> 3) * 8 + (lane & 7);
+    double x = ((col[0] + col[10]) + (col[20] + col[30])) + ((col[40] + col[50]) + (col[60] + col[70]));
+    x += __shfl_xor_sync(0xffffffffu, x, 8);
+    x += __shfl_xor_sync(0xffffffffu, x, 16);
+    double* tot = pad + 360;
+    if (lane < 8) tot[lane] = x;
+    __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const double send = b3 ? t[j] : t[j + 2], keep = b3 ? t[j + 2] : t[j];
-        u[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    for (int k = 0; k < 8; k += 2) {
+        const double2 a = *reinterpret_cast<const double2*>(tot + k), b = *reinterpret_cast<const double2*>(hrow + k);
+        v[k] = a.x; v[k + 1] = a.y; h[k] = b.x; h[k + 1] = b.y;
     }
-    double x = (b2 ? u[1] : u[0]) + __shfl_xor_sync(0xffffffffu, b2 ? u[0] : u[1], 4);
-    x += __shfl_xor_sync(0xffffffffu, x, 2);
-    x += __shfl_xor_sync(0xffffffffu, x, 1);
-    // lane group g = lane >> 2 now holds value g
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = __shfl_sync(0xffffffffu, x, 4 * k);
+    __syncwarp();   // the pad is rewritten by the next call
 }
 
 // Householder QR of a 64 x 8 panel held by one warp (lane l: rows l and l + 32 in a0 / a1).  Branch-free; one reduction round per
@@ -119,9 +123,9 @@ __device__ __forceinline__ void warp_sum8(double (&v)[8], int lane) {
 // the earlier reflectors in the slots k < i, column i of V^T V for the compact-WY factor T (row l of T lives in lane l).
 // Writes V (three layouts) and T to vs, and the factored panel ([R; 0]) to the global tiles (I0 + k, Jp), k = 0..7.
 #ifdef FKMC_SBR_TIMING
-__device__ __forceinline__ void qr_panel(double (&a0)[8], double (&a1)[8], vset& vs, double* band, int I0, int Jp, int lane, long long* qt) {
+__device__ __forceinline__ void qr_panel(double (&a0)[8], double (&a1)[8], vset& vs, double* pad, double* band, int I0, int Jp, int lane, long long* qt) {
 #else
-__device__ __forceinline__ void qr_panel(double (&a0)[8], double (&a1)[8], vset& vs, double* band, int I0, int Jp, int lane) {
+__device__ __forceinline__ void qr_panel(double (&a0)[8], double (&a1)[8], vset& vs, double* pad, double* band, int I0, int Jp, int lane) {
 #endif
 #ifdef FKMC_SBR_TIMING
     long long q0 = clock64();
@@ -131,19 +135,20 @@ __device__ __forceinline__ void qr_panel(double (&a0)[8], double (&a1)[8], vset&
 #endif
     const int r0 = lane, r1 = lane + 32, l = lane & 7;
     const int p0 = (r0 & ~7) + ((r0 & 1) * 4 + ((r0 & 7) >> 1)), p1 = (r1 & ~7) + ((r1 & 1) * 4 + ((r1 & 7) >> 1));
-    double trow[8];
+    double trow[8], rdiag[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
+        // columns k < i of the register panel hold the earlier reflectors below their diagonal (LAPACK storage), so one formula serves the
+        // projections (k > i), the norm (k = i) and column i of V^T V (k < i)
         const double m0 = (lane > i) ? a0[i] : 0.0;
         double r[8], head[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const double b0 = (k >= i) ? a0[k] : vs.Vn[r0 * VS + k], b1 = (k >= i) ? a1[k] : vs.Vn[r1 * VS + k];
-            r[k] = fma(m0, b0, a1[i] * b1);
-            head[k] = __shfl_sync(0xffffffffu, b0, i);
+            r[k] = fma(m0, a0[k], a1[i] * a1[k]);
+            head[k] = a0[k];   // row i (lane i) is broadcast together with the sums
         }
         QR_TICK(0)
-        warp_sum8(r, lane);
+        warp_sum8_bcast(r, head, i, lane, pad);
         QR_TICK(1)
         const double sigma = r[i], alpha = head[i];
         const bool zero = sigma == 0.0;
@@ -168,12 +173,15 @@ __device__ __forceinline__ void qr_panel(double (&a0)[8], double (&a1)[8], vset&
             a0[k] = fma(-wk, v0, a0[k]);
             a1[k] = fma(-wk, v1, a1[k]);
         }
-        if (lane == i) a0[i] = zero ? alpha : -copysign(nrm, alpha);
+        rdiag[i] = zero ? alpha : -copysign(nrm, alpha);
         // column i of T: T[l][i] = -tau sum_{m=l}^{i-1} T[l][m] (V_m^T v_i),  V_m^T v_i = V_m[i] + s * raw_m
         double t = 0.0;
 #pragma unroll
         for (int m = 0; m < i; ++m) t = fma(trow[m], fma(s, r[m], head[m]), t);   // trow[m] = 0 for m < l
         trow[i] = (l == i) ? tau : ((l < i) ? -tau * t : 0.0);
+        // v_i replaces the column below the diagonal (lane i keeps the implicit 1 as 0 products: row i is never part of a later sum)
+        if (lane >= i) a0[i] = v0;
+        a1[i] = v1;
         const int pi = (i & 1) * 4 + (i >> 1);
         vs.Vn[r0 * VS + i] = v0;
         vs.Vn[r1 * VS + i] = v1;
@@ -187,6 +195,7 @@ __device__ __forceinline__ void qr_panel(double (&a0)[8], double (&a1)[8], vset&
 #pragma unroll
         for (int i = 0; i < 8; ++i) vs.Tn[l * VS + i] = trow[i];
     }
+    bar_arrive(1, SBR_SYNC);   // V and T are complete: the compute warps start while the factored panel goes out
     // factored panel to global memory: R in the first tile (rows 0..7 = lanes 0..7), zeros below
     {
         const int k0 = lane >> 3, r = lane & 7;
@@ -195,8 +204,8 @@ __device__ __forceinline__ void qr_panel(double (&a0)[8], double (&a1)[8], vset&
 #pragma unroll
         for (int c = 0; c < 8; c += 2) {
             double2 o;
-            o.x = (lane < 8 && c >= lane) ? a0[c] : 0.0;
-            o.y = (lane < 8 && c + 1 >= lane) ? a0[c + 1] : 0.0;
+            o.x = (lane < 8 && c >= lane) ? (c == lane ? rdiag[c] : a0[c]) : 0.0;
+            o.y = (lane < 8 && c + 1 >= lane) ? (c + 1 == lane ? rdiag[c + 1] : a0[c + 1]) : 0.0;
             *reinterpret_cast<double2*>(t0 + c) = o;
             *reinterpret_cast<double2*>(t1 + c) = make_double2(0.0, 0.0);
         }
@@ -225,12 +234,37 @@ __global__ void __launch_bounds__(SBR_THREADS, SBR_CTAS) sb2sb_kernel(double* ba
     double* band = band_all + (size_t)blockIdx.x * mat_stride;
     const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, q = lane & 3;
     const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: the role branches below are convergent
-#if FKMC_SBR_ISOLATE
-    // role: -1 idle, 8 panel, 0..7 compute row block
-    const int w = (wid == 0) ? 8 : (((wid & 3) == 0 || wid == 11) ? -1 : (wid - 1 - (wid >> 2)));
-#else
-    const int w = wid;
-#endif
+    // roles from the hardware warp slots: 8 = panel, 0..7 = compute row block, -1 = idle
+    __shared__ int s_slot[SBR_WARPS];
+    {
+        unsigned hw;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw));
+        if (lane == 0) s_slot[wid] = (int)(hw & 3u);
+    }
+    __syncthreads();
+    int w;
+    {
+        int n0 = 0, before0 = 0, before_other = 0;
+        for (int i = 0; i < SBR_WARPS; ++i) {
+            const bool z = s_slot[i] == 0;
+            n0 += z;
+            if (i < wid) { before0 += z; before_other += !z; }
+        }
+        const int n_other = SBR_WARPS - n0;
+        if (n0 >= 1 && n_other + n0 - 1 >= 8) {
+            // panel: the first warp of sub-partition 0; compute: the warps of the other sub-partitions first, then (if those are fewer
+            // than eight) the remaining warps of sub-partition 0
+            if (s_slot[wid] == 0) {
+                const int k = n_other + before0 - 1;   // rank among the compute candidates for the second, third ... warp of sub-partition 0
+                w = (before0 == 0) ? 8 : (k < 8 ? k : -1);
+            } else {
+                w = before_other < 8 ? before_other : -1;
+            }
+        } else {
+            w = wid < 9 ? wid : -1;   // unexpected slot pattern: plain assignment (slower, still correct)
+        }
+        w = __shfl_sync(0xffffffffu, w, 0);
+    }
     const int nsweeps = (N + 7) / 8;
     const int cswz = (2 * q) ^ (((g >> 1) & 1) << 2);       // accumulator-layout column pair inside a swizzled tile
 #ifdef FKMC_SBR_TIMING
@@ -280,12 +314,11 @@ __global__ void __launch_bounds__(SBR_THREADS, SBR_CTAS) sb2sb_kernel(double* ba
                 }
                 SBR_TICK(0)
 #ifdef FKMC_SBR_TIMING
-                qr_panel(a0, a1, sm.V[vpar & 1], band, I0, p == 0 ? I0 - 1 : I0 - 8, lane, qt);
+                qr_panel(a0, a1, sm.V[vpar & 1], sm.pad, band, I0, p == 0 ? I0 - 1 : I0 - 8, lane, qt);
 #else
-                qr_panel(a0, a1, sm.V[vpar & 1], band, I0, p == 0 ? I0 - 1 : I0 - 8, lane);
+                qr_panel(a0, a1, sm.V[vpar & 1], sm.pad, band, I0, p == 0 ? I0 - 1 : I0 - 8, lane);
 #endif
                 SBR_TICK(1)
-                bar_arrive(1, SBR_SYNC);
             }
         }
 #ifdef FKMC_SBR_TIMING
