@@ -101,6 +101,9 @@ int fkmc_sb2st_batched(fkmc_ctx* ctx, const double* AB, int N, int B, double* d,
  *          "kpm_generic" = 1 forces the full-lattice-vector KPM kernel (default 0: local-patch kernel when it applies)
  *          "kpm_v1" = 1 forces the single-kernel KPM path (csrc/kpm.cu) where the two-kernel 2-D path (csrc/kpm2d.cu:
  *          strip Lanczos + ring-ordered patch recursion) would apply; for cross-checks
+ *          "band_path" = 0 sends eigenvalue-only solves through the dense N^3 reduction (default 1: lattices whose matrix has
+ *          half-bandwidth <= 64 after folding the slow coordinate start from the band, csrc/sb2sb.cu); "band_min" = n: smallest N
+ *          served by the band path (default 256)
  *          "sy2sb_tiled_min" = n: smallest N served by the tiled dense->band kernel (per context, default 256; below it the
  *          column-major small-matrix kernel runs); for cross-checks
  *          "kpm_generic_schedule" = 1 keeps the moments kernel of csrc/kpm2d.cu on its run-time slot schedule (default 0: the
