@@ -431,16 +431,25 @@ def main():
         ebmu = math.exp(beta * U / 2)
         h2d = d2h = 0
 
-        def weight_eval(fh):
+        def weight_eval(fh, f_ref=None, state_ref=None):
             nonlocal h2d, d2h
             h2d += fh.nbytes
             if cheb:
-                r = ctx.logz_kpm(fh, U, U / 2, beta, M, G)
-                d2h += r["moments"].nbytes + 4 * 8 * chains + r["logZ"].nbytes
+                # fkmc_logz_kpm_batched_local: the proposal is evaluated against the configuration it was made from (the reference's
+                # new_config = config; ...; new_config.calc_chebyshev()), whose trace-sum record travels with that configuration
+                r = ctx.logz_kpm_local(fh, U, U / 2, beta, M, G, f_ref=f_ref, state_ref=state_ref)
+                if f_ref is not None:
+                    h2d += f_ref.nbytes + state_ref.nbytes
+                d2h += r["moments"].nbytes + 4 * 8 * chains + r["logZ"].nbytes + r["state"].nbytes
             else:
                 r = ctx.logz_ed(fh, U, U / 2, beta)
                 d2h += r["spectrum"].nbytes + r["logZ"].nbytes
             return r
+
+        f_cur_pin = torch.zeros((chains, N), dtype=torch.int32).pin_memory()
+        f_cur_host = f_cur_pin.numpy()
+        f_cur_host[:] = f_host
+        ks_cur = [None]
 
         def e2e_step(lz_cur):
             nonlocal h2d, d2h
@@ -448,11 +457,15 @@ def main():
                 sites = rng.integers(0, N, size=chains)
                 rows = np.arange(chains)
                 f_host[rows, sites] ^= 1                      # propose in place
-                lz_new = weight_eval(f_host)["logZ"]
+                r = weight_eval(f_host, f_cur_host if (cheb and ks_cur[0] is not None) else None, ks_cur[0] if cheb else None)
+                lz_new = r["logZ"]
                 occ = f_host[rows, sites] == 1
                 w = np.exp(lz_new - lz_cur) * np.where(occ, ebmu, 1 / ebmu)
                 acc = np.abs(w) > rng.random(chains)
                 f_host[rows[~acc], sites[~acc]] ^= 1          # reject: undo
+                f_cur_host[rows[acc], sites[acc]] ^= 1        # accept: the current configuration (and its record) follows
+                if cheb:
+                    ks_cur[0][acc] = r["state"][acc]
                 lz_cur = np.where(acc, lz_new, lz_cur)
             if args.measure_ipr:                              # measurement sweep with eigenvectors: spectrum + IPR of every eigenstate
                 h2d += f_host.nbytes
@@ -464,7 +477,10 @@ def main():
                 d2h += r["spectrum"].nbytes + r["logZ"].nbytes
             return lz_cur
 
-        lz = weight_eval(f_host)["logZ"]
+        r0 = weight_eval(f_host)
+        lz = r0["logZ"]
+        if cheb:
+            ks_cur[0] = r0["state"].copy()
         lz = e2e_step(lz)  # warm-up
         h2d = d2h = 0
         barrier()
@@ -479,7 +495,7 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": proposals / (float(te.item()) * 1e-3), "unit": "proposals/s", "h2d_bytes_per_step": h2d // args.steps,
                "d2h_bytes_per_step": d2h // args.steps,
-               "path": "fkmc_logz_kpm_batched / fkmc_logz_ed_batched with pinned host f, host-side proposal + accept"}
+               "path": "fkmc_logz_kpm_batched_local / fkmc_logz_ed_batched with pinned host f, host-side proposal + accept"}
 
     # ---- final collective: gather the per-chain series (the only inter-GPU traffic of a run) ----
     gather_ms = None

@@ -222,6 +222,22 @@ class Context:
                                                 _ptr(lz, C.c_double)))
         return dict(moments=mom, e_min=ab[:, 0], e_max=ab[:, 1], a=ab[:, 2], b=ab[:, 3], logZ=lz)
 
+    def logz_kpm_local(self, f, U, mu_c, beta, M, G, f_ref=None, state_ref=None):
+        """calc_chebyshev for configurations that differ from f_ref in one or two sites (fkmc_logz_kpm_batched_local); returns the dict of
+        logz_kpm plus state [B, 64], the record to pass as state_ref when f becomes the reference."""
+        f = self._f(f)
+        B = f.shape[0]
+        mom, ab, lz, st = np.zeros((B, M)), np.zeros((B, 4)), np.zeros(B), np.zeros((B, 64))
+        fr = sr = None
+        if f_ref is not None:
+            fr = self._f(f_ref)
+            sr = np.ascontiguousarray(state_ref, dtype=np.float64).reshape(B, 64)
+        self._ck(self.lib.fkmc_logz_kpm_batched_local(self.h, _ptr(f, C.c_int32), _ptr(fr, C.c_int32) if fr is not None else None,
+                                                      _ptr(sr, C.c_double) if sr is not None else None, B, C.c_double(U), C.c_double(mu_c),
+                                                      C.c_double(beta), int(M), int(G), _ptr(mom, C.c_double), _ptr(ab, C.c_double),
+                                                      _ptr(lz, C.c_double), _ptr(st, C.c_double)))
+        return dict(moments=mom, e_min=ab[:, 0], e_max=ab[:, 1], a=ab[:, 2], b=ab[:, 3], logZ=lz, state=st)
+
     def energy_from_spectrum(self, evals, beta):
         ev = np.ascontiguousarray(evals, dtype=np.float64)
         if ev.ndim == 1:

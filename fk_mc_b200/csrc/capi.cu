@@ -190,7 +190,7 @@ int fkmc_destroy(fkmc_ctx* ctx) {
     fkmc_comm_destroy(ctx);
     cudaFree(ctx->d_gather);
     cudaFree(ctx->d_ev_scratch);
-    cudaFree(ctx->d_band0); cudaFree(ctx->d_band_perm); cudaFree(ctx->d_band);
+    cudaFree(ctx->d_kpm_hop0); cudaFree(ctx->d_ks_io); cudaFree(ctx->d_f_ref); cudaFree(ctx->d_band0); cudaFree(ctx->d_band_perm); cudaFree(ctx->d_band);
     fkmc_chain_free(ctx);
     cudaFree(ctx->d_AB); cudaFree(ctx->d_kpm_steps); cudaFree(ctx->d_s1_scratch);
     cudaFree(ctx->d_nbr_idx); cudaFree(ctx->d_nbr_val); cudaFree(ctx->d_A); cudaFree(ctx->d_W); cudaFree(ctx->d_d);
@@ -296,6 +296,45 @@ int fkmc_logz_kpm_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, doub
     if (moments) FKMC_CUDA(ctx, cudaMemcpyAsync(moments, ctx->d_moments, sizeof(double) * (size_t)B * M, cudaMemcpyDeviceToHost, ctx->stream));
     if (ab) FKMC_CUDA(ctx, cudaMemcpyAsync(ab, ctx->d_ab, sizeof(double) * (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (logZ) FKMC_CUDA(ctx, cudaMemcpyAsync(logZ, ctx->d_out, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    return check_flag(ctx);
+}
+
+int fkmc_logz_kpm_batched_local(fkmc_ctx* ctx, const int32_t* f, const int32_t* f_ref, const double* state_ref, int B, double U, double mu_c,
+                                double beta, int M, int G, double* moments, double* ab, double* logZ, double* state_out) {
+    if (!ctx) return FKMC_ERR_INVALID;
+    if (M < 2 || M % 2 || M > 2 * FKMC_MAX_HALF) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "M must be even and in [2, 32]");
+    if ((f_ref == nullptr) != (state_ref == nullptr)) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "f_ref and state_ref go together");
+    int rc = upload_f(ctx, f, B);
+    if (rc) return rc;
+    const size_t N = ctx->N, nb = ctx->max_batch;
+    if (!ctx->d_ks_io) {
+        FKMC_CUDA(ctx, cudaMalloc(&ctx->d_ks_io, sizeof(double) * 2 * nb * FKMC_KPM_STATE));
+        FKMC_CUDA(ctx, cudaMalloc(&ctx->d_f_ref, sizeof(int32_t) * nb * N));
+    }
+    double* ks_in = ctx->d_ks_io;
+    double* ks_out = ctx->d_ks_io + nb * FKMC_KPM_STATE;
+    if (f_ref) {
+        FKMC_CUDA(ctx, cudaMemcpyAsync(ctx->d_f_ref, f_ref, sizeof(int32_t) * (size_t)B * N, cudaMemcpyHostToDevice, ctx->stream));
+        FKMC_CUDA(ctx, cudaMemcpyAsync(ks_in, state_ref, sizeof(double) * (size_t)B * FKMC_KPM_STATE, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->kpm_f_cur = ctx->d_f_ref;
+        ctx->kpm_ks_in = ks_in;
+    }
+    ctx->kpm_ks_out = state_out ? ks_out : nullptr;
+    rc = fkmc_launch_kpm(ctx, ctx->d_f, B, U, mu_c, beta, M, G, ctx->d_moments, ctx->d_ab, ctx->d_out);
+    const bool wrote_state = ctx->kpm_state_written;
+    ctx->kpm_f_cur = nullptr; ctx->kpm_ks_in = nullptr; ctx->kpm_ks_out = nullptr;
+    if (rc) return rc;
+    if (moments) FKMC_CUDA(ctx, cudaMemcpyAsync(moments, ctx->d_moments, sizeof(double) * (size_t)B * M, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ab) FKMC_CUDA(ctx, cudaMemcpyAsync(ab, ctx->d_ab, sizeof(double) * (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (logZ) FKMC_CUDA(ctx, cudaMemcpyAsync(logZ, ctx->d_out, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    if (state_out) {
+        if (wrote_state) {
+            FKMC_CUDA(ctx, cudaMemcpyAsync(state_out, ks_out, sizeof(double) * (size_t)B * FKMC_KPM_STATE, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            // lattices served by the full-lattice-vector kernel keep no trace sums: the record says "not valid" and every call is a full one
+            for (size_t i = 0; i < (size_t)B * FKMC_KPM_STATE; ++i) state_out[i] = 0.0;
+        }
+    }
     return check_flag(ctx);
 }
 
@@ -406,6 +445,15 @@ int fkmc_set_option(fkmc_ctx* ctx, const char* name, int value) {
     }
     if (std::string(name) == "kpm_generic_schedule") {
         ctx->kpm_no_sched = value != 0;
+        return FKMC_OK;
+    }
+    if (std::string(name) == "kpm_local") {  // 1 (default): Chebyshev moves of the chain engine re-evaluate only the columns near the changed sites
+        ctx->kpm_local = value != 0;     // (takes effect at the next fkmc_chain_init)
+        return FKMC_OK;
+    }
+    if (std::string(name) == "kpm_rebase_sweeps") {  // local KPM scheme: sweeps between recomputations from scratch (default 16; 0: never)
+        if (value < 0) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "kpm_rebase_sweeps must be >= 0");
+        ctx->kpm_rebase = value;
         return FKMC_OK;
     }
     if (std::string(name) == "band_path") {  // 1 (default): eigenvalue-only solves of banded lattice matrices start from the band (sb2sb.cu)

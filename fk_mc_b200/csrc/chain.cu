@@ -28,6 +28,7 @@ struct chain_dev {
     int32_t* acc_flag;  // [n_chains] accept decision of the last step (fast update), may be null
     double *ec_cur, *d2_cur;
     double *eff_cur, *eff_prop;  // calc_ff_energy() of the current / proposed configuration
+    double *ks_cur, *ks_prop;    // [n_chains][FKMC_KPM_STATE] trace sums of the local KPM scheme (null: off)
     const double* W;             // f-f interaction W[0..nW) (1-D lattices only; nW = 0 otherwise)
     int nW;
     int V, n_chains;
@@ -217,6 +218,9 @@ __global__ void chain_accept_kernel(chain_dev C, const double* __restrict__ logz
         const int32_t* fp = C.f_prop + (size_t)c * V;
         int32_t* f = C.f_cur + (size_t)c * V;
         for (int i = lane; i < V; i += 32) f[i] = fp[i];
+        if (C.ks_cur) {
+            for (int i = lane; i < FKMC_KPM_STATE; i += 32) C.ks_cur[(size_t)c * FKMC_KPM_STATE + i] = C.ks_prop[(size_t)c * FKMC_KPM_STATE + i];
+        }
     }
 }
 
@@ -294,6 +298,7 @@ chain_dev make_dev(fkmc_ctx* ctx) {
     C.cur_slot = S.cur_slot; C.prop_slot = S.prop_slot; C.prop_move = S.prop_move; C.prop_a = S.prop_a; C.prop_b = S.prop_b;
     C.nf_cur = S.nf_cur; C.nf_prop = S.nf_prop; C.naccept = S.naccept; C.ec_cur = S.ec_cur; C.d2_cur = S.d2_cur;
     C.acc_flag = S.fu_acc;
+    C.ks_cur = S.ks_cur; C.ks_prop = S.ks_prop;
     C.eff_cur = S.eff_cur; C.eff_prop = S.eff_prop; C.W = S.d_W; C.nW = (ctx->ndim == 1) ? S.p.n_W : 0;
     C.V = ctx->N; C.n_chains = S.n_chains; C.n_moves = S.n_moves;
     for (int i = 0; i < 3; ++i) { C.move_kind[i] = S.move_kind[i]; C.move_cp[i] = S.move_cp[i]; }
@@ -306,7 +311,13 @@ int evaluate_proposals(fkmc_ctx* ctx, const double** lz, int* lz_stride, const d
     fkmc_chain_state& S = ctx->chain;
     const int C = S.n_chains, N = ctx->N;
     if (S.p.cheb_moves) {
+        // local scheme (kpm2d.cu): the trace sums of the current configuration are kept per chain, a one- or two-site proposal only
+        // recomputes the columns within M/2 hops of the changed sites; full_solve = the periodic re-base from scratch
+        ctx->kpm_f_cur = (S.ks_cur && !full_solve) ? S.f_cur : nullptr;
+        ctx->kpm_ks_in = (S.ks_cur && !full_solve) ? S.ks_cur : nullptr;
+        ctx->kpm_ks_out = S.ks_prop;
         int rc = fkmc_launch_kpm(ctx, S.f_prop, C, S.p.U, S.p.mu_c, S.p.beta, S.M, S.G, ctx->d_moments, ctx->d_ab, S.logz_prop);
+        ctx->kpm_f_cur = nullptr; ctx->kpm_ks_in = nullptr; ctx->kpm_ks_out = nullptr;
         if (rc) return rc;
         *lz = S.logz_prop; *lz_stride = 1; *ecd2 = nullptr; *ecd2_stride = 0;
     } else if (S.fu_vt && !full_solve) {
@@ -331,7 +342,7 @@ int evaluate_proposals(fkmc_ctx* ctx, const double** lz, int* lz_stride, const d
 int fkmc_chain_free(fkmc_ctx* ctx) {
     fkmc_chain_state& S = ctx->chain;
     if (!S.active) return FKMC_OK;
-    cudaFree(S.mt); cudaFree(S.f_cur); cudaFree(S.f_prop); cudaFree(S.logz_cur); cudaFree(S.logz_prop);
+    cudaFree(S.mt); cudaFree(S.f_cur); cudaFree(S.f_prop); cudaFree(S.logz_cur); cudaFree(S.logz_prop); cudaFree(S.ks_cur); cudaFree(S.ks_prop);
     cudaFree(S.spec[0]); cudaFree(S.cur_slot); cudaFree(S.prop_move); cudaFree(S.prop_a); cudaFree(S.prop_b);
     cudaFree(S.naccept); cudaFree(S.s_energy); cudaFree(S.s_d2energy); cudaFree(S.s_cenergy); cudaFree(S.s_nf); cudaFree(S.s_nfpi);
     cudaFree(S.t_move); cudaFree(S.t_a); cudaFree(S.t_b); cudaFree(S.t_acc); cudaFree(S.t_w); cudaFree(S.t_u); cudaFree(S.t_lz);
@@ -401,6 +412,11 @@ extern "C" int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_par
     rc |= dev_alloc(ctx, &S.f_prop, C * V);
     rc |= dev_alloc(ctx, &S.logz_cur, C);
     rc |= dev_alloc(ctx, &S.logz_prop, C);
+    if (p->cheb_moves && ctx->kpm_local) {
+        rc |= dev_alloc(ctx, &S.ks_cur, (size_t)C * FKMC_KPM_STATE);
+        rc |= dev_alloc(ctx, &S.ks_prop, (size_t)C * FKMC_KPM_STATE);
+        if (!rc) cudaMemsetAsync(S.ks_cur, 0, sizeof(double) * (size_t)C * FKMC_KPM_STATE, ctx->stream);   // valid = 0
+    }
     rc |= dev_alloc(ctx, &S.spec[0], 2 * C * V);
     rc |= dev_alloc(ctx, &S.cur_slot, C);
     rc |= dev_alloc(ctx, &S.prop_move, C);
@@ -611,6 +627,14 @@ extern "C" int fkmc_chain_run_sweeps(fkmc_ctx* ctx, int n_sweeps) {
                 if (exact_measure) S.spec_count++;
             }
             S.measured++;
+        }
+        if (S.ks_cur && ctx->kpm_rebase > 0 && (S.sweeps_done + 1) % ctx->kpm_rebase == 0) {
+            // local KPM scheme: fresh trace sums of the current configurations under their own scaling (bounds the rounding that the
+            // incremental sums pick up and re-centres the scaling the affected columns are evaluated with)
+            ctx->kpm_ks_out = S.ks_cur;
+            int rc = fkmc_launch_kpm(ctx, S.f_cur, C, S.p.U, S.p.mu_c, S.p.beta, S.M, S.G, ctx->d_moments, ctx->d_ab, ctx->d_out);
+            ctx->kpm_ks_out = nullptr;
+            if (rc) return rc;
         }
         S.sweeps_done++;
     }

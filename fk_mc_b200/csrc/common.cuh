@@ -11,6 +11,7 @@
 
 #define FKMC_MAX_Z 8        // max neighbours per site (triangular: 6)
 #define FKMC_SYTRD_NB 32    // panel width of the blocked tridiagonalisation
+#define FKMC_KPM_STATE 64   // doubles per chain of the local KPM scheme (kpm2d.cu)
 #define FKMC_MAX_HALF 16    // KPM: M/2 <= 16
 
 struct fkmc_profile_entry {
@@ -41,6 +42,7 @@ struct fkmc_chain_state {
     int32_t* f_prop = nullptr;  // [n_chains][V]
     double* logz_cur = nullptr;
     double* logz_prop = nullptr;
+    double *ks_cur = nullptr, *ks_prop = nullptr;   // [n_chains][FKMC_KPM_STATE] local KPM scheme (kpm2d.cu)
     double* spec[2] = {nullptr, nullptr};  // [n_chains][N] double-buffered spectrum (exact moves)
     int32_t* cur_slot = nullptr;           // [n_chains] which of spec[] is current
     int32_t* prop_move = nullptr;          // [n_chains] move kind of the pending proposal (-1: early-out, weight 0)
@@ -142,6 +144,15 @@ struct fkmc_ctx {
     int* d_flag = nullptr;      // non-convergence flag
     double* d_moments = nullptr;  // [max_batch][2*FKMC_MAX_HALF]
     double* d_ab = nullptr;       // [max_batch][4]
+    // local KPM re-evaluation (kpm2d.cu): set by the chain engine around its launches
+    int kpm_local = 1, kpm_rebase = 16;   // rebase: every so many sweeps the chain engine recomputes the trace sums from scratch
+    const int32_t* kpm_f_cur = nullptr;
+    const double* kpm_ks_in = nullptr;
+    double* kpm_ks_out = nullptr;
+    unsigned char* d_kpm_hop0 = nullptr;   // [N] hop distance from site 0
+    double* d_ks_io = nullptr;             // [2][max_batch][FKMC_KPM_STATE] records of fkmc_logz_kpm_batched_local
+    int32_t* d_f_ref = nullptr;            // [max_batch][N] its reference configurations
+    bool kpm_state_written = false;        // the last KPM launch produced state records (two-kernel 2-D path)
     int* d_kpm_steps = nullptr;   // [max_batch] Lanczos steps of the last KPM launch (diagnostics)
     double* d_aux = nullptr;      // [max_batch][2][N] cached_exp / cached_fermi staging
     double* d_ev_scratch = nullptr;  // eigenvector path: tridiagonal eigenvectors | inverse-iteration factors | T factors (grown on demand)

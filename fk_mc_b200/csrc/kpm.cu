@@ -583,6 +583,7 @@ int fkmc_launch_kpm(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double m
     P.chebt = ctx->d_chebt; P.lobatto = ctx->d_lobatto; P.dtheta = ctx->d_dtheta;
     P.moments = d_moments; P.ab = d_ab; P.logz = d_logz; P.flag = ctx->d_flag; P.steps = ctx->d_kpm_steps;
     P.kmax = ctx->lanczos_cap > 0 ? std::min(ctx->lanczos_cap, KPM_KMAX) : KPM_KMAX;
+    ctx->kpm_state_written = false;
     if (fkmc_kpm2d_applicable(ctx, M)) return fkmc_launch_kpm2d(ctx, d_f, B, U, mu_c, beta, M, G, P.slot_val, d_moments, d_ab, d_logz);
     switch (M / 2) {
 #define FKMC_KPM_CASE(H) case H: return launch_kpm_t<H>(ctx, P, B);

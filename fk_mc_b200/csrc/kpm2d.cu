@@ -457,7 +457,20 @@ struct mom_args {
     double* logz;           // [B]
     double* part;           // [B][MOM_SPLIT][3][FKMC_MAX_HALF + 1] partial traces of the CTAs of one proposal
     int* arrived;           // [B] CTAs of the proposal that have delivered their partial traces (self-resetting)
+    // local re-evaluation (chain engine): f_cur = the chain's current configuration, ks_in = trace sums of f_cur under the scaling (a0, b0)
+    // they were computed with, ks_out = the same record for f (written always when given), hop0 = hop distance from site 0
+    const int32_t* f_cur;
+    const double* ks_in;
+    double* ks_out;
+    const unsigned char* hop0;
+    double guard;
 };
+// per-chain record of the local scheme: [3][FKMC_MAX_HALF + 1] sums (T_m)_jj, <T_(m-1) e_j|T_m e_j>, <T_m e_j|T_m e_j> over all columns j,
+// then sum x, a0, b0, valid
+// then sum x, a0, b0, valid, and what the sums were computed for: M, U, mu_c
+constexpr int KS_TRX = 3 * (FKMC_MAX_HALF + 1), KS_A = KS_TRX + 1, KS_B = KS_TRX + 2, KS_VALID = KS_TRX + 3, KS_M = KS_TRX + 4, KS_U = KS_TRX + 5,
+              KS_MU = KS_TRX + 6;
+static_assert(KS_MU < FKMC_KPM_STATE, "state record too small");
 
 constexpr int MOM_WARPS = 8;
 constexpr int MOM_SPLIT = 2;  // CTAs per proposal (the columns are dealt out round robin): 2 B CTAs fill the last wave much better than B
@@ -479,10 +492,39 @@ __global__ void __launch_bounds__(MOM_WARPS * 32, 2) kpm_moments2d_kernel(mom_ar
     double* Fg = msc + 64;                     // [G]
     double* acc = Fg + ((G + 1) & ~1);         // [MOM_WARPS][3][HALF+1]
     double* vec = acc + MOM_WARPS * 3 * (HALF + 1);  // [MOM_WARPS][2][PV]
+    int* cols = reinterpret_cast<int*>(vec + (size_t)MOM_WARPS * 2 * PV);  // [N] columns of the local scheme
 
     const double e_min = P.ab[(size_t)b * 4 + 0], e_max = P.ab[(size_t)b * 4 + 1];
-    const double a = (e_max - e_min) / 2., bsh = (e_max + e_min) / 2.;
+    const double a_new = (e_max - e_min) / 2., b_new = (e_max + e_min) / 2.;
     const int32_t* f = P.f + (size_t)b * N;
+    // ---- local scheme?  The proposal differs from the chain's current configuration in one or two sites: only the columns within HALF
+    // hops of those sites change, PROVIDED the scaling is kept; so the recursion runs under the scaling (a0, b0) of the stored sums for the
+    // affected columns of both configurations, and the moments are re-expanded for the proposal's own scaling at the end.
+    __shared__ int s_nd, s_sites[2], s_ncols, s_local;
+    const int32_t* fc = P.f_cur ? P.f_cur + (size_t)b * N : nullptr;
+    const double* ksi = P.ks_in ? P.ks_in + (size_t)b * FKMC_KPM_STATE : nullptr;
+    if (tid == 0) s_nd = 0;
+    __syncthreads();
+    if (fc && ksi && P.ncls == 1) {
+        for (int i = tid; i < N; i += T)
+            if (f[i] != fc[i]) {
+                const int k = atomicAdd(&s_nd, 1);
+                if (k < 2) s_sites[k] = i;
+            }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int loc = 0;
+        if (fc && ksi && P.ncls == 1 && s_nd >= 1 && s_nd <= 2 && ksi[KS_VALID] == 1.0 && ksi[KS_M] == (double)M && ksi[KS_U] == P.U &&
+            ksi[KS_MU] == P.mu_c) {
+            const double alpha = ksi[KS_A] / a_new, beta_s = (ksi[KS_B] - b_new) / a_new;
+            loc = fabs(alpha - 1.0) <= P.guard && fabs(beta_s) <= P.guard;
+        }
+        s_local = loc;
+    }
+    __syncthreads();
+    const bool local = s_local != 0;
+    const double a = local ? ksi[KS_A] : a_new, bsh = local ? ksi[KS_B] : b_new;   // scaling of the recursion
     double part = 0.0;
     for (int i = tid; i < N; i += T) {
         const double x = ((P.U * (double)f[i] - P.mu_c) - bsh) / a;
@@ -491,6 +533,52 @@ __global__ void __launch_bounds__(MOM_WARPS * 32, 2) kpm_moments2d_kernel(mom_ar
         part += x;
     }
     const double trx = block_sum(part, red);
+    int ncols = N;
+    if (local) {
+        // affected columns in increasing order (the order fixes which warp sums what: results do not depend on scheduling).
+        // T_m e_j sees the diagonal entry of site i only if a walk from j reaches i in at most m - 1 <= HALF - 1 hops.
+        __shared__ unsigned s_mask[64];
+        __shared__ int s_sidx[64];
+        const int nd = s_nd, nchunk = (N + 31) / 32;   // nchunk <= 64 (N <= 2048 on this path)
+        for (int ch = warp; ch < nchunk; ch += MOM_WARPS) {
+            const int j = ch * 32 + lane;
+            bool hit = false;
+            if (j < N) {
+                const int yj = j / L, xj = j - yj * L;
+                for (int k = 0; k < nd; ++k) {
+                    const int sk = s_sites[k], ys = sk / L, xs = sk - ys * L;
+                    int dy = yj - ys, dx = xj - xs;
+                    dy += dy < 0 ? L : 0;
+                    dx += dx < 0 ? L : 0;
+                    hit = hit || P.hop0[dy * L + dx] < HALF;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) s_mask[ch] = m;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            // exclusive prefix of the chunk counts (two chunks per lane)
+            const int c0 = (2 * lane < nchunk) ? __popc(s_mask[2 * lane]) : 0, c1 = (2 * lane + 1 < nchunk) ? __popc(s_mask[2 * lane + 1]) : 0;
+            int incl = c0 + c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int excl = incl - (c0 + c1);
+            if (2 * lane < nchunk) s_sidx[2 * lane] = excl;
+            if (2 * lane + 1 < nchunk) s_sidx[2 * lane + 1] = excl + c0;
+            if (lane == 31) s_ncols = incl;
+        }
+        __syncthreads();
+        for (int ch = warp; ch < nchunk; ch += MOM_WARPS) {
+            const unsigned m = s_mask[ch];
+            if (m >> lane & 1u) cols[s_sidx[ch] + __popc(m & ((1u << lane) - 1u))] = ch * 32 + lane;
+        }
+        __syncthreads();
+        ncols = s_ncols;
+    }
     double sv2[Z];
 #pragma unroll
     for (int z = 0; z < Z; ++z) sv2[z] = 2.0 * (P.slot_val[z] / a);
@@ -504,6 +592,18 @@ __global__ void __launch_bounds__(MOM_WARPS * 32, 2) kpm_moments2d_kernel(mom_ar
 #pragma unroll
     for (int m = 0; m <= HALF; ++m) tr[m] = d01[m] = d11[m] = 0.0;
 
+    for (int pass = 0; pass < (local ? 2 : 1); ++pass) {
+    if (pass == 1) {
+        // second pass of the local scheme: the same columns for the current configuration, subtracted
+        __syncthreads();
+        if (tid < s_nd) {
+            const int i = s_sites[tid], y = i / L;
+            xd[y * PX + (i - y * L)] = ((P.U * (double)fc[i] - P.mu_c) - bsh) / a;
+        }
+#pragma unroll
+        for (int m = 0; m <= HALF; ++m) { tr[m] = -tr[m]; d01[m] = -d01[m]; d11[m] = -d11[m]; }
+        __syncthreads();
+    }
     for (int cls = 0; cls < P.ncls; ++cls) {
         // this lane's elements: table index 32 s + lane
         int dyx[S], nbi[Z + 1][S], ns[HALF + 1];
@@ -518,7 +618,8 @@ __global__ void __launch_bounds__(MOM_WARPS * 32, 2) kpm_moments2d_kernel(mom_ar
             for (int z = 0; z <= Z; ++z) nbi[z][s] = P.nb[((size_t)cls * (Z + 1) + z) * EP + e];
         }
         const double h1 = P.h1[cls * 32 + lane] / a;  // (X e_j)(e) for the slot-0 element next to the centre
-        for (int j = warp + MOM_WARPS * cta_part; j < N; j += MOM_WARPS * MOM_SPLIT) {
+        for (int idx = warp + MOM_WARPS * cta_part; idx < ncols; idx += MOM_WARPS * MOM_SPLIT) {
+            const int j = local ? cols[idx] : idx;
             const int y0 = j / L, x0 = j - y0 * L;
             if (P.ncls > 1 && ((y0 + x0) & 1) != cls) continue;
             double xd2[S], va[S], vb[S];
@@ -583,6 +684,11 @@ __global__ void __launch_bounds__(MOM_WARPS * 32, 2) kpm_moments2d_kernel(mom_ar
             }
         }
     }
+    }
+    if (local) {
+#pragma unroll
+        for (int m = 0; m <= HALF; ++m) { tr[m] = -tr[m]; d01[m] = -d01[m]; d11[m] = -d11[m]; }   // proposal minus current
+    }
 #pragma unroll
     for (int m = 2; m <= HALF; ++m) {
         const double a0 = warp_sum(tr[m]), a1 = warp_sum(d01[m]), a2 = warp_sum(d11[m]);
@@ -637,6 +743,17 @@ __global__ void __launch_bounds__(MOM_WARPS * 32, 2) kpm_moments2d_kernel(mom_ar
                     t2 += acc[(w * 3 + 2) * (HALF + 1) + m];
                 }
             }
+            if (local) {   // sums of the proposal = sums of the current configuration + (affected columns: proposal - current)
+                t0 += ksi[m];
+                t1 += ksi[(FKMC_MAX_HALF + 1) + m];
+                t2 += ksi[2 * (FKMC_MAX_HALF + 1) + m];
+            }
+            if (P.ks_out) {
+                double* kso = P.ks_out + (size_t)b * FKMC_KPM_STATE;
+                kso[m] = t0;
+                kso[(FKMC_MAX_HALF + 1) + m] = t1;
+                kso[2 * (FKMC_MAX_HALF + 1) + m] = t2;
+            }
             if (!is_set[m]) { mom[m] = t0 / N; is_set[m] = true; }
             int kk = 2 * m - 1;
             if (kk < M && kk >= HALF) {
@@ -645,7 +762,43 @@ __global__ void __launch_bounds__(MOM_WARPS * 32, 2) kpm_moments2d_kernel(mom_ar
             }
         }
     }
-    for (int i = tid; i < G; i += T) Fg[i] = N * log(1. + exp(-P.beta * (a * P.lobatto[i] + bsh)));
+    if (tid == 0 && P.ks_out) {
+        double* kso = P.ks_out + (size_t)b * FKMC_KPM_STATE;
+        kso[KS_TRX] = trx; kso[KS_A] = a; kso[KS_B] = bsh; kso[KS_VALID] = 1.0;
+        kso[KS_M] = (double)M; kso[KS_U] = P.U; kso[KS_MU] = P.mu_c;
+    }
+    if (local) {
+        // moments under the proposal's own scaling y = (H - b_new) / a_new = alpha x + beta with x = (H - b0) / a0:
+        // T_m(alpha x + beta) = sum_k c_mk T_k(x), rows by the three-term recurrence in the Chebyshev basis (x T_k = (T_(k+1) + T_|k-1|) / 2);
+        // lane k of warp 0 holds coefficient k of the two latest rows, the products c_mk mu_k go to shared memory and are summed per row
+        __syncthreads();   // mom[] of thread 0
+        double* cm = vec;  // [M][32] (the patch buffers are free now)
+        if (warp == 0) {
+            const double alpha = a / a_new, beta_s = (bsh - b_new) / a_new;
+            const double mk = (lane < M) ? mom[lane] : 0.0;
+            double pm1 = (lane == 0) ? 1.0 : 0.0;                                   // P_0
+            double pm = (lane == 0) ? beta_s : ((lane == 1) ? alpha : 0.0);         // P_1
+            cm[0 * 32 + lane] = pm1 * mk;
+            cm[1 * 32 + lane] = pm * mk;
+            for (int m = 2; m < M; ++m) {
+                const double up = __shfl_down_sync(0xffffffffu, pm, 1);              // p_(k+1)
+                double dn = __shfl_up_sync(0xffffffffu, pm, 1);                      // p_(k-1)
+                dn = (lane == 0) ? 0.0 : ((lane == 1) ? 2.0 * dn : dn);
+                const double pn = (lane <= m) ? fma(alpha, (lane == 31 ? 0.0 : up) + dn, fma(2.0 * beta_s, pm, -pm1)) : 0.0;
+                cm[m * 32 + lane] = pn * mk;
+                pm1 = pm;
+                pm = pn;
+            }
+        }
+        __syncthreads();
+        if (tid < M) {
+            double sacc = 0.0;
+            for (int k = M - 1; k >= 0; --k) sacc += cm[tid * 32 + k];
+            mom[tid] = sacc;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < G; i += T) Fg[i] = N * log(1. + exp(-P.beta * (a_new * P.lobatto[i] + b_new)));
     __syncthreads();
     if (tid < M) {
         const double* Tm = P.chebt + (size_t)tid * G;
@@ -658,8 +811,8 @@ __global__ void __launch_bounds__(MOM_WARPS * 32, 2) kpm_moments2d_kernel(mom_ar
         double s = acc[0];
         for (int m = 1; m < M; ++m) s += 2. * acc[m] * mom[m];
         P.logz[b] = s;
-        P.ab[(size_t)b * 4 + 2] = a;
-        P.ab[(size_t)b * 4 + 3] = bsh;
+        P.ab[(size_t)b * 4 + 2] = a_new;
+        P.ab[(size_t)b * 4 + 3] = b_new;
     }
     if (tid < M && P.moments) P.moments[(size_t)b * M + tid] = mom[tid];
 }
@@ -820,7 +973,7 @@ template <int HALF, int Z, int S, unsigned long long SCHED, bool UNI>
 static int launch_moments2d_s(fkmc_ctx* ctx, mom_args& P, int B) {
     const int PW = ctx->kpm2_P, PX = P.L + (((PW - P.L) % 16) + 16) % 16;
     const size_t smem = sizeof(double) * ((size_t)P.L * PX + 48 + 64 + ((P.G + 1) & ~1) + (size_t)MOM_WARPS * 3 * (HALF + 1) +
-                                          (size_t)MOM_WARPS * 2 * ctx->kpm2_PV);
+                                          (size_t)MOM_WARPS * 2 * ctx->kpm2_PV) + sizeof(int) * (size_t)((P.N + 1) & ~1);
     if (smem > ctx->smem_optin - 1024) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: lattice too large for the shared-memory kernel");
     FKMC_CUDA(ctx, cudaFuncSetAttribute(kpm_moments2d_kernel<HALF, Z, S, SCHED, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kpm_moments2d_kernel<HALF, Z, S, SCHED, UNI><<<B * MOM_SPLIT, MOM_WARPS * 32, smem, ctx->stream>>>(P);
@@ -926,6 +1079,31 @@ int fkmc_launch_kpm2d(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double
     for (int z = 0; z < FKMC_MAX_Z; ++z) P.slot_val[z] = slot_val[z];
     P.chebt = ctx->d_chebt; P.lobatto = ctx->d_lobatto; P.dtheta = ctx->d_dtheta;
     P.moments = d_moments; P.ab = d_ab; P.logz = d_logz;
+    // local re-evaluation (set by the chain engine around its launches; translation-invariant one-class lattices only)
+    P.ks_out = ctx->kpm_ks_out;
+    ctx->kpm_state_written = P.ks_out != nullptr;
+    P.guard = 0.02;
+    if (ctx->kpm_f_cur && ctx->kpm_ks_in && P.ncls == 1 && ctx->kpm_local) {
+        if (!ctx->d_kpm_hop0) {
+            const int N = ctx->N, Z = ctx->Z;
+            std::vector<unsigned char> hop(N, 255);
+            std::queue<int> q;
+            hop[0] = 0;
+            q.push(0);
+            while (!q.empty()) {
+                const int sidx = q.front();
+                q.pop();
+                for (int z = 0; z < Z; ++z) {
+                    const int t = ctx->h_nbr_idx[(size_t)z * N + sidx];
+                    if (t < N && ctx->h_nbr_val[(size_t)z * N + sidx] != 0.0 && hop[t] == 255 && hop[sidx] < 254) { hop[t] = hop[sidx] + 1; q.push(t); }
+                }
+            }
+            FKMC_CUDA(ctx, cudaMalloc(&ctx->d_kpm_hop0, N));
+            FKMC_CUDA(ctx, cudaMemcpyAsync(ctx->d_kpm_hop0, hop.data(), N, cudaMemcpyHostToDevice, ctx->stream));
+            FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // hop is a local
+        }
+        P.f_cur = ctx->kpm_f_cur; P.ks_in = ctx->kpm_ks_in; P.hop0 = ctx->d_kpm_hop0;
+    }
     fkmc_prof_scope ps(ctx, "kpm_moments");
     if (ctx->kind == FKMC_CUBIC2D) return launch_moments2d_half<FKMC_CUBIC2D>(ctx, P, B, M / 2);
     if (ctx->kind == FKMC_TRIANGULAR) return launch_moments2d_half<FKMC_TRIANGULAR>(ctx, P, B, M / 2);

@@ -168,6 +168,11 @@ struct chebyshev_cache {
     double e_max = 0, e_min = 0, a = 0, b = 0;
     std::vector<double> moments;
     double logZ = 0.0;
+    // not in the reference: the trace-sum record of fkmc_logz_kpm_batched_local and the configuration it belongs to.  It survives
+    // reset_cache / calc_hamiltonian, so that a proposal (a copy of the current configuration with one or two sites changed) is
+    // re-evaluated locally against the configuration it was copied from.
+    std::vector<double> kpm_state;
+    std::vector<int32_t> kpm_state_f;
 };
 
 /// include/fk_mc/configuration.hpp:52-87
@@ -227,8 +232,13 @@ struct configuration_t {
         if (int(cheb_data_.status) >= int(chebyshev_cache::logz)) return;
         double ab[4];
         cheb_data_.moments.resize(cheb.cheb_size());
-        fkmc_check(fkmc_logz_kpm_batched(lattice_.ctx(), f_config_.data(), 1, params_.U, params_.mu_c, params_.beta, cheb.cheb_size(), cheb.grid_size(),
-                                         cheb_data_.moments.data(), ab, &cheb_data_.logZ), lattice_.ctx());
+        const bool have_ref = cheb_data_.kpm_state.size() == FKMC_KPM_STATE_DOUBLES && cheb_data_.kpm_state_f.size() == f_config_.size();
+        std::vector<double> state_out(FKMC_KPM_STATE_DOUBLES);
+        fkmc_check(fkmc_logz_kpm_batched_local(lattice_.ctx(), f_config_.data(), have_ref ? cheb_data_.kpm_state_f.data() : nullptr,
+                                               have_ref ? cheb_data_.kpm_state.data() : nullptr, 1, params_.U, params_.mu_c, params_.beta, cheb.cheb_size(),
+                                               cheb.grid_size(), cheb_data_.moments.data(), ab, &cheb_data_.logZ, state_out.data()), lattice_.ctx());
+        cheb_data_.kpm_state.swap(state_out);
+        cheb_data_.kpm_state_f.assign(f_config_.begin(), f_config_.end());
         cheb_data_.e_min = ab[0]; cheb_data_.e_max = ab[1]; cheb_data_.a = ab[2]; cheb_data_.b = ab[3];
         cheb_data_.status = chebyshev_cache::logz;
     }

@@ -83,6 +83,17 @@ int fkmc_stiffness_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, dou
 int fkmc_logz_kpm_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, double mu_c, double beta, int M, int G,
                           double* moments, double* ab, double* logZ);
 
+/* The same evaluation for a configuration f that differs from a reference configuration f_ref in one or two sites (what a move
+ * proposes: src/moves_chebyshev.cpp:8-24, 41-58), given the record state_ref [B][FKMC_KPM_STATE_DOUBLES] an earlier call returned for
+ * f_ref: only the lattice columns within M/2 - 1 hops of the changed sites are re-evaluated (both configurations, under the scaling of
+ * the record) and the moments are re-expanded for f's own e_min / e_max; same results to rounding.  state_out (may be NULL) receives
+ * the record of f -- keep it with the configuration it belongs to (configuration_t::cheb_data_) and pass it when that configuration is
+ * the reference.  f_ref = state_ref = NULL, more than two changed sites, a record marked invalid or a scaling that moved by more than
+ * 2 % make the call a full evaluation.  Lattices outside the two-kernel 2-D path return records marked invalid. */
+#define FKMC_KPM_STATE_DOUBLES 64
+int fkmc_logz_kpm_batched_local(fkmc_ctx* ctx, const int32_t* f, const int32_t* f_ref, const double* state_ref, int B, double U,
+                                double mu_c, double beta, int M, int G, double* moments, double* ab, double* logZ, double* state_out);
+
 /* measure_energy::accumulate, src/measures/energy.cpp:6-26, from a spectrum: out [B][3] = {E_c, d2E, logZ};
  * E = E_c - mu_f*N_f + E_ff is finished by the caller. */
 int fkmc_energy_from_spectrum(fkmc_ctx* ctx, const double* evals, int B, double beta, double* out3);
@@ -101,6 +112,9 @@ int fkmc_sb2st_batched(fkmc_ctx* ctx, const double* AB, int N, int B, double* d,
  *          "kpm_generic" = 1 forces the full-lattice-vector KPM kernel (default 0: local-patch kernel when it applies)
  *          "kpm_v1" = 1 forces the single-kernel KPM path (csrc/kpm.cu) where the two-kernel 2-D path (csrc/kpm2d.cu:
  *          strip Lanczos + ring-ordered patch recursion) would apply; for cross-checks
+ *          "kpm_local" = 0: Chebyshev moves of the chain engine evaluate the full trace for every proposal (default 1: only the
+ *          columns near the changed sites, csrc/kpm2d.cu; takes effect at the next fkmc_chain_init); "kpm_rebase_sweeps" = n: sweeps
+ *          between recomputations of the per-chain trace sums from scratch (default 16, 0 = never)
  *          "band_path" = 0 sends eigenvalue-only solves through the dense N^3 reduction (default 1: lattices whose matrix has
  *          half-bandwidth <= 64 after folding the slow coordinate start from the band, csrc/sb2sb.cu); "band_min" = n: smallest N
  *          served by the band path (default 256)

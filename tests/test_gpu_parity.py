@@ -954,6 +954,88 @@ def test_stiffness_rejects_other_lattices():
     c.close()
 
 
+# ---------------- local KPM re-evaluation (kpm2d.cu) ----------------
+@pytest.mark.parametrize("kind,L,M", [("cubic2d", 32, 16), ("cubic2d", 16, 12), ("triangular", 24, 14)])
+def test_kpm_local_matches_full(kind, L, M):
+    """fkmc_logz_kpm_batched_local: configurations that differ from a reference in one site (add / remove) or two (flip) re-evaluated from
+    the reference's trace-sum record, against the full evaluation and the oracle; a chain of 40 accepted single-site changes without a
+    full evaluation in between; fall-backs: many changed sites, a record of another M, no reference."""
+    U, beta, B = 2.0, 8.0, 6
+    G = 2 * M
+    c = fk.Context(kind, L, max_batch=B)
+    n = c.N
+    rng = np.random.default_rng(17)
+    f0 = np.stack([o.randomize_f(50 + i, n, n // 2)[0] for i in range(B)])
+    r0 = c.logz_kpm_local(f0, U, U / 2, beta, M, G)                        # no reference: full, returns the records
+    full0 = c.logz_kpm(f0, U, U / 2, beta, M, G)
+    assert np.array_equal(r0["logZ"], full0["logZ"]) and np.all(r0["state"][:, 54] == 1.0)
+    f1 = f0.copy()
+    for b in range(B):
+        if b % 2 == 0:
+            f1[b, rng.integers(n)] ^= 1                                       # add / remove
+        else:
+            occ, emp = np.flatnonzero(f1[b] == 1), np.flatnonzero(f1[b] == 0)  # flip: move one f-electron
+            f1[b, rng.choice(occ)] = 0
+            f1[b, rng.choice(emp)] = 1
+    r1 = c.logz_kpm_local(f1, U, U / 2, beta, M, G, f_ref=f0, state_ref=r0["state"])
+    full1 = c.logz_kpm(f1, U, U / 2, beta, M, G)
+    assert np.abs(r1["logZ"] - full1["logZ"]).max() <= 1e-12 * np.abs(full1["logZ"]).max()
+    assert np.abs(r1["moments"] - full1["moments"]).max() <= 1e-12
+    assert np.array_equal(r1["a"], full1["a"]) and np.array_equal(r1["b"], full1["b"])
+    ref = o.calc_chebyshev(o.KINDS[kind], L, f1[0], U, U / 2, beta, M, G)
+    assert abs(r1["logZ"][0] - ref["logZ"]) <= TOL * abs(ref["logZ"])
+    # the record of a locally evaluated configuration serves as the next reference: 40 steps, then compare with a fresh full evaluation
+    f, st = f1.copy(), r1["state"]
+    for _ in range(40):
+        g = f.copy()
+        g[np.arange(B), rng.integers(n, size=B)] ^= 1
+        r = c.logz_kpm_local(g, U, U / 2, beta, M, G, f_ref=f, state_ref=st)
+        f, st = g, r["state"]
+    fullN = c.logz_kpm(f, U, U / 2, beta, M, G)
+    assert np.abs(r["logZ"] - fullN["logZ"]).max() <= 1e-11 * np.abs(fullN["logZ"]).max()
+    assert np.abs(r["moments"] - fullN["moments"]).max() <= 1e-11
+    # fall-backs are full evaluations: bit-identical to fkmc_logz_kpm_batched
+    g = f.copy()
+    g[:, :5] ^= 1
+    rf = c.logz_kpm_local(g, U, U / 2, beta, M, G, f_ref=f, state_ref=st)
+    assert np.array_equal(rf["logZ"], c.logz_kpm(g, U, U / 2, beta, M, G)["logZ"])
+    g = f.copy()
+    g[:, 7] ^= 1
+    rm = c.logz_kpm_local(g, U, U / 2, beta, M - 2, 2 * (M - 2), f_ref=f, state_ref=st)   # the record was made for another M
+    assert np.array_equal(rm["logZ"], c.logz_kpm(g, U, U / 2, beta, M - 2, 2 * (M - 2))["logZ"])
+    c.close()
+
+
+def test_kpm_local_chain_equals_full_chain():
+    """Chebyshev-move chains with the local scheme on (default) and off: identical accept / reject sequences, logZ of every proposal within
+    1e-12, also across a re-base (kpm_rebase_sweeps = 2) and with reshuffle moves (always full) mixed in."""
+    out = []
+    for loc in (1, 0):
+        c = fk.Context("cubic2d", 16, max_batch=8)
+        c.set_option("kpm_local", loc)
+        c.set_option("kpm_rebase_sweeps", 2)
+        c.chain_init(8, 6.0, 2.0, cheb_moves=True, seed=3, sweep_len=8, ntherm_sweeps=0, measure_energy=False, mc_flip=0.3, mc_add_remove=0.6,
+                     mc_reshuffle=0.1, record_trace=True, max_sweeps=6)
+        c.chain_run_sweeps(6)
+        out.append((c.chain_get_trace(), c.chain_get_state()))
+        c.close()
+    (t1, s1), (t0, s0) = out
+    assert np.array_equal(t1["accepted"], t0["accepted"]) and np.array_equal(s1["f"], s0["f"])
+    assert np.abs(t1["logz_new"] - t0["logz_new"]).max() <= 1e-12 * np.abs(t0["logz_new"]).max()
+
+
+def test_kpm_local_other_lattices_return_invalid_records():
+    c = fk.Context("cubic3d", 6, max_batch=2)
+    f = np.stack([o.randomize_f(1 + i, c.N, c.N // 2)[0] for i in range(2)])
+    r = c.logz_kpm_local(f, 1.0, 0.5, 2.0, 8, 16)
+    assert np.all(r["state"] == 0.0)
+    g = f.copy()
+    g[:, 3] ^= 1
+    r2 = c.logz_kpm_local(g, 1.0, 0.5, 2.0, 8, 16, f_ref=f, state_ref=r["state"])
+    assert np.array_equal(r2["logZ"], c.logz_kpm(g, 1.0, 0.5, 2.0, 8, 16)["logZ"])
+    c.close()
+
+
 # ---------------- band path: folded lattice ordering, band -> band (sb2sb.cu) -> tridiagonal ----------------
 @pytest.mark.parametrize("kind,L,U", [("cubic2d", 16, 2.0), ("cubic2d", 24, 0.5), ("cubic2d", 26, 4.0), ("cubic2d", 32, 1.0), ("triangular", 24, 2.0),
                                       ("triangular", 31, 2.0), ("honeycomb", 24, 2.0), ("honeycomb", 32, 1.0)])
