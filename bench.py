@@ -217,6 +217,7 @@ def main():
     ap.add_argument("--measure-ipr", action="store_true",
                     help="measurement path (c): every sweep also measures the IPR of all eigenstates (calc_ed(true) per chain, ipr.hpp:39-56)")
     ap.add_argument("--dense-path", action="store_true", help="full solves through the dense N^3 reduction (sy2sb) instead of the band path (sb2sb)")
+    ap.add_argument("--kpm-full", action="store_true", help="Chebyshev moves evaluate the full trace for every proposal (option kpm_local = 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the short dense-move lines (c2 / c3, full solve and fast update) appended to the default run")
@@ -258,6 +259,8 @@ def main():
     ctx = fk.Context(kind, L, max_batch=chains, device=local_rank)
     if args.dense_path:
         ctx.set_option("band_path", 0)
+    if args.kpm_full:
+        ctx.set_option("kpm_local", 0)
     ctx.set_stream(stream.cuda_stream)
     N = ctx.N
     M, G = fk.cheb_sizes(N, 2.2)
@@ -346,10 +349,19 @@ def main():
         except Exception:
             lz_steps = 135.0
         f_lz = 2 * lz_steps * N * (2 * zc + 7) / 2  # one Lanczos run delivers both e_min and e_max
+        f_mom_full = f_mom
+        kpm_local = kind in ("cubic2d", "triangular") and not getattr(args, "kpm_full", False)
+        if kpm_local:
+            # local scheme of the chain engine (csrc/kpm2d.cu): a one-site proposal recomputes the columns within M/2 - 1 hops of the changed site
+            # for both configurations instead of all N columns
+            n_aff = sup(half - 1)
+            f_mom = 2 * n_aff * (sum(sup(m) * (2 * zc + 3) for m in range(2, half + 1)) + 4 * sup(half))
         a_fp = (f_mom + f_lz) * chains / (fam["kpm"]["ms_per_launch"] * 1e-3) * 1e-12
         rl_kpm = {"kernel": "lanczos2d_kernel + kpm_moments2d_kernel" if sub else "kpm_kernel", "bound": "fp64", "achieved": a_fp, "peak": DFMA_PEAK_TFLOPS,
                   "unit": "TFLOP/s", "frac": a_fp / DFMA_PEAK_TFLOPS, "traffic": tr_k, "peak_source": "measured FP64 DFMA (tools/probe_dmma.cu)",
-                  "flop_per_proposal": {"moments": f_mom, "lanczos": f_lz, "lanczos_steps": lz_steps},
+                  "flop_per_proposal": {"moments": f_mom, "lanczos": f_lz, "lanczos_steps": lz_steps, "moments_full_trace": f_mom_full,
+                                        "local_scheme": kpm_local},
+                  "full_trace_equivalent_tflops": (f_mom_full + f_lz) * chains / (fam["kpm"]["ms_per_launch"] * 1e-3) * 1e-12,
                   "hbm_contract": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                                    "peak_source": peak_src,
                                    "note": "algorithmic bytes of the STREAMING formulation (SURVEY 8d: 24 N^2 (M/2-1) + 16 N^2 per proposal); the kernels keep "
