@@ -47,6 +47,9 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // named barriers: 1 = reflectors ready (panel warp arrives, compute warps wait), 2 = next panel ready (compute warps arrive, panel warp
 // waits), 3 = compute warps only
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// The sweep barrier of the whole CTA.  Every role (panel warp, compute warps, idle warps) calls it from its own loop; keeping it in one
+// non-inlined function makes that a single barrier instruction (the tools that check barrier convergence key on the instruction).
+__device__ __noinline__ void sweep_barrier() { __syncthreads(); }
 __device__ __forceinline__ void bar_arrive(int id, int n) {
     __threadfence_block();
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(SBR_THREADS, SBR_CTAS) sb2sb_kernel(double* ba
     if (w < 0) {
         for (int j = 0; j < nsweeps; ++j) {
             if (8 * j + 8 >= N) break;
-            __syncthreads();
+            sweep_barrier();
         }
         return;
     }
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(SBR_THREADS, SBR_CTAS) sb2sb_kernel(double* ba
         for (int j = 0; j < nsweeps; ++j) {
             const int c0 = 8 * j;
             if (c0 + 8 >= N) break;
-            __syncthreads();
+            sweep_barrier();
             for (int p = 0;; ++p, ++vpar) {
                 const int r0 = c0 + 8 + 64 * p;
                 if (r0 >= N) break;
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(SBR_THREADS, SBR_CTAS) sb2sb_kernel(double* ba
     for (int j = 0; j < nsweeps; ++j) {
         const int c0 = 8 * j;
         if (c0 + 8 >= N) break;
-        __syncthreads();   // the previous sweep's global stores are visible to every warp of the CTA
+        sweep_barrier();   // the previous sweep's global stores are visible to every warp of the CTA
         for (int p = 0;; ++p, ++vpar) {
             const int r0 = c0 + 8 + 64 * p;
             if (r0 >= N) break;
