@@ -57,10 +57,13 @@ __device__ __forceinline__ void prog_store(int* p, int v) {
 }
 
 // sum over the 8 lanes of a group (m: the group's lane mask)
-__device__ __forceinline__ double gsum8(double x, unsigned m) {
-    x += __shfl_xor_sync(m, x, 1);
-    x += __shfl_xor_sync(m, x, 2);
-    x += __shfl_xor_sync(m, x, 4);
+// sum over the eight lanes of a sweep group.  Full-mask shuffles: the whole warp executes every step together (inactive groups run
+// the same instructions on dummy data), which spares the MATCH / REDUX / VOTE sequence the compiler puts in front of every collective
+// with a partial mask.
+__device__ __forceinline__ double gsum8(double x) {
+    x += __shfl_xor_sync(0xffffffffu, x, 1);
+    x += __shfl_xor_sync(0xffffffffu, x, 2);
+    x += __shfl_xor_sync(0xffffffffu, x, 4);
     return x;
 }
 
@@ -71,10 +74,10 @@ struct refl {
 };
 
 // Householder reflector for x (x_l in lane l of the group, l < n; zero beyond n)
-__device__ __forceinline__ refl make_reflector(double x, int l, int n, unsigned m, int gbase) {
+__device__ __forceinline__ refl make_reflector(double x, int l, int n, int gbase) {
     refl R;
-    const double tail2 = gsum8((l >= 1 && l < n) ? x * x : 0.0, m);
-    const double x0 = __shfl_sync(m, x, gbase);
+    const double tail2 = gsum8((l >= 1 && l < n) ? x * x : 0.0);
+    const double x0 = __shfl_sync(0xffffffffu, x, gbase);
     const bool triv = tail2 <= DBL_MIN;
     // |beta| = sqrt(x0^2 + tail2) through one reciprocal square root; tau = (beta - x0) / beta = 1 + |x0| / |beta| needs no division
     const double s2 = fma(x0, x0, triv ? 1.0 : tail2);
@@ -91,10 +94,10 @@ __device__ __forceinline__ refl make_reflector(double x, int l, int n, unsigned 
 
 // The same reflector with the group's x vector exchanged through its shared-memory pad (one store, four 128-bit loads, the norm
 // summed in the lane) instead of three shuffle stages + one broadcast shuffle.  pad: 8 doubles, 16-byte aligned.
-__device__ __forceinline__ refl make_reflector_pad(double x, int l, int n, unsigned m, double* pad) {
+__device__ __forceinline__ refl make_reflector_pad(double x, int l, int n, double* pad) {
     refl R;
     pad[l] = x;
-    __syncwarp(m);
+    __syncwarp();
     double xs[SB];
 #pragma unroll
     for (int i = 0; i < SB; i += 2) {
@@ -142,8 +145,10 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
 
     const int l = lane & 7, q = lane >> 3, gbase = lane & 24;
     double* bc = bcast + (size_t)(warp * 4 + q) * 24;  // [0..7] v, [8..15] u, [16..23] x
-    const unsigned gmask = 0xffu << gbase;
     const int nsweeps = N - 2;
+    int doff[SB];   // element (i, l) of the symmetric diagonal block in column storage
+#pragma unroll
+    for (int i = 0; i < SB; ++i) doff[i] = min(i, l) * (WD - 1) + max(i, l);
     for (int jb = 4 * warp; jb < nsweeps; jb += 4 * nwarps) {
         const int j = jb + q;
         int p = j + 1;                  // first row of the current reflector's index set
@@ -161,23 +166,28 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
             }
             __syncwarp();
             sched_fence();
-            if (act) {
-                if (s == 0) {
+            // Every lane runs the step; `act` only gates what a group stores and how its state advances (tau = 0, v = 0 in a group that
+            // has not started, so its arithmetic is the identity on dummy loads).
+            {
+                const bool first = act && s == 0;
+                if (__any_sync(0xffffffffu, first)) {
                     // ---- step 0: annihilate column j below the sub-diagonal ----
-                    const double x = Wb[(size_t)j * WD + 1 + l];  // rows p..p+7 of column j (zero beyond the matrix)
-                    const refl R = make_reflector(x, l, n, gmask, gbase);
-                    if (l < n) Wb[(size_t)j * WD + 1 + l] = (l == 0) ? R.beta : 0.0;
-                    vl = R.v;
-                    tau = R.tau;
+                    const double x = first ? Wb[j * WD + 1 + l] : 0.0;  // rows p..p+7 of column j (zero beyond the matrix)
+                    const refl R = make_reflector(x, l, n, gbase);
+                    if (first) {
+                        if (l < n) Wb[j * WD + 1 + l] = (l == 0) ? R.beta : 0.0;
+                        vl = R.v;
+                        tau = R.tau;
+                    }
                     bc[l] = vl;
-                    __syncwarp(gmask);
+                    __syncwarp();
 #pragma unroll
                     for (int i = 0; i < SB; i += 2) {
                         const double2 t = *reinterpret_cast<const double2*>(bc + i);
                         v[i] = t.x;
                         v[i + 1] = t.y;
                     }
-                    __syncwarp(gmask);
+                    __syncwarp();
                 }
                 // One step = three independent block updates with the same reflector (tau = 0 makes all of them the identity):
                 //   (i)   [s >= 1] left-apply H to columns p-7 .. p-1 of the bulge block A(J, .): lane l owns column p-8+l
@@ -187,16 +197,16 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
                 // sqrt / divisions interleave), then the stores.
                 const int pn = p + SB;
                 const int nn = min(SB, N - pn);
-                const bool c1 = (s >= 1) && (l >= 1);
-                const bool c3 = (n == SB) && (nn > 0);
-                double* col = Wb + (size_t)(c1 ? (p - SB + l) : p) * WD + (SB - l);
-                double* D0 = Wb + (size_t)p * WD;
-                double* B0 = Wb + (size_t)p * WD + SB + l;
+                const bool c1 = act && (s >= 1) && (l >= 1);
+                const bool c3 = act && (n == SB) && (nn > 0);
+                double* col = Wb + (c1 ? (p - SB + l) : p) * WD + (SB - l);
+                double* D0 = Wb + p * WD;
+                double* B0 = Wb + p * WD + SB + l;
                 double a[SB], dcol[SB], bel[SB];
 #pragma unroll
                 for (int i = 0; i < SB; ++i) {
                     bel[i] = c3 ? B0[i * (WD - 1)] : 0.0;
-                    dcol[i] = D0[min(i, l) * (WD - 1) + max(i, l)];
+                    dcol[i] = act ? D0[doff[i]] : 0.0;
                     a[i] = c1 ? col[i] : 0.0;
                 }
                 // (iii) first: the next reflector hangs on it
@@ -209,9 +219,9 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
                 const double z = tau * (z0 + z1);
 #pragma unroll
                 for (int c = 0; c < SB; ++c) bel[c] = fma(-z, v[c], bel[c]);
-                const bool more = (n == SB && nn >= 2);
+                const bool more = act && (n == SB && nn >= 2);
                 // next reflector from the first column of the block below (rows pn.., column p): only this sweep touches it now
-                const refl R = make_reflector_pad(bel[0], l, nn, gmask, bc + 16);
+                const refl R = make_reflector_pad(bel[0], l, nn, bc + 16);
                 // (i)
                 double w0 = 0.0, w1 = 0.0;
 #pragma unroll
@@ -230,10 +240,10 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
                     u1 = fma(dcol[i + 1], v[i + 1], u1);
                 }
                 double u = tau * (u0 + u1);                        // u_l = tau (D v)_l
-                const double alpha = -0.5 * tau * gsum8(u * vl, gmask);
+                const double alpha = -0.5 * tau * gsum8(u * vl);
                 u = fma(alpha, vl, u);
                 bc[8 + l] = u;
-                __syncwarp(gmask);
+                __syncwarp();
 #pragma unroll
                 for (int i = 0; i < SB; i += 2) {
                     const double2 t = *reinterpret_cast<const double2*>(bc + 8 + i);
@@ -244,26 +254,23 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
 #pragma unroll
                 for (int i = 0; i < SB; ++i) {
                     if (c1) col[i] = a[i];
-                    if (i >= l) D0[l * (WD - 1) + i] = dcol[i];
+                    if (act && i >= l) D0[l * (WD - 1) + i] = dcol[i];
                     if (c3) B0[i * (WD - 1)] = bel[i];
                 }
-                if (more) {
-                    if (l < nn) Wb[(size_t)p * WD + SB + l] = (l == 0) ? R.beta : 0.0;
-                    vl = R.v;
-                    tau = R.tau;
-                    bc[l] = vl;
-                    __syncwarp(gmask);
+                if (more && l < nn) Wb[p * WD + SB + l] = (l == 0) ? R.beta : 0.0;
+                vl = more ? R.v : vl;
+                tau = more ? R.tau : tau;
+                bc[l] = vl;     // (a group that does not advance broadcasts the reflector it already holds)
+                __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < SB; i += 2) {
-                        const double2 t = *reinterpret_cast<const double2*>(bc + i);
-                        v[i] = t.x;
-                        v[i + 1] = t.y;
-                    }
-                    p = pn;
-                    n = nn;
-                } else {
-                    done = true;
+                for (int i = 0; i < SB; i += 2) {
+                    const double2 t = *reinterpret_cast<const double2*>(bc + i);
+                    v[i] = t.x;
+                    v[i + 1] = t.y;
                 }
+                p = more ? pn : p;
+                n = more ? nn : n;
+                done = done || (act && !more);
             }
             // publish progress: the writes of this step are visible before the counter moves
             __syncwarp();
