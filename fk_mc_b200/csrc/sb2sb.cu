@@ -349,14 +349,24 @@ __global__ void __launch_bounds__(SBR_THREADS, SBR_CTAS) sb2sb_kernel(double* ba
             double2 S[8], G[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                if (c <= w) {
-                    S[c] = *reinterpret_cast<const double2*>(tile_ptr(band, I0 + w, I0 + c) + 2 * lane);
-                } else {
-                    const double* tp = tile_ptr(band, I0 + c, I0 + w);
-                    S[c].x = tp[(2 * q) * 8 + g];
-                    S[c].y = tp[(2 * q + 1) * 8 + g];
-                }
+                // lower tiles as stored; an upper tile is the transpose of the stored tile (c, w): loaded like any tile (one 512-byte
+                // access) and transposed below with two shuffles instead of two strided loads that touch all 16 sectors each
+                S[c] = *reinterpret_cast<const double2*>((c <= w ? tile_ptr(band, I0 + w, I0 + c) : tile_ptr(band, I0 + c, I0 + w)) + 2 * lane);
                 G[c] = *reinterpret_cast<const double2*>(tile_ptr(band, I0 + 8 + w, I0 + c) + 2 * lane);
+            }
+            {
+                // transpose of an accumulator-layout tile: element (g, 2q + e) of the transpose = element (2q + e, g) of the tile, held by
+                // lane (2q + e, g >> 1) in component g & 1
+                const int src0 = ((2 * q) << 2) | (g >> 1), src1 = ((2 * q + 1) << 2) | (g >> 1);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c > w) {   // warp-uniform
+                        const double ax = __shfl_sync(0xffffffffu, S[c].x, src0), ay = __shfl_sync(0xffffffffu, S[c].y, src0);
+                        const double bx = __shfl_sync(0xffffffffu, S[c].x, src1), by = __shfl_sync(0xffffffffu, S[c].y, src1);
+                        S[c].x = (g & 1) ? ay : ax;
+                        S[c].y = (g & 1) ? by : bx;
+                    }
+                }
             }
             SBR_TICK(0)
             bar_sync(1, SBR_SYNC);   // V, T of this step ready; the B block in shared memory complete
