@@ -314,6 +314,7 @@ int fkmc_logz_kpm_batched_local(fkmc_ctx* ctx, const int32_t* f, const int32_t* 
     double* ks_in = ctx->d_ks_io;
     double* ks_out = ctx->d_ks_io + nb * FKMC_KPM_STATE;
     if (f_ref) {
+        if ((rc = fkmc_kpm_prepare_local(ctx))) return rc;
         FKMC_CUDA(ctx, cudaMemcpyAsync(ctx->d_f_ref, f_ref, sizeof(int32_t) * (size_t)B * N, cudaMemcpyHostToDevice, ctx->stream));
         FKMC_CUDA(ctx, cudaMemcpyAsync(ks_in, state_ref, sizeof(double) * (size_t)B * FKMC_KPM_STATE, cudaMemcpyHostToDevice, ctx->stream));
         ctx->kpm_f_cur = ctx->d_f_ref;

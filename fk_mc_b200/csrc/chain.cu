@@ -416,6 +416,7 @@ extern "C" int fkmc_chain_init(fkmc_ctx* ctx, int n_chains, const fkmc_chain_par
         rc |= dev_alloc(ctx, &S.ks_cur, (size_t)C * FKMC_KPM_STATE);
         rc |= dev_alloc(ctx, &S.ks_prop, (size_t)C * FKMC_KPM_STATE);
         if (!rc) cudaMemsetAsync(S.ks_cur, 0, sizeof(double) * (size_t)C * FKMC_KPM_STATE, ctx->stream);   // valid = 0
+        if (!rc) rc |= fkmc_kpm_prepare_local(ctx);
     }
     rc |= dev_alloc(ctx, &S.spec[0], 2 * C * V);
     rc |= dev_alloc(ctx, &S.cur_slot, C);

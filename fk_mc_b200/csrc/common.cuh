@@ -240,6 +240,7 @@ int fkmc_launch_kpm(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double m
                     double* d_moments, double* d_ab, double* d_logz);
 // two-kernel variant for the regular 2-D lattices (kpm2d.cu); slot_val = per-slot hopping constants
 bool fkmc_kpm2d_applicable(const fkmc_ctx* ctx, int M);
+int fkmc_kpm_prepare_local(fkmc_ctx* ctx);
 int fkmc_launch_kpm2d(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double mu_c, double beta, int M, int G, const double* slot_val,
                       double* d_moments, double* d_ab, double* d_logz);
 // eigenvector path (measurement sweeps): evals/out on the device, eigenvectors and IPR to the host (or IPR to d_ipr)

@@ -1039,6 +1039,28 @@ static int launch_moments2d_half(fkmc_ctx* ctx, mom_args& P, int B, int half) {
     return fkmc_set_error(ctx, FKMC_ERR_INVALID, "KPM: unsupported M for the 2-D kernels");
 }
 
+// Hop distances from site 0 (breadth-first search over the stencil): what the local scheme needs to list the columns near a changed site.
+// Called outside any stream capture (chain set-up, fkmc_logz_kpm_batched_local).
+int fkmc_kpm_prepare_local(fkmc_ctx* ctx) {
+    if (ctx->d_kpm_hop0) return FKMC_OK;
+    const int N = ctx->N, Z = ctx->Z;
+    std::vector<unsigned char> hop(N, 255);
+    std::queue<int> q;
+    hop[0] = 0;
+    q.push(0);
+    while (!q.empty()) {
+        const int sidx = q.front();
+        q.pop();
+        for (int z = 0; z < Z; ++z) {
+            const int t = ctx->h_nbr_idx[(size_t)z * N + sidx];
+            if (t < N && ctx->h_nbr_val[(size_t)z * N + sidx] != 0.0 && hop[t] == 255 && hop[sidx] < 254) { hop[t] = hop[sidx] + 1; q.push(t); }
+        }
+    }
+    FKMC_CUDA(ctx, cudaMalloc(&ctx->d_kpm_hop0, N));
+    FKMC_CUDA(ctx, cudaMemcpy(ctx->d_kpm_hop0, hop.data(), N, cudaMemcpyHostToDevice));
+    return FKMC_OK;
+}
+
 // true when (lattice, M) is served by the two-kernel path
 bool fkmc_kpm2d_applicable(const fkmc_ctx* ctx, int M) {
     const int half = M / 2;
@@ -1083,25 +1105,7 @@ int fkmc_launch_kpm2d(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double
     P.ks_out = ctx->kpm_ks_out;
     ctx->kpm_state_written = P.ks_out != nullptr;
     P.guard = 0.02;
-    if (ctx->kpm_f_cur && ctx->kpm_ks_in && P.ncls == 1 && ctx->kpm_local) {
-        if (!ctx->d_kpm_hop0) {
-            const int N = ctx->N, Z = ctx->Z;
-            std::vector<unsigned char> hop(N, 255);
-            std::queue<int> q;
-            hop[0] = 0;
-            q.push(0);
-            while (!q.empty()) {
-                const int sidx = q.front();
-                q.pop();
-                for (int z = 0; z < Z; ++z) {
-                    const int t = ctx->h_nbr_idx[(size_t)z * N + sidx];
-                    if (t < N && ctx->h_nbr_val[(size_t)z * N + sidx] != 0.0 && hop[t] == 255 && hop[sidx] < 254) { hop[t] = hop[sidx] + 1; q.push(t); }
-                }
-            }
-            FKMC_CUDA(ctx, cudaMalloc(&ctx->d_kpm_hop0, N));
-            FKMC_CUDA(ctx, cudaMemcpyAsync(ctx->d_kpm_hop0, hop.data(), N, cudaMemcpyHostToDevice, ctx->stream));
-            FKMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // hop is a local
-        }
+    if (ctx->kpm_f_cur && ctx->kpm_ks_in && P.ncls == 1 && ctx->kpm_local && ctx->d_kpm_hop0) {
         P.f_cur = ctx->kpm_f_cur; P.ks_in = ctx->kpm_ks_in; P.hop0 = ctx->d_kpm_hop0;
     }
     fkmc_prof_scope ps(ctx, "kpm_moments");
