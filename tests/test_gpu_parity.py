@@ -1067,6 +1067,24 @@ def test_band_path_spectra(kind, L, U):
     c.close()
 
 
+@pytest.mark.parametrize("kind,L,t,tp", [("cubic2d", 16, 0.7, 1.0), ("triangular", 16, 1.0, 0.45), ("triangular", 24, 1.3, -0.6), ("honeycomb_ref_lower", 24, 1.0, 1.0)])
+def test_band_path_hoppings(kind, L, t, tp):
+    """Band path with hopping constants other than 1 (triangular: t' on the diagonal bonds, which sit at distance 2L + 1 in the folded
+    ordering) and for the literal lower-triangle honeycomb of the reference against the oracle."""
+    U, beta = 1.5, 6.0
+    c = fk.Context(kind, L, t=t, tp=tp, max_batch=2)
+    n = c.N
+    fs = np.stack([o.randomize_f(21 + i, n, n // 3)[0] for i in range(2)])
+    c.profile_enable(True)
+    r = c.logz_ed(fs, U, U / 2, beta)
+    assert c.profile_get("sb2sb")[1] >= 1
+    for b in range(2):
+        ref = o.calc_ed(o.KINDS[kind], L, fs[b], U, U / 2, beta, t=t, tp=tp)
+        assert np.abs(r["spectrum"][b] - ref["spectrum"]).max() <= TOL * np.abs(ref["spectrum"]).max()
+        assert abs(r["logZ"][b] - ref["logZ"]) <= TOL * abs(ref["logZ"])
+    c.close()
+
+
 def test_band_path_selection():
     """The band path needs half-bandwidth <= 64 after folding and N >= band_min: cubic3d (2 L^2 = 128), triangular L = 32 (65) and small
     lattices stay on the dense reduction; the option band_min moves the threshold."""
