@@ -158,8 +158,7 @@ __device__ __forceinline__ void qr_panel(double (&a0)[8], double (&a1)[8], vset&
         const double n2 = zero ? 1.0 : fma(alpha, alpha, sigma), aa = fabs(alpha);
         double rn = rsqrt_seed(n2);
         double rc = rcp_seed(fma(n2, rn, aa));   // seed of 1 / (|alpha| + norm), refined below against the accurate norm
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
+        {   // seed good to 2^-20: one third-order step reaches rounding level (tools/ubench/seedacc.cu)
             const double e = fma(-n2 * rn, rn, 1.0);
             rn = fma(rn * e, fma(e, 0.375, 0.5), rn);
         }

@@ -67,6 +67,23 @@ __device__ __forceinline__ double gsum8(double x) {
     return x;
 }
 
+// Branch-free reciprocal square root and reciprocal (MUFU seed + Newton steps).  The library versions carry a slow-path branch,
+// which ends the basic block: without it the scheduler can run the block updates of a step under the latency of this chain.
+__device__ __forceinline__ double rsqrt_nb(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    // the seed is good to 2^-20 (tools/ubench/seedacc.cu): one third-order step reaches 2.7e-16, two quadratic steps of the reciprocal are exact
+    const double e = fma(-x * y, y, 1.0);
+    return fma(y * e, fma(e, 0.375, 0.5), y);
+}
+__device__ __forceinline__ double rcp_nb(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+    for (int it = 0; it < 2; ++it) y = fma(y, fma(-x, y, 1.0), y);
+    return y;
+}
+
 struct refl {
     double v;    // lane l of the group holds v_l; v_0 = 1
     double tau;
@@ -81,11 +98,11 @@ __device__ __forceinline__ refl make_reflector(double x, int l, int n, int gbase
     const bool triv = tail2 <= DBL_MIN;
     // |beta| = sqrt(x0^2 + tail2) through one reciprocal square root; tau = (beta - x0) / beta = 1 + |x0| / |beta| needs no division
     const double s2 = fma(x0, x0, triv ? 1.0 : tail2);
-    const double rs = rsqrt(s2);
+    const double rs = rsqrt_nb(s2);
     const double nrm = s2 * rs;
     const double beta = (x0 >= 0.0) ? -nrm : nrm;
     const double tau = fma(fabs(x0), rs, 1.0);
-    const double inv = 1.0 / (x0 - beta);
+    const double inv = rcp_nb(x0 - beta);
     R.beta = triv ? x0 : beta;
     R.tau = triv ? 0.0 : tau;
     R.v = (l == 0) ? 1.0 : ((l < n && !triv) ? x * inv : 0.0);
@@ -114,11 +131,11 @@ __device__ __forceinline__ refl make_reflector_pad(double x, int l, int n, doubl
     const double tail2 = t0 + t1, x0 = xs[0];
     const bool triv = tail2 <= DBL_MIN;
     const double s2 = fma(x0, x0, triv ? 1.0 : tail2);
-    const double rs = rsqrt(s2);
+    const double rs = rsqrt_nb(s2);
     const double nrm = s2 * rs;
     const double beta = (x0 >= 0.0) ? -nrm : nrm;
     const double tau = fma(fabs(x0), rs, 1.0);
-    const double inv = 1.0 / (x0 - beta);
+    const double inv = rcp_nb(x0 - beta);
     R.beta = triv ? x0 : beta;
     R.tau = triv ? 0.0 : tau;
     R.v = (l == 0) ? 1.0 : ((l < n && !triv) ? x * inv : 0.0);
