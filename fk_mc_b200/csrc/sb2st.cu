@@ -142,7 +142,7 @@ __device__ __forceinline__ refl make_reflector_pad(double x, int l, int n, doubl
     return R;
 }
 
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(384, 1)
 sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_all, double* __restrict__ e_all) {
     extern __shared__ double smem[];
     double* Wb = smem;                                         // [N + 16][16]
@@ -257,16 +257,23 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
                     u1 = fma(dcol[i + 1], v[i + 1], u1);
                 }
                 double u = tau * (u0 + u1);                        // u_l = tau (D v)_l
-                const double alpha = -0.5 * tau * gsum8(u * vl);
-                u = fma(alpha, vl, u);
+                // every lane reads the whole (uncorrected) u from the group's pad and forms alpha = -tau v^T u / 2 itself: one exchange
+                // instead of a three-stage shuffle sum followed by the exchange of the corrected vector
                 bc[8 + l] = u;
                 __syncwarp();
+                double ur[SB], q0 = 0.0, q1 = 0.0;
 #pragma unroll
                 for (int i = 0; i < SB; i += 2) {
                     const double2 t = *reinterpret_cast<const double2*>(bc + 8 + i);
-                    dcol[i] = dcol[i] - v[i] * u - t.x * vl;
-                    dcol[i + 1] = dcol[i + 1] - v[i + 1] * u - t.y * vl;
+                    ur[i] = t.x;
+                    ur[i + 1] = t.y;
+                    q0 = fma(t.x, v[i], q0);
+                    q1 = fma(t.y, v[i + 1], q1);
                 }
+                const double alpha = -0.5 * tau * (q0 + q1);
+                u = fma(alpha, vl, u);
+#pragma unroll
+                for (int i = 0; i < SB; ++i) dcol[i] = dcol[i] - v[i] * u - fma(alpha, v[i], ur[i]) * vl;
                 // stores
 #pragma unroll
                 for (int i = 0; i < SB; ++i) {
@@ -309,7 +316,7 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
 
 // band, counters, broadcast pads (24 doubles per sweep group, four groups per warp)
 static size_t sb2st_smem(int N, int nwarps) { return sizeof(double) * ((size_t)(N + 16) * WD + (N + 1) / 2 + 3 + (size_t)nwarps * 4 * 24) + 16; }
-size_t fkmc_sb2st_smem(int N) { return sb2st_smem(N, 16); }  // upper bound (the warp-count override goes up to 16)
+size_t fkmc_sb2st_smem(int N) { return sb2st_smem(N, 12); }  // upper bound (at most twelve warps)
 
 int fkmc_launch_sb2st(fkmc_ctx* ctx, const double* d_AB, int N, int B, double* d_d, double* d_e) {
     fkmc_prof_scope ps(ctx, "sb2st");
@@ -318,7 +325,7 @@ int fkmc_launch_sb2st(fkmc_ctx* ctx, const double* d_AB, int N, int B, double* d
     int nwarps = ((nblk + LAG - 1) / LAG + 3) / 4;  // measured: N=1024 flat from 8 to 12 warps, N=256 best at 3 (several CTAs share an SM)
     if (nwarps < 1) nwarps = 1;
     if (nwarps > 12) nwarps = 12;
-    if (ctx->sb2st_warps > 0) nwarps = ctx->sb2st_warps;  // tuning override (fkmc_set_option "sb2st_warps")
+    if (ctx->sb2st_warps > 0) nwarps = std::min(ctx->sb2st_warps, 12);  // tuning override (fkmc_set_option "sb2st_warps")
     const size_t smem = sb2st_smem(N, nwarps);  // small matrices share an SM: no more shared memory than this launch needs
     if (smem > ctx->smem_optin) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sb2st: matrix too large for shared memory");
     FKMC_CUDA(ctx, cudaFuncSetAttribute(sb2st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
