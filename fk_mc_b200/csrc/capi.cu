@@ -436,7 +436,7 @@ int fkmc_set_option(fkmc_ctx* ctx, const char* name, int value) {
         return FKMC_OK;
     }
     if (std::string(name) == "sb2st_warps") {
-        if (value < 0 || value > 12) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sb2st_warps must be in [0, 12]");
+        if (value < 0 || value > 16) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sb2st_warps must be in [0, 16]");
         ctx->sb2st_warps = value;
         return FKMC_OK;
     }

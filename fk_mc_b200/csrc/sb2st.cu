@@ -7,7 +7,12 @@
 // Storage: Wb[c][d] = A(c+d, c), d = 0..15 (band 0..8 plus room for the transient fill 9..15), i.e. each
 // matrix column from its diagonal downward in 16 consecutive doubles.  Sweep j annihilates column j below
 // the sub-diagonal with an 8-row reflector and chases the resulting bulge down the band in blocks of 8
-// (Murata-Horikoshi / Lang).  Sweep j+1 may execute its step s once sweep j has finished step s+2.
+// (Murata-Horikoshi / Lang).  Sweep j+1 may execute its step t once sweep j has finished step t+1: with p = j + 1 + 8t, step u of
+// sweep j touches rows / columns [p + 8(u-t) - 7, p + 8(u-t) + 16) -- block (i) rows [P, P+8) x columns [P-7, P-1], block (ii) [P, P+8)^2,
+// block (iii) rows [P+8, P+16) x columns [P, P+8) with P = p + 8(u-t) -- and step t of sweep j+1 the same sets shifted by one, i.e.
+// columns < p + 9 and rows < p + 17.  For u = t+2 the three blocks of sweep j have columns >= p + 9 (block (i)) or >= p + 16, so they are
+// disjoint from everything step t of sweep j+1 reads or writes; u = t+1 does overlap (its block (i) is rows [p+8, p+16) x columns [p+1, p+7]).
+// Hence a lag of two steps (round 1 used three); tools/sb2st_lag_check.py compares the two builds bit for bit.
 //
 // Work decomposition: EIGHT LANES PER SWEEP, four consecutive sweeps per warp.  Every lane keeps the whole
 // reflector (8 doubles) in registers and owns one column (left update of the previous block, two-sided update of
@@ -30,7 +35,10 @@ constexpr int SB = 8;     // half bandwidth
 #endif
 constexpr int WD = FKMC_SB2ST_WD;    // doubles per stored column: 16 sub-diagonals (band 0..8 + transient fill 9..15) padded to a stride that spreads the three
                           // access patterns of a step (and the four sweeps of a warp, 24 columns apart) over the banks: 78 wavefronts per step instead of 120
-constexpr int LAG = 3;    // steps between consecutive sweeps
+#ifndef FKMC_SB2ST_LAG
+#define FKMC_SB2ST_LAG 2
+#endif
+constexpr int LAG = FKMC_SB2ST_LAG;    // steps between consecutive sweeps (see the dependence analysis above; 3 = the conservative value of round 1)
 
 // Ordering of the band updates against the progress counters.  Writer: band stores (all lanes), __syncwarp, counter store (one
 // lane); reader: counter load, __syncwarp, band loads.  Both sides are plain shared-memory accesses of one SM, which the LSU
@@ -142,7 +150,10 @@ __device__ __forceinline__ refl make_reflector_pad(double x, int l, int n, doubl
     return R;
 }
 
-__global__ void __launch_bounds__(384, 1)
+// BIG: one CTA per SM anyway (N > 848: the band alone is more than half of the shared memory), up to twelve warps with as many registers
+// as they like; otherwise at most eight warps and 128 registers, so that two or more CTAs share an SM.
+template <bool BIG>
+__global__ void __launch_bounds__(BIG ? 384 : 256, BIG ? 1 : 2)
 sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_all, double* __restrict__ e_all) {
     extern __shared__ double smem[];
     double* Wb = smem;                                         // [N + 16][16]
@@ -320,16 +331,24 @@ size_t fkmc_sb2st_smem(int N) { return sb2st_smem(N, 12); }  // upper bound (at 
 
 int fkmc_launch_sb2st(fkmc_ctx* ctx, const double* d_AB, int N, int B, double* d_d, double* d_e) {
     fkmc_prof_scope ps(ctx, "sb2st");
-    // sweeps in flight <= blocks along the band / lag, four sweeps per warp
+    // sweeps in flight <= blocks along the band / lag, four sweeps per warp (measured with tools/sb2st_warps_scan.py: N = 1024 flat from 8
+    // to 16 warps, N = 576 best at 8 with two CTAs per SM, N = 256 best at 3)
     const int nblk = (N + SB - 1) / SB;
-    int nwarps = ((nblk + LAG - 1) / LAG + 3) / 4;  // measured: N=1024 flat from 8 to 12 warps, N=256 best at 3 (several CTAs share an SM)
+    const bool big = N > 848;
+    const int cap = big ? 12 : 8;
+    int nwarps = ((nblk + LAG - 1) / LAG + 3) / 4 - 1;
     if (nwarps < 1) nwarps = 1;
-    if (nwarps > 12) nwarps = 12;
-    if (ctx->sb2st_warps > 0) nwarps = std::min(ctx->sb2st_warps, 12);  // tuning override (fkmc_set_option "sb2st_warps")
+    if (nwarps > cap) nwarps = cap;
+    if (ctx->sb2st_warps > 0) nwarps = std::min(ctx->sb2st_warps, cap);  // tuning override (fkmc_set_option "sb2st_warps")
     const size_t smem = sb2st_smem(N, nwarps);  // small matrices share an SM: no more shared memory than this launch needs
     if (smem > ctx->smem_optin) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sb2st: matrix too large for shared memory");
-    FKMC_CUDA(ctx, cudaFuncSetAttribute(sb2st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sb2st_kernel<<<B, nwarps * 32, smem, ctx->stream>>>(d_AB, N, d_d, d_e);
+    if (big) {
+        FKMC_CUDA(ctx, cudaFuncSetAttribute(sb2st_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sb2st_kernel<true><<<B, nwarps * 32, smem, ctx->stream>>>(d_AB, N, d_d, d_e);
+    } else {
+        FKMC_CUDA(ctx, cudaFuncSetAttribute(sb2st_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sb2st_kernel<false><<<B, nwarps * 32, smem, ctx->stream>>>(d_AB, N, d_d, d_e);
+    }
     ctx->launches++;
     FKMC_CUDA(ctx, cudaGetLastError());
     return FKMC_OK;
