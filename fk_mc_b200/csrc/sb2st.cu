@@ -150,7 +150,7 @@ __device__ __forceinline__ refl make_reflector_pad(double x, int l, int n, doubl
     return R;
 }
 
-// BIG: one CTA per SM anyway (N > 848: the band alone is more than half of the shared memory), up to twelve warps with as many registers
+// BIG: one CTA per SM anyway (N > 700 or so: the band alone is more than half of the shared memory), up to twelve warps with as many registers
 // as they like; otherwise at most eight warps and 128 registers, so that two or more CTAs share an SM.
 template <bool BIG>
 __global__ void __launch_bounds__(BIG ? 384 : 256, BIG ? 1 : 2)
@@ -334,7 +334,7 @@ int fkmc_launch_sb2st(fkmc_ctx* ctx, const double* d_AB, int N, int B, double* d
     // sweeps in flight <= blocks along the band / lag, four sweeps per warp (measured with tools/sb2st_warps_scan.py: N = 1024 flat from 8
     // to 16 warps, N = 576 best at 8 with two CTAs per SM, N = 256 best at 3)
     const int nblk = (N + SB - 1) / SB;
-    const bool big = N > 848;
+    const bool big = sb2st_smem(N, 12) > 115712;   // more than half of an SM's shared memory: one CTA per SM whatever the warp count
     const int cap = big ? 12 : 8;
     int nwarps = ((nblk + LAG - 1) / LAG + 3) / 4 - 1;
     if (nwarps < 1) nwarps = 1;
