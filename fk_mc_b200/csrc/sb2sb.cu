@@ -126,9 +126,9 @@ __device__ __forceinline__ void warp_sum8_bcast(double (&v)[8], double (&h)[8], 
 // the earlier reflectors in the slots k < i, column i of V^T V for the compact-WY factor T (row l of T lives in lane l).
 // Writes V (three layouts) and T to vs, and the factored panel ([R; 0]) to the global tiles (I0 + k, Jp), k = 0..7.
 #ifdef FKMC_SBR_TIMING
-__device__ __forceinline__ void qr_panel(double (&a0)[8], double (&a1)[8], vset& vs, double* pad, double* band, int I0, int Jp, int lane, long long* qt) {
+__device__ __forceinline__ void qr_panel(double (&a0)[8], double (&a1)[8], vset& vs, double* pad, double* band, int I0, int Jp, int lane, bool arrive, long long* qt) {
 #else
-__device__ __forceinline__ void qr_panel(double (&a0)[8], double (&a1)[8], vset& vs, double* pad, double* band, int I0, int Jp, int lane) {
+__device__ __forceinline__ void qr_panel(double (&a0)[8], double (&a1)[8], vset& vs, double* pad, double* band, int I0, int Jp, int lane, bool arrive) {
 #endif
 #ifdef FKMC_SBR_TIMING
     long long q0 = clock64();
@@ -197,7 +197,7 @@ __device__ __forceinline__ void qr_panel(double (&a0)[8], double (&a1)[8], vset&
 #pragma unroll
         for (int i = 0; i < 8; ++i) vs.Tn[l * VS + i] = trow[i];
     }
-    bar_arrive(1, SBR_SYNC);   // V and T are complete: the compute warps start while the factored panel goes out
+    if (arrive) bar_arrive(1, SBR_SYNC);   // V and T are complete: the compute warps start while the factored panel goes out
     // factored panel to global memory: R in the first tile (rows 0..7 = lanes 0..7), zeros below
     {
         const int k0 = lane >> 3, r = lane & 7;
@@ -223,6 +223,10 @@ __device__ __forceinline__ void times_T(double& r0, double& r1, const double* Tn
     r0 = c0;
     r1 = c1;
 }
+
+// the next sweep's first panel can be factored during the last step of the sweep that starts at column c0: there is a next sweep with work and
+// this sweep has at least two steps (the panel needs step 0's symmetric block and step 1's factored panel)
+__device__ __forceinline__ bool sbr_lookahead(int N, int c0) { return c0 + 16 < N && (N - c0 - 8 + 63) / 64 >= 2; }
 
 #ifdef FKMC_SBR_TIMING
 #define SBR_TICK(i) { const long long now__ = clock64(); tk[i] += now__ - tq; tq = now__; }
@@ -283,10 +287,12 @@ __global__ void __launch_bounds__(SBR_THREADS, SBR_CTAS) sb2sb_kernel(double* ba
     if (w == 8) {
         // ================= panel warp =================
         int vpar = 0;
+        bool ahead = false;   // the first panel of this sweep was factored at the end of the previous one
         for (int j = 0; j < nsweeps; ++j) {
             const int c0 = 8 * j;
             if (c0 + 8 >= N) break;
             sweep_barrier();
+            const int k0 = lane >> 3, r = lane & 7;
             for (int p = 0;; ++p, ++vpar) {
                 const int r0 = c0 + 8 + 64 * p;
                 if (r0 >= N) break;
@@ -294,8 +300,11 @@ __global__ void __launch_bounds__(SBR_THREADS, SBR_CTAS) sb2sb_kernel(double* ba
 #ifdef FKMC_SBR_TIMING
                 tq = clock64(); ++nst;
 #endif
+                if (p == 0 && ahead) {
+                    bar_arrive(1, SBR_SYNC);
+                    continue;
+                }
                 double a0[8], a1[8];
-                const int k0 = lane >> 3, r = lane & 7;
                 if (p == 0) {
                     const double* t0 = tile_ptr(band, I0 + k0, I0 - 1) + r * 8;
                     const double* t1 = tile_ptr(band, I0 + k0 + 4, I0 - 1) + r * 8;
@@ -316,11 +325,35 @@ __global__ void __launch_bounds__(SBR_THREADS, SBR_CTAS) sb2sb_kernel(double* ba
                 }
                 SBR_TICK(0)
 #ifdef FKMC_SBR_TIMING
-                qr_panel(a0, a1, sm.V[vpar & 1], sm.pad, band, I0, p == 0 ? I0 - 1 : I0 - 8, lane, qt);
+                qr_panel(a0, a1, sm.V[vpar & 1], sm.pad, band, I0, p == 0 ? I0 - 1 : I0 - 8, lane, true, qt);
 #else
-                qr_panel(a0, a1, sm.V[vpar & 1], sm.pad, band, I0, p == 0 ? I0 - 1 : I0 - 8, lane);
+                qr_panel(a0, a1, sm.V[vpar & 1], sm.pad, band, I0, p == 0 ? I0 - 1 : I0 - 8, lane, true);
 #endif
                 SBR_TICK(1)
+            }
+            // Look-ahead: the first panel of the next sweep (columns c0+8 .. c0+15, rows c0+16 .. c0+79) is final once step 0 of this sweep
+            // has stored its symmetric block and step 1 its factored panel, so it is factored now, while the compute warps apply this
+            // sweep's last step, instead of at the start of the next sweep with every compute warp waiting.  The compute warps arrive
+            // on barrier 2 in their last step: they are past the step that still read the reflector buffer written here.
+            ahead = sbr_lookahead(N, c0);
+            if (ahead) {
+                bar_sync(2, SBR_SYNC);
+                __threadfence_block();   // (the factored panel of step 1 was stored by other lanes of this warp)
+                __syncwarp();
+                const int I0 = (c0 + 16) >> 3;
+                double a0[8], a1[8];
+                const double* t0 = tile_ptr(band, I0 + k0, I0 - 1) + r * 8;
+                const double* t1 = tile_ptr(band, I0 + k0 + 4, I0 - 1) + r * 8;
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    const double2 x = *reinterpret_cast<const double2*>(t0 + c), y = *reinterpret_cast<const double2*>(t1 + c);
+                    a0[c] = x.x; a0[c + 1] = x.y; a1[c] = y.x; a1[c + 1] = y.y;
+                }
+#ifdef FKMC_SBR_TIMING
+                qr_panel(a0, a1, sm.V[vpar & 1], sm.pad, band, I0, I0 - 1, lane, false, qt);
+#else
+                qr_panel(a0, a1, sm.V[vpar & 1], sm.pad, band, I0, I0 - 1, lane, false);
+#endif
             }
         }
 #ifdef FKMC_SBR_TIMING
@@ -390,6 +423,8 @@ __global__ void __launch_bounds__(SBR_THREADS, SBR_CTAS) sb2sb_kernel(double* ba
                     if (c == 0 && has_next) {
                         *reinterpret_cast<double2*>(sm.P + w * 64 + g * 8 + cswz) = G[0];
                         bar_arrive(2, SBR_SYNC);
+                    } else if (c == 0 && sbr_lookahead(N, c0)) {
+                        bar_arrive(2, SBR_SYNC);   // last step of the sweep: releases the panel warp's look-ahead factorisation
                     }
                 }
             }
