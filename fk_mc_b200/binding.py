@@ -166,11 +166,23 @@ class Context:
             raise FkmcError(1, "f must have shape [B, V]")
         return f
 
-    def logz_ed(self, f, U, mu_c, beta, want_caches=False):
-        """configuration_t::calc_ed(false): returns dict(spectrum [B,N], logZ [B], cached_exp, cached_fermi)."""
+    @staticmethod
+    def _out(out, key, shape):
+        """Result buffer: the caller's (e.g. page-locked, reused from call to call: the device -> host copies then run at full PCIe rate
+        and nothing is allocated per call) or a fresh array."""
+        if out is None or key not in out:
+            return np.zeros(shape)
+        a = out[key]
+        if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.shape == tuple(shape)):
+            raise FkmcError(1, "out[%r] must be a C-contiguous float64 array of shape %r" % (key, tuple(shape)))
+        return a
+
+    def logz_ed(self, f, U, mu_c, beta, want_caches=False, out=None):
+        """configuration_t::calc_ed(false): returns dict(spectrum [B,N], logZ [B], cached_exp, cached_fermi).
+        out: optional dict of preallocated result arrays (spectrum, logZ)."""
         f = self._f(f)
         B = f.shape[0]
-        ev, lz = np.zeros((B, self.N)), np.zeros(B)
+        ev, lz = self._out(out, "spectrum", (B, self.N)), self._out(out, "logZ", (B,))
         ex = np.zeros((B, self.N)) if want_caches else None
         fe = np.zeros((B, self.N)) if want_caches else None
         self._ck(self.lib.fkmc_logz_ed_batched(self.h, _ptr(f, C.c_int32), B, C.c_double(U), C.c_double(mu_c), C.c_double(beta),
@@ -222,12 +234,13 @@ class Context:
                                                 _ptr(lz, C.c_double)))
         return dict(moments=mom, e_min=ab[:, 0], e_max=ab[:, 1], a=ab[:, 2], b=ab[:, 3], logZ=lz)
 
-    def logz_kpm_local(self, f, U, mu_c, beta, M, G, f_ref=None, state_ref=None):
+    def logz_kpm_local(self, f, U, mu_c, beta, M, G, f_ref=None, state_ref=None, out=None):
         """calc_chebyshev for configurations that differ from f_ref in one or two sites (fkmc_logz_kpm_batched_local); returns the dict of
-        logz_kpm plus state [B, 64], the record to pass as state_ref when f becomes the reference."""
+        logz_kpm plus state [B, 64], the record to pass as state_ref when f becomes the reference.
+        out: optional dict of preallocated result arrays (moments, ab [B, 4], logZ, state)."""
         f = self._f(f)
         B = f.shape[0]
-        mom, ab, lz, st = np.zeros((B, M)), np.zeros((B, 4)), np.zeros(B), np.zeros((B, 64))
+        mom, ab, lz, st = self._out(out, "moments", (B, M)), self._out(out, "ab", (B, 4)), self._out(out, "logZ", (B,)), self._out(out, "state", (B, 64))
         fr = sr = None
         if f_ref is not None:
             fr = self._f(f_ref)

@@ -202,6 +202,9 @@ int fkmc_destroy(fkmc_ctx* ctx) {
     cudaFree(ctx->d_kpm2_part); cudaFree(ctx->d_kpm2_arrived); cudaFree(ctx->d_kpm2_order);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_f_up) cudaEventDestroy(ctx->ev_f_up);
+    if (ctx->ev_ref_up) cudaEventDestroy(ctx->ev_ref_up);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return FKMC_OK;
@@ -310,18 +313,32 @@ int fkmc_logz_kpm_batched_local(fkmc_ctx* ctx, const int32_t* f, const int32_t* 
     if (!ctx->d_ks_io) {
         FKMC_CUDA(ctx, cudaMalloc(&ctx->d_ks_io, sizeof(double) * 2 * nb * FKMC_KPM_STATE));
         FKMC_CUDA(ctx, cudaMalloc(&ctx->d_f_ref, sizeof(int32_t) * nb * N));
+        FKMC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        FKMC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_f_up, cudaEventDisableTiming));
+        FKMC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ref_up, cudaEventDisableTiming));
     }
     double* ks_in = ctx->d_ks_io;
     double* ks_out = ctx->d_ks_io + nb * FKMC_KPM_STATE;
     if (f_ref) {
         if ((rc = fkmc_kpm_prepare_local(ctx))) return rc;
-        FKMC_CUDA(ctx, cudaMemcpyAsync(ctx->d_f_ref, f_ref, sizeof(int32_t) * (size_t)B * N, cudaMemcpyHostToDevice, ctx->stream));
-        FKMC_CUDA(ctx, cudaMemcpyAsync(ks_in, state_ref, sizeof(double) * (size_t)B * FKMC_KPM_STATE, cudaMemcpyHostToDevice, ctx->stream));
+        // the previous call ended with a stream synchronisation, so nothing still reads d_f_ref / ks_in; the second stream starts after
+        // the proposals have arrived (the two uploads would only share the link) and runs under the Lanczos kernel
+        FKMC_CUDA(ctx, cudaEventRecord(ctx->ev_f_up, ctx->stream));
+        FKMC_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_f_up, 0));
+        FKMC_CUDA(ctx, cudaMemcpyAsync(ctx->d_f_ref, f_ref, sizeof(int32_t) * (size_t)B * N, cudaMemcpyHostToDevice, ctx->copy_stream));
+        FKMC_CUDA(ctx, cudaMemcpyAsync(ks_in, state_ref, sizeof(double) * (size_t)B * FKMC_KPM_STATE, cudaMemcpyHostToDevice, ctx->copy_stream));
+        FKMC_CUDA(ctx, cudaEventRecord(ctx->ev_ref_up, ctx->copy_stream));
+        if (fkmc_kpm2d_applicable(ctx, M)) ctx->kpm_wait_event = ctx->ev_ref_up;  // consumed between the Lanczos and the moments launch
+        else FKMC_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_ref_up, 0));
         ctx->kpm_f_cur = ctx->d_f_ref;
         ctx->kpm_ks_in = ks_in;
     }
     ctx->kpm_ks_out = state_out ? ks_out : nullptr;
     rc = fkmc_launch_kpm(ctx, ctx->d_f, B, U, mu_c, beta, M, G, ctx->d_moments, ctx->d_ab, ctx->d_out);
+    if (ctx->kpm_wait_event) {  // a launch path that did not reach the moments kernel: the stream still has to see the uploads finished
+        cudaStreamWaitEvent(ctx->stream, ctx->kpm_wait_event, 0);
+        ctx->kpm_wait_event = nullptr;
+    }
     const bool wrote_state = ctx->kpm_state_written;
     ctx->kpm_f_cur = nullptr; ctx->kpm_ks_in = nullptr; ctx->kpm_ks_out = nullptr;
     if (rc) return rc;

@@ -153,6 +153,10 @@ struct fkmc_ctx {
     double* d_ks_io = nullptr;             // [2][max_batch][FKMC_KPM_STATE] records of fkmc_logz_kpm_batched_local
     int32_t* d_f_ref = nullptr;            // [max_batch][N] its reference configurations
     bool kpm_state_written = false;        // the last KPM launch produced state records (two-kernel 2-D path)
+    // fkmc_logz_kpm_batched_local: the reference configurations and records are uploaded on a second stream under the Lanczos kernel
+    // (which only reads the proposals); the moments launch waits for kpm_wait_event when it is set
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_f_up = nullptr, ev_ref_up = nullptr, kpm_wait_event = nullptr;
     int* d_kpm_steps = nullptr;   // [max_batch] Lanczos steps of the last KPM launch (diagnostics)
     double* d_aux = nullptr;      // [max_batch][2][N] cached_exp / cached_fermi staging
     double* d_ev_scratch = nullptr;  // eigenvector path: tridiagonal eigenvectors | inverse-iteration factors | T factors (grown on demand)

@@ -1111,6 +1111,10 @@ int fkmc_launch_kpm2d(fkmc_ctx* ctx, const int32_t* d_f, int B, double U, double
     if (ctx->kpm_f_cur && ctx->kpm_ks_in && P.ncls == 1 && ctx->kpm_local && ctx->d_kpm_hop0) {
         P.f_cur = ctx->kpm_f_cur; P.ks_in = ctx->kpm_ks_in; P.hop0 = ctx->d_kpm_hop0;
     }
+    if (ctx->kpm_wait_event) {  // reference configurations / records uploaded on the copy stream (fkmc_logz_kpm_batched_local)
+        FKMC_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->kpm_wait_event, 0));
+        ctx->kpm_wait_event = nullptr;
+    }
     fkmc_prof_scope ps(ctx, "kpm_moments");
     if (ctx->kind == FKMC_CUBIC2D) return launch_moments2d_half<FKMC_CUBIC2D>(ctx, P, B, M / 2);
     if (ctx->kind == FKMC_TRIANGULAR) return launch_moments2d_half<FKMC_TRIANGULAR>(ctx, P, B, M / 2);
