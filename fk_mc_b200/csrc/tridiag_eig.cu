@@ -15,8 +15,11 @@
 
 #include "common.cuh"
 
+#ifndef FKMC_EIG_PREDSTOP
+#define FKMC_EIG_PREDSTOP 1  // stop the Newton phase on the predicted (quadratic) error instead of a confirming evaluation
+#endif
 #ifndef FKMC_EIG_BISECT
-#define FKMC_EIG_BISECT 6  // bisection steps every lane takes before the Newton phase (measured: 0 -> 14.0 ms, 4 -> 7.9, 6 -> 7.4, 9 -> 7.9, 12 -> 8.5 per 1024 matrices of N = 1024)
+#define FKMC_EIG_BISECT 6  // bisection steps every lane takes before the Newton phase (measured per 1024 matrices of N = 1024 with the grouped recurrences: 5 -> 4.88 ms, 6 -> 4.74, 8 -> 5.06, 10 -> 5.23)
 #endif
 
 namespace {
@@ -48,31 +51,58 @@ __device__ __noinline__ int sturm_count_guarded(const double2* __restrict__ de, 
     return cnt;
 }
 
-// Fast form: three FP64 instructions per row (subtract, multiply, FMA), signs counted on the integer pipe from the high words.
+// Fast form: three FP64 instructions per row (subtract, multiply, FMA); the sign of every p_i is shifted into a history word by one
+// funnel shift on the integer pipe and the sign changes of a group of 16 rows are counted at once (popc of the word against itself
+// shifted by one) - the kernel is issue-bound, so instructions per row are what matters.  The pair (p, p_{-1}) grows or shrinks by at
+// most 5x per row (|d_i - x| <= 4, e^2 <= 1 after scaling), so a range check per group keeps it away from overflow; shrinking is only
+// bounded by the e_i^2, see STURM_TINY below.
 // An isolated exact zero needs no care (p_{i+1} = -e_i^2 p_{i-1} then has the sign opposite to p_{i-1}: one sign change whichever
 // sign the zero is given); only a zero followed by e_i = 0 sticks, which shows as p = p_{-1} = 0 at the next rescaling check and is
 // sent to the guarded form.
+#ifndef FKMC_STURM_GROUP
+#define FKMC_STURM_GROUP 24  // measured at N = 1024, 1024 matrices: 8 -> 5.75 ms, 16 -> 4.74, 24 -> 4.53, 31 -> 4.59
+#endif
+// A pair that ends a group below 2^-700 may have passed through the denormal range inside it (it grows by at most 5x per row, so a
+// pair that was below 2^-1022 anywhere in a group of <= 31 rows ends it below 2^-950) and is re-evaluated by the guarded form; a pair
+// whose maximum stays normal loses nothing: a denormal member then is negligible against the other term of the recurrence.
+constexpr double STURM_TINY = 0x1p-700;
+constexpr int STURM_GROUP = FKMC_STURM_GROUP;  // <= 31: the history word holds the group and the sign before it
+
 __device__ __forceinline__ int sturm_count(const double2* __restrict__ de, int n, double x) {
     double pm1 = 1.0, p = de[0].x - x;
-    int sprev = __double2hiint(p);
-    int cnt = (int)((unsigned)sprev >> 31);
-    for (int i0 = 1; i0 < n; i0 += 8) {
-        const int i1 = min(i0 + 8, n);
-        for (int i = i0; i < i1; ++i) {
-            const double2 q = de[i];
+    unsigned hist = (unsigned)__double2hiint(p) >> 31;  // bit k = sign of p_{i-k}
+    int cnt = (int)hist;
+    int i = 1;
+    for (; i + STURM_GROUP <= n; i += STURM_GROUP) {
+        hist &= 1u;
+#pragma unroll
+        for (int k = 0; k < STURM_GROUP; ++k) {
+            const double2 q = de[i + k];
             const double pn = fma(q.x - x, p, -(q.y * pm1));
-            const int sn = __double2hiint(pn);
-            cnt += (int)((unsigned)(sn ^ sprev) >> 31);
-            sprev = sn;
+            hist = __funnelshift_l((unsigned)__double2hiint(pn), hist, 1);
             pm1 = p;
             p = pn;
         }
+        cnt += __popc((hist ^ (hist >> 1)) & ((1u << STURM_GROUP) - 1u));
         const double m = fmax(fabs(p), fabs(pm1));
         if (m > 1.157920892373162e77) { p *= 8.636168555094445e-78; pm1 *= 8.636168555094445e-78; }
         else if (m < 8.636168555094445e-78) {
-            if (m == 0.0) return sturm_count_guarded(de, n, x);
+            if (m < STURM_TINY) return sturm_count_guarded(de, n, x);
             p *= 1.157920892373162e77; pm1 *= 1.157920892373162e77;
         }
+    }
+    if (i < n) {  // last, shorter group
+        const int r = n - i;
+        hist &= 1u;
+        for (; i < n; ++i) {
+            const double2 q = de[i];
+            const double pn = fma(q.x - x, p, -(q.y * pm1));
+            hist = __funnelshift_l((unsigned)__double2hiint(pn), hist, 1);
+            pm1 = p;
+            p = pn;
+        }
+        cnt += __popc((hist ^ (hist >> 1)) & ((1u << r) - 1u));
+        if (fmax(fabs(p), fabs(pm1)) < STURM_TINY) return sturm_count_guarded(de, n, x);
     }
     return cnt;
 }
@@ -110,32 +140,48 @@ __device__ __noinline__ int sturm_newton_guarded(const double2* __restrict__ de,
     return cnt;
 }
 
-// Fast form of the above (same treatment of zeros as sturm_count).
+// Fast form of the above (same treatment of zeros and the same sign bookkeeping as sturm_count).
 __device__ __forceinline__ int sturm_newton(const double2* __restrict__ de, int n, double x, double& pn_out, double& dpn_out) {
     double pm1 = 1.0, p = de[0].x - x, dpm1 = 0.0, dp = -1.0;
-    int sprev = __double2hiint(p);
-    int cnt = (int)((unsigned)sprev >> 31);
-    for (int i0 = 1; i0 < n; i0 += 8) {
-        const int i1 = min(i0 + 8, n);
-        for (int i = i0; i < i1; ++i) {
-            const double2 q = de[i];
+    unsigned hist = (unsigned)__double2hiint(p) >> 31;
+    int cnt = (int)hist;
+    int i = 1;
+    for (; i + STURM_GROUP <= n; i += STURM_GROUP) {
+        hist &= 1u;
+#pragma unroll
+        for (int k = 0; k < STURM_GROUP; ++k) {
+            const double2 q = de[i + k];
             const double t = q.x - x;
             const double pn = fma(t, p, -(q.y * pm1));
             const double dpn = fma(t, dp, -fma(q.y, dpm1, p));
-            const int sn = __double2hiint(pn);
-            cnt += (int)((unsigned)(sn ^ sprev) >> 31);
-            sprev = sn;
+            hist = __funnelshift_l((unsigned)__double2hiint(pn), hist, 1);
             pm1 = p; p = pn;
             dpm1 = dp; dp = dpn;
         }
+        cnt += __popc((hist ^ (hist >> 1)) & ((1u << STURM_GROUP) - 1u));
         const double mp = fmax(fabs(p), fabs(pm1));
-        if (mp == 0.0) return sturm_newton_guarded(de, n, x, pn_out, dpn_out);
+        if (mp < STURM_TINY) return sturm_newton_guarded(de, n, x, pn_out, dpn_out);
         const double m = fmax(mp, fmax(fabs(dp), fabs(dpm1)) * 0x1p-60);
         if (m > 1.157920892373162e77) {
             p *= 8.636168555094445e-78; pm1 *= 8.636168555094445e-78; dp *= 8.636168555094445e-78; dpm1 *= 8.636168555094445e-78;
         } else if (m < 8.636168555094445e-78) {
             p *= 1.157920892373162e77; pm1 *= 1.157920892373162e77; dp *= 1.157920892373162e77; dpm1 *= 1.157920892373162e77;
         }
+    }
+    if (i < n) {  // last, shorter group
+        const int r = n - i;
+        hist &= 1u;
+        for (; i < n; ++i) {
+            const double2 q = de[i];
+            const double t = q.x - x;
+            const double pn = fma(t, p, -(q.y * pm1));
+            const double dpn = fma(t, dp, -fma(q.y, dpm1, p));
+            hist = __funnelshift_l((unsigned)__double2hiint(pn), hist, 1);
+            pm1 = p; p = pn;
+            dpm1 = dp; dp = dpn;
+        }
+        cnt += __popc((hist ^ (hist >> 1)) & ((1u << r) - 1u));
+        if (fmax(fabs(p), fabs(pm1)) < STURM_TINY) return sturm_newton_guarded(de, n, x, pn_out, dpn_out);
     }
     pn_out = p;
     dpn_out = dp;
@@ -245,7 +291,15 @@ tridiag_eig_kernel(const double* __restrict__ d_all, const double* __restrict__ 
             // also stop when the correction has stopped contracting (rounding floor of p/p' near the root)
             const double stepn = fabs(xn - x);
             const bool floor_hit = ok && nnewt >= 3 && stepn <= 64.0 * tolw && stepn >= 0.25 * prev_step;
-            if (floor_hit || !(c - a > tolw) || xn <= a || xn >= c) {
+#if FKMC_EIG_PREDSTOP
+            // two Newton steps in a row that contract at least 16-fold: e_{k+1} = K e_k^2 with K = s_k / s_{k-1}^2 read off the steps, so
+            // the error left after this step is s_k^3 / s_{k-1}^2; below a quarter of the tolerance the confirming evaluation is skipped
+            const bool pred_hit = ok && prev_step < 0.5 * DBL_MAX && stepn <= 0.0625 * prev_step &&
+                                  stepn * stepn * stepn <= 0.25 * tolw * prev_step * prev_step;
+#else
+            const bool pred_hit = false;
+#endif
+            if (floor_hit || pred_hit || !(c - a > tolw) || xn <= a || xn >= c) {
                 if (ok) { a = xn; c = xn; }
                 done = true;
             }

@@ -70,6 +70,28 @@ def test_tridiag_bisection(ctx8, n):
         assert (np.diff(ev[b]) >= 0).all()
 
 
+@pytest.mark.parametrize("n", [97, 1024])
+def test_tridiag_tiny_offdiagonals(ctx8, n):
+    """Runs of tiny off-diagonal entries shrink the Sturm pair (p_i, p_{i-1}) by e_i^2 per row: through the rescaling threshold, the
+    denormal range and to zero inside one group of rows - the grouped recurrences must notice and take the guarded form."""
+    rng = np.random.default_rng(n + 1)
+    d = rng.normal(size=(6, n)) * 2
+    e = rng.normal(size=(6, n - 1))
+    e[0, 10:18] = 1e-40                                   # 8 in a row: 2^-2126, exact zero inside a group
+    e[1, 5::7] *= 1e-30                                   # isolated tiny entries
+    e[2, 20:24] = 3e-39                                   # 4 in a row: 2^-1020, the edge of the denormal range
+    e[2, 40:45] = 1e-38
+    e[3] *= 10.0 ** -rng.integers(0, 60, size=n - 1)      # every scale at once
+    e[4, :] = 1e-25                                        # diagonal matrix to working precision
+    d[5] = np.round(d[5])                                  # degenerate diagonal ...
+    e[5] *= 1e-20                                          # ... barely coupled
+    ev = ctx8.tridiag_eigvals(d, e)
+    for b in range(6):
+        ref = sl.eigvalsh_tridiagonal(d[b], e[b])
+        assert np.abs(ev[b] - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max()), b
+        assert (np.diff(ev[b]) >= 0).all()
+
+
 def test_tridiag_matches_oracle_ql(ctx8):
     A = o.hopping_dense(o.CUBIC2D, 8) + np.diag(np.arange(64) % 2 * 1.0)
     d, s = o.tridiag(A)
