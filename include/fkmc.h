@@ -89,7 +89,10 @@ int fkmc_logz_kpm_batched(fkmc_ctx* ctx, const int32_t* f, int B, double U, doub
  * the record) and the moments are re-expanded for f's own e_min / e_max; same results to rounding.  state_out (may be NULL) receives
  * the record of f -- keep it with the configuration it belongs to (configuration_t::cheb_data_) and pass it when that configuration is
  * the reference.  f_ref = state_ref = NULL, more than two changed sites, a record marked invalid or a scaling that moved by more than
- * 2 % make the call a full evaluation.  Lattices outside the two-kernel 2-D path return records marked invalid. */
+ * 2 % make the call a full evaluation.  Lattices outside the two-kernel 2-D path return records marked invalid.
+ * Host buffers: any memory works; page-locked buffers (cudaHostAlloc / cudaHostRegister) that are reused from call to call make the copies
+ * asynchronous at full link rate -- f_ref and state_ref then travel on a second stream while the e_min / e_max kernel, which only reads f,
+ * already runs (the call still returns with all results in place). */
 #define FKMC_KPM_STATE_DOUBLES 64
 int fkmc_logz_kpm_batched_local(fkmc_ctx* ctx, const int32_t* f, const int32_t* f_ref, const double* state_ref, int B, double U,
                                 double mu_c, double beta, int M, int G, double* moments, double* ab, double* logZ, double* state_out);
