@@ -22,7 +22,8 @@ if len(sys.argv) > 1:
     worker(sys.argv[1])
 else:
     outs = []
-    for tag, lib in (("lag2", "fk_mc_b200/lib/libfkmc_b200.so"), ("lag3", "fk_mc_b200/lib_lag3/libfkmc_b200.so")):
+    other = os.environ.get("FKMC_LIB_B", "fk_mc_b200/lib_lag3/libfkmc_b200.so")  # any other developer build to compare bit for bit
+    for tag, lib in (("lag2", "fk_mc_b200/lib/libfkmc_b200.so"), ("lag3", other)):
         out = "/tmp/sb2st_%s.npz" % tag
         subprocess.check_call([sys.executable, __file__, out], env=dict(os.environ, FKMC_LIB=lib))
         outs.append(np.load(out))
