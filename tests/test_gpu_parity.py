@@ -1058,6 +1058,47 @@ def test_kpm_local_other_lattices_return_invalid_records():
     c.close()
 
 
+def test_seam_calls_with_caller_owned_page_locked_buffers():
+    """The evaluator seam with page-locked, reused host buffers (what a host loop holds; bench.py's e2e path): the reference configurations
+    and records then travel on the library's second stream under the Lanczos kernel.  Results must be those of the plain calls, placed
+    in the caller's arrays; a buffer of the wrong shape is refused."""
+    import torch
+
+    def pinned(*shape, dtype=torch.float64):
+        return torch.zeros(shape, dtype=dtype).pin_memory().numpy()
+
+    B, L, M, G = 6, 16, 12, 24
+    c = fk.Context("cubic2d", L, max_batch=B)
+    n = c.N
+    f = pinned(B, n, dtype=torch.int32)
+    f[:] = np.stack([o.randomize_f(3 + i, n, n // 2)[0] for i in range(B)])
+    g = pinned(B, n, dtype=torch.int32)
+    out = dict(moments=pinned(B, M), ab=pinned(B, 4), logZ=pinned(B), state=pinned(B, 64))
+    ks = pinned(B, 64)
+    r0 = c.logz_kpm_local(f, 2.0, 1.0, 5.0, M, G)
+    ks[:] = r0["state"]
+    for step in range(3):                      # the same buffers call after call
+        g[:] = f
+        g[np.arange(B), (7 * np.arange(B) + 11 * step) % n] ^= 1
+        plain = c.logz_kpm_local(np.array(g), 2.0, 1.0, 5.0, M, G, f_ref=np.array(f), state_ref=np.array(ks))
+        r = c.logz_kpm_local(g, 2.0, 1.0, 5.0, M, G, f_ref=f, state_ref=ks, out=out)
+        assert r["logZ"] is out["logZ"] and r["state"] is out["state"] and r["moments"] is out["moments"]
+        for k in ("logZ", "moments", "state", "e_min", "e_max"):
+            assert np.array_equal(r[k], plain[k]), k
+        full = c.logz_kpm(np.array(g), 2.0, 1.0, 5.0, M, G)
+        assert np.abs(r["logZ"] - full["logZ"]).max() <= 1e-12 * np.abs(full["logZ"]).max()
+        f[:] = g
+        ks[:] = r["state"]
+    oe = dict(spectrum=pinned(B, n), logZ=pinned(B))
+    re_ = c.logz_ed(f, 2.0, 1.0, 5.0, out=oe)
+    assert re_["spectrum"] is oe["spectrum"] and np.array_equal(re_["spectrum"], c.logz_ed(np.array(f), 2.0, 1.0, 5.0)["spectrum"])
+    with pytest.raises(fk.FkmcError):
+        c.logz_ed(f, 2.0, 1.0, 5.0, out=dict(spectrum=np.zeros((B, n + 1))))
+    with pytest.raises(fk.FkmcError):
+        c.logz_kpm_local(f, 2.0, 1.0, 5.0, M, G, out=dict(state=np.zeros((B, 64), dtype=np.float32)))
+    c.close()
+
+
 # ---------------- band path: folded lattice ordering, band -> band (sb2sb.cu) -> tridiagonal ----------------
 @pytest.mark.parametrize("kind,L,U", [("cubic2d", 16, 2.0), ("cubic2d", 24, 0.5), ("cubic2d", 26, 4.0), ("cubic2d", 32, 1.0), ("triangular", 24, 2.0),
                                       ("triangular", 31, 2.0), ("honeycomb", 24, 2.0), ("honeycomb", 32, 1.0)])
