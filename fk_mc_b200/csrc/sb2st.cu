@@ -33,11 +33,20 @@ constexpr int SB = 8;     // half bandwidth
 #ifndef FKMC_SB2ST_WD
 #define FKMC_SB2ST_WD 19
 #endif
-constexpr int WD = FKMC_SB2ST_WD;    // doubles per stored column: 16 sub-diagonals (band 0..8 + transient fill 9..15) padded to a stride that spreads the three
+#ifndef FKMC_SB2ST_WD_BIG
+#define FKMC_SB2ST_WD_BIG 24
+#endif
+constexpr int WD_SMALL = FKMC_SB2ST_WD;    // doubles per stored column: 16 sub-diagonals (band 0..8 + transient fill 9..15) padded to a stride that spreads the three
                           // access patterns of a step (and the four sweeps of a warp, 24 columns apart) over the banks: 78 wavefronts per step instead of 120
 #ifndef FKMC_SB2ST_LAG
 #define FKMC_SB2ST_LAG 2
 #endif
+// Stride of the one-CTA-per-SM instantiation.  A 64-bit shared access is served per half-warp, i.e. per pair of sweep groups, whose columns are
+// 8 LAG - 1 = 15 apart: the eight consecutive doubles each group reads from the block below fall on the same banks unless 15 WD = 8 (mod 16),
+// i.e. WD = 8 (mod 16).  Modelled wavefronts of the band accesses per warp-step: 142 at WD = 19 (ncu: 26 % excess), 108 at WD = 24, 96 ideal;
+// measured 13.78 -> 12.33 ms per 1024 matrices at N = 1024, bit-identical spectra (tools/sb2st_wd_check.py).  206 KB at N = 1024, so only
+// matrices that own an SM anyway take it.
+constexpr int WD_BIG = FKMC_SB2ST_WD_BIG;
 constexpr int LAG = FKMC_SB2ST_LAG;    // steps between consecutive sweeps (see the dependence analysis above; 3 = the conservative value of round 1)
 
 // Ordering of the band updates against the progress counters.  Writer: band stores (all lanes), __syncwarp, counter store (one
@@ -152,7 +161,7 @@ __device__ __forceinline__ refl make_reflector_pad(double x, int l, int n, doubl
 
 // BIG: one CTA per SM anyway (N > 700 or so: the band alone is more than half of the shared memory), up to twelve warps with as many registers
 // as they like; otherwise at most eight warps and 128 registers, so that two or more CTAs share an SM.
-template <bool BIG>
+template <bool BIG, int WD>
 __global__ void __launch_bounds__(BIG ? 384 : 256, BIG ? 1 : 2)
 sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_all, double* __restrict__ e_all) {
     extern __shared__ double smem[];
@@ -326,7 +335,7 @@ sb2st_kernel(const double* __restrict__ AB_all, int N, double* __restrict__ d_al
 }  // namespace
 
 // band, counters, broadcast pads (24 doubles per sweep group, four groups per warp)
-static size_t sb2st_smem(int N, int nwarps) { return sizeof(double) * ((size_t)(N + 16) * WD + (N + 1) / 2 + 3 + (size_t)nwarps * 4 * 24) + 16; }
+static size_t sb2st_smem(int N, int nwarps, int WD = WD_SMALL) { return sizeof(double) * ((size_t)(N + 16) * WD + (N + 1) / 2 + 3 + (size_t)nwarps * 4 * 24) + 16; }
 size_t fkmc_sb2st_smem(int N) { return sb2st_smem(N, 12); }  // upper bound (at most twelve warps)
 
 int fkmc_launch_sb2st(fkmc_ctx* ctx, const double* d_AB, int N, int B, double* d_d, double* d_e) {
@@ -340,14 +349,19 @@ int fkmc_launch_sb2st(fkmc_ctx* ctx, const double* d_AB, int N, int B, double* d
     if (nwarps < 1) nwarps = 1;
     if (nwarps > cap) nwarps = cap;
     if (ctx->sb2st_warps > 0) nwarps = std::min(ctx->sb2st_warps, cap);  // tuning override (fkmc_set_option "sb2st_warps")
-    const size_t smem = sb2st_smem(N, nwarps);  // small matrices share an SM: no more shared memory than this launch needs
+    // matrices that own an SM anyway take the conflict-free column stride WD_BIG when the wider band still fits (N <= 1122), else the compact one
+    const bool wide = big && WD_BIG != WD_SMALL && sb2st_smem(N, nwarps, WD_BIG) <= ctx->smem_optin;
+    const size_t smem = sb2st_smem(N, nwarps, wide ? WD_BIG : WD_SMALL);  // small matrices share an SM: no more shared memory than this launch needs
     if (smem > ctx->smem_optin) return fkmc_set_error(ctx, FKMC_ERR_INVALID, "sb2st: matrix too large for shared memory");
-    if (big) {
-        FKMC_CUDA(ctx, cudaFuncSetAttribute(sb2st_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sb2st_kernel<true><<<B, nwarps * 32, smem, ctx->stream>>>(d_AB, N, d_d, d_e);
+    if (wide) {
+        FKMC_CUDA(ctx, cudaFuncSetAttribute(sb2st_kernel<true, WD_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sb2st_kernel<true, WD_BIG><<<B, nwarps * 32, smem, ctx->stream>>>(d_AB, N, d_d, d_e);
+    } else if (big) {
+        FKMC_CUDA(ctx, cudaFuncSetAttribute(sb2st_kernel<true, WD_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sb2st_kernel<true, WD_SMALL><<<B, nwarps * 32, smem, ctx->stream>>>(d_AB, N, d_d, d_e);
     } else {
-        FKMC_CUDA(ctx, cudaFuncSetAttribute(sb2st_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sb2st_kernel<false><<<B, nwarps * 32, smem, ctx->stream>>>(d_AB, N, d_d, d_e);
+        FKMC_CUDA(ctx, cudaFuncSetAttribute(sb2st_kernel<false, WD_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sb2st_kernel<false, WD_SMALL><<<B, nwarps * 32, smem, ctx->stream>>>(d_AB, N, d_d, d_e);
     }
     ctx->launches++;
     FKMC_CUDA(ctx, cudaGetLastError());
